@@ -1,0 +1,169 @@
+// extern "C" boundary (include/athtd.h).  Never throws, never allocates device memory, never syncs.
+#include "plan.h"
+#include "../../include/athtd.h"
+#include <string>
+#include <mutex>
+
+using namespace athtd;
+
+static thread_local std::string g_err;
+static const ParamTable& param_table() { static ParamTable t = build_param_table(); return t; }
+static const PackLayout& pack_layout(int dtype) {
+  static PackLayout l0(0), l1(1);
+  return dtype == 0 ? l0 : l1;
+}
+static int fail(const std::string& m) { g_err = m; return 1; }
+static int check_cuda(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" {
+
+const char* athtd_last_error(void) { return g_err.c_str(); }
+int athtd_version(void) { return 1; }
+
+int athtd_param_count(void) { return (int)param_table().items.size(); }
+const char* athtd_param_name(int i) { return param_table().items[i].name.c_str(); }
+long athtd_param_numel(int i) { return param_table().items[i].numel; }
+long athtd_param_offset(int i) { return param_table().items[i].offset; }
+long athtd_params_total(void) { return param_table().total; }
+
+long athtd_packed_bytes(int dtype) { return pack_layout(dtype).total_bytes; }
+
+int athtd_pack_weights(const float* params_dev, void* packed_dev, int dtype, void* stream) {
+  try {
+    if (dtype == 0) pack_weights<float>(param_table(), pack_layout(0), params_dev, packed_dev, (cudaStream_t)stream);
+    else if (dtype == 1) pack_weights<bf16>(param_table(), pack_layout(1), params_dev, packed_dev, (cudaStream_t)stream);
+    else return fail("athtd_pack_weights: dtype must be 0 (fp32) or 1 (bf16)");
+  } catch (const std::exception& e) { return fail(e.what()); }
+  return check_cuda("athtd_pack_weights");
+}
+
+static int check_shape(int B, int L, int P, int dtype) {
+  if (B < 1 || P < 1) return fail("athtd: B and P must be >= 1");
+  if (L < 4096) return fail("athtd: segment length must be >= 4096 samples");
+  if (dtype != 0 && dtype != 1) return fail("athtd: dtype must be 0 (fp32) or 1 (bf16)");
+  return 0;
+}
+
+long athtd_workspace_bytes(int B, int L, int P, int dtype) {
+  if (check_shape(B, L, P, dtype)) return -1;
+  PlanConsts c{};
+  if (dtype == 0) { PlanT<float> p(B, L, P, &param_table(), &pack_layout(0), nullptr, nullptr, nullptr, c); return p.workspace_bytes(); }
+  PlanT<bf16> p(B, L, P, &param_table(), &pack_layout(1), nullptr, nullptr, nullptr, c);
+  return p.workspace_bytes();
+}
+
+void* athtd_plan_create(int B, int L, int P, int dtype, const float* params_dev, const void* packed_dev, void* workspace_dev,
+                        long workspace_bytes, const float* tw_dev, const float* win_dev, const float* pe2d_dev,
+                        const float* pe1d_dev) {
+  if (check_shape(B, L, P, dtype)) return nullptr;
+  int dev = 0; cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    fail("athtd_plan_create: no CUDA device (this library has no CPU fallback)"); return nullptr;
+  }
+  if (prop.major != 10) { fail("athtd_plan_create: built for sm_100a (B200) only"); return nullptr; }
+  PlanConsts c{(const float2*)tw_dev, win_dev, pe2d_dev, pe1d_dev};
+  PlanBase* p = nullptr;
+  try {
+    if (dtype == 0) p = new PlanT<float>(B, L, P, &param_table(), &pack_layout(0), params_dev, packed_dev, workspace_dev, c);
+    else p = new PlanT<bf16>(B, L, P, &param_table(), &pack_layout(1), params_dev, packed_dev, workspace_dev, c);
+  } catch (const std::exception& e) { fail(e.what()); return nullptr; }
+  if (p->workspace_bytes() > workspace_bytes) { delete p; fail("athtd_plan_create: workspace too small"); return nullptr; }
+  return p;
+}
+void athtd_plan_destroy(void* plan) { delete (PlanBase*)plan; }
+
+int athtd_plan_tokens(void* plan, int* Tf, int* Sf, int* St) {
+  TapInfo ti;
+  PlanBase* p = (PlanBase*)plan;
+  if (!p->tap("tokf", ti)) return fail("tokf"); *Sf = ti.dims[1];
+  if (!p->tap("tokt", ti)) return fail("tokt"); *St = ti.dims[1];
+  *Tf = *Sf / 8;
+  return 0;
+}
+
+#define GUARD(expr, tag)                                          \
+  try { expr; } catch (const std::exception& e) { return fail(e.what()); } \
+  return check_cuda(tag);
+
+int athtd_forward(void* plan, const float* wav_dev, const float* emb_dev, float* out_dev, void* stream) {
+  GUARD(((PlanBase*)plan)->forward(wav_dev, emb_dev, out_dev, (cudaStream_t)stream), "athtd_forward");
+}
+int athtd_encode(void* plan, const float* wav_dev, void* stream) {
+  GUARD(((PlanBase*)plan)->encode_only(wav_dev, (cudaStream_t)stream), "athtd_encode");
+}
+int athtd_decode(void* plan, const float* emb_dev, float* out_dev, void* stream) {
+  GUARD(((PlanBase*)plan)->decode_only(emb_dev, out_dev, (cudaStream_t)stream), "athtd_decode");
+}
+int athtd_plan_launches(void* plan) { return ((PlanBase*)plan)->launches(); }
+
+int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[4]) {
+  TapInfo ti;
+  if (!((PlanBase*)plan)->tap(name, ti)) return fail(std::string("athtd_tap: unknown buffer ") + name);
+  *ptr = ti.ptr; *numel = ti.numel; *dtype = ti.dtype;
+  for (int i = 0; i < 4; ++i) dims[i] = ti.dims[i];
+  return 0;
+}
+
+int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* stream) {
+  cudaError_t e = cudaMemcpyAsync(dst_dev, src_dev, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(std::string("athtd_memcpy_d2d: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int athtd_stft_cac(const float* wav_dev, int B, int L, float* Z_dev, double* stats_dev, const float* tw_dev,
+                   const float* win_dev, void* stream) {
+  if (L < 4096) return fail("athtd_stft_cac: L must be >= 4096");
+  launch_stft_cac(wav_dev, B, L, (L + 1023) / 1024, Z_dev, stats_dev, (const float2*)tw_dev, win_dev, (cudaStream_t)stream);
+  return check_cuda("athtd_stft_cac");
+}
+
+int athtd_istft(const float* Z_dev, int B, int L, float* frames_dev, float* out_dev, const float* tw_dev,
+                const float* win_dev, void* stream) {
+  const int Tf = (L + 1023) / 1024;
+  RowSpace none{};
+  launch_mask_istft<float>(Z_dev, Tf, B, 1, nullptr, none, 0, nullptr, nullptr, frames_dev, (const float2*)tw_dev, win_dev,
+                           (cudaStream_t)stream);
+  launch_ola_combine<float>(frames_dev, Tf, L, B, nullptr, none, nullptr, nullptr, nullptr, 1, out_dev, 2L * L,
+                            (cudaStream_t)stream);
+  return check_cuda("athtd_istft");
+}
+
+int athtd_gather_chunks(const float* track_dev, long T, int C, const long* starts_dev, int n_chunks, int chunk_len,
+                        float* segs_dev, void* stream) {
+  launch_gather_chunks(track_dev, T, C, starts_dev, n_chunks, chunk_len, segs_dev, (cudaStream_t)stream);
+  return check_cuda("athtd_gather_chunks");
+}
+
+int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int chunk_len, const long* starts_dev,
+                    const int* actual_len_dev, const int* fade_len_dev, const int* flags_dev, int n_chunks, long stride,
+                    const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
+                    long t_begin, long t_end, void* stream) {
+  if (C < 1 || C > 2) return fail("athtd_chunk_ola: C must be 1 or 2");
+  launch_chunk_ola(seg_out_dev, seg_stride, k_base, chunk_len, starts_dev, actual_len_dev, fade_len_dev, flags_dev, n_chunks,
+                   stride, ramp_up_dev, ramp_down_dev, ramp_off_dev, out_dev, C, t_begin, t_end, (cudaStream_t)stream);
+  return check_cuda("athtd_chunk_ola");
+}
+
+int athtd_gemm_test(const void* A_dev, const void* B_dev, const float* bias_dev, void* C_dev, int M, int N, int K, int dtype,
+                    int use_tensor_cores, void* stream) {
+  GemmDesc d = gemm_desc_zero();
+  d.Mg = M; d.N = N; d.K = K; d.Ktap = K; d.A = A_dev; d.sAm = K; d.B = B_dev; d.sBn = K; d.sBk = 1;
+  d.C = C_dev; d.sCm = N; d.bias = bias_dev;
+  if (use_tensor_cores) {
+#ifdef ATHTD_HAVE_TC
+    if (dtype != 1) return fail("athtd_gemm_test: tensor-core path is bf16");
+    if (!gemm_tc_supported(d)) return fail("athtd_gemm_test: shape not supported by the tcgen05 kernel");
+    launch_gemm_tc(d, (cudaStream_t)stream);
+#else
+    return fail("athtd_gemm_test: built without the tcgen05 kernel");
+#endif
+  } else if (dtype == 0) launch_gemm_simt<float>(d, (cudaStream_t)stream);
+  else launch_gemm_simt<bf16>(d, (cudaStream_t)stream);
+  return check_cuda("athtd_gemm_test");
+}
+
+}  // extern "C"

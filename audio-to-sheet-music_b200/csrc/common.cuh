@@ -1,0 +1,59 @@
+// Common device helpers for the AudioTextHTDemucs B200 path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace athtd {
+
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// exact (erf) GELU: torch F.gelu default / nn.GELU(approximate='none')
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// mean / rstd from double (sum, sumsq) accumulators, biased variance (GroupNorm / LayerNorm)
+__device__ __forceinline__ void stats_to_mean_rstd(const double* st, double count, float eps,
+                                                   float& mean, float& rstd) {
+  double m = st[0] / count;
+  double var = st[1] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// A padded row space: G groups, each with R interior rows stored inside Rp rows (pf front pad rows).
+struct RowSpace {
+  int G;    // number of groups
+  int R;    // interior rows per group
+  int Rp;   // stored rows per group (R + pads)
+  int pf;   // front pad rows
+  int C;    // channels per row (row pitch in elements)
+  __host__ __device__ long row_off(int g, int r) const { return ((long)g * Rp + pf + r) * (long)C; }
+  __host__ __device__ long elems() const { return (long)G * Rp * C; }
+};
+
+}  // namespace athtd

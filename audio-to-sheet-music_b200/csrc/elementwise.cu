@@ -1,0 +1,341 @@
+// Bandwidth-bound kernels of the path: input normalisation, GroupNorm/LayerNorm applies,
+// GLU/LayerScale residuals, softmax, decoder resize+skip, weight packing.
+// All activation tensors are channels-last inside padded row spaces (common.cuh: RowSpace).
+#include "kernels.cuh"
+
+namespace athtd {
+
+// ------------------------------------------------------------------ per-sample sum / sumsq
+__global__ void sum_sumsq_kernel(const float* __restrict__ x, long n_per_sample, double* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const float* p = x + (long)b * n_per_sample;
+  float s = 0.f, ss = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_sample; i += (long)gridDim.x * blockDim.x) {
+    float v = p[i]; s += v; ss += v * v;
+  }
+  __shared__ float sh[2][32];
+  s = warp_sum(s); ss = warp_sum(ss);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s; sh[1][w] = ss; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    double a = l < nw ? (double)sh[0][l] : 0.0, c = l < nw ? (double)sh[1][l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if (l == 0) { atomicAdd(stats + 2 * b, a); atomicAdd(stats + 2 * b + 1, c); }
+  }
+}
+void launch_sum_sumsq(const float* x, int B, long n_per_sample, double* stats, cudaStream_t st) {
+  int blocks = (int)min((n_per_sample + 256 * 8 - 1) / (256 * 8), (long)296);
+  if (blocks < 1) blocks = 1;
+  sum_sumsq_kernel<<<dim3(blocks, B), 256, 0, st>>>(x, n_per_sample, stats);
+}
+
+// (sum, sumsq) double accumulators -> (mean, rstd) floats, biased variance (GroupNorm semantics)
+__global__ void finalize_gn_kernel(const double* __restrict__ stats, double count, float* __restrict__ mr, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { float m, r; stats_to_mean_rstd(stats + 2 * i, count, 1e-5f, m, r); mr[2 * i] = m; mr[2 * i + 1] = r; }
+}
+void launch_finalize_gn(const double* stats, double count, float* mr, long n, cudaStream_t st) {
+  finalize_gn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stats, count, mr, n);
+}
+
+// torch.std default (unbiased) and the reference guard (x - mean) / (1e-5 + std)   ATHTDemucs_v2.py:268-275
+__device__ __forceinline__ void unbiased_mean_std(const double* st, double n, float& mean, float& std_) {
+  double m = st[0] / n;
+  double var = (st[1] - st[0] * m) / (n - 1.0);
+  if (var < 0.0) var = 0.0;
+  mean = (float)m; std_ = (float)sqrt(var);
+}
+
+__global__ void finalize_meanstd_kernel(const double* __restrict__ stats, double n, float* __restrict__ out, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { float m, s; unbiased_mean_std(stats + 2 * b, n, m, s); out[2 * b] = m; out[2 * b + 1] = s; }
+}
+void launch_finalize_meanstd(const double* stats, double n, float* out, int B, cudaStream_t st) {
+  finalize_meanstd_kernel<<<(B + 127) / 128, 128, 0, st>>>(stats, n, out, B);
+}
+
+// wav [B,2,L] fp32 -> normalised channels-last padded [B, Rp, 2]
+template <typename T>
+__global__ void pack_wav_kernel(const float* __restrict__ wav, const float* __restrict__ meanstd, T* __restrict__ out,
+                                RowSpace rs, int L) {
+  int b = blockIdx.y;
+  float mean = meanstd[2 * b], inv = 1.0f / (1e-5f + meanstd[2 * b + 1]);
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
+    float a = (wav[((long)b * 2 + 0) * L + l] - mean) * inv;
+    float c = (wav[((long)b * 2 + 1) * L + l] - mean) * inv;
+    long o = rs.row_off(b, l);
+    out[o] = from_f<T>(a); out[o + 1] = from_f<T>(c);
+  }
+}
+template <typename T>
+void launch_pack_wav(const float* wav, const float* meanstd, T* out, RowSpace rs, int L, cudaStream_t st) {
+  pack_wav_kernel<T><<<dim3(min((L + 255) / 256, 1024), rs.G), 256, 0, st>>>(wav, meanstd, out, rs, L);
+}
+
+// Z [B, Tf, 2048, 4] fp32 -> normalised padded [B*Tf, Rp, 4]
+template <typename T>
+__global__ void pack_spec_kernel(const float4* __restrict__ Z, const float* __restrict__ meanstd, T* __restrict__ out,
+                                 RowSpace rs, int Tf) {
+  int g = blockIdx.y;           // b*Tf + t
+  int b = g / Tf;
+  float mean = meanstd[2 * b], inv = 1.0f / (1e-5f + meanstd[2 * b + 1]);
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < rs.R; f += gridDim.x * blockDim.x) {
+    float4 v = Z[(long)g * rs.R + f];
+    long o = rs.row_off(g, f);
+    out[o] = from_f<T>((v.x - mean) * inv); out[o + 1] = from_f<T>((v.y - mean) * inv);
+    out[o + 2] = from_f<T>((v.z - mean) * inv); out[o + 3] = from_f<T>((v.w - mean) * inv);
+  }
+}
+template <typename T>
+void launch_pack_spec(const float* Z, const float* meanstd, T* out, RowSpace rs, int Tf, cudaStream_t st) {
+  pack_spec_kernel<T><<<dim3((rs.R + 255) / 256, rs.G), 256, 0, st>>>((const float4*)Z, meanstd, out, rs, Tf);
+}
+
+// ------------------------------------------------------------------ GroupNorm(1,C) + GELU, in place
+// stat index: per_row ? (g/G2)*R + r : g/G2 ; count given by the caller.
+template <typename T>
+__global__ void gn_gelu_kernel(T* __restrict__ h, RowSpace rs, int G2, int per_row, const float* __restrict__ mr,
+                               const float* __restrict__ w, const float* __restrict__ bvec) {
+  long total = (long)rs.G * rs.R * rs.C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % rs.C); long row = i / rs.C;
+    int r = (int)(row % rs.R); int g = (int)(row / rs.R);
+    long si = per_row ? (long)(g / G2) * rs.R + r : (long)(g / G2);
+    float mean = mr[2 * si], rstd = mr[2 * si + 1];
+    long o = rs.row_off(g, r) + c;
+    float v = (to_f<T>(h[o]) - mean) * rstd * w[c] + bvec[c];
+    h[o] = from_f<T>(gelu_erf(v));
+  }
+}
+template <typename T>
+void launch_gn_gelu(T* h, RowSpace rs, int G2, int per_row, const float* mr, const float* w,
+                    const float* b, cudaStream_t st) {
+  long total = (long)rs.G * rs.R * rs.C;
+  int blocks = (int)min((total + 255) / 256, (long)148 * 16);
+  gn_gelu_kernel<T><<<blocks, 256, 0, st>>>(h, rs, G2, per_row, mr, w, b);
+}
+
+// x <- x + scale[c] * ( GN(e)[c] * sigmoid(GN(e)[c+C]) )     DConv tail (demucs DConv layers 4..6)
+template <typename T>
+__global__ void gn_glu_res_kernel(T* __restrict__ x, RowSpace xs, const T* __restrict__ e, RowSpace es, int G2, int per_row,
+                                  const float* __restrict__ mr, const float* __restrict__ w,
+                                  const float* __restrict__ bvec, const float* __restrict__ scale) {
+  const int C = xs.C;
+  long total = (long)xs.G * xs.R * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long row = i / C;
+    int r = (int)(row % xs.R); int g = (int)(row / xs.R);
+    long si = per_row ? (long)(g / G2) * xs.R + r : (long)(g / G2);
+    float mean = mr[2 * si], rstd = mr[2 * si + 1];
+    long eo = es.row_off(g, r);
+    float a = (to_f<T>(e[eo + c]) - mean) * rstd * w[c] + bvec[c];
+    float gt = (to_f<T>(e[eo + c + C]) - mean) * rstd * w[c + C] + bvec[c + C];
+    long o = xs.row_off(g, r) + c;
+    x[o] = from_f<T>(to_f<T>(x[o]) + scale[c] * (a * sigmoid_acc(gt)));
+  }
+}
+template <typename T>
+void launch_gn_glu_res(T* x, RowSpace xs, const T* e, RowSpace es, int G2, int per_row, const float* mr,
+                       const float* w, const float* b, const float* scale, cudaStream_t st) {
+  long total = (long)xs.G * xs.R * xs.C;
+  int blocks = (int)min((total + 255) / 256, (long)148 * 16);
+  gn_glu_res_kernel<T><<<blocks, 256, 0, st>>>(x, xs, e, es, G2, per_row, mr, w, b, scale);
+}
+
+// ------------------------------------------------------------------ (GroupNorm apply) + LayerNorm (+pos-emb)
+// One warp per token row of C <= 512 channels.  x: [rows, C] contiguous.
+//   if gstats: x' = (x-mu_b)*rstd_b*gw + gb  is written to xout (MyGroupNorm over all tokens of a sample)
+//   if lw:     y  = LN(x')*lw + lb (+ pe[row % S])   is written to y
+template <typename T>
+__global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, T* __restrict__ y, long rows, int C, int S,
+                                 const float* __restrict__ gmr, const float* __restrict__ gw,
+                                 const float* __restrict__ gb, const float* __restrict__ lw, const float* __restrict__ lb,
+                                 const float* __restrict__ pe, int yR, int yRp, int ypf) {
+  int lane = threadIdx.x & 31;
+  long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * C;
+  float v[16];
+  int cnt = 0;
+  float gm = 0.f, gr = 1.f;
+  if (gmr) { gm = gmr[2 * (row / S)]; gr = gmr[2 * (row / S) + 1]; }
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32, ++cnt) {
+    float t = to_f<T>(xr[c]);
+    if (gmr) { t = (t - gm) * gr * gw[c] + gb[c]; xout[row * C + c] = from_f<T>(t); }
+    v[cnt] = t; s += t;
+  }
+  if (!lw) return;
+  s = warp_sum(s);
+  float mean = s / C;
+  float q = 0.f;
+  for (int i = 0; i < cnt; ++i) { float dlt = v[i] - mean; q += dlt * dlt; }
+  q = warp_sum(q);
+  float rstd = rsqrtf(q / C + 1e-5f);
+  long srow = row % S;
+  long yrow = row;
+  if (yR > 0) yrow = (row / yR) * yRp + ypf + (row % yR);   // scatter into a padded row space
+  cnt = 0;
+  for (int c = lane; c < C; c += 32, ++cnt) {
+    float t = (v[cnt] - mean) * rstd * lw[c] + lb[c];
+    if (pe) t += pe[srow * C + c];
+    y[yrow * C + c] = from_f<T>(t);
+  }
+}
+template <typename T>
+void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const float* gmr,
+                      const float* gw, const float* gb, const float* lw, const float* lb, const float* pe,
+                      int yR, int yRp, int ypf, cudaStream_t st) {
+  int wpb = 8;
+  norm_rows_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, xout, y, rows, C, S, gmr,
+                                                                                gw, gb, lw, lb, pe, yR, yRp, ypf);
+}
+
+// ------------------------------------------------------------------ row softmax, in place (fp32 math)
+template <typename T>
+__global__ void softmax_rows_kernel(T* __restrict__ s, long rows, int n) {
+  long row = blockIdx.x;
+  T* p = s + row * n;
+  __shared__ float sh[32];
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, to_f<T>(p[i]));
+  mx = warp_max(mx);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (l == 0) sh[w] = mx;
+  __syncthreads();
+  mx = l < nw ? sh[l] : -INFINITY; mx = warp_max(mx);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += expf(to_f<T>(p[i]) - mx);
+  sum = warp_sum(sum);
+  if (l == 0) sh[w] = sum;
+  __syncthreads();
+  sum = l < nw ? sh[l] : 0.f; sum = warp_sum(sum);
+  float inv = 1.0f / sum;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = from_f<T>(expf(to_f<T>(p[i]) - mx) * inv);
+}
+template <typename T>
+void launch_softmax_rows(T* s, long rows, int n, cudaStream_t st) {
+  softmax_rows_kernel<T><<<(unsigned)rows, 256, 0, st>>>(s, rows, n);
+}
+
+// ------------------------------------------------------------------ y[b, r, :] = x[b, r, :] + vec[b*vstride, :]
+template <typename T>
+__global__ void add_rowvec_kernel(const T* __restrict__ x, T* __restrict__ y, long rows_per_b, int C, int B,
+                                  const float* __restrict__ vec, long vstride) {
+  long total = (long)B * rows_per_b * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long b = i / ((long)rows_per_b * C);
+    y[i] = from_f<T>(to_f<T>(x[i]) + vec[b * vstride + c]);
+  }
+}
+template <typename T>
+void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const float* vec, long vstride, cudaStream_t st) {
+  long total = (long)B * rows_per_b * C;
+  add_rowvec_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(x, y, rows_per_b, C, B, vec, vstride);
+}
+
+// ------------------------------------------------------------------ decoder layer tail
+// out[g, d, c] = lerp_rows( act(GN(u))[g, :, c] )(d) + 0.1 * lerp_rows( skip[g, :, c] )(d)
+//   u    : transposed-conv output in phase layout, row fo of group g lives at u[(g*Urows + fo + 2)*Cu + c]
+//   GN   : GroupNorm(1,C) statistics per sample (g / G2), biased variance, then exact GELU  (has_gn)
+//   lerp : F.interpolate(mode=linear/bilinear along one axis, align_corners=False)   
+// Follows FreqDecoder.forward / TimeDecoder.forward, ATHTDemucs_v2.py:82-104 / 125-139.
+__device__ __forceinline__ void lerp_coords(int d, int in, int out, int& i0, int& i1, float& lam) {
+  if (in == out) { i0 = d; i1 = d; lam = 0.f; return; }
+  float scale = (float)in / (float)out;
+  float src = scale * ((float)d + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  lam = src - (float)i0;
+}
+template <typename T>
+__global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, long u_group_stride, int Cu, T* __restrict__ out,
+                                 RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
+                                 const float* __restrict__ gw, const float* __restrict__ gb, const T* __restrict__ skip,
+                                 RowSpace ss) {
+  const int C = os.C;
+  long total = (long)os.G * os.R * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long row = i / C;
+    int d = (int)(row % os.R); int g = (int)(row / os.R);
+    int i0, i1; float lam;
+    lerp_coords(d, Uin, os.R, i0, i1, lam);
+    const T* ug = u + (long)g * u_group_stride;
+    float a0 = to_f<T>(ug[(long)(i0 + 2) * Cu + c]);
+    float a1 = to_f<T>(ug[(long)(i1 + 2) * Cu + c]);
+    if (has_gn) {
+      float mean = mr[2 * (g / G2)], rstd = mr[2 * (g / G2) + 1];
+      a0 = gelu_erf((a0 - mean) * rstd * gw[c] + gb[c]);
+      a1 = gelu_erf((a1 - mean) * rstd * gw[c] + gb[c]);
+    }
+    float v = (1.f - lam) * a0 + lam * a1;
+    int j0, j1; float mu;
+    lerp_coords(d, ss.R, os.R, j0, j1, mu);
+    float s0 = to_f<T>(skip[ss.row_off(g, j0) + c]);
+    float s1 = to_f<T>(skip[ss.row_off(g, j1) + c]);
+    v += 0.1f * ((1.f - mu) * s0 + mu * s1);
+    out[os.row_off(g, d) + c] = from_f<T>(v);
+  }
+}
+template <typename T>
+void launch_dec_apply(const T* u, int Uin, long u_group_stride, int Cu, T* out, RowSpace os, int G2, int has_gn,
+                      const float* mr, const float* gw, const float* gb, const T* skip, RowSpace ss,
+                      cudaStream_t st) {
+  long total = (long)os.G * os.R * os.C;
+  dec_apply_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(u, Uin, u_group_stride, Cu, out, os, G2,
+                                                                                    has_gn, mr, gw, gb, skip, ss);
+}
+
+// ------------------------------------------------------------------ weight packing (fp32 params -> T, GEMM layouts)
+// kind 0: plain copy               dst[i] = src[i]
+// kind 1: conv k-major             src [Co][Ci][K] -> dst [Co][K*Ci]              (k*Ci + ci)
+// kind 2: conv-transpose phases    src [Ci][Co][8] -> dst [4*Co][2*Ci], row r*Co+co, col j*Ci+ci, tap = j==0 ? r+4 : r
+// kind 3: GLU interleave rows      src [2C][K]     -> dst row 2j = src row j, row 2j+1 = src row j+C
+// kind 4: replicate                src [d0]        -> dst[i] = src[i % d0]
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, long n, int kind, int d0, int d1, int d2) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    long s = i;
+    if (kind == 1) {           // d0=Co d1=Ci d2=K ; dst index i = (co*K + k)*Ci + ci
+      int ci = (int)(i % d1); long t = i / d1; int k = (int)(t % d2); int co = (int)(t / d2);
+      s = ((long)co * d1 + ci) * d2 + k;
+    } else if (kind == 2) {    // d0=Ci d1=Co ; dst index i = (r*Co+co)*(2*Ci) + j*Ci + ci
+      int ci = (int)(i % d0); long t = i / d0; int j = (int)(t % 2); t /= 2; int co = (int)(t % d1); int r = (int)(t / d1);
+      int tap = j == 0 ? r + 4 : r;
+      s = ((long)ci * d1 + co) * 8 + tap;
+    } else if (kind == 3) {    // d0=2C d1=K
+      int k = (int)(i % d1); int row = (int)(i / d1); int j = row >> 1; int half = row & 1;
+      s = (long)(j + half * (d0 / 2)) * d1 + k;
+    } else if (kind == 4) {    // replicate a [d0] vector
+      s = i % d0;
+    }
+    dst[i] = from_f<T>(src[s]);
+  }
+}
+template <typename T>
+void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int d1, int d2, cudaStream_t st) {
+  pack_weight_kernel<T><<<(int)min((n + 255) / 256, (long)2048), 256, 0, st>>>(src, dst, n, kind, d0, d1, d2);
+}
+
+#define INST(T)                                                                                                         \
+  template void launch_pack_wav<T>(const float*, const float*, T*, RowSpace, int, cudaStream_t);                        \
+  template void launch_pack_spec<T>(const float*, const float*, T*, RowSpace, int, cudaStream_t);                       \
+  template void launch_gn_gelu<T>(T*, RowSpace, int, int, const float*, const float*, const float*, cudaStream_t); \
+  template void launch_gn_glu_res<T>(T*, RowSpace, const T*, RowSpace, int, int, const float*, const float*,            \
+                                     const float*, const float*, cudaStream_t);                                         \
+  template void launch_norm_rows<T>(const T*, T*, T*, long, int, int, const float*, const float*, const float*,         \
+                                    const float*, const float*, const float*, int, int, int, cudaStream_t);                            \
+  template void launch_softmax_rows<T>(T*, long, int, cudaStream_t);                                                    \
+  template void launch_add_rowvec<T>(const T*, T*, long, int, int, const float*, long, cudaStream_t);                   \
+  template void launch_dec_apply<T>(const T*, int, long, int, T*, RowSpace, int, int, const float*,                     \
+                                    const float*, const float*, const T*, RowSpace, cudaStream_t);                      \
+  template void launch_pack_weight<T>(const float*, T*, long, int, int, int, int, cudaStream_t);
+INST(float)
+INST(bf16)
+
+}  // namespace athtd

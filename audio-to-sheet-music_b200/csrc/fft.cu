@@ -1,0 +1,309 @@
+// Spectral front / back end of the path, replacing htdemucs._spec / _magnitude / _ispec
+// (call sites /root/reference/src/models/stem_separation/ATHTDemucs_v2.py:261-262, 297-310;
+//  semantics: demucs 4.0.1 spec.py / htdemucs.py).
+//
+// One CTA of 256 threads transforms one (segment, frame): the stereo pair is packed as
+// real=left, imag=right into ONE 4096-point complex FFT held in shared memory
+// (radix-16 x radix-16 x radix-16, three register passes with padded transposes), and the two
+// real spectra are recovered from the Hermitian symmetry.  Fused around it:
+//   forward : single-level reflect padding, periodic hann window, 1/64 (normalized=True),
+//             Nyquist-bin drop, complex-as-channels packing [B,Tf,2048,(Lre,Lim,Rre,Rim)],
+//             per-segment sum / sum-of-squares partials for the input normalisation.
+//   inverse : freq_out 1x1 conv, 259->2048 linear resize of the mask logits, sigmoid,
+//             the signed-CaC mask*phase product (quirk Q4), Hermitian extension with zero
+//             Nyquist, inverse FFT, window and 1/64 scale -> windowed frames.
+// A second bandwidth kernel overlap-adds 4 frames per sample in fixed order, divides by the
+// constant window-sum envelope 1.5, adds the de-normalised time branch and writes [B,2,L].
+#include "kernels.cuh"
+
+namespace athtd {
+
+#define FFT_N 4096
+#define FFT_PITCH 272          // 256 + 16: half-warps land on disjoint banks
+#define FFT_SMEM (16 * FFT_PITCH)
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// 4-point DFT, forward uses W4 = -i, inverse +i
+template <bool INV>
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+  float2 s0 = make_float2(a.x + c.x, a.y + c.y), s1 = make_float2(a.x - c.x, a.y - c.y);
+  float2 s2 = make_float2(b.x + d.x, b.y + d.y), s3 = make_float2(b.x - d.x, b.y - d.y);
+  // forward: y1 = s1 - i*s3 ; y3 = s1 + i*s3.   (-i)*(x+iy) = y - ix
+  float2 is3 = INV ? make_float2(-s3.y, s3.x) : make_float2(s3.y, -s3.x);
+  a = make_float2(s0.x + s2.x, s0.y + s2.y);
+  c = make_float2(s0.x - s2.x, s0.y - s2.y);
+  b = make_float2(s1.x + is3.x, s1.y + is3.y);
+  d = make_float2(s1.x - is3.x, s1.y - is3.y);
+}
+
+// 16-point DFT in registers, natural order in and out.
+template <bool INV>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+  // step 1: for each n2, DFT4 over n1 of v[4*n1 + n2]  -> t[n2][k1] stored back at v[4*k1 + n2]
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) dft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+  // step 2: twiddle W16^(n2*k1)
+  const float sg = INV ? 1.f : -1.f;
+  const float cs[10] = {1.f, C1, C2, S1, 0.f, -S1, -C2, -C1, -1.f, -C1};
+  const float sn[10] = {0.f, S1, C2, C1, 1.f, C1, C2, S1, 0.f, -S1};
+#pragma unroll
+  for (int k1 = 1; k1 < 4; ++k1)
+#pragma unroll
+    for (int n2 = 1; n2 < 4; ++n2) {
+      const int m = k1 * n2;
+      v[4 * k1 + n2] = cmul(v[4 * k1 + n2], make_float2(cs[m], sg * sn[m]));
+    }
+  // step 3: for each k1, DFT4 over n2 -> X[k1 + 4*k2] ; currently at v[4*k1 + n2]
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4<INV>(v[4 * k1 + 0], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+  // now v[4*k1 + k2] = X[k1 + 4*k2] : transpose the 4x4 to natural order
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) { float2 t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
+}
+
+// Passes 2 and 3 plus the natural-order write-back; on entry v holds pass-1 outputs V[k1]
+// (already multiplied by W4096^(t*k1)) of thread t.  On exit sr/si hold X[k] at index k + (k>>4).
+template <bool INV>
+__device__ __forceinline__ void fft4096_tail(float2 (&v)[16], float* sr, float* si, const float2* __restrict__ tw) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) { sr[k1 * FFT_PITCH + t] = v[k1].x; si[k1 * FFT_PITCH + t] = v[k1].y; }
+  __syncthreads();
+  const int hi = t >> 4, lo = t & 15;     // pass 2: (k1 = hi, m2 = lo)
+#pragma unroll
+  for (int m1 = 0; m1 < 16; ++m1) {
+    v[m1].x = sr[hi * FFT_PITCH + 16 * m1 + lo]; v[m1].y = si[hi * FFT_PITCH + 16 * m1 + lo];
+  }
+  dft16<INV>(v);
+#pragma unroll
+  for (int j1 = 1; j1 < 16; ++j1) {
+    float2 w = tw[16 * lo * j1];
+    if (INV) w.y = -w.y;
+    v[j1] = cmul(v[j1], w);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j1 = 0; j1 < 16; ++j1) { sr[hi * FFT_PITCH + lo * 17 + j1] = v[j1].x; si[hi * FFT_PITCH + lo * 17 + j1] = v[j1].y; }
+  __syncthreads();
+  // pass 3: (k1 = hi, j1 = lo) reads over m2
+#pragma unroll
+  for (int m2 = 0; m2 < 16; ++m2) {
+    v[m2].x = sr[hi * FFT_PITCH + m2 * 17 + lo]; v[m2].y = si[hi * FFT_PITCH + m2 * 17 + lo];
+  }
+  dft16<INV>(v);
+  __syncthreads();
+#pragma unroll
+  for (int j2 = 0; j2 < 16; ++j2) {
+    int k = hi + 16 * lo + 256 * j2;
+    int a = k + (k >> 4);
+    sr[a] = v[j2].x; si[a] = v[j2].y;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(256) stft_cac_kernel(const float* __restrict__ wav, int L, int Tf, float4* __restrict__ Z,
+                                                        double* __restrict__ stats, const float2* __restrict__ tw,
+                                                        const float* __restrict__ win) {
+  __shared__ float sr[FFT_SMEM], si[FFT_SMEM];
+  __shared__ float red[2][8];
+  const int t = threadIdx.x, frame = blockIdx.x, b = blockIdx.y;
+  const float* wl = wav + (long)b * 2 * L;
+  const float* wr = wl + L;
+  float2 v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    int n = 256 * n1 + t;
+    int idx = frame * 1024 - 1536 + n;       // kept frame `frame` of _spec == stft frame frame+2
+    if (idx < 0) idx = -idx;
+    if (idx >= L) idx = 2 * (L - 1) - idx;
+    float w = win[n];
+    v[n1] = make_float2(wl[idx] * w, wr[idx] * w);
+  }
+  dft16<false>(v);
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tw[t * k1]);
+  fft4096_tail<false>(v, sr, si, tw);
+  float s = 0.f, ss = 0.f;
+  float4* zo = Z + ((long)b * Tf + frame) * 2048;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int k = t + 256 * i;
+    int kn = (FFT_N - k) & (FFT_N - 1);
+    float ar = sr[k + (k >> 4)], ai = si[k + (k >> 4)];
+    float br = sr[kn + (kn >> 4)], bi = si[kn + (kn >> 4)];
+    float4 o;
+    o.x = (ar + br) * (0.5f / 64.f);       // L.re
+    o.y = (ai - bi) * (0.5f / 64.f);       // L.im   (exactly +0 at k = 0)
+    o.z = (ai + bi) * (0.5f / 64.f);       // R.re
+    o.w = (br - ar) * (0.5f / 64.f);       // R.im   (exactly +0 at k = 0)
+    zo[k] = o;
+    s += o.x + o.y + o.z + o.w;
+    ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+  }
+  s = warp_sum(s); ss = warp_sum(ss);
+  if ((t & 31) == 0) { red[0][t >> 5] = s; red[1][t >> 5] = ss; }
+  __syncthreads();
+  if (t == 0) {
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; c += red[1][i]; }
+    atomicAdd(stats + 2 * b, a); atomicAdd(stats + 2 * b + 1, c);
+  }
+}
+
+void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
+                     cudaStream_t st) {
+  stft_cac_kernel<<<dim3(Tf, B), 256, 0, st>>>(wav, L, Tf, (float4*)Z, stats, tw, win);
+}
+
+// ------------------------------------------------------------------ inverse: mask + iFFT -> windowed frames
+__device__ __forceinline__ void lerp_coords_f(int d, int in, int out, int& i0, int& i1, float& lam) {
+  if (in == out) { i0 = d; i1 = d; lam = 0.f; return; }
+  float scale = (float)in / (float)out;
+  float src = scale * ((float)d + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  lam = src - (float)i0;
+}
+
+// dec : FreqDecoder output rows [g = zb*? ...] see launch; fo_w [2][4], fo_b [2]
+// If dec == nullptr the mask is 1 (plain _ispec of Z[:, :2] semantics is NOT this; used only with use_mask=0 where
+// masked_z := z, i.e. channel 0 = L, channel 1 = R, for the STFT->iSTFT microbenchmark).
+template <typename T>
+__global__ void __launch_bounds__(256) mask_istft_kernel(const float4* __restrict__ Z, int Tf, int zb_div,
+                                                          const T* __restrict__ dec, RowSpace ds, int use_mask,
+                                                          const float* __restrict__ fo_w, const float* __restrict__ fo_b,
+                                                          float* __restrict__ frames, const float2* __restrict__ tw,
+                                                          const float* __restrict__ win) {
+  __shared__ float sr[FFT_SMEM], si[FFT_SMEM];
+  const int t = threadIdx.x, frame = blockIdx.x, bo = blockIdx.y;   // bo: output batch index (b*P + p or b)
+  const int bz = bo / zb_div;                                        // spectrogram batch index
+  const float4* zi = Z + ((long)bz * Tf + frame) * 2048;
+  const int g = bo * Tf + frame;                                     // decoder row-space group
+  float w00 = 0, w01 = 0, w02 = 0, w03 = 0, w10 = 0, w11 = 0, w12 = 0, w13 = 0, b0 = 0, b1 = 0;
+  if (use_mask) {
+    w00 = fo_w[0]; w01 = fo_w[1]; w02 = fo_w[2]; w03 = fo_w[3];
+    w10 = fo_w[4]; w11 = fo_w[5]; w12 = fo_w[6]; w13 = fo_w[7]; b0 = fo_b[0]; b1 = fo_b[1];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int k = t + 256 * i;
+    float4 z = zi[k];
+    float2 xl, xr;
+    if (use_mask) {
+      int i0, i1; float lam;
+      lerp_coords_f(k, ds.R, 2048, i0, i1, lam);
+      const T* r0 = dec + ds.row_off(g, i0);
+      const T* r1 = dec + ds.row_off(g, i1);
+      float a0 = to_f<T>(r0[0]), a1 = to_f<T>(r0[1]), a2 = to_f<T>(r0[2]), a3 = to_f<T>(r0[3]);
+      float c0 = to_f<T>(r1[0]), c1 = to_f<T>(r1[1]), c2 = to_f<T>(r1[2]), c3 = to_f<T>(r1[3]);
+      float l0a = w00 * a0 + w01 * a1 + w02 * a2 + w03 * a3 + b0;
+      float l1a = w10 * a0 + w11 * a1 + w12 * a2 + w13 * a3 + b1;
+      float l0b = w00 * c0 + w01 * c1 + w02 * c2 + w03 * c3 + b0;
+      float l1b = w10 * c0 + w11 * c1 + w12 * c2 + w13 * c3 + b1;
+      float m0 = sigmoid_acc((1.f - lam) * l0a + lam * l0b);
+      float m1 = sigmoid_acc((1.f - lam) * l1a + lam * l1b);
+      // quirk Q4 (ATHTDemucs_v2.py:303-309): "magnitudes" are the signed CaC planes L.re and L.im
+      float ms0 = z.x * m0, ms1 = z.y * m1;
+      float inv0 = 1.0f / (z.x + 1e-8f), inv1 = 1.0f / (z.y + 1e-8f);
+      xl = make_float2(ms0 * (z.x * inv0), ms0 * (z.y * inv0));
+      xr = make_float2(ms1 * (z.z * inv1), ms1 * (z.w * inv1));
+    } else {
+      xl = make_float2(z.x, z.y); xr = make_float2(z.z, z.w);
+    }
+    if (k == 0) { xl.y = 0.f; xr.y = 0.f; }        // C2R ignores the imaginary part of DC
+    // Y[k] = XL[k] + i XR[k] ; Y[N-k] = conj(XL[k]) + i conj(XR[k])
+    sr[k] = xl.x - xr.y; si[k] = xl.y + xr.x;
+    if (k > 0) { sr[FFT_N - k] = xl.x + xr.y; si[FFT_N - k] = xr.x - xl.y; }
+  }
+  if (t == 0) { sr[2048] = 0.f; si[2048] = 0.f; }   // Nyquist bin is zero-padded by _ispec
+  __syncthreads();
+  float2 v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) { v[n1].x = sr[256 * n1 + t]; v[n1].y = si[256 * n1 + t]; }
+  dft16<true>(v);
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) { float2 w = tw[t * k1]; w.y = -w.y; v[k1] = cmul(v[k1], w); }
+  __syncthreads();
+  fft4096_tail<true>(v, sr, si, tw);
+  float* fl = frames + (((long)bo * 2 + 0) * Tf + frame) * FFT_N;
+  float* fr = frames + (((long)bo * 2 + 1) * Tf + frame) * FFT_N;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int n = t + 256 * i;
+    float w = win[n] * (1.0f / 64.0f);
+    fl[n] = sr[n + (n >> 4)] * w;
+    fr[n] = si[n + (n >> 4)] * w;
+  }
+}
+
+template <typename T>
+void launch_mask_istft(const float* Z, int Tf, int Bout, int zb_div, const T* dec, RowSpace ds, int use_mask,
+                       const float* fo_w, const float* fo_b, float* frames, const float2* tw, const float* win,
+                       cudaStream_t st) {
+  mask_istft_kernel<T><<<dim3(Tf, Bout), 256, 0, st>>>((const float4*)Z, Tf, zb_div, dec, ds, use_mask, fo_w, fo_b, frames, tw, win);
+}
+
+// ------------------------------------------------------------------ frame overlap-add + time branch
+// out[bo, ch, s] = (sum_t frames[bo,ch,t, s+1536-1024t]) / 1.5  +  (time_out(tdec)[ch] * std_t + mean_t)
+//   (_ispec envelope is the constant 1.5 on the kept samples, SURVEY.md Appendix A1;
+//    time branch: ATHTDemucs_v2.py:313-324).   tdec == nullptr -> frequency branch only.
+template <typename T>
+__global__ void ola_combine_kernel(const float* __restrict__ frames, int Tf, int L, const T* __restrict__ tdec, RowSpace ts,
+                                   const float* __restrict__ to_w, const float* __restrict__ to_b,
+                                   const float* __restrict__ meanstd_t, int ms_div, float* __restrict__ out, long out_bstride) {
+  const int bo = blockIdx.y;
+  float w[8], bb[2], mean = 0.f, sd = 1.f;
+  if (tdec) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = to_w[i];
+    bb[0] = to_b[0]; bb[1] = to_b[1];
+    mean = meanstd_t[2 * (bo / ms_div)]; sd = meanstd_t[2 * (bo / ms_div) + 1];
+  }
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < L; s += gridDim.x * blockDim.x) {
+    int p = s + 1536;
+    int t_hi = p >> 10; if (t_hi > Tf - 1) t_hi = Tf - 1;
+    int t_lo = (p - 4095 + 1023) >> 10; if (t_lo < 0) t_lo = 0;
+    float a0 = 0.f, a1 = 0.f;
+    for (int t = t_lo; t <= t_hi; ++t) {
+      int n = p - 1024 * t;
+      a0 += frames[(((long)bo * 2 + 0) * Tf + t) * FFT_N + n];
+      a1 += frames[(((long)bo * 2 + 1) * Tf + t) * FFT_N + n];
+    }
+    a0 *= (1.0f / 1.5f); a1 *= (1.0f / 1.5f);
+    if (tdec) {
+      const T* r = tdec + ts.row_off(bo, s);
+      float x0 = to_f<T>(r[0]), x1 = to_f<T>(r[1]), x2 = to_f<T>(r[2]), x3 = to_f<T>(r[3]);
+      float y0 = w[0] * x0 + w[1] * x1 + w[2] * x2 + w[3] * x3 + bb[0];
+      float y1 = w[4] * x0 + w[5] * x1 + w[6] * x2 + w[7] * x3 + bb[1];
+      a0 += y0 * sd + mean; a1 += y1 * sd + mean;
+    }
+    out[(long)bo * out_bstride + s] = a0;
+    out[(long)bo * out_bstride + L + s] = a1;
+  }
+}
+template <typename T>
+void launch_ola_combine(const float* frames, int Tf, int L, int Bout, const T* tdec, RowSpace ts, const float* to_w,
+                        const float* to_b, const float* meanstd_t, int ms_div, float* out, long out_bstride, cudaStream_t st) {
+  ola_combine_kernel<T><<<dim3(min((L + 255) / 256, 1024), Bout), 256, 0, st>>>(frames, Tf, L, tdec, ts, to_w, to_b, meanstd_t,
+                                                                              ms_div, out, out_bstride);
+}
+
+template void launch_mask_istft<float>(const float*, int, int, int, const float*, RowSpace, int, const float*, const float*,
+                                       float*, const float2*, const float*, cudaStream_t);
+template void launch_mask_istft<bf16>(const float*, int, int, int, const bf16*, RowSpace, int, const float*, const float*,
+                                      float*, const float2*, const float*, cudaStream_t);
+template void launch_ola_combine<float>(const float*, int, int, int, const float*, RowSpace, const float*, const float*,
+                                        const float*, int, float*, long, cudaStream_t);
+template void launch_ola_combine<bf16>(const float*, int, int, int, const bf16*, RowSpace, const float*, const float*,
+                                       const float*, int, float*, long, cudaStream_t);
+
+}  // namespace athtd

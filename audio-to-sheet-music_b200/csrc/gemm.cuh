@@ -1,0 +1,54 @@
+// Generic "conv-as-GEMM" problem descriptor shared by the SIMT (fp32-accurate) and the
+// tcgen05 (bf16 tensor-core) GEMM kernels.
+//
+//   C[g1,g2,m,n] = epilogue( alpha * sum_{tap,k} A[g1, g2+shG2[tap], m+shM[tap], k] * B[g1,g2,n,tap*Ktap+k] )
+//
+// Row space: groups (g1 in [0,G1), g2 in [0,G2)), Mg rows per group.  A rows are addressed as
+//   A + g1*sAg1 + g2*sAg2 + m*sAm + k   (k contiguous; sAm may be SMALLER than K: the strided
+// convolutions and the transposed convolutions are plain GEMMs over overlapping row windows of a
+// channels-last activation buffer, see DESIGN.md "conv as overlapping-row GEMM").
+// A tap whose g2+shG2 falls outside [0,G2) contributes zeros (time-axis zero padding of DConv).
+#pragma once
+#include "common.cuh"
+
+namespace athtd {
+
+enum { ACT_NONE = 0, ACT_GELU = 1 };
+enum { STAT_NONE = 0, STAT_PER_G1 = 1, STAT_PER_G1_M = 2 };
+
+struct GemmDesc {
+  int G1, G2, Mg;
+  int N, K;            // N = number of B rows (before GLU pairing); K = ntaps*Ktap
+  int ntaps, Ktap;
+  int shG2[3], shM[3];
+  const void* A; long sAg1, sAg2, sAm;
+  const void* B; long sBg1, sBg2, sBn, sBk;
+  void* C; long sCg1, sCg2, sCm;
+  int c_is_f32;        // C (and res) stored as fp32 regardless of the activation type
+  float alpha;
+  const float* bias;       // [N]
+  int act;
+  int glu;                 // adjacent column pairs (2j, 2j+1) -> a*sigmoid(b), N/2 outputs
+  const float* colscale;   // [Nout]
+  const void* res; long sRg1, sRg2, sRm;   // residual (same type as C), added last
+  const float* rowtab; float rowtab_scale; // table[m][Nout] added (freq_emb), indexed by m
+  const float* gbias; long sGb;            // per-g1 bias row: gbias[g1*sGb + n]
+  double* stats; int stat_mode;            // accumulates (sum, sumsq) of the stored values
+  int convt_cout;          // >0: transposed-conv phase layout, mask the two cropped rows per edge
+  int grouped;             // 1: tiles never span groups (B or stats differ per group)
+};
+
+inline GemmDesc gemm_desc_zero() {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.G1 = d.G2 = 1; d.ntaps = 1; d.alpha = 1.0f; d.sBk = 1;
+  return d;
+}
+
+template <typename T> void launch_gemm_simt(const GemmDesc& d, cudaStream_t st);
+#ifdef ATHTD_HAVE_TC
+void launch_gemm_tc(const GemmDesc& d, cudaStream_t st);   // bf16 tcgen05
+bool gemm_tc_supported(const GemmDesc& d);
+#endif
+
+}  // namespace athtd

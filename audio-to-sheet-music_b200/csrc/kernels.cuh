@@ -1,0 +1,48 @@
+// Launcher declarations for every kernel of the path (definitions: elementwise.cu, fft.cu, ola.cu,
+// gemm_simt.cu, gemm_tc.cu, attention.cu).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace athtd {
+
+// ---- elementwise.cu
+void launch_sum_sumsq(const float* x, int B, long n_per_sample, double* stats, cudaStream_t st);
+void launch_finalize_gn(const double* stats, double count, float* mr, long n, cudaStream_t st);
+void launch_finalize_meanstd(const double* stats, double n, float* out, int B, cudaStream_t st);
+template <typename T> void launch_pack_wav(const float* wav, const float* meanstd, T* out, RowSpace rs, int L, cudaStream_t st);
+template <typename T> void launch_pack_spec(const float* Z, const float* meanstd, T* out, RowSpace rs, int Tf, cudaStream_t st);
+template <typename T> void launch_gn_gelu(T* h, RowSpace rs, int G2, int per_row, const float* mr, const float* w,
+                                          const float* b, cudaStream_t st);
+template <typename T> void launch_gn_glu_res(T* x, RowSpace xs, const T* e, RowSpace es, int G2, int per_row, const float* mr,
+                                             const float* w, const float* b, const float* scale, cudaStream_t st);
+template <typename T> void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const float* gmr,
+                                            const float* gw, const float* gb, const float* lw, const float* lb,
+                                            const float* pe, int yR, int yRp, int ypf, cudaStream_t st);
+template <typename T> void launch_softmax_rows(T* s, long rows, int n, cudaStream_t st);
+template <typename T> void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const float* vec, long vstride,
+                                             cudaStream_t st);
+template <typename T> void launch_dec_apply(const T* u, int Uin, long u_group_stride, int Cu, T* out, RowSpace os, int G2,
+                                            int has_gn, const float* mr, const float* gw, const float* gb, const T* skip,
+                                            RowSpace ss, cudaStream_t st);
+template <typename T> void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int d1, int d2, cudaStream_t st);
+
+// ---- fft.cu
+void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
+                     cudaStream_t st);
+template <typename T> void launch_mask_istft(const float* Z, int Tf, int Bout, int zb_div, const T* dec, RowSpace ds,
+                                             int use_mask, const float* fo_w, const float* fo_b, float* frames,
+                                             const float2* tw, const float* win, cudaStream_t st);
+template <typename T> void launch_ola_combine(const float* frames, int Tf, int L, int Bout, const T* tdec, RowSpace ts,
+                                              const float* to_w, const float* to_b, const float* meanstd_t, int ms_div,
+                                              float* out, long out_bstride, cudaStream_t st);
+
+// ---- ola.cu  (track-level chunk gather / weighted overlap-add, benchmark.py:155-204)
+void launch_gather_chunks(const float* track, long T, int C, const long* starts, int n_chunks, int chunk_len, float* segs,
+                          cudaStream_t st);
+void launch_chunk_ola(const float* seg_out, long seg_stride, int k_base, int chunk_len, const long* starts,
+                      const int* actual_len, const int* fade_len, const int* flags, int n_chunks, long stride,
+                      const float* ramp_up, const float* ramp_down, const int* ramp_off, float* out, int C, long t_begin,
+                      long t_end, cudaStream_t st);
+
+}  // namespace athtd

@@ -1,0 +1,510 @@
+// Host-side launch sequence of the segment-batched separation forward (one CUDA stream, no
+// allocation, no synchronisation): replaces AudioTextHTDemucs.forward
+// (/root/reference/src/models/stem_separation/ATHTDemucs_v2.py:250-326) for a batch of B segments
+// and P prompts per segment.  The prompt-independent part (STFT, normalisation, both encoder
+// branches, cross-transformer) runs once; text conditioning, both decoders, the mask/iSTFT tail
+// and the time-branch sum run once per prompt over the shared encoder state.
+#include "plan.h"
+#include <string.h>
+#include <stdio.h>
+
+namespace athtd {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------- packed blob layout
+PackLayout::PackLayout(int dtype) {
+  items = build_pack_list();
+  size_t esz = dtype == 0 ? 4 : 2;
+  size_t off = 0;
+  for (auto& it : items) {
+    off = align_up(off, 256);
+    it.offset_bytes = (long)off;
+    off += (size_t)it.numel * (it.is_f32 ? 4 : esz);
+    index[it.key] = (int)(&it - &items[0]);
+  }
+  total_bytes = (long)align_up(off, 256);
+}
+
+template <typename T>
+int pack_weights(const ParamTable& pt, const PackLayout& pl, const float* params, void* packed, cudaStream_t st) {
+  for (auto& it : pl.items) {
+    const float* src = params + pt.off(it.src) + it.src_off;
+    char* dst = (char*)packed + it.offset_bytes;
+    if (it.is_f32) launch_pack_weight<float>(src, (float*)dst, it.numel, it.kind, it.d0, it.d1, it.d2, st);
+    else launch_pack_weight<T>(src, (T*)dst, it.numel, it.kind, it.d0, it.d1, it.d2, st);
+  }
+  return (int)cudaGetLastError();
+}
+template int pack_weights<float>(const ParamTable&, const PackLayout&, const float*, void*, cudaStream_t);
+template int pack_weights<bf16>(const ParamTable&, const PackLayout&, const float*, void*, cudaStream_t);
+
+// ---------------------------------------------------------------------------------- shapes
+Shapes::Shapes(int B_, int L_, int P_) : B(B_), L(L_), P(P_) {
+  Tf = (L + 1023) / 1024;
+  Fr[0] = 2048; for (int i = 1; i <= 4; ++i) Fr[i] = Fr[i - 1] / 4;
+  Lt[0] = L; for (int i = 1; i <= 4; ++i) Lt[i] = (Lt[i - 1] + 3) / 4;
+  Sf = Tf * 8; St = Lt[4];
+}
+
+// ---------------------------------------------------------------------------------- plan
+template <typename T>
+void PlanT<T>::layout(char* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> char* {
+    off = align_up(off, 256);
+    char* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  };
+  const Shapes& s = sh;
+  const int B = s.B, Tf = s.Tf;
+  auto space = [&](int G, int R, int Rp, int pf, int C) { RowSpace r; r.G = G; r.R = R; r.Rp = Rp; r.pf = pf; r.C = C; return r; };
+  // ---- zero-initialised region (pads must stay zero; interior is always overwritten)
+  xf0_rs = space(B * Tf, 2048, 2052, 2, 4);
+  xf0 = (T*)take(xf0_rs.elems() * sizeof(T));
+  xt0_rs = space(B, s.L, s.L + 8, 2, 2);
+  xt0 = (T*)take(xt0_rs.elems() * sizeof(T));
+  for (int i = 0; i < 4; ++i) {
+    yf_rs[i] = space(B * Tf, s.Fr[i + 1], s.Fr[i + 1] + 4, 2, kCh[i]);
+    yf[i] = (T*)take(yf_rs[i].elems() * sizeof(T));
+    ef[i] = (T*)take(yf_rs[i].elems() * sizeof(T));
+    yt_rs[i] = space(B, s.Lt[i + 1], s.Lt[i + 1] + 8, 2, kCh[i]);
+    yt[i] = (T*)take(yt_rs[i].elems() * sizeof(T));
+    et[i] = (T*)take(yt_rs[i].elems() * sizeof(T));
+  }
+  xc_rs = space(B * Tf, 8, 12, 2, 384);
+  xc = (T*)take(xc_rs.elems() * sizeof(T));
+  xtc_rs = space(B, s.St, s.St + 8, 2, 384);
+  xtc = (T*)take(xtc_rs.elems() * sizeof(T));
+  for (int i = 0; i < 4; ++i) {
+    df_rs[i] = space(B * Tf, Tf, Tf + 4, 2, kDecCh[i + 1]);
+    df[i] = (T*)take(df_rs[i].elems() * sizeof(T));
+    dt_rs[i] = space(B, s.Lt[3 - i], s.Lt[3 - i] + 8, 2, kDecCh[i + 1]);
+    dt[i] = (T*)take(dt_rs[i].elems() * sizeof(T));
+  }
+  zero_bytes = align_up(off, 256);
+  // ---- statistics (zeroed every forward)
+  off = zero_bytes;
+  stats_begin = off;
+  st_spec = (double*)take(sizeof(double) * 2 * B);
+  st_wav = (double*)take(sizeof(double) * 2 * B);
+  for (int i = 0; i < 4; ++i)
+    for (int d = 0; d < 2; ++d)
+      for (int k = 0; k < 2; ++k) {
+        st_df[i][d][k] = (double*)take(sizeof(double) * 2 * B * s.Fr[i + 1]);
+        st_dt[i][d][k] = (double*)take(sizeof(double) * 2 * B);
+      }
+  for (int l = 0; l < 5; ++l) { st_xf[l][0] = (double*)take(sizeof(double) * 2 * B); st_xf[l][1] = (double*)take(sizeof(double) * 2 * B); }
+  st_dec = (double*)take(sizeof(double) * 2 * B * 6 * s.P);
+  stats_bytes = align_up(off, 256) - stats_begin;
+  off = stats_begin + stats_bytes;
+  // ---- plain scratch
+  mr = (float*)take(sizeof(float) * 2 * (size_t)B * 512);
+  ms_spec = (float*)take(sizeof(float) * 2 * B);
+  ms_wav = (float*)take(sizeof(float) * 2 * B);
+  Z = (float*)take(sizeof(float) * (size_t)B * Tf * 2048 * 4);
+  size_t hmax = 0, emax = 0;
+  for (int i = 0; i < 4; ++i) {
+    size_t rf = (size_t)B * Tf * s.Fr[i + 1], rt = (size_t)B * s.Lt[i + 1];
+    hmax = std::max(hmax, std::max(rf, rt) * (kCh[i] / 8));
+    emax = std::max(emax, std::max(rf, rt) * (2 * kCh[i]));
+  }
+  hbuf = (T*)take(hmax * sizeof(T));
+  ebuf = (T*)take(emax * sizeof(T));
+  const size_t Smax = std::max(s.Sf, s.St);
+  tokf = (T*)take((size_t)B * s.Sf * 512 * sizeof(T));
+  tokt = (T*)take((size_t)B * s.St * 512 * sizeof(T));
+  for (int i = 0; i < 4; ++i) hn[i] = (T*)take((size_t)B * Smax * 512 * sizeof(T));
+  qkv = (T*)take((size_t)B * Smax * 1536 * sizeof(T));
+  kvb = (T*)take((size_t)B * Smax * 1024 * sizeof(T));
+  obuf = (T*)take((size_t)B * Smax * 512 * sizeof(T));
+  ffn = (T*)take((size_t)B * Smax * 2048 * sizeof(T));
+  scores = (T*)take((size_t)B * 8 * Smax * Smax * sizeof(T));
+  xenc = (T*)take((size_t)B * s.Sf * 384 * sizeof(T));
+  xtenc = (T*)take((size_t)B * s.St * 384 * sizeof(T));
+  cvec = (float*)take(sizeof(float) * (size_t)B * s.P * 384 * 3);
+  t1 = (T*)take((size_t)B * Smax * 384 * sizeof(T));
+  t2 = (T*)take((size_t)B * Smax * 384 * sizeof(T));
+  size_t umax = 0;
+  {
+    int rin = 8;
+    for (int i = 0; i < 4; ++i) { umax = std::max(umax, (size_t)B * Tf * (rin + 1) * 4 * kDecCh[i + 1]); rin = Tf; }
+    for (int i = 0; i < 4; ++i) umax = std::max(umax, (size_t)B * (s.Lt[4 - i] + 1) * 4 * kDecCh[i + 1]);
+  }
+  ubuf = (T*)take(umax * sizeof(T));
+  frames = (float*)take(sizeof(float) * (size_t)B * 2 * Tf * 4096);
+  total_bytes = align_up(off, 256);
+}
+
+template <typename T>
+PlanT<T>::PlanT(int B, int L, int P, const ParamTable* pt_, const PackLayout* pl_, const float* params_, const void* packed_,
+                void* workspace, const PlanConsts& c)
+    : sh(B, L, P), pt(pt_), pl(pl_), params(params_), packed((const char*)packed_), consts(c) {
+  base_ = (char*)workspace;
+  layout((char*)workspace);
+}
+
+template <typename T>
+const float* PlanT<T>::P32(const std::string& name) const { return params + pt->off(name); }
+template <typename T>
+const T* PlanT<T>::PW(const std::string& key) const {
+  auto it = pl->index.find(key);
+  if (it == pl->index.end()) throw std::runtime_error("athtd: unknown packed weight " + key);
+  return (const T*)(packed + pl->items[it->second].offset_bytes);
+}
+template <typename T>
+const float* PlanT<T>::PA(const std::string& key) const {
+  auto it = pl->index.find(key);
+  if (it == pl->index.end()) throw std::runtime_error("athtd: unknown packed aux " + key);
+  return (const float*)(packed + pl->items[it->second].offset_bytes);
+}
+
+template <typename T>
+void PlanT<T>::gemm(const GemmDesc& d, cudaStream_t st) {
+  launch_gemm_simt<T>(d, st);
+  ++n_launches;
+}
+
+// ---- one HEncLayer (demucs hdemucs.py:HEncLayer) on a channels-last row space.
+//   x   : input activation (padded row space xin, C_in channels)
+//   y   : conv+GELU output, updated in place by the two DConv residual layers (space ys, C channels)
+//   out : rewrite+GLU output (same geometry as ys)
+template <typename T>
+void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSpace ys, T* out, cudaStream_t st) {
+  const Shapes& s = sh;
+  const int C = kCh[i], Cin = xin.C, H = C / 8;
+  const std::string p = std::string("htdemucs.") + (freq ? "encoder." : "tencoder.") + std::to_string(i);
+  const int G2 = freq ? s.Tf : 1;
+  const int R = ys.R;
+  {  // strided conv k8 s4 p2 (+ right zero pad to a multiple of 4 on the time branch) + GELU
+    GemmDesc d = gemm_desc_zero();
+    d.G1 = ys.G; d.G2 = 1; d.Mg = R; d.N = C; d.K = 8 * Cin; d.Ktap = d.K;
+    d.A = x + (long)(xin.pf - 2) * Cin; d.sAg1 = (long)xin.Rp * Cin; d.sAm = 4L * Cin;
+    d.B = PW(p + ".conv.w"); d.sBn = d.K; d.sBk = 1;
+    d.C = y + (long)ys.pf * C; d.sCg1 = (long)ys.Rp * C; d.sCm = C;
+    d.bias = P32(p + ".conv.bias"); d.act = ACT_GELU;
+    gemm(d, st);
+  }
+  RowSpace hs = ys; hs.Rp = R; hs.pf = 0; hs.C = H;
+  RowSpace es = ys; es.Rp = R; es.pf = 0; es.C = 2 * C;
+  for (int dd = 0; dd < 2; ++dd) {
+    const std::string q = p + ".dconv.layers." + std::to_string(dd);
+    const int dil = 1 << dd;
+    double* st_h = freq ? st_df[i][dd][0] : st_dt[i][dd][0];
+    double* st_e = freq ? st_df[i][dd][1] : st_dt[i][dd][1];
+    const long nstat = freq ? (long)s.B * R : s.B;
+    {  // dilated k3 conv C -> C/8 along time (freq branch: taps shift the frame group index)
+      GemmDesc d = gemm_desc_zero();
+      d.G1 = s.B; d.G2 = G2; d.Mg = R; d.N = H; d.ntaps = 3; d.Ktap = C; d.K = 3 * C;
+      for (int k = 0; k < 3; ++k) { d.shG2[k] = freq ? (k - 1) * dil : 0; d.shM[k] = freq ? 0 : (k - 1) * dil; }
+      d.A = y + (long)ys.pf * C; d.sAg1 = (long)G2 * ys.Rp * C; d.sAg2 = (long)ys.Rp * C; d.sAm = C;
+      d.B = PW(q + ".0.w"); d.sBn = d.K; d.sBk = 1;
+      d.C = hbuf; d.sCg1 = (long)G2 * R * H; d.sCg2 = (long)R * H; d.sCm = H;
+      d.bias = P32(q + ".0.bias");
+      d.stats = st_h; d.stat_mode = freq ? STAT_PER_G1_M : STAT_PER_G1;
+      gemm(d, st);
+    }
+    launch_finalize_gn(st_h, (double)H * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
+    launch_gn_gelu<T>(hbuf, hs, G2, freq ? 1 : 0, mr, P32(q + ".1.weight"), P32(q + ".1.bias"), st); ++n_launches;
+    {  // 1x1 expand C/8 -> 2C
+      GemmDesc d = gemm_desc_zero();
+      d.G1 = s.B; d.G2 = G2; d.Mg = R; d.N = 2 * C; d.K = H; d.Ktap = H;
+      d.A = hbuf; d.sAg1 = (long)G2 * R * H; d.sAg2 = (long)R * H; d.sAm = H;
+      d.B = PW(q + ".3.w"); d.sBn = H; d.sBk = 1;
+      d.C = ebuf; d.sCg1 = (long)G2 * R * 2 * C; d.sCg2 = (long)R * 2 * C; d.sCm = 2 * C;
+      d.bias = P32(q + ".3.bias");
+      d.stats = st_e; d.stat_mode = freq ? STAT_PER_G1_M : STAT_PER_G1;
+      gemm(d, st);
+    }
+    launch_finalize_gn(st_e, (double)2 * C * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
+    launch_gn_glu_res<T>(y, ys, ebuf, es, G2, freq ? 1 : 0, mr, P32(q + ".4.weight"), P32(q + ".4.bias"),
+                         P32(q + ".6.scale"), st); ++n_launches;
+  }
+  {  // 1x1 rewrite C -> 2C, GLU (+ frequency embedding after encoder 0, ATHTDemucs_v2.py:212-215)
+    GemmDesc d = gemm_desc_zero();
+    d.G1 = ys.G; d.G2 = 1; d.Mg = R; d.N = 2 * C; d.K = C; d.Ktap = C;
+    d.A = y + (long)ys.pf * C; d.sAg1 = (long)ys.Rp * C; d.sAm = C;
+    d.B = PW(p + ".rewrite.w"); d.sBn = C; d.sBk = 1;
+    d.C = out + (long)ys.pf * C; d.sCg1 = (long)ys.Rp * C; d.sCm = C;
+    d.bias = PA(p + ".rewrite.b"); d.glu = 1;
+    if (freq && i == 0) { d.rowtab = P32("htdemucs.freq_emb.embedding.weight"); d.rowtab_scale = 10.0f * 0.2f; }
+    gemm(d, st);
+  }
+}
+
+// ---- attention for one branch: scores = (Q K^T)/sqrt(64), softmax, O = P V   (8 heads of 64)
+template <typename T>
+void PlanT<T>::attention(const T* q, long ldq, const T* k, const T* v, long ldkv, int Sq, int Sk, T* o, cudaStream_t st) {
+  const int B = sh.B;
+  {
+    GemmDesc d = gemm_desc_zero();
+    d.G1 = B; d.G2 = 8; d.Mg = Sq; d.N = Sk; d.K = 64; d.Ktap = 64; d.grouped = 1;
+    d.A = q; d.sAg1 = (long)Sq * ldq; d.sAg2 = 64; d.sAm = ldq;
+    d.B = k; d.sBg1 = (long)Sk * ldkv; d.sBg2 = 64; d.sBn = ldkv; d.sBk = 1;
+    d.C = scores; d.sCg1 = 8L * Sq * Sk; d.sCg2 = (long)Sq * Sk; d.sCm = Sk;
+    d.alpha = 0.125f;
+    gemm(d, st);
+  }
+  launch_softmax_rows<T>(scores, (long)B * 8 * Sq, Sk, st); ++n_launches;
+  {
+    GemmDesc d = gemm_desc_zero();
+    d.G1 = B; d.G2 = 8; d.Mg = Sq; d.N = 64; d.K = Sk; d.Ktap = Sk; d.grouped = 1;
+    d.A = scores; d.sAg1 = 8L * Sq * Sk; d.sAg2 = (long)Sq * Sk; d.sAm = Sk;
+    d.B = v; d.sBg1 = (long)Sk * ldkv; d.sBg2 = 64; d.sBn = 1; d.sBk = ldkv;
+    d.C = o; d.sCg1 = (long)Sq * 512; d.sCg2 = 64; d.sCm = 512;
+    gemm(d, st);
+  }
+}
+
+template <typename T>
+void PlanT<T>::linear(const T* a, long rows, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st) {
+  GemmDesc d = gemm_desc_zero();
+  d.G1 = 1; d.G2 = 1; d.Mg = (int)rows; d.N = N; d.K = K; d.Ktap = K;
+  d.A = a; d.sAm = K; d.B = w; d.sBn = K; d.sBk = 1; d.C = c; d.sCm = N; d.bias = bias; d.act = act;
+  gemm(d, st);
+}
+
+// x <- x + gamma * (a W^T + b), optional per-sample (sum, sumsq) of the result
+template <typename T>
+void PlanT<T>::linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x,
+                          double* stats, cudaStream_t st) {
+  GemmDesc d = gemm_desc_zero();
+  d.G1 = sh.B; d.G2 = 1; d.Mg = S; d.N = N; d.K = K; d.Ktap = K;
+  d.A = a; d.sAg1 = (long)S * K; d.sAm = K; d.B = w; d.sBn = K; d.sBk = 1;
+  d.C = x; d.sCg1 = (long)S * N; d.sCm = N; d.bias = bias; d.colscale = gamma;
+  d.res = x; d.sRg1 = (long)S * N; d.sRm = N;
+  if (stats) { d.stats = stats; d.stat_mode = STAT_PER_G1; }
+  gemm(d, st);
+}
+
+template <typename T>
+void PlanT<T>::xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, cudaStream_t st) {
+  const long rows = (long)sh.B * S;
+  launch_norm_rows<T>(x, nullptr, hn[0], rows, 512, S, nullptr, nullptr, nullptr, P32(p + "." + ffn_norm + ".weight"),
+                      P32(p + "." + ffn_norm + ".bias"), nullptr, 0, 0, 0, st); ++n_launches;
+  linear(hn[0], rows, 512, PW(p + ".linear1.w"), 2048, P32(p + ".linear1.bias"), ACT_GELU, ffn, st);
+  linear_res(ffn, S, 2048, PW(p + ".linear2.w"), 512, P32(p + ".linear2.bias"), P32(p + ".gamma_2.scale"), x, stats, st);
+  launch_finalize_gn(stats, (double)S * 512, mr, sh.B, st); ++n_launches;
+  launch_norm_rows<T>(x, x, nullptr, rows, 512, S, mr, P32(p + ".norm_out.weight"), P32(p + ".norm_out.bias"), nullptr,
+                      nullptr, nullptr, 0, 0, 0, st); ++n_launches;
+}
+
+template <typename T>
+void PlanT<T>::cross_transformer(cudaStream_t st) {
+  const Shapes& s = sh;
+  const std::string xp = "htdemucs.crosstransformer";
+  const int B = s.B;
+  T* X[2] = {tokf, tokt};
+  const int S[2] = {s.Sf, s.St};
+  const char* stacks[2] = {".layers.", ".layers_t."};
+  for (int l = 0; l < 5; ++l) {
+    if (l % 2 == 0) {
+      for (int br = 0; br < 2; ++br) {
+        const std::string p = xp + stacks[br] + std::to_string(l);
+        const long rows = (long)B * S[br];
+        launch_norm_rows<T>(X[br], nullptr, hn[0], rows, 512, S[br], nullptr, nullptr, nullptr, P32(p + ".norm1.weight"),
+                            P32(p + ".norm1.bias"), nullptr, 0, 0, 0, st); ++n_launches;
+        linear(hn[0], rows, 512, PW(p + ".in_proj.w"), 1536, P32(p + ".self_attn.in_proj_bias"), ACT_NONE, qkv, st);
+        attention(qkv, 1536, qkv + 512, qkv + 1024, 1536, S[br], S[br], obuf, st);
+        linear_res(obuf, S[br], 512, PW(p + ".out_proj.w"), 512, P32(p + ".self_attn.out_proj.bias"),
+                   P32(p + ".gamma_1.scale"), X[br], nullptr, st);
+        xf_ffn_and_norm(p, "norm2", X[br], S[br], st_xf[l][br], st);
+      }
+    } else {
+      // both branches read the PRE-update other branch (old_x, demucs transformer.py) -> normalise first
+      for (int br = 0; br < 2; ++br) {
+        const std::string p = xp + stacks[br] + std::to_string(l);
+        const int o = 1 - br;
+        launch_norm_rows<T>(X[br], nullptr, hn[2 * br], (long)B * S[br], 512, S[br], nullptr, nullptr, nullptr,
+                            P32(p + ".norm1.weight"), P32(p + ".norm1.bias"), nullptr, 0, 0, 0, st); ++n_launches;
+        launch_norm_rows<T>(X[o], nullptr, hn[2 * br + 1], (long)B * S[o], 512, S[o], nullptr, nullptr, nullptr,
+                            P32(p + ".norm2.weight"), P32(p + ".norm2.bias"), nullptr, 0, 0, 0, st); ++n_launches;
+      }
+      for (int br = 0; br < 2; ++br) {
+        const std::string p = xp + stacks[br] + std::to_string(l);
+        const int o = 1 - br;
+        const T* w_in = PW(p + ".in_proj.w");
+        const float* b_in = P32(p + ".cross_attn.in_proj_bias");
+        linear(hn[2 * br], (long)B * S[br], 512, w_in, 512, b_in, ACT_NONE, qkv, st);
+        linear(hn[2 * br + 1], (long)B * S[o], 512, w_in + 512L * 512, 1024, b_in + 512, ACT_NONE, kvb, st);
+        attention(qkv, 512, kvb, kvb + 512, 1024, S[br], S[o], obuf, st);
+        linear_res(obuf, S[br], 512, PW(p + ".out_proj.w"), 512, P32(p + ".cross_attn.out_proj.bias"),
+                   P32(p + ".gamma_1.scale"), X[br], nullptr, st);
+        xf_ffn_and_norm(p, "norm3", X[br], S[br], st_xf[l][br], st);
+      }
+    }
+  }
+}
+
+template <typename T>
+void PlanT<T>::encode(const float* wav, cudaStream_t st) {
+  const Shapes& s = sh;
+  const int B = s.B, Tf = s.Tf;
+  cudaMemsetAsync((char*)ws_base() + stats_begin, 0, stats_bytes, st);
+  // spectral front end + input normalisation (ATHTDemucs_v2.py:261-275)
+  launch_stft_cac(wav, B, s.L, Tf, Z, st_spec, consts.tw, consts.win, st); ++n_launches;
+  launch_sum_sumsq(wav, B, 2L * s.L, st_wav, st); ++n_launches;
+  launch_finalize_meanstd(st_spec, 4.0 * 2048.0 * Tf, ms_spec, B, st); ++n_launches;
+  launch_finalize_meanstd(st_wav, 2.0 * s.L, ms_wav, B, st); ++n_launches;
+  launch_pack_spec<T>(Z, ms_spec, xf0, xf0_rs, Tf, st); ++n_launches;
+  launch_pack_wav<T>(wav, ms_wav, xt0, xt0_rs, s.L, st); ++n_launches;
+  // interleaved encoders (ATHTDemucs_v2.py:196-217)
+  const T* xf = xf0; RowSpace xfs = xf0_rs;
+  const T* xt = xt0; RowSpace xts = xt0_rs;
+  for (int i = 0; i < 4; ++i) {
+    enc_layer(false, i, xt, xts, yt[i], yt_rs[i], et[i], st);
+    xt = et[i]; xts = yt_rs[i];
+    enc_layer(true, i, xf, xfs, yf[i], yf_rs[i], ef[i], st);
+    xf = ef[i]; xfs = yf_rs[i];
+  }
+  // bottleneck: 1x1 up-sample 384->512, norm_in + positional embeddings, 5 layers, 1x1 down-sample
+  const std::string hp = "htdemucs.";
+  {
+    GemmDesc d = gemm_desc_zero();
+    d.G1 = B * Tf; d.Mg = 8; d.N = 512; d.K = 384; d.Ktap = 384;
+    d.A = ef[3] + 2L * 384; d.sAg1 = 12L * 384; d.sAm = 384;
+    d.B = PW(hp + "channel_upsampler.w"); d.sBn = 384;
+    d.C = hn[1]; d.sCg1 = 8L * 512; d.sCm = 512; d.bias = P32(hp + "channel_upsampler.bias");
+    gemm(d, st);
+    d = gemm_desc_zero();
+    d.G1 = B; d.Mg = s.St; d.N = 512; d.K = 384; d.Ktap = 384;
+    d.A = et[3] + 2L * 384; d.sAg1 = (long)yt_rs[3].Rp * 384; d.sAm = 384;
+    d.B = PW(hp + "channel_upsampler_t.w"); d.sBn = 384;
+    d.C = hn[2]; d.sCg1 = (long)s.St * 512; d.sCm = 512; d.bias = P32(hp + "channel_upsampler_t.bias");
+    gemm(d, st);
+  }
+  const std::string xp = "htdemucs.crosstransformer";
+  launch_norm_rows<T>(hn[1], nullptr, tokf, (long)B * s.Sf, 512, s.Sf, nullptr, nullptr, nullptr, P32(xp + ".norm_in.weight"),
+                      P32(xp + ".norm_in.bias"), consts.pe2d, 0, 0, 0, st); ++n_launches;
+  launch_norm_rows<T>(hn[2], nullptr, tokt, (long)B * s.St, 512, s.St, nullptr, nullptr, nullptr, P32(xp + ".norm_in_t.weight"),
+                      P32(xp + ".norm_in_t.bias"), consts.pe1d, 0, 0, 0, st); ++n_launches;
+  cross_transformer(st);
+  linear(tokf, (long)B * s.Sf, 512, PW(hp + "channel_downsampler.w"), 384, P32(hp + "channel_downsampler.bias"), ACT_NONE, xenc, st);
+  linear(tokt, (long)B * s.St, 512, PW(hp + "channel_downsampler_t.w"), 384, P32(hp + "channel_downsampler_t.bias"), ACT_NONE, xtenc, st);
+}
+
+// text conditioning for prompt p (TextCrossAttention, ATHTDemucs_v2.py:38-58): with a single key the
+// softmax is exactly 1, so attn_out is one 384-vector per (segment, prompt) -- SURVEY.md quirk Q3.
+template <typename T>
+void PlanT<T>::text_vectors(const float* emb, cudaStream_t st) {
+  const int rows = sh.B * sh.P;
+  float* v1 = cvec + (size_t)rows * 384, *v2 = cvec + (size_t)rows * 768;
+  auto lin32 = [&](const float* a, int K, const float* w, const float* b, float* c) {
+    GemmDesc d = gemm_desc_zero();
+    d.Mg = rows; d.N = 384; d.K = K; d.Ktap = K; d.A = a; d.sAm = K; d.B = w; d.sBn = K; d.sBk = 1;
+    d.C = c; d.sCm = 384; d.bias = b;
+    launch_gemm_simt<float>(d, st); ++n_launches;
+  };
+  lin32(emb, 512, P32("text_attn.v_proj.weight"), P32("text_attn.v_proj.bias"), v1);
+  lin32(v1, 384, P32("text_attn.attn.in_proj_weight") + 768L * 384, P32("text_attn.attn.in_proj_bias") + 768, v2);
+  lin32(v2, 384, P32("text_attn.attn.out_proj.weight"), P32("text_attn.attn.out_proj.bias"), cvec);
+}
+
+template <typename T>
+void PlanT<T>::text_condition(int p, const T* x, int S, T* out, int yR, int yRp, int ypf, cudaStream_t st) {
+  const long rows = (long)sh.B * S;
+  launch_add_rowvec<T>(x, t1, S, 384, sh.B, cvec + (size_t)p * 384, (long)sh.P * 384, st); ++n_launches;
+  linear(t1, rows, 384, PW("text_attn.out_mlp.0.w"), 384, P32("text_attn.out_mlp.0.bias"), ACT_GELU, t2, st);
+  {
+    GemmDesc d = gemm_desc_zero();
+    d.Mg = (int)rows; d.N = 384; d.K = 384; d.Ktap = 384; d.A = t2; d.sAm = 384;
+    d.B = PW("text_attn.out_mlp.2.w"); d.sBn = 384; d.C = t1; d.sCm = 384; d.bias = P32("text_attn.out_mlp.2.bias");
+    d.res = t1; d.sRm = 384;
+    gemm(d, st);
+  }
+  launch_norm_rows<T>(t1, nullptr, out, rows, 384, S, nullptr, nullptr, nullptr, P32("text_attn.norm_out.weight"),
+                      P32("text_attn.norm_out.bias"), nullptr, yR, yRp, ypf, st); ++n_launches;
+}
+
+// one FreqDecoder / TimeDecoder layer (ATHTDemucs_v2.py:82-104, 125-139): transposed conv as ONE GEMM
+// over [x[q-1], x[q]] row pairs producing the 4 output phases, GroupNorm statistics in the epilogue,
+// then GN + GELU + linear resize to the target length + 0.1 * resized truncated skip.
+template <typename T>
+void PlanT<T>::dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* out, RowSpace os, const T* skip, RowSpace ss,
+                         cudaStream_t st) {
+  const Shapes& s = sh;
+  const int Cin = kDecCh[i], Cout = kDecCh[i + 1];
+  const int G2 = freq ? s.Tf : 1;
+  const int Rin = xs.R;
+  const std::string q = std::string(freq ? "freq_decoder" : "time_decoder") + ".layers." + std::to_string(i);
+  double* stt = st_dec + 2L * s.B * ((size_t)p * 6 + (freq ? 0 : 3) + (i < 3 ? i : 0));
+  GemmDesc d = gemm_desc_zero();
+  d.G1 = s.B; d.G2 = G2; d.Mg = Rin + 1; d.N = 4 * Cout; d.K = 2 * Cin; d.Ktap = d.K;
+  d.A = x + (long)(xs.pf - 1) * Cin; d.sAg1 = (long)G2 * xs.Rp * Cin; d.sAg2 = (long)xs.Rp * Cin; d.sAm = Cin;
+  d.B = PW(q + ".0.w"); d.sBn = d.K; d.sBk = 1;
+  const long ug = (long)(Rin + 1) * 4 * Cout;
+  d.C = ubuf; d.sCg1 = (long)G2 * ug; d.sCg2 = ug; d.sCm = 4L * Cout;
+  d.bias = PA(q + ".0.b4");
+  d.convt_cout = Cout;
+  if (i < 3) { d.stats = stt; d.stat_mode = STAT_PER_G1; }
+  gemm(d, st);
+  if (i < 3) { launch_finalize_gn(stt, (double)Cout * 4.0 * Rin * G2, mr, s.B, st); ++n_launches; }
+  launch_dec_apply<T>(ubuf, 4 * Rin, ug, Cout, out, os, G2, i < 3 ? 1 : 0, mr, i < 3 ? P32(q + ".1.weight") : nullptr,
+                      i < 3 ? P32(q + ".1.bias") : nullptr, skip, ss, st); ++n_launches;
+}
+
+template <typename T>
+void PlanT<T>::decode(const float* emb, float* out, cudaStream_t st) {
+  const Shapes& s = sh;
+  const int B = s.B, Tf = s.Tf;
+  text_vectors(emb, st);
+  for (int p = 0; p < s.P; ++p) {
+    text_condition(p, xenc, s.Sf, xc, 8, 12, 2, st);
+    text_condition(p, xtenc, s.St, xtc, s.St, s.St + 8, 2, st);
+    const T* x = xc; RowSpace xs = xc_rs;
+    for (int i = 0; i < 4; ++i) { dec_layer(true, i, p, x, xs, df[i], df_rs[i], ef[3 - i], yf_rs[3 - i], st); x = df[i]; xs = df_rs[i]; }
+    launch_mask_istft<T>(Z, Tf, B, 1, df[3], df_rs[3], 1, P32("freq_out.weight"), P32("freq_out.bias"), frames, consts.tw,
+                         consts.win, st); ++n_launches;
+    x = xtc; xs = xtc_rs;
+    for (int i = 0; i < 4; ++i) { dec_layer(false, i, p, x, xs, dt[i], dt_rs[i], et[3 - i], yt_rs[3 - i], st); x = dt[i]; xs = dt_rs[i]; }
+    launch_ola_combine<T>(frames, Tf, s.L, B, dt[3], dt_rs[3], P32("time_out.weight"), P32("time_out.bias"), ms_wav, 1,
+                          out + (size_t)p * 2 * s.L, (long)s.P * 2 * s.L, st); ++n_launches;
+  }
+}
+
+template <typename T>
+int PlanT<T>::forward(const float* wav, const float* emb, float* out, cudaStream_t st) {
+  n_launches = 0;
+  encode(wav, st);
+  decode(emb, out, st);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+bool PlanT<T>::tap(const std::string& name, TapInfo& ti) const {
+  const Shapes& s = sh;
+  auto set = [&](const void* p, int dt, long n, int d0, int d1, int d2, int d3) {
+    ti.ptr = p; ti.dtype = dt; ti.numel = n; ti.dims[0] = d0; ti.dims[1] = d1; ti.dims[2] = d2; ti.dims[3] = d3; return true;
+  };
+  const int TD = sizeof(T) == 4 ? 0 : 1;
+  auto rs = [&](const T* p, const RowSpace& r) { return set(p, TD, r.elems(), r.G, r.Rp, r.C, r.pf); };
+  if (name == "Z") return set(Z, 0, (long)s.B * s.Tf * 2048 * 4, s.B, s.Tf, 2048, 4);
+  if (name == "ms_spec") return set(ms_spec, 0, 2L * s.B, s.B, 2, 1, 1);
+  if (name == "ms_wav") return set(ms_wav, 0, 2L * s.B, s.B, 2, 1, 1);
+  if (name == "xf0") return rs(xf0, xf0_rs);
+  if (name == "xt0") return rs(xt0, xt0_rs);
+  for (int i = 0; i < 4; ++i) {
+    std::string k = std::to_string(i);
+    if (name == "yf" + k) return rs(yf[i], yf_rs[i]);
+    if (name == "yt" + k) return rs(yt[i], yt_rs[i]);
+    if (name == "enc" + k) return rs(ef[i], yf_rs[i]);
+    if (name == "tenc" + k) return rs(et[i], yt_rs[i]);
+    if (name == "fdec" + k) return rs(df[i], df_rs[i]);
+    if (name == "tdec" + k) return rs(dt[i], dt_rs[i]);
+  }
+  if (name == "tokf") return set(tokf, TD, (long)s.B * s.Sf * 512, s.B, s.Sf, 512, 0);
+  if (name == "tokt") return set(tokt, TD, (long)s.B * s.St * 512, s.B, s.St, 512, 0);
+  if (name == "xenc") return set(xenc, TD, (long)s.B * s.Sf * 384, s.B, s.Sf, 384, 0);
+  if (name == "xtenc") return set(xtenc, TD, (long)s.B * s.St * 384, s.B, s.St, 384, 0);
+  if (name == "xc") return rs(xc, xc_rs);
+  if (name == "xtc") return rs(xtc, xtc_rs);
+  if (name == "cvec") return set(cvec, 0, (long)s.B * s.P * 384, s.B * s.P, 384, 1, 0);
+  if (name == "frames") return set(frames, 0, (long)s.B * 2 * s.Tf * 4096, s.B, 2, s.Tf, 4096);
+  return false;
+}
+
+template struct PlanT<float>;
+template struct PlanT<bf16>;
+
+}  // namespace athtd

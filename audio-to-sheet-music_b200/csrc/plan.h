@@ -1,0 +1,96 @@
+// Plan = shapes + workspace layout + launch sequence for one (B segments, L samples, P prompts) shape.
+#pragma once
+#include <algorithm>
+#include "kernels.cuh"
+#include "model.cuh"
+
+namespace athtd {
+
+struct PackLayout {
+  std::vector<PackItem> items;
+  std::map<std::string, int> index;
+  long total_bytes;
+  explicit PackLayout(int dtype);
+};
+
+template <typename T>
+int pack_weights(const ParamTable& pt, const PackLayout& pl, const float* params, void* packed, cudaStream_t st);
+
+struct Shapes {
+  int B, L, P, Tf;
+  int Fr[5];   // frequency rows per level: 2048, 512, 128, 32, 8
+  int Lt[5];   // time-branch lengths per level: L, ceil(L/4), ...
+  int Sf, St;  // transformer tokens per branch
+  Shapes(int B, int L, int P);
+};
+
+struct PlanConsts {
+  const float2* tw;    // exp(-2 pi i k / 4096), k in [0,4096)
+  const float* win;    // periodic hann(4096)
+  const float* pe2d;   // [Sf, 512] 2-D sinusoidal embedding in (t1 fr) token order
+  const float* pe1d;   // [St, 512]
+};
+
+struct TapInfo { const void* ptr; int dtype; long numel; int dims[4]; };
+
+struct PlanBase {
+  virtual ~PlanBase() {}
+  virtual int forward(const float* wav, const float* emb, float* out, cudaStream_t st) = 0;
+  virtual int encode_only(const float* wav, cudaStream_t st) = 0;
+  virtual int decode_only(const float* emb, float* out, cudaStream_t st) = 0;
+  virtual bool tap(const std::string& name, TapInfo& ti) const = 0;
+  virtual long workspace_bytes() const = 0;
+  virtual long zero_region_bytes() const = 0;
+  virtual int launches() const = 0;
+};
+
+template <typename T>
+struct PlanT : PlanBase {
+  Shapes sh;
+  const ParamTable* pt;
+  const PackLayout* pl;
+  const float* params;
+  const char* packed;
+  PlanConsts consts;
+  char* base_ = nullptr;
+  size_t total_bytes = 0, zero_bytes = 0, stats_begin = 0, stats_bytes = 0;
+  int n_launches = 0;
+  // buffers
+  RowSpace xf0_rs, xt0_rs, yf_rs[4], yt_rs[4], xc_rs, xtc_rs, df_rs[4], dt_rs[4];
+  T *xf0, *xt0, *yf[4], *ef[4], *yt[4], *et[4], *xc, *xtc, *df[4], *dt[4];
+  double *st_spec, *st_wav, *st_df[4][2][2], *st_dt[4][2][2], *st_xf[5][2], *st_dec;
+  float *mr, *ms_spec, *ms_wav, *Z, *cvec, *frames;
+  T *hbuf, *ebuf, *tokf, *tokt, *hn[4], *qkv, *kvb, *obuf, *ffn, *scores, *xenc, *xtenc, *t1, *t2, *ubuf;
+
+  PlanT(int B, int L, int P, const ParamTable* pt, const PackLayout* pl, const float* params, const void* packed,
+        void* workspace, const PlanConsts& c);
+  void layout(char* base);
+  char* ws_base() const { return base_; }
+  const float* P32(const std::string& name) const;
+  const T* PW(const std::string& key) const;
+  const float* PA(const std::string& key) const;
+  void gemm(const GemmDesc& d, cudaStream_t st);
+  void enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSpace ys, T* out, cudaStream_t st);
+  void attention(const T* q, long ldq, const T* k, const T* v, long ldkv, int Sq, int Sk, T* o, cudaStream_t st);
+  void linear(const T* a, long rows, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st);
+  void linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x, double* stats,
+                  cudaStream_t st);
+  void xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, cudaStream_t st);
+  void cross_transformer(cudaStream_t st);
+  void encode(const float* wav, cudaStream_t st);
+  void text_vectors(const float* emb, cudaStream_t st);
+  void text_condition(int p, const T* x, int S, T* out, int yR, int yRp, int ypf, cudaStream_t st);
+  void dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* out, RowSpace os, const T* skip, RowSpace ss,
+                 cudaStream_t st);
+  void decode(const float* emb, float* out, cudaStream_t st);
+
+  int forward(const float* wav, const float* emb, float* out, cudaStream_t st) override;
+  int encode_only(const float* wav, cudaStream_t st) override { n_launches = 0; encode(wav, st); return (int)cudaGetLastError(); }
+  int decode_only(const float* emb, float* out, cudaStream_t st) override { decode(emb, out, st); return (int)cudaGetLastError(); }
+  bool tap(const std::string& name, TapInfo& ti) const override;
+  long workspace_bytes() const override { return (long)total_bytes; }
+  long zero_region_bytes() const override { return (long)zero_bytes; }
+  int launches() const override { return n_launches; }
+};
+
+}  // namespace athtd

@@ -1,0 +1,89 @@
+/* athtd.h -- C ABI of the B200-native (sm_100a) AudioTextHTDemucs separation path.
+ *
+ * Drop-in boundary for the hot path of savage-hacker14/audio-to-sheet-music:
+ *   AudioTextHTDemucs.forward            src/models/stem_separation/ATHTDemucs_v2.py:250-326
+ *   OurModel._chunked_inference          benchmark.py:155-204   (== app.py:129-178)
+ * The reference is pure Python/PyTorch; a reference-side binding is a ctypes (or torch-extension)
+ * stub that passes tensor.data_ptr() values -- see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every pointer named *_dev is a CUDA device pointer
+ * on the current device; `stream` is a cudaStream_t passed as void*; no function allocates device
+ * memory, synchronises, or throws.  Return value 0 = ok, non-zero = error (text via
+ * athtd_last_error()).  dtype: 0 = fp32 activations + fp32 SIMT GEMMs (parity build),
+ * 1 = bf16 activations, fp32 accumulation (performance build).  There is no CPU fallback.
+ */
+#ifndef ATHTD_H
+#define ATHTD_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* athtd_last_error(void);
+int athtd_version(void);
+
+/* ---- parameters: replaces nn.Module.state_dict() traffic (SURVEY.md Appendix E key layout).
+ * The live tensors are copied, by name, into ONE flat fp32 device buffer at these offsets. */
+int athtd_param_count(void);
+const char* athtd_param_name(int i);
+long athtd_param_numel(int i);
+long athtd_param_offset(int i);      /* in floats */
+long athtd_params_total(void);       /* in floats */
+
+/* GEMM-layout copies (k-major conv taps, transposed-conv phases, GLU-interleaved rewrites) in the
+ * activation dtype.  Replaces nothing in the reference (PyTorch re-lays-out weights inside cuDNN). */
+long athtd_packed_bytes(int dtype);
+int athtd_pack_weights(const float* params_dev, void* packed_dev, int dtype, void* stream);
+
+/* ---- plan: one (B segments, L samples, P prompts per segment) shape */
+long athtd_workspace_bytes(int B, int L, int P, int dtype);
+/* consts: tw_dev float2[4096] = exp(-2*pi*i*k/4096); win_dev float[4096] periodic hann;
+ * pe2d_dev float[8*Tf][512], pe1d_dev float[St][512] (demucs create_2d_sin_embedding /
+ * create_sin_embedding, token order "(t1 fr)").  workspace_dev must be zero-filled once by the caller. */
+void* athtd_plan_create(int B, int L, int P, int dtype, const float* params_dev, const void* packed_dev,
+                        void* workspace_dev, long workspace_bytes, const float* tw_dev, const float* win_dev,
+                        const float* pe2d_dev, const float* pe1d_dev);
+void athtd_plan_destroy(void* plan);
+int athtd_plan_tokens(void* plan, int* Tf, int* Sf, int* St);
+
+/* AudioTextHTDemucs.forward (ATHTDemucs_v2.py:250-326) with the CLAP call (:282) replaced by the
+ * embedding: wav [B,2,L] fp32, emb [B,P,512] fp32 -> out [B,P,2,L] fp32. */
+int athtd_forward(void* plan, const float* wav_dev, const float* emb_dev, float* out_dev, void* stream);
+/* prompt-independent half (_spec, normalise, _encode; ATHTDemucs_v2.py:261-279) ... */
+int athtd_encode(void* plan, const float* wav_dev, void* stream);
+/* ... and the per-prompt half (text_attn, decoders, mask, _ispec, time branch; :282-324). */
+int athtd_decode(void* plan, const float* emb_dev, float* out_dev, void* stream);
+int athtd_plan_launches(void* plan);   /* kernels launched by the last forward */
+
+/* debug / test access to intermediate buffers of the last forward (dims: see plan.cu tap()) */
+int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[4]);
+
+/* async device-to-device copy on `stream` (lets tests read taps without a second CUDA binding) */
+int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* stream);
+
+/* ---- spectral front / back end on their own (htdemucs._spec+_magnitude / _ispec, BASELINE config 2)
+ * Z layout: [B, Tf, 2048, 4] fp32 with channels (L.re, L.im, R.re, R.im); stats: double[2*B] zeroed by caller. */
+int athtd_stft_cac(const float* wav_dev, int B, int L, float* Z_dev, double* stats_dev, const float* tw_dev,
+                   const float* win_dev, void* stream);
+/* inverse of channels (L, R) of Z: frames_dev scratch float[B*2*Tf*4096], out [B,2,L] */
+int athtd_istft(const float* Z_dev, int B, int L, float* frames_dev, float* out_dev, const float* tw_dev,
+                const float* win_dev, void* stream);
+
+/* ---- track-level chunk loop (benchmark.py:155-204) */
+int athtd_gather_chunks(const float* track_dev, long T, int C, const long* starts_dev, int n_chunks, int chunk_len,
+                        float* segs_dev, void* stream);
+/* seg_out_dev: per-chunk model outputs [C, chunk_len] of global chunk k at seg_out + (k-k_base)*seg_stride.
+ * flags bit0 = fade-in, bit1 = fade-out; ramps are torch.linspace(0,1,n) / (1,0,n) tables concatenated,
+ * ramp_off[k] = table offset for chunk k.  Writes out[c, s - t_begin] for s in [t_begin, t_end), pitch t_end-t_begin. */
+int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int chunk_len, const long* starts_dev,
+                    const int* actual_len_dev, const int* fade_len_dev, const int* flags_dev, int n_chunks, long stride,
+                    const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
+                    long t_begin, long t_end, void* stream);
+
+/* ---- generic GEMM entry used by the kernel-level parity tests: C[M,N] = A[M,K] * B[N,K]^T (+bias), row-major */
+int athtd_gemm_test(const void* A_dev, const void* B_dev, const float* bias_dev, void* C_dev, int M, int N, int K,
+                    int dtype, int use_tensor_cores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,109 @@
+"""GPU (-m gpu): end-to-end parity of the CUDA path (through the module API -> C ABI) with the CPU oracle.
+Tolerances (BASELINE.json north_star): fp32 build max-abs <= 1e-3; bf16 build SNR >= 40 dB."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import athtd_b200
+from oracle import athtd_oracle, ola, weights
+
+
+@pytest.fixture(scope="module")
+def models(state_dict):
+    out = {}
+    for prec in ("fp32", "bf16"):
+        m = athtd_b200.AudioTextHTDemucsB200(precision=prec)
+        m.load_state_dict(state_dict, strict=False)
+        out[prec] = m.cuda().eval()
+    return out
+
+
+def test_native_library_is_loaded(models):
+    maps = open("/proc/self/maps").read()
+    assert "libathtd.so" in maps
+
+
+@pytest.mark.parametrize("B,L,norm", [(2, 40000, True), (1, 30000, False)])
+def test_fp32_forward_matches_golden_and_oracle(models, state_dict, golden_dir, B, L, norm):
+    g = np.load(os.path.join(golden_dir, "forward_short.npz"))
+    wav, emb = weights.make_inputs(11 if norm else 12, B, L, emb_norm=norm)
+    out = models["fp32"](wav.cuda(), emb.cuda()).cpu()
+    gold = torch.from_numpy(g["out"] if norm else g["out_unnorm"])
+    assert (out - gold).abs().max() < 1e-3            # fixture produced by the real reference module
+    ref = athtd_oracle.forward(state_dict, wav, emb)
+    assert (out - ref).abs().max() < 1e-3
+
+
+def test_fp32_forward_6s_matches_golden(models, golden_dir):
+    g = np.load(os.path.join(golden_dir, "forward_6s.npz"))
+    wav, emb = weights.make_inputs(1, 1, 264600)
+    out = models["fp32"](wav.cuda(), emb.cuda()).cpu()
+    assert (out[..., ::37] - torch.from_numpy(g["out_dec37"])).abs().max() < 1e-3
+    assert abs(float((out.double() ** 2).sum()) - float(g["out_sumsq"])) < 1e-3 * float(g["out_sumsq"])
+
+
+def test_bf16_forward_snr(models, state_dict):
+    wav, emb = weights.make_inputs(1, 1, 264600)
+    ref = athtd_oracle.forward(state_dict, wav, emb)
+    out = models["bf16"](wav.cuda(), emb.cuda()).cpu()
+    assert athtd_oracle.snr_db(out, ref) >= 40.0
+
+
+def test_batch_invariance_and_mixed_prompts(models, state_dict):
+    wav, emb = weights.make_inputs(21, 3, 20000)
+    m = models["fp32"]
+    full = m(wav.cuda(), emb.cuda()).cpu()
+    for b in range(3):
+        one = m(wav[b:b + 1].cuda(), emb[b:b + 1].cuda()).cpu()
+        assert (one[0] - full[b]).abs().max() < 1e-5
+    ref = athtd_oracle.forward(state_dict, wav, emb)       # three different prompts in one batch
+    assert (full - ref).abs().max() < 1e-3
+
+
+def test_encode_once_decode_per_prompt(models, state_dict):
+    wav, emb0 = weights.make_inputs(31, 2, 20000)
+    embs = torch.stack([emb0] + [weights.make_inputs(40 + p, 2, 4096)[1] for p in range(2)], dim=1)   # [2,3,512]
+    m = models["fp32"]
+    out = m.separate_batch(wav.cuda(), embs.cuda()).cpu()                                           # [2,3,2,L]
+    for p in range(3):
+        ref = athtd_oracle.forward(state_dict, wav, embs[:, p])
+        assert (out[:, p] - ref).abs().max() < 1e-3
+        again = m(wav.cuda(), embs[:, p].cuda()).cpu()
+        assert (again - out[:, p]).abs().max() < 1e-5
+
+
+def test_prompt_strings_and_bare_str(models):
+    m = models["fp32"]
+    _, emb = weights.make_inputs(51, 1, 4096)
+    m.register_prompt_embedding("drums", emb[0])
+    wav, _ = weights.make_inputs(52, 1, 20000)
+    a = m(wav.cuda(), ["drums"])
+    b = m(wav.cuda(), "drums")                              # test_inference.py:120 passes a bare str
+    c = m(wav.cuda(), emb.cuda())
+    assert torch.equal(a, b) and torch.equal(a, c)
+    with pytest.raises(athtd_b200.AthtdError):
+        m(wav.cuda(), ["unknown prompt"])
+
+
+def test_track_separation_matches_reference_loop(models, state_dict):
+    """separate_many (gather -> batched forward -> OLA kernel) vs the restated benchmark.py loop driving the
+    oracle forward, on a 2.2-chunk track with a short segment length to keep the CPU oracle fast."""
+    m = models["fp32"]
+    sep = athtd_b200.B200SeparationModel(m, "cuda", segment_seconds=1.0, overlap_seconds=0.25, batch=2)
+    T = 44100 * 2 + 5000
+    wav, emb = weights.make_inputs(61, 1, T)
+    mix = wav[0]
+    ref = ola.chunked_inference(lambda c: athtd_oracle.forward(state_dict, c, emb), mix, 1.0, 0.25)
+    out, _ = sep.separate_many(mix, emb)
+    assert out.shape == (1, 2, T)
+    assert (out[0].cpu() - ref).abs().max() < 1e-3
+    # two spans + halo == one span, bit for bit (multi-GPU stitch rule)
+    n = len(athtd_b200.segment_plan(T, 1.0, 0.25).starts)
+    k = n // 2
+    left, halo = sep.separate_many(mix, emb, span=(0, k))
+    right, _ = sep.separate_many(mix, emb, span=(k, n), halo_in=halo)
+    assert torch.equal(torch.cat([left, right], dim=-1), out)

@@ -1,0 +1,100 @@
+"""CPU: host-side logic of the product (no CUDA compute): segment plan, ramp tables, module API /
+state_dict layout, C-ABI exports."""
+import os
+import re
+
+import pytest
+import torch
+
+import athtd_b200
+from athtd_b200 import lib as alib
+from oracle import ola, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("T", [1, 66149, 66150, 198449, 198450, 198451, 264600, 264601, 10584000, 50803200, 158760000,
+                               123457, 7000001])
+def test_segment_plan_matches_oracle(T):
+    mine = athtd_b200.segment_plan(T)
+    ref = ola.chunk_plan(T)
+    assert len(mine.starts) == len(ref)
+    for k, c in enumerate(ref):
+        assert (mine.starts[k], mine.ends[k], mine.actual_len[k], mine.fade_len[k]) == (c.start, c.end, c.actual_len, c.fade_len)
+        assert mine.flags[k] == (1 if c.fade_in else 0) | (2 if c.fade_out else 0)
+
+
+def test_segment_plan_app_overlap():
+    mine = athtd_b200.segment_plan(1_000_000, 6.0, 0.1)     # app.py:29-33 / config.yaml:7
+    ref = ola.chunk_plan(1_000_000, 6.0, 0.1)
+    assert mine.starts == [c.start for c in ref] and mine.fade_len == [c.fade_len for c in ref]
+
+
+def test_segment_plan_rejects_triple_overlap():
+    with pytest.raises(ValueError):
+        athtd_b200.segment_plan(10 ** 6, 6.0, 3.5)
+
+
+def test_ramp_tables_bit_exact():
+    plan = athtd_b200.segment_plan(240 * 44100)
+    tab = athtd_b200.OlaTables(plan, "cpu")
+    for k, c in enumerate(ola.chunk_plan(240 * 44100)):
+        w = ola.chunk_weight(c)
+        off = int(tab.ramp_off[k])
+        if c.fade_in:
+            assert torch.equal(tab.ramp_up[off:off + c.fade_len], w[:c.fade_len])
+        if c.fade_out:
+            assert torch.equal(tab.ramp_down[off:off + c.fade_len], w[-c.fade_len:])
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "athtd.h")).read()
+    declared = set(re.findall(r"\b(athtd_[a-z0-9_]+)\s*\(", hdr))
+    bound = {s[0] for s in alib.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    lib = alib.load()                      # dlopen + getattr on every symbol
+    assert lib.athtd_version() >= 1
+    assert lib.athtd_param_count() == 407
+
+
+def test_param_table_is_the_reference_state_dict_layout():
+    table = {n: numel for n, numel, _ in alib.param_table()}
+    ref = {n: int(torch.tensor(s).prod()) for n, s, _ in weights.live_param_table()}
+    assert table == ref
+
+
+def test_module_state_dict_layout_and_dead_keys():
+    model = athtd_b200.AudioTextHTDemucsB200()
+    sd = weights.make_state_dict(0, include_dead=True)
+    res = model.load_state_dict(sd, strict=False)
+    assert res.missing_keys == []
+    assert all(k.startswith(("clap.", "htdemucs.decoder.", "htdemucs.tdecoder.")) for k in res.unexpected_keys)
+    live = {n for n, _, _ in weights.live_param_table()}
+    assert set(model.state_dict().keys()) == live
+    for k, v in model.state_dict().items():
+        assert v.shape == sd[k].shape, k
+    assert all(not p.requires_grad for p in model.htdemucs.parameters())
+    assert any(p.requires_grad for p in model.text_attn.parameters())
+
+
+def test_no_cpu_fallback():
+    model = athtd_b200.AudioTextHTDemucsB200()
+    with pytest.raises(athtd_b200.AthtdError):
+        model(torch.zeros(1, 2, 44100), torch.zeros(1, 512))
+    assert isinstance(athtd_b200.B200SeparationModel.__mro__[1], type) and issubclass(athtd_b200.B200SeparationModel, athtd_b200.SeparationModel)
+
+
+def test_workspace_query():
+    lib = alib.load()
+    assert lib.athtd_workspace_bytes(1, 264600, 1, 0) > 0
+    assert lib.athtd_workspace_bytes(1, 100, 1, 0) == -1          # too short: explicit error, not UB
+    assert b"4096" in lib.athtd_last_error()
+
+
+def test_positional_tables_match_oracle():
+    from athtd_b200.engine import sin_embedding_1d, sin_embedding_2d
+    from oracle.demucs_shim import create_2d_sin_embedding, create_sin_embedding
+    ref2 = create_2d_sin_embedding(512, 8, 40).permute(0, 3, 2, 1).reshape(320, 512)
+    assert torch.equal(sin_embedding_2d(512, 8, 40), ref2)
+    ref1 = create_sin_embedding(157, 512).permute(1, 0, 2)[0]
+    assert torch.equal(sin_embedding_1d(157, 512), ref1)
