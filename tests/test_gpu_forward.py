@@ -23,6 +23,7 @@ def models(state_dict):
 
 
 def test_native_library_is_loaded(models):
+    models["fp32"].engine()
     maps = open("/proc/self/maps").read()
     assert "libathtd.so" in maps
 
