@@ -99,6 +99,11 @@ int athtd_decode(void* plan, const float* emb_dev, float* out_dev, void* stream)
   GUARD(((PlanBase*)plan)->decode_only(emb_dev, out_dev, (cudaStream_t)stream), "athtd_decode");
 }
 int athtd_plan_launches(void* plan) { return ((PlanBase*)plan)->launches(); }
+int athtd_plan_set_profile(void* plan, int on) { ((PlanBase*)plan)->set_profile(on != 0); return 0; }
+int athtd_plan_get_profile(void* plan, double* gemm_ms, double* gemm_gflop, int* gemm_launches) {
+  ((PlanBase*)plan)->get_profile(gemm_ms, gemm_gflop, gemm_launches);
+  return 0;
+}
 
 int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[4]) {
   TapInfo ti;

@@ -162,8 +162,24 @@ const float* PlanT<T>::PA(const std::string& key) const {
 
 template <typename T>
 void PlanT<T>::gemm(const GemmDesc& d, cudaStream_t st) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (profiling) {      // per-launch CUDA-event timing of the GEMM kernel (bench.py roofline pass only)
+    while (prof_ev.size() < prof_used + 2) { cudaEvent_t e; cudaEventCreate(&e); prof_ev.push_back(e); }
+    e0 = prof_ev[prof_used++]; e1 = prof_ev[prof_used++];
+    prof_gflop += 2.0 * (double)d.G1 * d.G2 * d.Mg * d.N * d.K * 1e-9;
+    cudaEventRecord(e0, st);
+  }
   launch_gemm_simt<T>(d, st);
+  if (profiling) cudaEventRecord(e1, st);
   ++n_launches;
+}
+
+template <typename T>
+void PlanT<T>::get_profile(double* ms, double* gflop, int* n) {
+  double total = 0.0;
+  if (prof_used) cudaEventSynchronize(prof_ev[prof_used - 1]);
+  for (size_t i = 0; i + 1 < prof_used; i += 2) { float t = 0.f; cudaEventElapsedTime(&t, prof_ev[i], prof_ev[i + 1]); total += t; }
+  *ms = total; *gflop = prof_gflop; *n = (int)(prof_used / 2);
 }
 
 // ---- one HEncLayer (demucs hdemucs.py:HEncLayer) on a channels-last row space.

@@ -42,6 +42,8 @@ struct PlanBase {
   virtual long workspace_bytes() const = 0;
   virtual long zero_region_bytes() const = 0;
   virtual int launches() const = 0;
+  virtual void set_profile(bool on) = 0;
+  virtual void get_profile(double* ms, double* gflop, int* n) = 0;
 };
 
 template <typename T>
@@ -55,6 +57,10 @@ struct PlanT : PlanBase {
   char* base_ = nullptr;
   size_t total_bytes = 0, zero_bytes = 0, stats_begin = 0, stats_bytes = 0;
   int n_launches = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  double prof_gflop = 0.0;
   // buffers
   RowSpace xf0_rs, xt0_rs, yf_rs[4], yt_rs[4], xc_rs, xtc_rs, df_rs[4], dt_rs[4];
   T *xf0, *xt0, *yf[4], *ef[4], *yt[4], *et[4], *xc, *xtc, *df[4], *dt[4];
@@ -91,6 +97,8 @@ struct PlanT : PlanBase {
   long workspace_bytes() const override { return (long)total_bytes; }
   long zero_region_bytes() const override { return (long)zero_bytes; }
   int launches() const override { return n_launches; }
+  void set_profile(bool on) override { profiling = on; prof_used = 0; prof_gflop = 0.0; }
+  void get_profile(double* ms, double* gflop, int* n) override;
 };
 
 }  // namespace athtd

@@ -112,6 +112,14 @@ class Plan:
     def launches(self) -> int:
         return _lib.load().athtd_plan_launches(self.handle)
 
+    def set_profile(self, on: bool) -> None:
+        _lib.load().athtd_plan_set_profile(self.handle, 1 if on else 0)
+
+    def get_profile(self):
+        ms, gf, n = C.c_double(), C.c_double(), C.c_int()
+        _lib.load().athtd_plan_get_profile(self.handle, C.byref(ms), C.byref(gf), C.byref(n))
+        return ms.value, gf.value, n.value
+
     def tap(self, name: str) -> Tap:
         ptr, numel, dt = C.c_void_p(), C.c_long(), C.c_int()
         dims = (C.c_int * 4)()
@@ -164,6 +172,9 @@ class Engine:
             with torch.cuda.device(self.device):
                 self.plans[key] = Plan(self, B, L, P)
         return self.plans[key]
+
+    def gemm_kernel_name(self) -> str:
+        return "gemm_simt_kernel (CUDA-core fp32 accumulate)"
 
     def drop_plans(self) -> None:
         self.plans.clear()

@@ -53,6 +53,10 @@ int athtd_encode(void* plan, const float* wav_dev, void* stream);
 /* ... and the per-prompt half (text_attn, decoders, mask, _ispec, time branch; :282-324). */
 int athtd_decode(void* plan, const float* emb_dev, float* out_dev, void* stream);
 int athtd_plan_launches(void* plan);   /* kernels launched by the last forward */
+/* measurement aid (bench.py roofline pass): CUDA-event pairs around every GEMM launch of subsequent forwards;
+ * get_profile synchronises on the last event and returns summed GEMM ms, algorithmic GFLOP (2*M*N*K) and launches. */
+int athtd_plan_set_profile(void* plan, int on);
+int athtd_plan_get_profile(void* plan, double* gemm_ms, double* gemm_gflop, int* gemm_launches);
 
 /* debug / test access to intermediate buffers of the last forward (dims: see plan.cu tap()) */
 int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[4]);
