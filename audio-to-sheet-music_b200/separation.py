@@ -212,150 +212,6 @@ class B200SeparationModel(SeparationModel):
             pl.set_profile(False)
         return {"kernel": eng.gemm_kernel_name(), "ms": ms, "gflop": gf, "launches": n, "tflops": gf / ms if ms > 0 else 0.0}
 
-    def separate(self, mixture: torch.Tensor, stem_name: str) -> torch.Tensor: ...
-
-    @abstractmethod
-    def separate_all(self, mixture: torch.Tensor) -> Dict[str, torch.Tensor]: ...
-
-    @property
-    @abstractmethod
-    def name(self) -> str: ...
-
-
-class SegmentPlan(NamedTuple):
-    T: int
-    chunk_len: int
-    stride: int
-    starts: List[int]
-    ends: List[int]
-    actual_len: List[int]
-    fade_len: List[int]
-    flags: List[int]          # bit0 fade-in, bit1 fade-out
-
-
-def segment_plan(T: int, segment_seconds: float = 6.0, overlap_seconds: float = 1.5,
-                 sample_rate: int = SAMPLE_RATE) -> SegmentPlan:
-    """Integer arithmetic of benchmark.py:158-198 (loop bound ``start < T``, fade_len =
-    min(overlap, actual_len // 2), fade-in iff start > 0, fade-out iff end < T)."""
-    chunk_len = int(sample_rate * segment_seconds)
-    overlap = int(overlap_seconds * sample_rate)
-    stride = chunk_len - overlap
-    if stride <= 0 or 2 * stride <= chunk_len:
-        raise ValueError("overlap must be smaller than half a segment (at most two chunks may overlap a sample)")
-    starts, ends, actual, fades, flags = [], [], [], [], []
-    n = (T + stride - 1) // stride if T > 0 else 0
-    for k in range(n):
-        s = k * stride
-        e = min(s + chunk_len, T)
-        a = e - s
-        f = min(overlap, a // 2)
-        starts.append(s); ends.append(e); actual.append(a); fades.append(f)
-        flags.append((1 if (s > 0 and f > 0) else 0) | (2 if (e < T and f > 0) else 0))
-    return SegmentPlan(T, chunk_len, stride, starts, ends, actual, fades, flags)
-
-
-class OlaTables:
-    """Device-side description of a SegmentPlan for athtd_chunk_ola.  The fade ramps are produced by
-    ``torch.linspace`` on the CPU, exactly like the oracle's restatement of benchmark.py:187-192."""
-
-    def __init__(self, plan: SegmentPlan, device):
-        self.plan = plan
-        lens = sorted(set(f for f in plan.fade_len if f > 0))
-        offs, up, down, o = {}, [], [], 0
-        for f in lens:
-            offs[f] = o
-            up.append(torch.linspace(0, 1, f)); down.append(torch.linspace(1, 0, f)); o += f
-        z = torch.zeros(1)
-        self.ramp_up = (torch.cat(up) if up else z).float().to(device)
-        self.ramp_down = (torch.cat(down) if down else z).float().to(device)
-        self.ramp_off = torch.tensor([offs.get(f, 0) for f in plan.fade_len], dtype=torch.int32, device=device)
-        self.starts = torch.tensor(plan.starts, dtype=torch.int64, device=device)
-        self.actual = torch.tensor(plan.actual_len, dtype=torch.int32, device=device)
-        self.fade = torch.tensor(plan.fade_len, dtype=torch.int32, device=device)
-        self.flags = torch.tensor(plan.flags, dtype=torch.int32, device=device)
-
-
-def gather_chunks(track: torch.Tensor, tables: OlaTables, k0: int, k1: int) -> torch.Tensor:
-    """track [2,T] cuda -> segments [k1-k0, 2, chunk_len] (tail zero-padded, benchmark.py:170-172)."""
-    p = tables.plan
-    C, T = track.shape
-    segs = torch.empty(k1 - k0, C, p.chunk_len, dtype=torch.float32, device=track.device)
-    st = torch.cuda.current_stream(track.device).cuda_stream
-    _lib.check(_lib.load().athtd_gather_chunks(track.data_ptr(), T, C, tables.starts[k0:].data_ptr(), k1 - k0, p.chunk_len,
-                                               segs.data_ptr(), st), "athtd_gather_chunks")
-    return segs
-
-
-def chunk_ola(seg_out: torch.Tensor, seg_stride: int, k_base: int, tables: OlaTables, t_begin: int, t_end: int,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Weighted overlap-add of per-chunk outputs (benchmark.py:185-202) for track samples
-    [t_begin, t_end).  seg_out holds chunk k at element offset (k - k_base) * seg_stride as [2, chunk_len]."""
-    p = tables.plan
-    if out is None:
-        out = torch.empty(2, t_end - t_begin, dtype=torch.float32, device=seg_out.device)
-    st = torch.cuda.current_stream(seg_out.device).cuda_stream
-    _lib.check(_lib.load().athtd_chunk_ola(seg_out.data_ptr(), seg_stride, k_base, p.chunk_len, tables.starts.data_ptr(),
-                                           tables.actual.data_ptr(), tables.fade.data_ptr(), tables.flags.data_ptr(),
-                                           len(p.starts), p.stride, tables.ramp_up.data_ptr(), tables.ramp_down.data_ptr(),
-                                           tables.ramp_off.data_ptr(), out.data_ptr(), 2, t_begin, t_end, st),
-               "athtd_chunk_ola")
-    return out
-
-
-class B200SeparationModel(SeparationModel):
-    """``OurModel`` (benchmark.py:122-215) on the B200 path.  ``model`` is an AudioTextHTDemucsB200
-    whose weights were loaded the usual way (load_state_dict(ckpt["model_state_dict"], strict=False))."""
-
-    def __init__(self, model: AudioTextHTDemucsB200, device: str = "cuda", segment_seconds: float = 6.0,
-                 overlap_seconds: float = 1.5, batch: int = 32):
-        self.model = model.to(device).eval()
-        self.device = torch.device(device)
-        self.segment_seconds = segment_seconds
-        self.overlap = overlap_seconds
-        self.batch = batch
-
-    @property
-    def name(self) -> str:
-        return "AudioTextHTDemucs (B200)"
-
-    def prompt_embeddings(self, prompts: Sequence[str]) -> torch.Tensor:
-        return self.model._get_clap_embeddings(list(prompts), self.device)          # [P, 512]
-
-    @torch.no_grad()
-    def separate_many(self, mixture: torch.Tensor, emb: torch.Tensor, span=None, halo_in: Optional[torch.Tensor] = None):
-        """mixture [2,T], emb [P,512] -> [P,2,T'] for the chunk span ``span=(k0,k1)`` (default: whole track).
-
-        Returns (out, seg_out_last): ``out`` covers track samples [starts[k0], starts[k1]) (to T for the last
-        span); ``seg_out_last`` is the raw model output [P,2,chunk_len] of chunk k1-1 (the halo a right-hand
-        neighbour rank needs).  ``halo_in`` is the same tensor received from the left-hand neighbour."""
-        mixture = mixture.to(self.device, torch.float32).contiguous()
-        emb = emb.to(self.device, torch.float32).contiguous()
-        P = emb.shape[0]
-        plan = segment_plan(mixture.shape[-1], self.segment_seconds, self.overlap, self.model.sample_rate)
-        n = len(plan.starts)
-        k0, k1 = (0, n) if span is None else span
-        tables = OlaTables(plan, self.device)
-        L = plan.chunk_len
-        has_halo = k0 > 0
-        if has_halo and halo_in is None:
-            raise ValueError("span starts inside the track: the left neighbour's last chunk output (halo_in) is required")
-        nk = k1 - k0
-        # per-chunk outputs, one leading slot for the halo chunk: [slot, P, 2, L]
-        seg_out = torch.zeros(nk + 1, P, 2, L, dtype=torch.float32, device=self.device)
-        if has_halo:
-            seg_out[0].copy_(halo_in)
-        segs = gather_chunks(mixture, tables, k0, k1)
-        for b0 in range(0, nk, self.batch):
-            b1 = min(b0 + self.batch, nk)
-            e = emb.unsqueeze(0).expand(b1 - b0, P, 512).contiguous()
-            seg_out[1 + b0:1 + b1] = self.model.separate_batch(segs[b0:b1], e)
-        t_begin = plan.starts[k0]
-        t_end = plan.T if k1 == n else plan.starts[k1]
-        out = torch.empty(P, 2, t_end - t_begin, dtype=torch.float32, device=self.device)
-        for p in range(P):
-            chunk_ola(seg_out[:, p], P * 2 * L, k0 - 1, tables, t_begin, t_end, out[p])
-        return out, seg_out[nk]
-
     def separate(self, mixture: torch.Tensor, stem_name: str) -> torch.Tensor:
         out, _ = self.separate_many(mixture, self.prompt_embeddings([stem_name]))
         return out[0]
