@@ -3,6 +3,7 @@
 #include "../../include/athtd.h"
 #include <string>
 #include <mutex>
+#include <string.h>
 
 using namespace athtd;
 
@@ -105,13 +106,16 @@ int athtd_plan_get_profile(void* plan, double* gemm_ms, double* gemm_gflop, int*
   return 0;
 }
 
-int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[4]) {
+int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[8]) {
   TapInfo ti;
+  memset(&ti, 0, sizeof(ti));
   if (!((PlanBase*)plan)->tap(name, ti)) return fail(std::string("athtd_tap: unknown buffer ") + name);
   *ptr = ti.ptr; *numel = ti.numel; *dtype = ti.dtype;
-  for (int i = 0; i < 4; ++i) dims[i] = ti.dims[i];
+  for (int i = 0; i < 4; ++i) { dims[i] = ti.dims[i]; dims[4 + i] = ti.geom[i]; }
   return 0;
 }
+int athtd_plan_set_tc(void* plan, int on) { ((PlanBase*)plan)->set_use_tc(on != 0); return 0; }
+int athtd_plan_tc_launches(void* plan) { return ((PlanBase*)plan)->tc_launches(); }
 
 int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* stream) {
   cudaError_t e = cudaMemcpyAsync(dst_dev, src_dev, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
@@ -159,13 +163,14 @@ int athtd_gemm_test(const void* A_dev, const void* B_dev, const float* bias_dev,
   d.Mg = M; d.N = N; d.K = K; d.Ktap = K; d.A = A_dev; d.sAm = K; d.B = B_dev; d.sBn = K; d.sBk = 1;
   d.C = C_dev; d.sCm = N; d.bias = bias_dev;
   if (use_tensor_cores) {
-#ifdef ATHTD_HAVE_TC
     if (dtype != 1) return fail("athtd_gemm_test: tensor-core path is bf16");
-    if (!gemm_tc_supported(d)) return fail("athtd_gemm_test: shape not supported by the tcgen05 kernel");
-    launch_gemm_tc(d, (cudaStream_t)stream);
-#else
-    return fail("athtd_gemm_test: built without the tcgen05 kernel");
-#endif
+    TcFlat f;
+    memset(&f, 0, sizeof(f));
+    f.A = A_dev; f.a_rows = M; f.a_pitch = K; f.Ktap = K; f.ntaps = 1; f.B = B_dev; f.N = N; f.Mflat = M;
+    f.RpA = M; f.G2p = 1; f.gpf = 0; f.G2 = 1; f.vlo = 0; f.vhi = M; f.oG2p = 1; f.ogsh = 0; f.oRp = M; f.orsh = 0;
+    f.ldc = N; f.C = C_dev; f.alpha = 1.0f; f.bias = bias_dev;
+    if (!tc_flat_supported(f)) return fail("athtd_gemm_test: shape not supported by the tcgen05 kernel");
+    if (launch_gemm_tc_flat(f, (cudaStream_t)stream) != 0) return fail("athtd_gemm_test: cuTensorMapEncodeTiled failed");
   } else if (dtype == 0) launch_gemm_simt<float>(d, (cudaStream_t)stream);
   else launch_gemm_simt<bf16>(d, (cudaStream_t)stream);
   return check_cuda("athtd_gemm_test");

@@ -45,15 +45,29 @@ __device__ __forceinline__ void stats_to_mean_rstd(const double* st, double coun
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-// A padded row space: G groups, each with R interior rows stored inside Rp rows (pf front pad rows).
+// A padded channels-last row space.  G = B*G2 interior groups (G2 groups per segment: frames on the
+// frequency branch, 1 on the time branch); every segment stores G2p >= G2 groups (gpf zero groups in front) and
+// every group stores Rp >= R rows (pf zero rows in front).  Pads are written once (zero) and never again, which
+// is what lets every convolution of the path be a GEMM over row-shifted views of the same buffer.
 struct RowSpace {
-  int G;    // number of groups
+  int G;    // interior groups = B * G2
   int R;    // interior rows per group
-  int Rp;   // stored rows per group (R + pads)
+  int Rp;   // stored rows per group
   int pf;   // front pad rows
   int C;    // channels per row (row pitch in elements)
-  __host__ __device__ long row_off(int g, int r) const { return ((long)g * Rp + pf + r) * (long)C; }
-  __host__ __device__ long elems() const { return (long)G * Rp * C; }
+  int G2;   // interior groups per segment
+  int G2p;  // stored groups per segment
+  int gpf;  // front pad groups
+  __host__ __device__ long row_off(int g, int r) const {
+    int b = g / G2, t = g - b * G2;
+    return (((long)b * G2p + gpf + t) * Rp + pf + r) * (long)C;
+  }
+  __host__ __device__ long elems() const { return (long)(G / G2) * G2p * Rp * C; }
+  __host__ __device__ long rows_total() const { return (long)(G / G2) * G2p * Rp; }
+  __host__ __device__ long g1_stride() const { return (long)G2p * Rp * C; }
+  __host__ __device__ long g2_stride() const { return (long)Rp * C; }
+  __host__ __device__ long origin() const { return ((long)gpf * Rp + pf) * C; }
+  __host__ __device__ int batch() const { return G / G2; }
 };
 
 }  // namespace athtd

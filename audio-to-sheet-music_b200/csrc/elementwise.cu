@@ -152,7 +152,7 @@ template <typename T>
 __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, T* __restrict__ y, long rows, int C, int S,
                                  const float* __restrict__ gmr, const float* __restrict__ gw,
                                  const float* __restrict__ gb, const float* __restrict__ lw, const float* __restrict__ lb,
-                                 const float* __restrict__ pe, int yR, int yRp, int ypf) {
+                                 const float* __restrict__ pe, RowSpace yrs) {
   int lane = threadIdx.x & 31;
   long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -175,22 +175,22 @@ __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, 
   q = warp_sum(q);
   float rstd = rsqrtf(q / C + 1e-5f);
   long srow = row % S;
-  long yrow = row;
-  if (yR > 0) yrow = (row / yR) * yRp + ypf + (row % yR);   // scatter into a padded row space
+  long yoff = row * C;
+  if (yrs.C > 0) yoff = yrs.row_off((int)(row / yrs.R), (int)(row % yrs.R));   // scatter into a padded row space
   cnt = 0;
   for (int c = lane; c < C; c += 32, ++cnt) {
     float t = (v[cnt] - mean) * rstd * lw[c] + lb[c];
     if (pe) t += pe[srow * C + c];
-    y[yrow * C + c] = from_f<T>(t);
+    y[yoff + c] = from_f<T>(t);
   }
 }
 template <typename T>
 void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const float* gmr,
                       const float* gw, const float* gb, const float* lw, const float* lb, const float* pe,
-                      int yR, int yRp, int ypf, cudaStream_t st) {
+                      RowSpace yrs, cudaStream_t st) {
   int wpb = 8;
   norm_rows_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, xout, y, rows, C, S, gmr,
-                                                                                gw, gb, lw, lb, pe, yR, yRp, ypf);
+                                                                                gw, gb, lw, lb, pe, yrs);
 }
 
 // ------------------------------------------------------------------ row softmax, in place (fp32 math)
@@ -239,7 +239,7 @@ void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const fl
 
 // ------------------------------------------------------------------ decoder layer tail
 // out[g, d, c] = lerp_rows( act(GN(u))[g, :, c] )(d) + 0.1 * lerp_rows( skip[g, :, c] )(d)
-//   u    : transposed-conv output in phase layout, row fo of group g lives at u[(g*Urows + fo + 2)*Cu + c]
+//   u    : transposed-conv output in phase layout inside the INPUT's padded geometry (us, 4*Cu channels per row)
 //   GN   : GroupNorm(1,C) statistics per sample (g / G2), biased variance, then exact GELU  (has_gn)
 //   lerp : F.interpolate(mode=linear/bilinear along one axis, align_corners=False)   
 // Follows FreqDecoder.forward / TimeDecoder.forward, ATHTDemucs_v2.py:82-104 / 125-139.
@@ -254,7 +254,7 @@ __device__ __forceinline__ void lerp_coords(int d, int in, int out, int& i0, int
   lam = src - (float)i0;
 }
 template <typename T>
-__global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, long u_group_stride, int Cu, T* __restrict__ out,
+__global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, int Cu, T* __restrict__ out,
                                  RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
                                  const float* __restrict__ gw, const float* __restrict__ gb, const T* __restrict__ skip,
                                  RowSpace ss) {
@@ -265,9 +265,9 @@ __global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, long u_group_
     int d = (int)(row % os.R); int g = (int)(row / os.R);
     int i0, i1; float lam;
     lerp_coords(d, Uin, os.R, i0, i1, lam);
-    const T* ug = u + (long)g * u_group_stride;
-    float a0 = to_f<T>(ug[(long)(i0 + 2) * Cu + c]);
-    float a1 = to_f<T>(ug[(long)(i1 + 2) * Cu + c]);
+    // phase layout: output row fo = 4q + r - 2 lives in the row of x[q-1] (us geometry), columns r*Cu + c
+    float a0 = to_f<T>(u[us.row_off(g, ((i0 + 2) >> 2) - 1) + ((i0 + 2) & 3) * Cu + c]);
+    float a1 = to_f<T>(u[us.row_off(g, ((i1 + 2) >> 2) - 1) + ((i1 + 2) & 3) * Cu + c]);
     if (has_gn) {
       float mean = mr[2 * (g / G2)], rstd = mr[2 * (g / G2) + 1];
       a0 = gelu_erf((a0 - mean) * rstd * gw[c] + gb[c]);
@@ -283,11 +283,11 @@ __global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, long u_group_
   }
 }
 template <typename T>
-void launch_dec_apply(const T* u, int Uin, long u_group_stride, int Cu, T* out, RowSpace os, int G2, int has_gn,
+void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace os, int G2, int has_gn,
                       const float* mr, const float* gw, const float* gb, const T* skip, RowSpace ss,
                       cudaStream_t st) {
   long total = (long)os.G * os.R * os.C;
-  dec_apply_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(u, Uin, u_group_stride, Cu, out, os, G2,
+  dec_apply_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(u, Uin, us, Cu, out, os, G2,
                                                                                     has_gn, mr, gw, gb, skip, ss);
 }
 
@@ -329,10 +329,10 @@ void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int 
   template void launch_gn_glu_res<T>(T*, RowSpace, const T*, RowSpace, int, int, const float*, const float*,            \
                                      const float*, const float*, cudaStream_t);                                         \
   template void launch_norm_rows<T>(const T*, T*, T*, long, int, int, const float*, const float*, const float*,         \
-                                    const float*, const float*, const float*, int, int, int, cudaStream_t);                            \
+                                    const float*, const float*, const float*, RowSpace, cudaStream_t);                            \
   template void launch_softmax_rows<T>(T*, long, int, cudaStream_t);                                                    \
   template void launch_add_rowvec<T>(const T*, T*, long, int, int, const float*, long, cudaStream_t);                   \
-  template void launch_dec_apply<T>(const T*, int, long, int, T*, RowSpace, int, int, const float*,                     \
+  template void launch_dec_apply<T>(const T*, int, RowSpace, int, T*, RowSpace, int, int, const float*,                     \
                                     const float*, const float*, const T*, RowSpace, cudaStream_t);                      \
   template void launch_pack_weight<T>(const float*, T*, long, int, int, int, int, cudaStream_t);
 INST(float)

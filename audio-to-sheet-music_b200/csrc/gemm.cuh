@@ -46,9 +46,21 @@ inline GemmDesc gemm_desc_zero() {
 }
 
 template <typename T> void launch_gemm_simt(const GemmDesc& d, cudaStream_t st);
-#ifdef ATHTD_HAVE_TC
-void launch_gemm_tc(const GemmDesc& d, cudaStream_t st);   // bf16 tcgen05
-bool gemm_tc_supported(const GemmDesc& d);
-#endif
+
+// Flat-row form of the same problem for the tcgen05 kernel (gemm_tc.cu): A is a 2-D [a_rows, Ktap] bf16 view with
+// row pitch a_pitch elements, taps shift the row index; the epilogue decodes a flat row rho into
+// (b, t', f') = (rho / RpA / G2p, rho / RpA % G2p, rho % RpA), keeps it iff f' in [vlo,vhi) and t' in [gpf,gpf+G2),
+// and stores it at row ((b*oG2p + t' + ogsh)*oRp + f' + orsh) of C (row pitch ldc).
+struct TcFlat {
+  const void* A; long a_rows; long a_pitch; int Ktap; int ntaps; int tapRow[3];
+  const void* B; int N;
+  long Mflat;
+  int RpA, G2p, gpf, G2, vlo, vhi;
+  int oG2p, ogsh, oRp, orsh; long ldc; void* C; int c_is_f32;
+  float alpha; const float* bias; int act; int glu; const float* colscale; const void* res;
+  const float* rowtab; float rowtab_scale; double* stats; int stat_mode; int statR; int convt_cout;
+};
+bool tc_flat_supported(const TcFlat& f);
+int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st);   // bf16 in, fp32 accumulate; 0 = launched
 
 }  // namespace athtd

@@ -1,0 +1,380 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: the tensor-core implementation of the conv-as-GEMM problem
+// in its FLAT-ROW form.
+//
+//   acc[rho, n] = sum_{tap} sum_{k < Ktap}  A[rho + tapRow[tap], k] * B[n, tap*Ktap + k]          (bf16 in, fp32 accumulate)
+//
+// A is a 2-D view (rows x Ktap, row pitch >= 16 B) of a channels-last activation buffer; every conv of the
+// path (1x1, strided k8s4, transposed k8s4 phases, dilated k3) is such a view plus 1..3 row-shifted taps, because
+// the buffers carry zero pad rows / pad frames (DESIGN.md "flat-row GEMM").  Rows that fall in padding are
+// computed and discarded by the epilogue's validity decode.
+//
+// Structure (one 128 x BN tile per CTA, 192 threads):
+//   warp 0      : TMA producer  - cp.async.bulk.tensor.2d (SWIZZLE_128B boxes 64 x 128 / 64 x BN) into a 4-stage ring
+//   warp 1      : TMEM allocator + MMA issuer - one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//                 (M=128, N=BN, K=16) x 4 per stage, tcgen05.commit releases the stage / signals the epilogue
+//   warps 2..5  : epilogue - tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused bias / GELU / GLU /
+//                 LayerScale / residual / frequency-embedding / GroupNorm partial sums, vectorised global stores
+#include "gemm.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <stdio.h>
+
+namespace athtd {
+
+static constexpr int TC_BM = 128;
+static constexpr int TC_BK = 64;
+static constexpr int TC_STAGES = 4;
+static constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int Mflat, N, BN;
+  int ntaps, kb_per_tap, Ktap;
+  int tapRow[3];
+  // flat row -> (b, t', f') decode and validity
+  int RpA, G2p, gpf, G2, vlo, vhi;
+  // output row mapping: ((b*oG2p + t' + ogsh) * oRp + f' + orsh) * ldc
+  int oG2p, ogsh, oRp, orsh;
+  long ldc;
+  void* C; int c_is_f32;
+  float alpha; const float* bias; int act; int glu; const float* colscale;
+  const void* res;
+  const float* rowtab; float rowtab_scale;
+  double* stats; int stat_mode; int statR;
+  int convt_cout;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bit 46)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stageA = TC_BM * TC_BK * 2;
+  const int stageB = p.BN * TC_BK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TC_STAGES * stageA;
+  uint64_t* bars = (uint64_t*)(sB + TC_STAGES * stageB);
+  uint64_t* full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * p.BN;
+  const int nkb = p.ntaps * p.kb_per_tap;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    mbar_init(smem_u32(tfull), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(stageA + stageB);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+        const int tap = kb / p.kb_per_tap;
+        const int kin = (kb - tap * p.kb_per_tap) * TC_BK;
+        const uint32_t fb = smem_u32(&full[s]);
+        mbar_expect_tx(fb, bytes);
+        tma_load_2d(smem_u32(sA + s * stageA), &tmA, fb, kin, row0 + p.tapRow[tap]);
+        tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(smem_u32(&full[s]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = make_sw128_desc(smem_u32(sA + s * stageA));
+        const uint64_t db = make_sw128_desc(smem_u32(sB + s * stageB));
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
+          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        umma_commit(smem_u32(&empty[s]));
+      }
+      umma_commit(smem_u32(tfull));
+    }
+  } else {
+    // ---------------- epilogue: thread <-> accumulator row (TMEM lane)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const long rho = (long)row0 + row;
+    int q2 = (int)(rho / p.RpA);
+    const int fp = (int)(rho - (long)q2 * p.RpA);
+    const int b = q2 / p.G2p;
+    const int tp = q2 - b * p.G2p;
+    const bool valid = rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2;
+    const long orow = ((long)b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
+    const int m = fp - p.vlo;
+    const int Nout = p.glu ? p.N / 2 : p.N;
+    float ssum = 0.f, ssq = 0.f;
+    mbar_wait(smem_u32(tfull), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      const int ncol = n0 + c0;
+      if (!valid || ncol >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = p.alpha * __uint_as_float(r[j]);
+        if (p.bias) x += p.bias[ncol + j];
+        if (p.act == ACT_GELU) x = gelu_erf(x);
+        v[j] = x;
+      }
+      if (p.glu) {
+        const int no = ncol >> 1;
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = v[2 * j] * sigmoid_acc(v[2 * j + 1]);
+          if (p.colscale) x *= p.colscale[no + j];
+          if (p.rowtab) x += p.rowtab_scale * p.rowtab[(long)m * Nout + no + j];
+          o[j] = x;
+        }
+        if (p.c_is_f32) {
+          float* cp = (float*)p.C + orow * p.ldc + no;
+          if (p.res) { const float* rp = (const float*)p.res + orow * p.ldc + no;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] += rp[j]; }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { ssum += o[j]; ssq += o[j] * o[j]; }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *(float4*)(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+          bf16* cp = (bf16*)p.C + orow * p.ldc + no;
+          if (p.res) { const bf16* rp = (const bf16*)p.res + orow * p.ldc + no;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] += __bfloat162float(rp[j]); }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { ssum += o[j]; ssq += o[j] * o[j]; }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { __nv_bfloat162 t = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]); pk[j] = *(uint32_t*)&t; }
+          *(uint4*)(cp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *(uint4*)(cp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (p.colscale) v[j] *= p.colscale[ncol + j];
+          if (p.rowtab) v[j] += p.rowtab_scale * p.rowtab[(long)m * Nout + ncol + j];
+        }
+        if (p.c_is_f32) {
+          float* cp = (float*)p.C + orow * p.ldc + ncol;
+          if (p.res) { const float* rp = (const float*)p.res + orow * p.ldc + ncol;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += rp[j]; }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          bf16* cp = (bf16*)p.C + orow * p.ldc + ncol;
+          if (p.res) {
+            const uint4* rp = (const uint4*)((const bf16*)p.res + orow * p.ldc + ncol);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 t = rp[j];
+              const __nv_bfloat162* h = (const __nv_bfloat162*)&t;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y; }
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]); pk[j] = *(uint32_t*)&t; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *(uint4*)(cp + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (p.stat_mode != STAT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            bool counted = true;
+            if (p.convt_cout > 0) {
+              const int phase = (ncol + j) / p.convt_cout;
+              counted = !((m == 0 && phase < 2) || (m == p.vhi - p.vlo - 1 && phase >= 2));
+            }
+            if (counted) { ssum += v[j]; ssq += v[j] * v[j]; }
+          }
+        }
+      }
+    }
+    if (p.stat_mode != STAT_NONE) {
+      if (p.stat_mode == STAT_PER_G1_M) {
+        if (valid) {
+          double* st = p.stats + 2 * ((long)b * p.statR + m);
+          atomicAdd(st, (double)ssum); atomicAdd(st + 1, (double)ssq);
+        }
+      } else {
+        const int key = valid ? b : -1;
+        const int key0 = __shfl_sync(0xffffffffu, key, 0);
+        const bool uniform = __all_sync(0xffffffffu, key == key0 || key == -1);
+        if (uniform && key0 >= 0) {
+          float a = valid ? ssum : 0.f, c = valid ? ssq : 0.f;
+          a = warp_sum(a); c = warp_sum(c);
+          if (lane == 0) { atomicAdd(p.stats + 2 * (long)key0, (double)a); atomicAdd(p.stats + 2 * (long)key0 + 1, (double)c); }
+        } else if (valid) {
+          atomicAdd(p.stats + 2 * (long)b, (double)ssum); atomicAdd(p.stats + 2 * (long)b + 1, (double)ssq);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+static bool make_map_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
+                        uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int tc_pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N <= 256 && N % 32 == 0) return N;
+  if (N % 128 == 0) return 128;
+  if (N % 192 == 0) return 192;
+  if (N % 64 == 0) return 64;
+  if (N % 32 == 0) return 32;
+  return 0;
+}
+
+bool tc_flat_supported(const TcFlat& f) {
+  if (f.Ktap < 64 || f.Ktap % 8) return false;
+  if (tc_pick_bn(f.N) == 0) return false;
+  if (f.glu && (f.N % 64)) return false;
+  if ((f.a_pitch * 2) % 16 || ((uintptr_t)f.A % 16) || ((uintptr_t)f.B % 16)) return false;
+  if (f.ldc % 8) return false;
+  return get_encode() != nullptr;
+}
+
+int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.Mflat = (int)f.Mflat; p.N = f.N; p.BN = tc_pick_bn(f.N);
+  p.ntaps = f.ntaps; p.Ktap = f.Ktap; p.kb_per_tap = (f.Ktap + TC_BK - 1) / TC_BK;
+  for (int i = 0; i < 3; ++i) p.tapRow[i] = f.tapRow[i];
+  p.RpA = f.RpA; p.G2p = f.G2p; p.gpf = f.gpf; p.G2 = f.G2; p.vlo = f.vlo; p.vhi = f.vhi;
+  p.oG2p = f.oG2p; p.ogsh = f.ogsh; p.oRp = f.oRp; p.orsh = f.orsh; p.ldc = f.ldc;
+  p.C = f.C; p.c_is_f32 = f.c_is_f32; p.alpha = f.alpha; p.bias = f.bias; p.act = f.act; p.glu = f.glu;
+  p.colscale = f.colscale; p.res = f.res; p.rowtab = f.rowtab; p.rowtab_scale = f.rowtab_scale;
+  p.stats = f.stats; p.stat_mode = f.stat_mode; p.statR = f.statR; p.convt_cout = f.convt_cout;
+  CUtensorMap tmA, tmB;
+  if (!make_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
+  if (!make_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
+  const size_t smem = 1024 + (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + p.BN * TC_BK * 2) + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + TC_STAGES * (16384 + 32768) + 256);
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((f.Mflat + TC_BM - 1) / TC_BM), (unsigned)(f.N / p.BN));
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  return 0;
+}
+
+}  // namespace athtd

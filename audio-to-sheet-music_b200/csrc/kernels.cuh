@@ -18,11 +18,11 @@ template <typename T> void launch_gn_glu_res(T* x, RowSpace xs, const T* e, RowS
                                              const float* w, const float* b, const float* scale, cudaStream_t st);
 template <typename T> void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const float* gmr,
                                             const float* gw, const float* gb, const float* lw, const float* lb,
-                                            const float* pe, int yR, int yRp, int ypf, cudaStream_t st);
+                                            const float* pe, RowSpace yrs, cudaStream_t st);
 template <typename T> void launch_softmax_rows(T* s, long rows, int n, cudaStream_t st);
 template <typename T> void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const float* vec, long vstride,
                                              cudaStream_t st);
-template <typename T> void launch_dec_apply(const T* u, int Uin, long u_group_stride, int Cu, T* out, RowSpace os, int G2,
+template <typename T> void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace os, int G2,
                                             int has_gn, const float* mr, const float* gw, const float* gb, const T* skip,
                                             RowSpace ss, cudaStream_t st);
 template <typename T> void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int d1, int d2, cudaStream_t st);

@@ -48,6 +48,20 @@ Shapes::Shapes(int B_, int L_, int P_) : B(B_), L(L_), P(P_) {
 }
 
 // ---------------------------------------------------------------------------------- plan
+static RowSpace make_space(int B, int G2, int R, int C, bool padded) {
+  RowSpace r;
+  r.G = B * G2; r.G2 = G2; r.R = R; r.C = C;
+  if (padded) {
+    r.pf = 2;
+    r.Rp = G2 > 1 ? R + 4 : (R + 8 + 3) / 4 * 4;   // multiple of 4: the k8/s4 conv reads the buffer as rows of 4*C
+    r.G2p = G2 > 1 ? G2 + 4 : 1;                    // 2 zero frames each side: DConv taps along time read zeros
+    r.gpf = G2 > 1 ? 2 : 0;
+  } else {
+    r.pf = 0; r.Rp = R; r.G2p = G2; r.gpf = 0;
+  }
+  return r;
+}
+
 template <typename T>
 void PlanT<T>::layout(char* base) {
   size_t off = 0;
@@ -59,28 +73,27 @@ void PlanT<T>::layout(char* base) {
   };
   const Shapes& s = sh;
   const int B = s.B, Tf = s.Tf;
-  auto space = [&](int G, int R, int Rp, int pf, int C) { RowSpace r; r.G = G; r.R = R; r.Rp = Rp; r.pf = pf; r.C = C; return r; };
   // ---- zero-initialised region (pads must stay zero; interior is always overwritten)
-  xf0_rs = space(B * Tf, 2048, 2052, 2, 4);
+  xf0_rs = make_space(B, Tf, 2048, 4, true);
   xf0 = (T*)take(xf0_rs.elems() * sizeof(T));
-  xt0_rs = space(B, s.L, s.L + 8, 2, 2);
+  xt0_rs = make_space(B, 1, s.L, 2, true);
   xt0 = (T*)take(xt0_rs.elems() * sizeof(T));
   for (int i = 0; i < 4; ++i) {
-    yf_rs[i] = space(B * Tf, s.Fr[i + 1], s.Fr[i + 1] + 4, 2, kCh[i]);
+    yf_rs[i] = make_space(B, Tf, s.Fr[i + 1], kCh[i], true);
     yf[i] = (T*)take(yf_rs[i].elems() * sizeof(T));
     ef[i] = (T*)take(yf_rs[i].elems() * sizeof(T));
-    yt_rs[i] = space(B, s.Lt[i + 1], s.Lt[i + 1] + 8, 2, kCh[i]);
+    yt_rs[i] = make_space(B, 1, s.Lt[i + 1], kCh[i], true);
     yt[i] = (T*)take(yt_rs[i].elems() * sizeof(T));
     et[i] = (T*)take(yt_rs[i].elems() * sizeof(T));
   }
-  xc_rs = space(B * Tf, 8, 12, 2, 384);
+  xc_rs = make_space(B, Tf, 8, 384, true);
   xc = (T*)take(xc_rs.elems() * sizeof(T));
-  xtc_rs = space(B, s.St, s.St + 8, 2, 384);
+  xtc_rs = make_space(B, 1, s.St, 384, true);
   xtc = (T*)take(xtc_rs.elems() * sizeof(T));
   for (int i = 0; i < 4; ++i) {
-    df_rs[i] = space(B * Tf, Tf, Tf + 4, 2, kDecCh[i + 1]);
+    df_rs[i] = make_space(B, Tf, Tf, kDecCh[i + 1], true);
     df[i] = (T*)take(df_rs[i].elems() * sizeof(T));
-    dt_rs[i] = space(B, s.Lt[3 - i], s.Lt[3 - i] + 8, 2, kDecCh[i + 1]);
+    dt_rs[i] = make_space(B, 1, s.Lt[3 - i], kDecCh[i + 1], true);
     dt[i] = (T*)take(dt_rs[i].elems() * sizeof(T));
   }
   zero_bytes = align_up(off, 256);
@@ -104,11 +117,11 @@ void PlanT<T>::layout(char* base) {
   ms_spec = (float*)take(sizeof(float) * 2 * B);
   ms_wav = (float*)take(sizeof(float) * 2 * B);
   Z = (float*)take(sizeof(float) * (size_t)B * Tf * 2048 * 4);
-  size_t hmax = 0, emax = 0;
+  size_t hmax = 0, emax = 0, umax = 0;
   for (int i = 0; i < 4; ++i) {
-    size_t rf = (size_t)B * Tf * s.Fr[i + 1], rt = (size_t)B * s.Lt[i + 1];
-    hmax = std::max(hmax, std::max(rf, rt) * (kCh[i] / 8));
-    emax = std::max(emax, std::max(rf, rt) * (2 * kCh[i]));
+    size_t rows = std::max((size_t)yf_rs[i].rows_total(), (size_t)yt_rs[i].rows_total());
+    hmax = std::max(hmax, rows * (kCh[i] / 8));
+    emax = std::max(emax, rows * (2 * kCh[i]));
   }
   hbuf = (T*)take(hmax * sizeof(T));
   ebuf = (T*)take(emax * sizeof(T));
@@ -126,11 +139,12 @@ void PlanT<T>::layout(char* base) {
   cvec = (float*)take(sizeof(float) * (size_t)B * s.P * 384 * 3);
   t1 = (T*)take((size_t)B * Smax * 384 * sizeof(T));
   t2 = (T*)take((size_t)B * Smax * 384 * sizeof(T));
-  size_t umax = 0;
-  {
-    int rin = 8;
-    for (int i = 0; i < 4; ++i) { umax = std::max(umax, (size_t)B * Tf * (rin + 1) * 4 * kDecCh[i + 1]); rin = Tf; }
-    for (int i = 0; i < 4; ++i) umax = std::max(umax, (size_t)B * (s.Lt[4 - i] + 1) * 4 * kDecCh[i + 1]);
+  // transposed-conv outputs in phase layout share the geometry of the layer INPUT with 4*Cout channels
+  umax = std::max(umax, (size_t)xc_rs.rows_total() * 4 * kDecCh[1]);
+  umax = std::max(umax, (size_t)xtc_rs.rows_total() * 4 * kDecCh[1]);
+  for (int i = 1; i < 4; ++i) {
+    umax = std::max(umax, (size_t)df_rs[i - 1].rows_total() * 4 * kDecCh[i + 1]);
+    umax = std::max(umax, (size_t)dt_rs[i - 1].rows_total() * 4 * kDecCh[i + 1]);
   }
   ubuf = (T*)take(umax * sizeof(T));
   frames = (float*)take(sizeof(float) * (size_t)B * 2 * Tf * 4096);
@@ -161,16 +175,22 @@ const float* PlanT<T>::PA(const std::string& key) const {
 }
 
 template <typename T>
+void PlanT<T>::prof_begin(double gflop, cudaStream_t st) {
+  if (!profiling) return;      // per-launch CUDA-event timing of the GEMM kernels (bench.py roofline pass only)
+  while (prof_ev.size() < prof_used + 2) { cudaEvent_t e; cudaEventCreate(&e); prof_ev.push_back(e); }
+  prof_gflop += gflop;
+  cudaEventRecord(prof_ev[prof_used++], st);
+}
+template <typename T>
+void PlanT<T>::prof_end(cudaStream_t st) {
+  if (profiling) cudaEventRecord(prof_ev[prof_used++], st);
+}
+
+template <typename T>
 void PlanT<T>::gemm(const GemmDesc& d, cudaStream_t st) {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (profiling) {      // per-launch CUDA-event timing of the GEMM kernel (bench.py roofline pass only)
-    while (prof_ev.size() < prof_used + 2) { cudaEvent_t e; cudaEventCreate(&e); prof_ev.push_back(e); }
-    e0 = prof_ev[prof_used++]; e1 = prof_ev[prof_used++];
-    prof_gflop += 2.0 * (double)d.G1 * d.G2 * d.Mg * d.N * d.K * 1e-9;
-    cudaEventRecord(e0, st);
-  }
+  prof_begin(2.0 * (double)d.G1 * d.G2 * d.Mg * d.N * d.K * 1e-9, st);
   launch_gemm_simt<T>(d, st);
-  if (profiling) cudaEventRecord(e1, st);
+  prof_end(st);
   ++n_launches;
 }
 
@@ -182,6 +202,79 @@ void PlanT<T>::get_profile(double* ms, double* gflop, int* n) {
   *ms = total; *gflop = prof_gflop; *n = (int)(prof_used / 2);
 }
 
+// ---- lower one convolution-shaped op either to the tcgen05 flat-row kernel (bf16 build, supported shapes) or to
+//      the SIMT kernel.  Both read the same buffers and produce the same layout.
+template <typename T>
+void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
+  const RowSpace& as = o.as;
+  const RowSpace& cs = o.cs;
+  const int C = as.C;
+  const int B = as.batch();
+  const bool freq = as.G2 > 1;
+  const int K = o.mode == CONV_ROWS ? C : o.mode == CONV_K8S4 ? 8 * C : o.mode == CONV_T ? 2 * C : 3 * C;
+  const int Mg = o.mode == CONV_K8S4 ? cs.R : o.mode == CONV_T ? as.R + 1 : as.R;
+  const double gflop = 2.0 * (double)B * as.G2 * Mg * o.N * K * 1e-9;
+  if (sizeof(T) == 2 && use_tc) {
+    TcFlat f;
+    memset(&f, 0, sizeof(f));
+    f.B = o.w; f.N = o.N; f.alpha = 1.0f;
+    f.G2p = as.G2p; f.gpf = as.gpf; f.G2 = as.G2;
+    f.tapRow[0] = 0;
+    if (o.mode == CONV_K8S4) {
+      f.A = o.a; f.a_rows = as.rows_total() / 4; f.a_pitch = 4L * C; f.Ktap = 4 * C; f.ntaps = 2; f.tapRow[1] = 1;
+      f.RpA = as.Rp / 4; f.vlo = 0; f.vhi = cs.R;
+    } else {
+      f.A = o.a; f.a_rows = as.rows_total(); f.a_pitch = C; f.Ktap = C; f.RpA = as.Rp;
+      if (o.mode == CONV_ROWS) { f.ntaps = 1; f.vlo = as.pf; f.vhi = as.pf + as.R; }
+      else if (o.mode == CONV_T) { f.ntaps = 2; f.tapRow[1] = 1; f.vlo = as.pf - 1; f.vhi = as.pf + as.R; }
+      else { f.ntaps = 3; const int sh_ = o.dil * (freq ? as.Rp : 1); f.tapRow[0] = -sh_; f.tapRow[1] = 0; f.tapRow[2] = sh_;
+             f.vlo = as.pf; f.vhi = as.pf + as.R; }
+    }
+    f.Mflat = f.a_rows;
+    f.oG2p = cs.G2p; f.ogsh = cs.gpf - as.gpf; f.oRp = cs.Rp; f.orsh = cs.pf - f.vlo; f.ldc = cs.C;
+    f.C = o.c; f.c_is_f32 = 0; f.bias = o.bias; f.act = o.act; f.glu = o.glu; f.colscale = o.colscale; f.res = o.res;
+    f.rowtab = o.rowtab; f.rowtab_scale = o.rowtab_scale; f.stats = o.stats; f.stat_mode = o.stat_mode; f.statR = as.R;
+    f.convt_cout = o.mode == CONV_T ? o.N / 4 : 0;
+    const bool geom_ok = (o.mode != CONV_K8S4) || (as.Rp % 4 == 0 && as.pf == 2);
+    if (geom_ok && tc_flat_supported(f)) {
+      prof_begin(gflop, st);
+      int rc = launch_gemm_tc_flat(f, st);
+      prof_end(st);
+      if (rc != 0) throw std::runtime_error("athtd: cuTensorMapEncodeTiled failed for a tcgen05 GEMM");
+      ++n_launches; ++n_tc;
+      return;
+    }
+  }
+  GemmDesc d = gemm_desc_zero();
+  d.G1 = B; d.G2 = as.G2; d.Mg = Mg; d.N = o.N; d.K = K; d.Ktap = K;
+  d.sAg1 = as.g1_stride(); d.sAg2 = as.g2_stride();
+  d.B = o.w; d.sBn = K; d.sBk = 1;
+  if (o.mode == CONV_ROWS) { d.A = o.a + as.origin(); d.sAm = C; }
+  else if (o.mode == CONV_K8S4) { d.A = o.a + as.origin() - 2L * C; d.sAm = 4L * C; }
+  else if (o.mode == CONV_T) { d.A = o.a + as.origin() - C; d.sAm = C; }
+  else {
+    d.A = o.a + as.origin(); d.sAm = C; d.ntaps = 3; d.Ktap = C;
+    for (int k = 0; k < 3; ++k) { d.shG2[k] = freq ? (k - 1) * o.dil : 0; d.shM[k] = freq ? 0 : (k - 1) * o.dil; }
+  }
+  // output rows: interior of cs, except the transposed conv whose row q sits one row before the interior (x[q-1])
+  const long c_origin = o.mode == CONV_T ? cs.origin() - cs.C : cs.origin();
+  d.C = o.c + c_origin; d.sCg1 = cs.g1_stride(); d.sCg2 = cs.g2_stride(); d.sCm = cs.C;
+  d.bias = o.bias; d.act = o.act; d.glu = o.glu; d.colscale = o.colscale;
+  if (o.res) { d.res = o.res + c_origin; d.sRg1 = d.sCg1; d.sRg2 = d.sCg2; d.sRm = d.sCm; }
+  d.rowtab = o.rowtab; d.rowtab_scale = o.rowtab_scale;
+  d.stats = o.stats; d.stat_mode = o.stat_mode;
+  d.convt_cout = o.mode == CONV_T ? o.N / 4 : 0;
+  gemm(d, st);
+}
+
+template <typename T>
+static ConvOp<T> conv_op(int mode, const T* a, RowSpace as, const T* w, int N, T* c, RowSpace cs) {
+  ConvOp<T> o;
+  memset(&o, 0, sizeof(o));
+  o.mode = mode; o.a = a; o.as = as; o.w = w; o.N = N; o.c = c; o.cs = cs; o.dil = 1;
+  return o;
+}
+
 // ---- one HEncLayer (demucs hdemucs.py:HEncLayer) on a channels-last row space.
 //   x   : input activation (padded row space xin, C_in channels)
 //   y   : conv+GELU output, updated in place by the two DConv residual layers (space ys, C channels)
@@ -189,63 +282,43 @@ void PlanT<T>::get_profile(double* ms, double* gflop, int* n) {
 template <typename T>
 void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSpace ys, T* out, cudaStream_t st) {
   const Shapes& s = sh;
-  const int C = kCh[i], Cin = xin.C, H = C / 8;
+  const int C = kCh[i], H = C / 8;
   const std::string p = std::string("htdemucs.") + (freq ? "encoder." : "tencoder.") + std::to_string(i);
-  const int G2 = freq ? s.Tf : 1;
+  const int G2 = ys.G2;
   const int R = ys.R;
   {  // strided conv k8 s4 p2 (+ right zero pad to a multiple of 4 on the time branch) + GELU
-    GemmDesc d = gemm_desc_zero();
-    d.G1 = ys.G; d.G2 = 1; d.Mg = R; d.N = C; d.K = 8 * Cin; d.Ktap = d.K;
-    d.A = x + (long)(xin.pf - 2) * Cin; d.sAg1 = (long)xin.Rp * Cin; d.sAm = 4L * Cin;
-    d.B = PW(p + ".conv.w"); d.sBn = d.K; d.sBk = 1;
-    d.C = y + (long)ys.pf * C; d.sCg1 = (long)ys.Rp * C; d.sCm = C;
-    d.bias = P32(p + ".conv.bias"); d.act = ACT_GELU;
-    gemm(d, st);
+    ConvOp<T> o = conv_op<T>(CONV_K8S4, x, xin, PW(p + ".conv.w"), C, y, ys);
+    o.bias = P32(p + ".conv.bias"); o.act = ACT_GELU;
+    conv(o, st);
   }
-  RowSpace hs = ys; hs.Rp = R; hs.pf = 0; hs.C = H;
-  RowSpace es = ys; es.Rp = R; es.pf = 0; es.C = 2 * C;
+  RowSpace hs = ys; hs.C = H;
+  RowSpace es = ys; es.C = 2 * C;
   for (int dd = 0; dd < 2; ++dd) {
     const std::string q = p + ".dconv.layers." + std::to_string(dd);
-    const int dil = 1 << dd;
     double* st_h = freq ? st_df[i][dd][0] : st_dt[i][dd][0];
     double* st_e = freq ? st_df[i][dd][1] : st_dt[i][dd][1];
     const long nstat = freq ? (long)s.B * R : s.B;
-    {  // dilated k3 conv C -> C/8 along time (freq branch: taps shift the frame group index)
-      GemmDesc d = gemm_desc_zero();
-      d.G1 = s.B; d.G2 = G2; d.Mg = R; d.N = H; d.ntaps = 3; d.Ktap = C; d.K = 3 * C;
-      for (int k = 0; k < 3; ++k) { d.shG2[k] = freq ? (k - 1) * dil : 0; d.shM[k] = freq ? 0 : (k - 1) * dil; }
-      d.A = y + (long)ys.pf * C; d.sAg1 = (long)G2 * ys.Rp * C; d.sAg2 = (long)ys.Rp * C; d.sAm = C;
-      d.B = PW(q + ".0.w"); d.sBn = d.K; d.sBk = 1;
-      d.C = hbuf; d.sCg1 = (long)G2 * R * H; d.sCg2 = (long)R * H; d.sCm = H;
-      d.bias = P32(q + ".0.bias");
-      d.stats = st_h; d.stat_mode = freq ? STAT_PER_G1_M : STAT_PER_G1;
-      gemm(d, st);
+    {  // dilated k3 conv C -> C/8 along time (freq branch: taps shift the frame index)
+      ConvOp<T> o = conv_op<T>(CONV_DIL3, y, ys, PW(q + ".0.w"), H, hbuf, hs);
+      o.dil = 1 << dd; o.bias = P32(q + ".0.bias"); o.stats = st_h; o.stat_mode = freq ? STAT_PER_G1_M : STAT_PER_G1;
+      conv(o, st);
     }
     launch_finalize_gn(st_h, (double)H * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
     launch_gn_gelu<T>(hbuf, hs, G2, freq ? 1 : 0, mr, P32(q + ".1.weight"), P32(q + ".1.bias"), st); ++n_launches;
     {  // 1x1 expand C/8 -> 2C
-      GemmDesc d = gemm_desc_zero();
-      d.G1 = s.B; d.G2 = G2; d.Mg = R; d.N = 2 * C; d.K = H; d.Ktap = H;
-      d.A = hbuf; d.sAg1 = (long)G2 * R * H; d.sAg2 = (long)R * H; d.sAm = H;
-      d.B = PW(q + ".3.w"); d.sBn = H; d.sBk = 1;
-      d.C = ebuf; d.sCg1 = (long)G2 * R * 2 * C; d.sCg2 = (long)R * 2 * C; d.sCm = 2 * C;
-      d.bias = P32(q + ".3.bias");
-      d.stats = st_e; d.stat_mode = freq ? STAT_PER_G1_M : STAT_PER_G1;
-      gemm(d, st);
+      ConvOp<T> o = conv_op<T>(CONV_ROWS, hbuf, hs, PW(q + ".3.w"), 2 * C, ebuf, es);
+      o.bias = P32(q + ".3.bias"); o.stats = st_e; o.stat_mode = freq ? STAT_PER_G1_M : STAT_PER_G1;
+      conv(o, st);
     }
     launch_finalize_gn(st_e, (double)2 * C * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
     launch_gn_glu_res<T>(y, ys, ebuf, es, G2, freq ? 1 : 0, mr, P32(q + ".4.weight"), P32(q + ".4.bias"),
                          P32(q + ".6.scale"), st); ++n_launches;
   }
   {  // 1x1 rewrite C -> 2C, GLU (+ frequency embedding after encoder 0, ATHTDemucs_v2.py:212-215)
-    GemmDesc d = gemm_desc_zero();
-    d.G1 = ys.G; d.G2 = 1; d.Mg = R; d.N = 2 * C; d.K = C; d.Ktap = C;
-    d.A = y + (long)ys.pf * C; d.sAg1 = (long)ys.Rp * C; d.sAm = C;
-    d.B = PW(p + ".rewrite.w"); d.sBn = C; d.sBk = 1;
-    d.C = out + (long)ys.pf * C; d.sCg1 = (long)ys.Rp * C; d.sCm = C;
-    d.bias = PA(p + ".rewrite.b"); d.glu = 1;
-    if (freq && i == 0) { d.rowtab = P32("htdemucs.freq_emb.embedding.weight"); d.rowtab_scale = 10.0f * 0.2f; }
-    gemm(d, st);
+    ConvOp<T> o = conv_op<T>(CONV_ROWS, y, ys, PW(p + ".rewrite.w"), 2 * C, out, ys);
+    o.bias = PA(p + ".rewrite.b"); o.glu = 1;
+    if (freq && i == 0) { o.rowtab = P32("htdemucs.freq_emb.embedding.weight"); o.rowtab_scale = 10.0f * 0.2f; }
+    conv(o, st);
   }
 }
 
@@ -274,36 +347,33 @@ void PlanT<T>::attention(const T* q, long ldq, const T* k, const T* v, long ldkv
 }
 
 template <typename T>
-void PlanT<T>::linear(const T* a, long rows, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st) {
-  GemmDesc d = gemm_desc_zero();
-  d.G1 = 1; d.G2 = 1; d.Mg = (int)rows; d.N = N; d.K = K; d.Ktap = K;
-  d.A = a; d.sAm = K; d.B = w; d.sBn = K; d.sBk = 1; d.C = c; d.sCm = N; d.bias = bias; d.act = act;
-  gemm(d, st);
+void PlanT<T>::linear(const T* a, int S, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st) {
+  ConvOp<T> o = conv_op<T>(CONV_ROWS, a, make_space(sh.B, 1, S, K, false), w, N, c, make_space(sh.B, 1, S, N, false));
+  o.bias = bias; o.act = act;
+  conv(o, st);
 }
 
 // x <- x + gamma * (a W^T + b), optional per-sample (sum, sumsq) of the result
 template <typename T>
 void PlanT<T>::linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x,
                           double* stats, cudaStream_t st) {
-  GemmDesc d = gemm_desc_zero();
-  d.G1 = sh.B; d.G2 = 1; d.Mg = S; d.N = N; d.K = K; d.Ktap = K;
-  d.A = a; d.sAg1 = (long)S * K; d.sAm = K; d.B = w; d.sBn = K; d.sBk = 1;
-  d.C = x; d.sCg1 = (long)S * N; d.sCm = N; d.bias = bias; d.colscale = gamma;
-  d.res = x; d.sRg1 = (long)S * N; d.sRm = N;
-  if (stats) { d.stats = stats; d.stat_mode = STAT_PER_G1; }
-  gemm(d, st);
+  ConvOp<T> o = conv_op<T>(CONV_ROWS, a, make_space(sh.B, 1, S, K, false), w, N, x, make_space(sh.B, 1, S, N, false));
+  o.bias = bias; o.colscale = gamma; o.res = x;
+  if (stats) { o.stats = stats; o.stat_mode = STAT_PER_G1; }
+  conv(o, st);
 }
 
 template <typename T>
 void PlanT<T>::xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, cudaStream_t st) {
   const long rows = (long)sh.B * S;
+  const RowSpace none{};
   launch_norm_rows<T>(x, nullptr, hn[0], rows, 512, S, nullptr, nullptr, nullptr, P32(p + "." + ffn_norm + ".weight"),
-                      P32(p + "." + ffn_norm + ".bias"), nullptr, 0, 0, 0, st); ++n_launches;
-  linear(hn[0], rows, 512, PW(p + ".linear1.w"), 2048, P32(p + ".linear1.bias"), ACT_GELU, ffn, st);
+                      P32(p + "." + ffn_norm + ".bias"), nullptr, none, st); ++n_launches;
+  linear(hn[0], S, 512, PW(p + ".linear1.w"), 2048, P32(p + ".linear1.bias"), ACT_GELU, ffn, st);
   linear_res(ffn, S, 2048, PW(p + ".linear2.w"), 512, P32(p + ".linear2.bias"), P32(p + ".gamma_2.scale"), x, stats, st);
   launch_finalize_gn(stats, (double)S * 512, mr, sh.B, st); ++n_launches;
   launch_norm_rows<T>(x, x, nullptr, rows, 512, S, mr, P32(p + ".norm_out.weight"), P32(p + ".norm_out.bias"), nullptr,
-                      nullptr, nullptr, 0, 0, 0, st); ++n_launches;
+                      nullptr, nullptr, none, st); ++n_launches;
 }
 
 template <typename T>
@@ -311,6 +381,7 @@ void PlanT<T>::cross_transformer(cudaStream_t st) {
   const Shapes& s = sh;
   const std::string xp = "htdemucs.crosstransformer";
   const int B = s.B;
+  const RowSpace none{};
   T* X[2] = {tokf, tokt};
   const int S[2] = {s.Sf, s.St};
   const char* stacks[2] = {".layers.", ".layers_t."};
@@ -320,8 +391,8 @@ void PlanT<T>::cross_transformer(cudaStream_t st) {
         const std::string p = xp + stacks[br] + std::to_string(l);
         const long rows = (long)B * S[br];
         launch_norm_rows<T>(X[br], nullptr, hn[0], rows, 512, S[br], nullptr, nullptr, nullptr, P32(p + ".norm1.weight"),
-                            P32(p + ".norm1.bias"), nullptr, 0, 0, 0, st); ++n_launches;
-        linear(hn[0], rows, 512, PW(p + ".in_proj.w"), 1536, P32(p + ".self_attn.in_proj_bias"), ACT_NONE, qkv, st);
+                            P32(p + ".norm1.bias"), nullptr, none, st); ++n_launches;
+        linear(hn[0], S[br], 512, PW(p + ".in_proj.w"), 1536, P32(p + ".self_attn.in_proj_bias"), ACT_NONE, qkv, st);
         attention(qkv, 1536, qkv + 512, qkv + 1024, 1536, S[br], S[br], obuf, st);
         linear_res(obuf, S[br], 512, PW(p + ".out_proj.w"), 512, P32(p + ".self_attn.out_proj.bias"),
                    P32(p + ".gamma_1.scale"), X[br], nullptr, st);
@@ -333,17 +404,17 @@ void PlanT<T>::cross_transformer(cudaStream_t st) {
         const std::string p = xp + stacks[br] + std::to_string(l);
         const int o = 1 - br;
         launch_norm_rows<T>(X[br], nullptr, hn[2 * br], (long)B * S[br], 512, S[br], nullptr, nullptr, nullptr,
-                            P32(p + ".norm1.weight"), P32(p + ".norm1.bias"), nullptr, 0, 0, 0, st); ++n_launches;
+                            P32(p + ".norm1.weight"), P32(p + ".norm1.bias"), nullptr, none, st); ++n_launches;
         launch_norm_rows<T>(X[o], nullptr, hn[2 * br + 1], (long)B * S[o], 512, S[o], nullptr, nullptr, nullptr,
-                            P32(p + ".norm2.weight"), P32(p + ".norm2.bias"), nullptr, 0, 0, 0, st); ++n_launches;
+                            P32(p + ".norm2.weight"), P32(p + ".norm2.bias"), nullptr, none, st); ++n_launches;
       }
       for (int br = 0; br < 2; ++br) {
         const std::string p = xp + stacks[br] + std::to_string(l);
         const int o = 1 - br;
         const T* w_in = PW(p + ".in_proj.w");
         const float* b_in = P32(p + ".cross_attn.in_proj_bias");
-        linear(hn[2 * br], (long)B * S[br], 512, w_in, 512, b_in, ACT_NONE, qkv, st);
-        linear(hn[2 * br + 1], (long)B * S[o], 512, w_in + 512L * 512, 1024, b_in + 512, ACT_NONE, kvb, st);
+        linear(hn[2 * br], S[br], 512, w_in, 512, b_in, ACT_NONE, qkv, st);
+        linear(hn[2 * br + 1], S[o], 512, w_in + 512L * 512, 1024, b_in + 512, ACT_NONE, kvb, st);
         attention(qkv, 512, kvb, kvb + 512, 1024, S[br], S[o], obuf, st);
         linear_res(obuf, S[br], 512, PW(p + ".out_proj.w"), 512, P32(p + ".cross_attn.out_proj.bias"),
                    P32(p + ".gamma_1.scale"), X[br], nullptr, st);
@@ -357,6 +428,7 @@ template <typename T>
 void PlanT<T>::encode(const float* wav, cudaStream_t st) {
   const Shapes& s = sh;
   const int B = s.B, Tf = s.Tf;
+  const RowSpace none{};
   cudaMemsetAsync((char*)ws_base() + stats_begin, 0, stats_bytes, st);
   // spectral front end + input normalisation (ATHTDemucs_v2.py:261-275)
   launch_stft_cac(wav, B, s.L, Tf, Z, st_spec, consts.tw, consts.win, st); ++n_launches;
@@ -377,27 +449,21 @@ void PlanT<T>::encode(const float* wav, cudaStream_t st) {
   // bottleneck: 1x1 up-sample 384->512, norm_in + positional embeddings, 5 layers, 1x1 down-sample
   const std::string hp = "htdemucs.";
   {
-    GemmDesc d = gemm_desc_zero();
-    d.G1 = B * Tf; d.Mg = 8; d.N = 512; d.K = 384; d.Ktap = 384;
-    d.A = ef[3] + 2L * 384; d.sAg1 = 12L * 384; d.sAm = 384;
-    d.B = PW(hp + "channel_upsampler.w"); d.sBn = 384;
-    d.C = hn[1]; d.sCg1 = 8L * 512; d.sCm = 512; d.bias = P32(hp + "channel_upsampler.bias");
-    gemm(d, st);
-    d = gemm_desc_zero();
-    d.G1 = B; d.Mg = s.St; d.N = 512; d.K = 384; d.Ktap = 384;
-    d.A = et[3] + 2L * 384; d.sAg1 = (long)yt_rs[3].Rp * 384; d.sAm = 384;
-    d.B = PW(hp + "channel_upsampler_t.w"); d.sBn = 384;
-    d.C = hn[2]; d.sCg1 = (long)s.St * 512; d.sCm = 512; d.bias = P32(hp + "channel_upsampler_t.bias");
-    gemm(d, st);
+    ConvOp<T> o = conv_op<T>(CONV_ROWS, ef[3], yf_rs[3], PW(hp + "channel_upsampler.w"), 512, hn[1], make_space(B, Tf, 8, 512, false));
+    o.bias = P32(hp + "channel_upsampler.bias");
+    conv(o, st);
+    o = conv_op<T>(CONV_ROWS, et[3], yt_rs[3], PW(hp + "channel_upsampler_t.w"), 512, hn[2], make_space(B, 1, s.St, 512, false));
+    o.bias = P32(hp + "channel_upsampler_t.bias");
+    conv(o, st);
   }
   const std::string xp = "htdemucs.crosstransformer";
   launch_norm_rows<T>(hn[1], nullptr, tokf, (long)B * s.Sf, 512, s.Sf, nullptr, nullptr, nullptr, P32(xp + ".norm_in.weight"),
-                      P32(xp + ".norm_in.bias"), consts.pe2d, 0, 0, 0, st); ++n_launches;
+                      P32(xp + ".norm_in.bias"), consts.pe2d, none, st); ++n_launches;
   launch_norm_rows<T>(hn[2], nullptr, tokt, (long)B * s.St, 512, s.St, nullptr, nullptr, nullptr, P32(xp + ".norm_in_t.weight"),
-                      P32(xp + ".norm_in_t.bias"), consts.pe1d, 0, 0, 0, st); ++n_launches;
+                      P32(xp + ".norm_in_t.bias"), consts.pe1d, none, st); ++n_launches;
   cross_transformer(st);
-  linear(tokf, (long)B * s.Sf, 512, PW(hp + "channel_downsampler.w"), 384, P32(hp + "channel_downsampler.bias"), ACT_NONE, xenc, st);
-  linear(tokt, (long)B * s.St, 512, PW(hp + "channel_downsampler_t.w"), 384, P32(hp + "channel_downsampler_t.bias"), ACT_NONE, xtenc, st);
+  linear(tokf, s.Sf, 512, PW(hp + "channel_downsampler.w"), 384, P32(hp + "channel_downsampler.bias"), ACT_NONE, xenc, st);
+  linear(tokt, s.St, 512, PW(hp + "channel_downsampler_t.w"), 384, P32(hp + "channel_downsampler_t.bias"), ACT_NONE, xtenc, st);
 }
 
 // text conditioning for prompt p (TextCrossAttention, ATHTDemucs_v2.py:38-58): with a single key the
@@ -418,19 +484,18 @@ void PlanT<T>::text_vectors(const float* emb, cudaStream_t st) {
 }
 
 template <typename T>
-void PlanT<T>::text_condition(int p, const T* x, int S, T* out, int yR, int yRp, int ypf, cudaStream_t st) {
+void PlanT<T>::text_condition(int p, const T* x, int S, T* out, RowSpace outs, cudaStream_t st) {
   const long rows = (long)sh.B * S;
   launch_add_rowvec<T>(x, t1, S, 384, sh.B, cvec + (size_t)p * 384, (long)sh.P * 384, st); ++n_launches;
-  linear(t1, rows, 384, PW("text_attn.out_mlp.0.w"), 384, P32("text_attn.out_mlp.0.bias"), ACT_GELU, t2, st);
+  linear(t1, S, 384, PW("text_attn.out_mlp.0.w"), 384, P32("text_attn.out_mlp.0.bias"), ACT_GELU, t2, st);
   {
-    GemmDesc d = gemm_desc_zero();
-    d.Mg = (int)rows; d.N = 384; d.K = 384; d.Ktap = 384; d.A = t2; d.sAm = 384;
-    d.B = PW("text_attn.out_mlp.2.w"); d.sBn = 384; d.C = t1; d.sCm = 384; d.bias = P32("text_attn.out_mlp.2.bias");
-    d.res = t1; d.sRm = 384;
-    gemm(d, st);
+    ConvOp<T> o = conv_op<T>(CONV_ROWS, t2, make_space(sh.B, 1, S, 384, false), PW("text_attn.out_mlp.2.w"), 384, t1,
+                             make_space(sh.B, 1, S, 384, false));
+    o.bias = P32("text_attn.out_mlp.2.bias"); o.res = t1;
+    conv(o, st);
   }
   launch_norm_rows<T>(t1, nullptr, out, rows, 384, S, nullptr, nullptr, nullptr, P32("text_attn.norm_out.weight"),
-                      P32("text_attn.norm_out.bias"), nullptr, yR, yRp, ypf, st); ++n_launches;
+                      P32("text_attn.norm_out.bias"), nullptr, outs, st); ++n_launches;
 }
 
 // one FreqDecoder / TimeDecoder layer (ATHTDemucs_v2.py:82-104, 125-139): transposed conv as ONE GEMM
@@ -440,23 +505,18 @@ template <typename T>
 void PlanT<T>::dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* out, RowSpace os, const T* skip, RowSpace ss,
                          cudaStream_t st) {
   const Shapes& s = sh;
-  const int Cin = kDecCh[i], Cout = kDecCh[i + 1];
-  const int G2 = freq ? s.Tf : 1;
+  const int Cout = kDecCh[i + 1];
+  const int G2 = xs.G2;
   const int Rin = xs.R;
   const std::string q = std::string(freq ? "freq_decoder" : "time_decoder") + ".layers." + std::to_string(i);
   double* stt = st_dec + 2L * s.B * ((size_t)p * 6 + (freq ? 0 : 3) + (i < 3 ? i : 0));
-  GemmDesc d = gemm_desc_zero();
-  d.G1 = s.B; d.G2 = G2; d.Mg = Rin + 1; d.N = 4 * Cout; d.K = 2 * Cin; d.Ktap = d.K;
-  d.A = x + (long)(xs.pf - 1) * Cin; d.sAg1 = (long)G2 * xs.Rp * Cin; d.sAg2 = (long)xs.Rp * Cin; d.sAm = Cin;
-  d.B = PW(q + ".0.w"); d.sBn = d.K; d.sBk = 1;
-  const long ug = (long)(Rin + 1) * 4 * Cout;
-  d.C = ubuf; d.sCg1 = (long)G2 * ug; d.sCg2 = ug; d.sCm = 4L * Cout;
-  d.bias = PA(q + ".0.b4");
-  d.convt_cout = Cout;
-  if (i < 3) { d.stats = stt; d.stat_mode = STAT_PER_G1; }
-  gemm(d, st);
+  RowSpace us = xs; us.C = 4 * Cout;
+  ConvOp<T> o = conv_op<T>(CONV_T, x, xs, PW(q + ".0.w"), 4 * Cout, ubuf, us);
+  o.bias = PA(q + ".0.b4");
+  if (i < 3) { o.stats = stt; o.stat_mode = STAT_PER_G1; }
+  conv(o, st);
   if (i < 3) { launch_finalize_gn(stt, (double)Cout * 4.0 * Rin * G2, mr, s.B, st); ++n_launches; }
-  launch_dec_apply<T>(ubuf, 4 * Rin, ug, Cout, out, os, G2, i < 3 ? 1 : 0, mr, i < 3 ? P32(q + ".1.weight") : nullptr,
+  launch_dec_apply<T>(ubuf, 4 * Rin, us, Cout, out, os, G2, i < 3 ? 1 : 0, mr, i < 3 ? P32(q + ".1.weight") : nullptr,
                       i < 3 ? P32(q + ".1.bias") : nullptr, skip, ss, st); ++n_launches;
 }
 
@@ -466,8 +526,8 @@ void PlanT<T>::decode(const float* emb, float* out, cudaStream_t st) {
   const int B = s.B, Tf = s.Tf;
   text_vectors(emb, st);
   for (int p = 0; p < s.P; ++p) {
-    text_condition(p, xenc, s.Sf, xc, 8, 12, 2, st);
-    text_condition(p, xtenc, s.St, xtc, s.St, s.St + 8, 2, st);
+    text_condition(p, xenc, s.Sf, xc, xc_rs, st);
+    text_condition(p, xtenc, s.St, xtc, xtc_rs, st);
     const T* x = xc; RowSpace xs = xc_rs;
     for (int i = 0; i < 4; ++i) { dec_layer(true, i, p, x, xs, df[i], df_rs[i], ef[3 - i], yf_rs[3 - i], st); x = df[i]; xs = df_rs[i]; }
     launch_mask_istft<T>(Z, Tf, B, 1, df[3], df_rs[3], 1, P32("freq_out.weight"), P32("freq_out.bias"), frames, consts.tw,
@@ -481,7 +541,7 @@ void PlanT<T>::decode(const float* emb, float* out, cudaStream_t st) {
 
 template <typename T>
 int PlanT<T>::forward(const float* wav, const float* emb, float* out, cudaStream_t st) {
-  n_launches = 0;
+  n_launches = 0; n_tc = 0;
   encode(wav, st);
   decode(emb, out, st);
   return (int)cudaGetLastError();
@@ -494,7 +554,8 @@ bool PlanT<T>::tap(const std::string& name, TapInfo& ti) const {
     ti.ptr = p; ti.dtype = dt; ti.numel = n; ti.dims[0] = d0; ti.dims[1] = d1; ti.dims[2] = d2; ti.dims[3] = d3; return true;
   };
   const int TD = sizeof(T) == 4 ? 0 : 1;
-  auto rs = [&](const T* p, const RowSpace& r) { return set(p, TD, r.elems(), r.G, r.Rp, r.C, r.pf); };
+  auto rs = [&](const T* p, const RowSpace& r) { ti.geom[0] = r.G2; ti.geom[1] = r.G2p; ti.geom[2] = r.gpf; ti.geom[3] = r.R;
+                                                    return set(p, TD, r.elems(), r.batch() * r.G2p, r.Rp, r.C, r.pf); };
   if (name == "Z") return set(Z, 0, (long)s.B * s.Tf * 2048 * 4, s.B, s.Tf, 2048, 4);
   if (name == "ms_spec") return set(ms_spec, 0, 2L * s.B, s.B, 2, 1, 1);
   if (name == "ms_wav") return set(ms_wav, 0, 2L * s.B, s.B, 2, 1, 1);

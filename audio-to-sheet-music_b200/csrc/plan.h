@@ -31,7 +31,22 @@ struct PlanConsts {
   const float* pe1d;   // [St, 512]
 };
 
-struct TapInfo { const void* ptr; int dtype; long numel; int dims[4]; };
+struct TapInfo { const void* ptr; int dtype; long numel; int dims[4]; int geom[4]; };
+
+enum { CONV_ROWS = 0, CONV_K8S4 = 1, CONV_T = 2, CONV_DIL3 = 3 };
+
+// One convolution-shaped op on channels-last row spaces (lowered to the tcgen05 or the SIMT GEMM by PlanT::conv).
+template <typename T>
+struct ConvOp {
+  int mode;                 // CONV_ROWS: 1x1 / linear; CONV_K8S4: kernel 8 stride 4 pad 2; CONV_T: transposed k8 s4 p2
+                            // (4 phases, output in the input's geometry); CONV_DIL3: kernel 3, dilation dil, along time
+  const T* a; RowSpace as;  // input buffer / space (as.C input channels)
+  int dil;
+  const T* w; int N;        // packed weights [N, K]
+  T* c; RowSpace cs;        // output buffer / space
+  const float* bias; int act; int glu; const float* colscale; const T* res;
+  const float* rowtab; float rowtab_scale; double* stats; int stat_mode;
+};
 
 struct PlanBase {
   virtual ~PlanBase() {}
@@ -43,6 +58,8 @@ struct PlanBase {
   virtual long zero_region_bytes() const = 0;
   virtual int launches() const = 0;
   virtual void set_profile(bool on) = 0;
+  virtual void set_use_tc(bool on) = 0;
+  virtual int tc_launches() const = 0;
   virtual void get_profile(double* ms, double* gflop, int* n) = 0;
 };
 
@@ -56,7 +73,8 @@ struct PlanT : PlanBase {
   PlanConsts consts;
   char* base_ = nullptr;
   size_t total_bytes = 0, zero_bytes = 0, stats_begin = 0, stats_bytes = 0;
-  int n_launches = 0;
+  int n_launches = 0, n_tc = 0;
+  bool use_tc = true;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
@@ -76,16 +94,19 @@ struct PlanT : PlanBase {
   const T* PW(const std::string& key) const;
   const float* PA(const std::string& key) const;
   void gemm(const GemmDesc& d, cudaStream_t st);
+  void conv(const ConvOp<T>& o, cudaStream_t st);
+  void prof_begin(double gflop, cudaStream_t st);
+  void prof_end(cudaStream_t st);
   void enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSpace ys, T* out, cudaStream_t st);
   void attention(const T* q, long ldq, const T* k, const T* v, long ldkv, int Sq, int Sk, T* o, cudaStream_t st);
-  void linear(const T* a, long rows, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st);
+  void linear(const T* a, int S, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st);
   void linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x, double* stats,
                   cudaStream_t st);
   void xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, cudaStream_t st);
   void cross_transformer(cudaStream_t st);
   void encode(const float* wav, cudaStream_t st);
   void text_vectors(const float* emb, cudaStream_t st);
-  void text_condition(int p, const T* x, int S, T* out, int yR, int yRp, int ypf, cudaStream_t st);
+  void text_condition(int p, const T* x, int S, T* out, RowSpace outs, cudaStream_t st);
   void dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* out, RowSpace os, const T* skip, RowSpace ss,
                  cudaStream_t st);
   void decode(const float* emb, float* out, cudaStream_t st);
@@ -98,6 +119,8 @@ struct PlanT : PlanBase {
   long zero_region_bytes() const override { return (long)zero_bytes; }
   int launches() const override { return n_launches; }
   void set_profile(bool on) override { profiling = on; prof_used = 0; prof_gflop = 0.0; }
+  void set_use_tc(bool on) override { use_tc = on; }
+  int tc_launches() const override { return n_tc; }
   void get_profile(double* ms, double* gflop, int* n) override;
 };
 

@@ -51,6 +51,12 @@ class Tap:
     def __init__(self, ptr: int, numel: int, dtype: int, dims):
         self.ptr, self.numel, self.dtype, self.dims = ptr, numel, dtype, tuple(dims)
 
+    def interior(self) -> torch.Tensor:
+        """Row-space buffers: strip pad groups / pad rows -> [B*G2, R, C]."""
+        groups, Rp, Cc, pf, G2, G2p, gpf, R = self.dims
+        t = self.to_torch().view(groups // G2p, G2p, Rp, Cc)
+        return t[:, gpf:gpf + G2, pf:pf + R].reshape(-1, R, Cc)
+
     def to_torch(self) -> torch.Tensor:
         tdt = torch.float32 if self.dtype == 0 else torch.bfloat16
         out = torch.empty(self.numel, dtype=tdt, device="cuda")
@@ -112,6 +118,13 @@ class Plan:
     def launches(self) -> int:
         return _lib.load().athtd_plan_launches(self.handle)
 
+    def set_tc(self, on: bool) -> None:
+        _lib.load().athtd_plan_set_tc(self.handle, 1 if on else 0)
+
+    @property
+    def tc_launches(self) -> int:
+        return _lib.load().athtd_plan_tc_launches(self.handle)
+
     def set_profile(self, on: bool) -> None:
         _lib.load().athtd_plan_set_profile(self.handle, 1 if on else 0)
 
@@ -122,7 +135,7 @@ class Plan:
 
     def tap(self, name: str) -> Tap:
         ptr, numel, dt = C.c_void_p(), C.c_long(), C.c_int()
-        dims = (C.c_int * 4)()
+        dims = (C.c_int * 8)()
         _lib.check(_lib.load().athtd_tap(self.handle, name.encode(), C.byref(ptr), C.byref(numel), C.byref(dt),
                                          C.byref(dims)), "athtd_tap")
         return Tap(ptr.value, numel.value, dt.value, list(dims))
@@ -174,7 +187,7 @@ class Engine:
         return self.plans[key]
 
     def gemm_kernel_name(self) -> str:
-        return "gemm_simt_kernel (CUDA-core fp32 accumulate)"
+        return "gemm_tc_kernel (tcgen05) + gemm_simt_kernel" if self.dtype == "bf16" else "gemm_simt_kernel (CUDA-core fp32)"
 
     def drop_plans(self) -> None:
         self.plans.clear()

@@ -58,8 +58,13 @@ int athtd_plan_launches(void* plan);   /* kernels launched by the last forward *
 int athtd_plan_set_profile(void* plan, int on);
 int athtd_plan_get_profile(void* plan, double* gemm_ms, double* gemm_gflop, int* gemm_launches);
 
-/* debug / test access to intermediate buffers of the last forward (dims: see plan.cu tap()) */
-int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[4]);
+/* debug / test access to intermediate buffers of the last forward.  Row-space buffers report
+ * dims = {stored groups, stored rows per group, channels, front pad rows, G2, G2p, gpf, R} (common.cuh RowSpace). */
+int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[8]);
+/* bf16 build only: route the supported GEMMs through the tcgen05 kernel (default on) or keep everything on the
+ * CUDA-core kernel (A/B measurements, kernel-level parity tests). */
+int athtd_plan_set_tc(void* plan, int on);
+int athtd_plan_tc_launches(void* plan);
 
 /* async device-to-device copy on `stream` (lets tests read taps without a second CUDA binding) */
 int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* stream);

@@ -108,3 +108,21 @@ def test_track_separation_matches_reference_loop(models, state_dict):
     left, halo = sep.separate_many(mix, emb, span=(0, k))
     right, _ = sep.separate_many(mix, emb, span=(k, n), halo_in=halo)
     assert torch.equal(torch.cat([left, right], dim=-1), out)
+
+
+def test_bf16_tensor_core_path_matches_cuda_core_path(models, state_dict):
+    """Same bf16 build with the supported GEMMs on tcgen05 vs all GEMMs on the CUDA-core kernel: both must hit the
+    oracle at >= 40 dB and agree with each other at >= 40 dB (different summation order only)."""
+    wav, emb = weights.make_inputs(1, 1, 264600)
+    m = models["bf16"]
+    plan = m.engine().plan(1, 264600, 1)
+    plan.set_tc(True)
+    a = m(wav.cuda(), emb.cuda()).cpu()
+    assert plan.tc_launches > 50
+    plan.set_tc(False)
+    b = m(wav.cuda(), emb.cuda()).cpu()
+    assert plan.tc_launches == 0
+    plan.set_tc(True)
+    ref = athtd_oracle.forward(state_dict, wav, emb)
+    assert athtd_oracle.snr_db(a, ref) >= 40.0 and athtd_oracle.snr_db(b, ref) >= 40.0
+    assert athtd_oracle.snr_db(a, b) >= 40.0

@@ -97,3 +97,20 @@ def test_chunk_gather_and_ola_bit_exact(T):
         left = athtd_b200.chunk_ola(seg_out[:k + 1], 2 * plan.chunk_len, -1, tab, 0, plan.starts[k])
         right = athtd_b200.chunk_ola(seg_out[k:], 2 * plan.chunk_len, k - 1, tab, plan.starts[k], T)
         assert torch.equal(torch.cat([left, right], dim=1).cpu(), ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 128), (1000, 512, 384), (777, 96, 1536), (4144, 2048, 512),
+                                   (2072, 192, 96), (515, 64, 72)])
+def test_tcgen05_gemm_matches_fp32_matmul(M, N, K):
+    """tcgen05/TMEM/TMA kernel: bf16 operands, fp32 accumulation, bf16 store.  K = 96 / 72 exercise the zero-filled
+    partial K block, M not a multiple of 128 the row masking.  Tolerance: bf16 output rounding (4e-3 relative)."""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = torch.randn(M, K, generator=g).bfloat16().cuda()
+    Bm = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    Cd = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    alib.check(alib.load().athtd_gemm_test(A.data_ptr(), Bm.data_ptr(), bias.data_ptr(), Cd.data_ptr(), M, N, K, 1, 1, _stream()))
+    ref = A.float().cpu() @ Bm.float().cpu().t() + bias.cpu()
+    got = Cd.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max() < 6e-3 * max(1.0, ref.abs().max().item())

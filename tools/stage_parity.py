@@ -52,14 +52,12 @@ def main():
     out = model.separate_batch(wav.cuda(), E)
     torch.cuda.synchronize()
     plan = model.engine().plan(a.B, a.L, a.P)
-    print("launches per forward:", plan.launches)
+    print("launches per forward:", plan.launches, "tcgen05 GEMM launches:", plan.tc_launches)
     B, L = a.B, a.L
     Tf = plan.Tf
 
     def rs(name):
-        tp = plan.tap(name)
-        G, Rp, C, pf = tp.dims
-        return tp.to_torch().view(G, Rp, C), pf
+        return plan.tap(name).interior(), 0
 
     z = plan.tap("Z").to_torch().view(B, Tf, 2048, 4).cpu()
     zr = torch.view_as_real(taps["z"])          # [B,2,F,T,2]
