@@ -226,12 +226,13 @@ void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
     } else {
       f.A = o.a; f.a_rows = as.rows_total(); f.a_pitch = C; f.Ktap = C; f.RpA = as.Rp;
       if (o.mode == CONV_ROWS) { f.ntaps = 1; f.vlo = as.pf; f.vhi = as.pf + as.R; }
-      else if (o.mode == CONV_T) { f.ntaps = 2; f.tapRow[1] = 1; f.vlo = as.pf - 1; f.vhi = as.pf + as.R; }
+      else if (o.mode == CONV_T) { f.ntaps = 2; f.tapRow[1] = 1; f.vlo = as.pf - 1; f.vhi = as.pf + as.R + 1; }
       else { f.ntaps = 3; const int sh_ = o.dil * (freq ? as.Rp : 1); f.tapRow[0] = -sh_; f.tapRow[1] = 0; f.tapRow[2] = sh_;
              f.vlo = as.pf; f.vhi = as.pf + as.R; }
     }
     f.Mflat = f.a_rows;
-    f.oG2p = cs.G2p; f.ogsh = cs.gpf - as.gpf; f.oRp = cs.Rp; f.orsh = cs.pf - f.vlo; f.ldc = cs.C;
+    f.oG2p = cs.G2p; f.ogsh = cs.gpf - as.gpf; f.oRp = cs.Rp; f.ldc = cs.C;
+    f.orsh = (o.mode == CONV_T ? cs.pf - 1 : cs.pf) - f.vlo;   // transposed conv: row q sits at the row of x[q-1]
     f.C = o.c; f.c_is_f32 = 0; f.bias = o.bias; f.act = o.act; f.glu = o.glu; f.colscale = o.colscale; f.res = o.res;
     f.rowtab = o.rowtab; f.rowtab_scale = o.rowtab_scale; f.stats = o.stats; f.stat_mode = o.stat_mode; f.statR = as.R;
     f.convt_cout = o.mode == CONV_T ? o.N / 4 : 0;
