@@ -115,6 +115,7 @@ int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* 
   return 0;
 }
 int athtd_plan_set_tc(void* plan, int on) { ((PlanBase*)plan)->set_use_tc(on != 0); return 0; }
+int athtd_plan_set_flash(void* plan, int on) { ((PlanBase*)plan)->set_use_flash(on != 0); return 0; }
 int athtd_plan_tc_launches(void* plan) { return ((PlanBase*)plan)->tc_launches(); }
 
 int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* stream) {
@@ -155,6 +156,14 @@ int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int c
   launch_chunk_ola(seg_out_dev, seg_stride, k_base, chunk_len, starts_dev, actual_len_dev, fade_len_dev, flags_dev, n_chunks,
                    stride, ramp_up_dev, ramp_down_dev, ramp_off_dev, out_dev, C, t_begin, t_end, (cudaStream_t)stream);
   return check_cuda("athtd_chunk_ola");
+}
+
+int athtd_attention_test(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev, int B, int Sq, int Sk, void* stream) {
+  if (!flash_attn_supported(512, 512, 512)) return fail("athtd_attention_test: tensor-map API unavailable");
+  int rc = launch_flash_attn((const bf16*)q_dev, 512, (const bf16*)k_dev, (const bf16*)v_dev, 512, B, Sq, Sk, (bf16*)o_dev, 512,
+                             (cudaStream_t)stream);
+  if (rc != 0) return fail("athtd_attention_test: cuTensorMapEncodeTiled failed");
+  return check_cuda("athtd_attention_test");
 }
 
 int athtd_gemm_test(const void* A_dev, const void* B_dev, const float* bias_dev, void* C_dev, int M, int N, int K, int dtype,

@@ -15,7 +15,7 @@
 //   warps 2..5  : epilogue - tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused bias / GELU / GLU /
 //                 LayerScale / residual / frequency-embedding / GroupNorm partial sums, vectorised global stores
 #include "gemm.cuh"
-#include <cuda.h>
+#include "tc_ptx.cuh"
 #include <mutex>
 #include <stdio.h>
 
@@ -23,11 +23,11 @@ namespace athtd {
 
 static constexpr int TC_BM = 128;
 static constexpr int TC_BK = 64;
-static constexpr int TC_STAGES = 4;
+static constexpr int TC_MAX_STAGES = 4;
 static constexpr int TC_THREADS = 192;
 
 struct TcParams {
-  int Mflat, N, BN;
+  int Mflat, N, BN, stages;
   int ntaps, kb_per_tap, Ktap;
   int tapRow[3];
   // flat row -> (b, t', f') decode and validity
@@ -43,74 +43,19 @@ struct TcParams {
   int convt_cout;
 };
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bit 46)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
 // ------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stageA = TC_BM * TC_BK * 2;
   const int stageB = p.BN * TC_BK * 2;
   uint8_t* sA = smem;
+  const int TC_STAGES = p.stages;
   uint8_t* sB = smem + TC_STAGES * stageA;
   uint64_t* bars = (uint64_t*)(sB + TC_STAGES * stageB);
-  uint64_t* full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+  uint64_t* full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * TC_BM;
@@ -319,7 +264,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static bool make_map_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
+bool make_tensor_map_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
                         uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
@@ -332,6 +277,8 @@ static bool make_map_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint6
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+
+bool tensor_map_api_available() { return get_encode() != nullptr; }
 
 int tc_pick_bn(int N) {
   if (N % 256 == 0) return 256;
@@ -364,12 +311,13 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   p.colscale = f.colscale; p.res = f.res; p.rowtab = f.rowtab; p.rowtab_scale = f.rowtab_scale;
   p.stats = f.stats; p.stat_mode = f.stat_mode; p.statR = f.statR; p.convt_cout = f.convt_cout;
   CUtensorMap tmA, tmB;
-  if (!make_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
-  if (!make_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
-  const size_t smem = 1024 + (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + p.BN * TC_BK * 2) + 256;
+  if (!make_tensor_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
+  if (!make_tensor_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
+  p.stages = p.BN > 128 ? 4 : 3;      // <= 97 KB for BN <= 128: two CTAs per SM overlap epilogue and main loop
+  const size_t smem = 1024 + (size_t)p.stages * (TC_BM * TC_BK * 2 + p.BN * TC_BK * 2) + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + TC_STAGES * (16384 + 32768) + 256);
+    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + TC_MAX_STAGES * (16384 + 32768) + 256);
     attr_set = true;
   }
   dim3 grid((unsigned)((f.Mflat + TC_BM - 1) / TC_BM), (unsigned)(f.N / p.BN));

@@ -37,6 +37,11 @@ template <typename T> void launch_ola_combine(const float* frames, int Tf, int L
                                               const float* to_w, const float* to_b, const float* meanstd_t, int ms_div,
                                               float* out, long out_bstride, cudaStream_t st);
 
+// ---- attention.cu (bf16 tcgen05 flash attention, 8 heads x 64)
+bool flash_attn_supported(long ldq, long ldkv, long ldo);
+int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, long ldkv, int B, int Sq, int Sk, bf16* o,
+                      long ldo, cudaStream_t st);
+
 // ---- ola.cu  (track-level chunk gather / weighted overlap-add, benchmark.py:155-204)
 void launch_gather_chunks(const float* track, long T, int C, const long* starts, int n_chunks, int chunk_len, float* segs,
                           cudaStream_t st);

@@ -324,9 +324,24 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
 }
 
 // ---- attention for one branch: scores = (Q K^T)/sqrt(64), softmax, O = P V   (8 heads of 64)
+static inline int flash_dispatch(const bf16* q, long ldq, const bf16* k, const bf16* v, long ldkv, int B, int Sq, int Sk, bf16* o,
+                                 cudaStream_t st) {
+  if (!flash_attn_supported(ldq, ldkv, 512)) return -1;
+  return launch_flash_attn(q, ldq, k, v, ldkv, B, Sq, Sk, o, 512, st);
+}
+static inline int flash_dispatch(const float*, long, const float*, const float*, long, int, int, int, float*, cudaStream_t) { return -1; }
+
 template <typename T>
 void PlanT<T>::attention(const T* q, long ldq, const T* k, const T* v, long ldkv, int Sq, int Sk, T* o, cudaStream_t st) {
   const int B = sh.B;
+  if (use_tc && use_flash) {
+    prof_begin(4.0 * (double)B * 8 * Sq * Sk * 64 * 1e-9, st);
+    int rc = flash_dispatch(q, ldq, k, v, ldkv, B, Sq, Sk, o, st);
+    prof_end(st);
+    if (rc == 0) { ++n_launches; ++n_tc; return; }
+    if (rc > 0) throw std::runtime_error("athtd: cuTensorMapEncodeTiled failed for the attention kernel");
+    if (profiling) { prof_used -= 2; }
+  }
   {
     GemmDesc d = gemm_desc_zero();
     d.G1 = B; d.G2 = 8; d.Mg = Sq; d.N = Sk; d.K = 64; d.Ktap = 64; d.grouped = 1;

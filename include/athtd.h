@@ -64,6 +64,7 @@ int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* 
 /* bf16 build only: route the supported GEMMs through the tcgen05 kernel (default on) or keep everything on the
  * CUDA-core kernel (A/B measurements, kernel-level parity tests). */
 int athtd_plan_set_tc(void* plan, int on);
+int athtd_plan_set_flash(void* plan, int on);   /* fused tcgen05 attention (default on) vs GEMM-softmax-GEMM */
 int athtd_plan_tc_launches(void* plan);
 
 /* async device-to-device copy on `stream` (lets tests read taps without a second CUDA binding) */
@@ -87,6 +88,10 @@ int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int c
                     const int* actual_len_dev, const int* fade_len_dev, const int* flags_dev, int n_chunks, long stride,
                     const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
                     long t_begin, long t_end, void* stream);
+
+/* kernel-level parity test of the fused attention: q [B*Sq,512], k/v [B*Sk,512] bf16 (8 heads x 64) -> o [B*Sq,512] */
+int athtd_attention_test(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev, int B, int Sq, int Sk,
+                         void* stream);
 
 /* ---- generic GEMM entry used by the kernel-level parity tests: C[M,N] = A[M,K] * B[N,K]^T (+bias), row-major */
 int athtd_gemm_test(const void* A_dev, const void* B_dev, const float* bias_dev, void* C_dev, int M, int N, int K,

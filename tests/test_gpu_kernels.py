@@ -114,3 +114,24 @@ def test_tcgen05_gemm_matches_fp32_matmul(M, N, K):
     got = Cd.float().cpu()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max() < 6e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,Sq,Sk", [(1, 128, 128), (2, 320, 157), (1, 2072, 1034), (2, 1034, 2072)])
+def test_fused_attention_matches_torch(B, Sq, Sk):
+    """tcgen05 flash attention (8 heads x 64, scale 1/8, no mask) vs fp32 softmax(QK^T/8)V on the bf16-rounded inputs.
+    Sk not a multiple of 128 exercises the key masking, Sq the row masking.  Tolerance 2e-2 abs on O(1) outputs
+    (bf16 P and bf16 output rounding)."""
+    g = torch.Generator().manual_seed(B * 1000 + Sq + Sk)
+    q = torch.randn(B, Sq, 512, generator=g).bfloat16()
+    k = torch.randn(B, Sk, 512, generator=g).bfloat16()
+    v = torch.randn(B, Sk, 512, generator=g).bfloat16()
+    o = torch.full((B, Sq, 512), float("nan"), dtype=torch.bfloat16, device="cuda")
+    qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+    alib.check(alib.load().athtd_attention_test(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, Sq, Sk, _stream()))
+    qh = q.float().view(B, Sq, 8, 64).transpose(1, 2)
+    kh = k.float().view(B, Sk, 8, 64).transpose(1, 2)
+    vh = v.float().view(B, Sk, 8, 64).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B, Sq, 512)
+    got = o.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max() < 2e-2
