@@ -297,6 +297,7 @@ void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace
 // kind 2: conv-transpose phases    src [Ci][Co][8] -> dst [4*Co][2*Ci], row r*Co+co, col j*Ci+ci, tap = j==0 ? r+4 : r
 // kind 3: GLU interleave rows      src [2C][K]     -> dst row 2j = src row j, row 2j+1 = src row j+C
 // kind 4: replicate                src [d0]        -> dst[i] = src[i % d0]
+// kind 5/6/7: zero-padded variants (hidden channels of the tensor-core DConv), see below
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, long n, int kind, int d0, int d1, int d2) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -313,6 +314,16 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
       s = (long)(j + half * (d0 / 2)) * d1 + k;
     } else if (kind == 4) {    // replicate a [d0] vector
       s = i % d0;
+    } else if (kind == 5) {    // conv k-major with zero-padded output rows: d0=Co d1=Ci d2=K ; dst [Cop][K*Ci]
+      int ci = (int)(i % d1); long t = i / d1; int k = (int)(t % d2); int co = (int)(t / d2);
+      if (co >= d0) { dst[i] = from_f<T>(0.f); continue; }
+      s = ((long)co * d1 + ci) * d2 + k;
+    } else if (kind == 6) {    // zero-pad a [d0] vector
+      if (i >= d0) { dst[i] = from_f<T>(0.f); continue; }
+    } else if (kind == 7) {    // GLU-interleaved rows with zero-padded columns: src [d0=2C][d1=K] -> dst [2C][d2=Kp]
+      int k = (int)(i % d2); int row = (int)(i / d2); int j = row >> 1; int half = row & 1;
+      if (k >= d1) { dst[i] = from_f<T>(0.f); continue; }
+      s = (long)(j + half * (d0 / 2)) * d1 + k;
     }
     dst[i] = from_f<T>(src[s]);
   }

@@ -59,7 +59,11 @@ struct TcFlat {
   int oG2p, ogsh, oRp, orsh; long ldc; void* C; int c_is_f32;
   float alpha; const float* bias; int act; int glu; const float* colscale; const void* res;
   const float* rowtab; float rowtab_scale; double* stats; int stat_mode; int statR; int convt_cout;
+  int n_store;          // store only the first n_store output columns (0 = all): zero-padded hidden channels
+  int no_store;         // statistics-only pass (the GroupNorm'd result is recomputed by a second pass instead of stored)
+  const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;   // GroupNorm apply right after the bias
 };
+bool tensor_map_api_available();              // cuTensorMapEncodeTiled reachable through the runtime's driver entry point
 bool tc_flat_supported(const TcFlat& f);
 int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st);   // bf16 in, fp32 accumulate; 0 = launched
 

@@ -6,14 +6,15 @@
 // A is a 2-D view (rows x Ktap, row pitch >= 16 B) of a channels-last activation buffer; every conv of the
 // path (1x1, strided k8s4, transposed k8s4 phases, dilated k3) is such a view plus 1..3 row-shifted taps, because
 // the buffers carry zero pad rows / pad frames (DESIGN.md "flat-row GEMM").  Rows that fall in padding are
-// computed and discarded by the epilogue's validity decode.
+// computed and discarded by the epilogue's validity decode.  Ktap need not be a multiple of the 64-element K block:
+// the TMA box is clipped by the tensor-map extent (zero fill) and only ceil(k/16) MMAs are issued.
 //
-// Structure (one 128 x BN tile per CTA, 192 threads):
-//   warp 0      : TMA producer  - cp.async.bulk.tensor.2d (SWIZZLE_128B boxes 64 x 128 / 64 x BN) into a 4-stage ring
+// Structure (one 128 x BN tile per CTA, 192 threads, up to two CTAs per SM):
+//   warp 0      : TMA producer  - cp.async.bulk.tensor.2d (SWIZZLE_128B boxes 64 x 128 / 64 x BN) into a 3-4 stage ring
 //   warp 1      : TMEM allocator + MMA issuer - one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//                 (M=128, N=BN, K=16) x 4 per stage, tcgen05.commit releases the stage / signals the epilogue
-//   warps 2..5  : epilogue - tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused bias / GELU / GLU /
-//                 LayerScale / residual / frequency-embedding / GroupNorm partial sums, vectorised global stores
+//                 (M=128, N=BN, K=16), tcgen05.commit releases the stage / signals the epilogue
+//   warps 2..5  : epilogue - tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused bias / GroupNorm apply /
+//                 GELU / GLU / LayerScale / residual / frequency-embedding / GroupNorm partial sums, 16-byte stores
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
@@ -35,13 +36,27 @@ struct TcParams {
   // output row mapping: ((b*oG2p + t' + ogsh) * oRp + f' + orsh) * ldc
   int oG2p, ogsh, oRp, orsh;
   long ldc;
-  void* C; int c_is_f32;
+  void* C; int n_store; int no_store;
   float alpha; const float* bias; int act; int glu; const float* colscale;
   const void* res;
   const float* rowtab; float rowtab_scale;
   double* stats; int stat_mode; int statR;
+  const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;
   int convt_cout;
 };
+
+__device__ __forceinline__ void store8(bf16* dst, const float* v) {
+  uint32_t pk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); pk[i] = *(uint32_t*)&t; }
+  *(uint4*)dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+__device__ __forceinline__ void load8_add(const bf16* src, float* v) {
+  uint4 t = *(const uint4*)src;
+  const __nv_bfloat162* h = (const __nv_bfloat162*)&t;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+}
 
 // ------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -49,11 +64,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stageA = TC_BM * TC_BK * 2;
-  const int stageB = p.BN * TC_BK * 2;
+  const int stageB = ((p.BN * TC_BK * 2) + 1023) & ~1023;
+  const int nst = p.stages;
   uint8_t* sA = smem;
-  const int TC_STAGES = p.stages;
-  uint8_t* sB = smem + TC_STAGES * stageA;
-  uint64_t* bars = (uint64_t*)(sB + TC_STAGES * stageB);
+  uint8_t* sB = smem + nst * stageA;
+  uint64_t* bars = (uint64_t*)(sB + nst * stageB);
   uint64_t* full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_MAX_STAGES + 1);
 
@@ -67,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int s = 0; s < nst; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
     mbar_init(smem_u32(tfull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -83,10 +98,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(stageA + stageB);
+      const uint32_t bytes = (uint32_t)(stageA + p.BN * TC_BK * 2);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        const int s = kb % nst;
+        const uint32_t ph = (uint32_t)(kb / nst) & 1u;
         mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
         const int tap = kb / p.kb_per_tap;
         const int kin = (kb - tap * p.kb_per_tap) * TC_BK;
@@ -101,14 +116,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        const int s = kb % nst;
+        const uint32_t ph = (uint32_t)(kb / nst) & 1u;
         mbar_wait(smem_u32(&full[s]), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t da = make_sw128_desc(smem_u32(sA + s * stageA));
         const uint64_t db = make_sw128_desc(smem_u32(sB + s * stageB));
-#pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
+        const int kin = (kb % p.kb_per_tap) * TC_BK;
+        const int nmma = (min(TC_BK, p.Ktap - kin) + 15) >> 4;     // columns past Ktap are zero-filled by TMA
+        for (int k = 0; k < nmma; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
           umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
         umma_commit(smem_u32(&empty[s]));
       }
@@ -127,6 +143,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const long orow = ((long)b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
     const int m = fp - p.vlo;
     const int Nout = p.glu ? p.N / 2 : p.N;
+    float gmean = 0.f, grstd = 1.f;
+    if (p.gn_mr && valid) {
+      const long gi = p.gn_mode == STAT_PER_G1_M ? (long)b * p.statR + m : (long)b;
+      gmean = p.gn_mr[2 * gi]; grstd = p.gn_mr[2 * gi + 1];
+    }
     float ssum = 0.f, ssq = 0.f;
     mbar_wait(smem_u32(tfull), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -134,89 +155,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int ncol = n0 + c0;
-      if (!valid || ncol >= p.N) continue;
+      const int nc = min(32, min(p.BN - c0, p.N - ncol));      // valid accumulator columns in this chunk (multiple of 8)
+      if (!valid || nc <= 0) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float x = p.alpha * __uint_as_float(r[j]);
-        if (p.bias) x += p.bias[ncol + j];
-        if (p.act == ACT_GELU) x = gelu_erf(x);
+        float x = 0.f;
+        if (j < nc) {
+          x = p.alpha * __uint_as_float(r[j]);
+          if (p.bias) x += p.bias[ncol + j];
+          if (p.gn_mr) x = (x - gmean) * grstd * p.gn_w[ncol + j] + p.gn_b[ncol + j];
+          if (p.act == ACT_GELU) x = gelu_erf(x);
+        }
         v[j] = x;
       }
+      int no = ncol, nco = nc;             // output column base / count
       if (p.glu) {
-        const int no = ncol >> 1;
-        float o[16];
+        no = ncol >> 1; nco = nc >> 1;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = v[2 * j] * sigmoid_acc(v[2 * j + 1]);
-          if (p.colscale) x *= p.colscale[no + j];
-          if (p.rowtab) x += p.rowtab_scale * p.rowtab[(long)m * Nout + no + j];
-          o[j] = x;
-        }
-        if (p.c_is_f32) {
-          float* cp = (float*)p.C + orow * p.ldc + no;
-          if (p.res) { const float* rp = (const float*)p.res + orow * p.ldc + no;
+        for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * sigmoid_acc(v[2 * j + 1]);
+      }
+      if (p.colscale || p.rowtab) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] += rp[j]; }
+        for (int j = 0; j < 32; ++j)
+          if (j < nco) {
+            if (p.colscale) v[j] *= p.colscale[no + j];
+            if (p.rowtab) v[j] += p.rowtab_scale * p.rowtab[(long)m * Nout + no + j];
+          }
+      }
+      if (p.res) {
+        const bf16* rp = (const bf16*)p.res + orow * p.ldc + no;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { ssum += o[j]; ssq += o[j] * o[j]; }
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) *(float4*)(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-        } else {
-          bf16* cp = (bf16*)p.C + orow * p.ldc + no;
-          if (p.res) { const bf16* rp = (const bf16*)p.res + orow * p.ldc + no;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] += __bfloat162float(rp[j]); }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { ssum += o[j]; ssq += o[j] * o[j]; }
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { __nv_bfloat162 t = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]); pk[j] = *(uint32_t*)&t; }
-          *(uint4*)(cp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *(uint4*)(cp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      } else {
+        for (int g = 0; g < 4; ++g)
+          if (8 * g < nco) load8_add(rp + 8 * g, v + 8 * g);
+      }
+      if (p.stat_mode != STAT_NONE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (p.colscale) v[j] *= p.colscale[ncol + j];
-          if (p.rowtab) v[j] += p.rowtab_scale * p.rowtab[(long)m * Nout + ncol + j];
-        }
-        if (p.c_is_f32) {
-          float* cp = (float*)p.C + orow * p.ldc + ncol;
-          if (p.res) { const float* rp = (const float*)p.res + orow * p.ldc + ncol;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += rp[j]; }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          bf16* cp = (bf16*)p.C + orow * p.ldc + ncol;
-          if (p.res) {
-            const uint4* rp = (const uint4*)((const bf16*)p.res + orow * p.ldc + ncol);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 t = rp[j];
-              const __nv_bfloat162* h = (const __nv_bfloat162*)&t;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y; }
-            }
+          bool counted = j < nco;
+          if (p.convt_cout > 0) {
+            const int phase = (no + j) / p.convt_cout;
+            counted = counted && !((m == 0 && phase < 2) || (m == p.vhi - p.vlo - 1 && phase >= 2));
           }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]); pk[j] = *(uint32_t*)&t; }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *(uint4*)(cp + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          if (counted) { ssum += v[j]; ssq += v[j] * v[j]; }
         }
-        if (p.stat_mode != STAT_NONE) {
+      }
+      if (!p.no_store) {
+        bf16* cp = (bf16*)p.C + orow * p.ldc + no;
+        const int nst_cols = min(nco, p.n_store - no);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            bool counted = true;
-            if (p.convt_cout > 0) {
-              const int phase = (ncol + j) / p.convt_cout;
-              counted = !((m == 0 && phase < 2) || (m == p.vhi - p.vlo - 1 && phase >= 2));
-            }
-            if (counted) { ssum += v[j]; ssq += v[j] * v[j]; }
-          }
-        }
+        for (int g = 0; g < 4; ++g)
+          if (8 * g < nst_cols) store8(cp + 8 * g, v + 8 * g);
       }
     }
     if (p.stat_mode != STAT_NONE) {
@@ -227,14 +216,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         const int key = valid ? b : -1;
-        const int key0 = __shfl_sync(0xffffffffu, key, 0);
+        int key0 = __reduce_max_sync(0xffffffffu, key);
         const bool uniform = __all_sync(0xffffffffu, key == key0 || key == -1);
-        if (uniform && key0 >= 0) {
-          float a = valid ? ssum : 0.f, c = valid ? ssq : 0.f;
-          a = warp_sum(a); c = warp_sum(c);
-          if (lane == 0) { atomicAdd(p.stats + 2 * (long)key0, (double)a); atomicAdd(p.stats + 2 * (long)key0 + 1, (double)c); }
-        } else if (valid) {
-          atomicAdd(p.stats + 2 * (long)b, (double)ssum); atomicAdd(p.stats + 2 * (long)b + 1, (double)ssq);
+        if (key0 >= 0) {
+          if (uniform) {
+            float a = valid ? ssum : 0.f, c = valid ? ssq : 0.f;
+            a = warp_sum(a); c = warp_sum(c);
+            if (lane == 0) { atomicAdd(p.stats + 2 * (long)key0, (double)a); atomicAdd(p.stats + 2 * (long)key0 + 1, (double)c); }
+          } else if (valid) {
+            atomicAdd(p.stats + 2 * (long)b, (double)ssum); atomicAdd(p.stats + 2 * (long)b + 1, (double)ssq);
+          }
         }
       }
     }
@@ -281,21 +272,22 @@ bool make_tensor_map_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint6
 bool tensor_map_api_available() { return get_encode() != nullptr; }
 
 int tc_pick_bn(int N) {
+  if (N % 16) return 0;
+  if (N <= 256) return N;
   if (N % 256 == 0) return 256;
-  if (N <= 256 && N % 32 == 0) return N;
   if (N % 128 == 0) return 128;
   if (N % 192 == 0) return 192;
   if (N % 64 == 0) return 64;
   if (N % 32 == 0) return 32;
-  return 0;
+  return 16;
 }
 
 bool tc_flat_supported(const TcFlat& f) {
-  if (f.Ktap < 64 || f.Ktap % 8) return false;
+  if (f.Ktap < 8 || f.Ktap % 8) return false;
   if (tc_pick_bn(f.N) == 0) return false;
-  if (f.glu && (f.N % 64)) return false;
+  if (f.glu && (f.N % 16)) return false;
   if ((f.a_pitch * 2) % 16 || ((uintptr_t)f.A % 16) || ((uintptr_t)f.B % 16)) return false;
-  if (f.ldc % 8) return false;
+  if (f.ldc % 8 || f.c_is_f32) return false;
   return get_encode() != nullptr;
 }
 
@@ -307,20 +299,24 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   for (int i = 0; i < 3; ++i) p.tapRow[i] = f.tapRow[i];
   p.RpA = f.RpA; p.G2p = f.G2p; p.gpf = f.gpf; p.G2 = f.G2; p.vlo = f.vlo; p.vhi = f.vhi;
   p.oG2p = f.oG2p; p.ogsh = f.ogsh; p.oRp = f.oRp; p.orsh = f.orsh; p.ldc = f.ldc;
-  p.C = f.C; p.c_is_f32 = f.c_is_f32; p.alpha = f.alpha; p.bias = f.bias; p.act = f.act; p.glu = f.glu;
+  p.C = f.C; p.alpha = f.alpha; p.bias = f.bias; p.act = f.act; p.glu = f.glu;
+  p.n_store = f.n_store > 0 ? f.n_store : (f.glu ? f.N / 2 : f.N);
+  p.no_store = f.no_store;
   p.colscale = f.colscale; p.res = f.res; p.rowtab = f.rowtab; p.rowtab_scale = f.rowtab_scale;
   p.stats = f.stats; p.stat_mode = f.stat_mode; p.statR = f.statR; p.convt_cout = f.convt_cout;
+  p.gn_mr = f.gn_mr; p.gn_w = f.gn_w; p.gn_b = f.gn_b; p.gn_mode = f.gn_mode;
   CUtensorMap tmA, tmB;
   if (!make_tensor_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
   if (!make_tensor_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
   p.stages = p.BN > 128 ? 4 : 3;      // <= 97 KB for BN <= 128: two CTAs per SM overlap epilogue and main loop
-  const size_t smem = 1024 + (size_t)p.stages * (TC_BM * TC_BK * 2 + p.BN * TC_BK * 2) + 256;
+  const int stageB = ((p.BN * TC_BK * 2) + 1023) & ~1023;
+  const size_t smem = 1024 + (size_t)p.stages * (TC_BM * TC_BK * 2 + stageB) + 256;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + TC_MAX_STAGES * (16384 + 32768) + 256);
     attr_set = true;
   }
-  dim3 grid((unsigned)((f.Mflat + TC_BM - 1) / TC_BM), (unsigned)(f.N / p.BN));
+  dim3 grid((unsigned)((f.Mflat + TC_BM - 1) / TC_BM), (unsigned)((f.N + p.BN - 1) / p.BN));
   gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
   return 0;
 }

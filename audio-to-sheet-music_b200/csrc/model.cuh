@@ -109,6 +109,8 @@ struct PackItem {
   long offset_bytes;    // filled by layout
 };
 
+inline int hidden_pad(int h) { return h <= 16 ? 16 : (h <= 32 ? 32 : (h + 15) / 16 * 16); }
+
 inline std::vector<PackItem> build_pack_list() {
   std::vector<PackItem> v;
   auto add = [&](const std::string& key, const std::string& src, long so, int kind, int d0, int d1, int d2, long n, bool f32) {
@@ -127,6 +129,16 @@ inline std::vector<PackItem> build_pack_list() {
         std::string q = p + ".dconv.layers." + std::to_string(d);
         add(q + ".0.w", q + ".0.weight", 0, 1, c / 8, c, 3, (long)(c / 8) * c * 3, false);
         add(q + ".3.w", q + ".3.weight", 0, 0, 0, 0, 0, (long)2 * c * (c / 8), false);
+        // tensor-core DConv: hidden channels zero-padded to hp (multiple of 16), expand rows GLU-interleaved
+        const int h = c / 8, hp = hidden_pad(h);
+        add(q + ".0.wp", q + ".0.weight", 0, 5, h, c, 3, (long)hp * c * 3, false);
+        add(q + ".0.bp", q + ".0.bias", 0, 6, h, 0, 0, hp, true);
+        add(q + ".1.wp", q + ".1.weight", 0, 6, h, 0, 0, hp, true);
+        add(q + ".1.bp", q + ".1.bias", 0, 6, h, 0, 0, hp, true);
+        add(q + ".3.wp", q + ".3.weight", 0, 7, 2 * c, h, hp, (long)2 * c * hp, false);
+        add(q + ".3.bi", q + ".3.bias", 0, 3, 2 * c, 1, 0, 2 * c, true);
+        add(q + ".4.wi", q + ".4.weight", 0, 3, 2 * c, 1, 0, 2 * c, true);
+        add(q + ".4.bi", q + ".4.bias", 0, 3, 2 * c, 1, 0, 2 * c, true);
       }
     }
   const char* ud[4] = {"htdemucs.channel_upsampler", "htdemucs.channel_downsampler", "htdemucs.channel_upsampler_t",

@@ -120,7 +120,7 @@ void PlanT<T>::layout(char* base) {
   size_t hmax = 0, emax = 0, umax = 0;
   for (int i = 0; i < 4; ++i) {
     size_t rows = std::max((size_t)yf_rs[i].rows_total(), (size_t)yt_rs[i].rows_total());
-    hmax = std::max(hmax, rows * (kCh[i] / 8));
+    hmax = std::max(hmax, rows * (size_t)hidden_pad(kCh[i] / 8));
     emax = std::max(emax, rows * (2 * kCh[i]));
   }
   hbuf = (T*)take(hmax * sizeof(T));
@@ -236,6 +236,7 @@ void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
     f.C = o.c; f.c_is_f32 = 0; f.bias = o.bias; f.act = o.act; f.glu = o.glu; f.colscale = o.colscale; f.res = o.res;
     f.rowtab = o.rowtab; f.rowtab_scale = o.rowtab_scale; f.stats = o.stats; f.stat_mode = o.stat_mode; f.statR = as.R;
     f.convt_cout = o.mode == CONV_T ? o.N / 4 : 0;
+    f.n_store = o.n_store; f.no_store = o.no_store; f.gn_mr = o.gn_mr; f.gn_w = o.gn_w; f.gn_b = o.gn_b; f.gn_mode = o.gn_mode;
     const bool geom_ok = (o.mode != CONV_K8S4) || (as.Rp % 4 == 0 && as.pf == 2);
     if (geom_ok && tc_flat_supported(f)) {
       prof_begin(gflop, st);
@@ -246,6 +247,7 @@ void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
       return;
     }
   }
+  if (o.no_store || o.gn_mr || o.n_store) throw std::runtime_error("athtd: fused DConv epilogue needs the tcgen05 kernel");
   GemmDesc d = gemm_desc_zero();
   d.G1 = B; d.G2 = as.G2; d.Mg = Mg; d.N = o.N; d.K = K; d.Ktap = K;
   d.sAg1 = as.g1_stride(); d.sAg2 = as.g2_stride();
@@ -292,23 +294,51 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
     o.bias = P32(p + ".conv.bias"); o.act = ACT_GELU;
     conv(o, st);
   }
-  RowSpace hs = ys; hs.C = H;
+  const bool tc_dconv = sizeof(T) == 2 && use_tc && tensor_map_api_available();
+  const int Hp = hidden_pad(H);
+  RowSpace hs = ys; hs.C = tc_dconv ? Hp : H;
   RowSpace es = ys; es.C = 2 * C;
   for (int dd = 0; dd < 2; ++dd) {
     const std::string q = p + ".dconv.layers." + std::to_string(dd);
     double* st_h = freq ? st_df[i][dd][0] : st_dt[i][dd][0];
     double* st_e = freq ? st_df[i][dd][1] : st_dt[i][dd][1];
     const long nstat = freq ? (long)s.B * R : s.B;
+    const int smode = freq ? STAT_PER_G1_M : STAT_PER_G1;
+    if (tc_dconv) {
+      // DConv layer on tensor cores in three passes over a narrow hidden buffer (C/8 channels zero-padded to Hp):
+      //   1. h = conv3(y) + GroupNorm partial sums     2. h <- GELU(GN(h))
+      //   3. e = W2 h: statistics only (not stored)    4. recompute e, GN, GLU, LayerScale, + y -> y
+      {
+        ConvOp<T> o = conv_op<T>(CONV_DIL3, y, ys, PW(q + ".0.wp"), Hp, hbuf, hs);
+        o.dil = 1 << dd; o.bias = PA(q + ".0.bp"); o.stats = st_h; o.stat_mode = smode;
+        conv(o, st);
+      }
+      launch_finalize_gn(st_h, (double)H * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
+      launch_gn_gelu<T>(hbuf, hs, G2, freq ? 1 : 0, mr, PA(q + ".1.wp"), PA(q + ".1.bp"), st); ++n_launches;
+      {
+        ConvOp<T> o = conv_op<T>(CONV_ROWS, hbuf, hs, PW(q + ".3.wp"), 2 * C, y, ys);
+        o.bias = PA(q + ".3.bi"); o.stats = st_e; o.stat_mode = smode; o.no_store = 1;
+        conv(o, st);
+      }
+      launch_finalize_gn(st_e, (double)2 * C * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
+      {
+        ConvOp<T> o = conv_op<T>(CONV_ROWS, hbuf, hs, PW(q + ".3.wp"), 2 * C, y, ys);
+        o.bias = PA(q + ".3.bi"); o.gn_mr = mr; o.gn_w = PA(q + ".4.wi"); o.gn_b = PA(q + ".4.bi"); o.gn_mode = smode;
+        o.glu = 1; o.colscale = P32(q + ".6.scale"); o.res = y;
+        conv(o, st);
+      }
+      continue;
+    }
     {  // dilated k3 conv C -> C/8 along time (freq branch: taps shift the frame index)
       ConvOp<T> o = conv_op<T>(CONV_DIL3, y, ys, PW(q + ".0.w"), H, hbuf, hs);
-      o.dil = 1 << dd; o.bias = P32(q + ".0.bias"); o.stats = st_h; o.stat_mode = freq ? STAT_PER_G1_M : STAT_PER_G1;
+      o.dil = 1 << dd; o.bias = P32(q + ".0.bias"); o.stats = st_h; o.stat_mode = smode;
       conv(o, st);
     }
     launch_finalize_gn(st_h, (double)H * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
     launch_gn_gelu<T>(hbuf, hs, G2, freq ? 1 : 0, mr, P32(q + ".1.weight"), P32(q + ".1.bias"), st); ++n_launches;
     {  // 1x1 expand C/8 -> 2C
       ConvOp<T> o = conv_op<T>(CONV_ROWS, hbuf, hs, PW(q + ".3.w"), 2 * C, ebuf, es);
-      o.bias = P32(q + ".3.bias"); o.stats = st_e; o.stat_mode = freq ? STAT_PER_G1_M : STAT_PER_G1;
+      o.bias = P32(q + ".3.bias"); o.stats = st_e; o.stat_mode = smode;
       conv(o, st);
     }
     launch_finalize_gn(st_e, (double)2 * C * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;

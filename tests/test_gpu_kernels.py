@@ -100,7 +100,8 @@ def test_chunk_gather_and_ola_bit_exact(T):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 128), (1000, 512, 384), (777, 96, 1536), (4144, 2048, 512),
-                                   (2072, 192, 96), (515, 64, 72)])
+                                   (2072, 192, 96), (515, 64, 72), (1000, 96, 48), (1000, 48, 32), (700, 48, 16),
+                                   (300, 16, 144), (260, 192, 16), (130, 384, 8)])
 def test_tcgen05_gemm_matches_fp32_matmul(M, N, K):
     """tcgen05/TMEM/TMA kernel: bf16 operands, fp32 accumulation, bf16 store.  K = 96 / 72 exercise the zero-filled
     partial K block, M not a multiple of 128 the row masking.  Tolerance: bf16 output rounding (4e-3 relative)."""
