@@ -32,12 +32,16 @@ void launch_sum_sumsq(const float* x, int B, long n_per_sample, double* stats, c
 }
 
 // (sum, sumsq) double accumulators -> (mean, rstd) floats, biased variance (GroupNorm semantics)
-__global__ void finalize_gn_kernel(const double* __restrict__ stats, double count, float* __restrict__ mr, long n) {
+__global__ void finalize_gn_kernel(const double* __restrict__ stats, double count, float* __restrict__ mr, long n, int nslot) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { float m, r; stats_to_mean_rstd(stats + 2 * i, count, 1e-5f, m, r); mr[2 * i] = m; mr[2 * i + 1] = r; }
+  if (i < n) {
+    double st[2] = {0.0, 0.0};
+    for (int s = 0; s < nslot; ++s) { st[0] += stats[2 * (i * nslot + s)]; st[1] += stats[2 * (i * nslot + s) + 1]; }
+    float m, r; stats_to_mean_rstd(st, count, 1e-5f, m, r); mr[2 * i] = m; mr[2 * i + 1] = r;
+  }
 }
-void launch_finalize_gn(const double* stats, double count, float* mr, long n, cudaStream_t st) {
-  finalize_gn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stats, count, mr, n);
+void launch_finalize_gn(const double* stats, double count, float* mr, long n, int nslot, cudaStream_t st) {
+  finalize_gn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stats, count, mr, n, nslot);
 }
 
 // torch.std default (unbiased) and the reference guard (x - mean) / (1e-5 + std)   ATHTDemucs_v2.py:268-275
@@ -253,42 +257,83 @@ __device__ __forceinline__ void lerp_coords(int d, int in, int out, int& i0, int
   i1 = i0 + (i0 < in - 1 ? 1 : 0);
   lam = src - (float)i0;
 }
-template <typename T>
+template <typename T, int VEC> struct VecIO;
+template <int VEC> struct VecIO<float, VEC> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) { float4 t = *(const float4*)(p + i); v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) *(float4*)(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+};
+template <int VEC> struct VecIO<bf16, VEC> {
+  static __device__ __forceinline__ void load(const bf16* p, float* v) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+      uint2 t = *(const uint2*)(p + i);
+      float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&t.x), c = __bfloat1622float2(*(const __nv_bfloat162*)&t.y);
+      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = c.x; v[i + 3] = c.y;
+    }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[i], v[i + 1]), c = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+      uint2 t; t.x = *(uint32_t*)&a; t.y = *(uint32_t*)&c;
+      *(uint2*)(p + i) = t;
+    }
+  }
+};
+
+template <typename T, int VEC>
 __global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, int Cu, T* __restrict__ out,
                                  RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
                                  const float* __restrict__ gw, const float* __restrict__ gb, const T* __restrict__ skip,
                                  RowSpace ss) {
-  const int C = os.C;
-  long total = (long)os.G * os.R * C;
+  const int CV = os.C / VEC;
+  long total = (long)os.G * os.R * CV;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C); long row = i / C;
+    int c = (int)(i % CV) * VEC; long row = i / CV;
     int d = (int)(row % os.R); int g = (int)(row / os.R);
     int i0, i1; float lam;
     lerp_coords(d, Uin, os.R, i0, i1, lam);
     // phase layout: output row fo = 4q + r - 2 lives in the row of x[q-1] (us geometry), columns r*Cu + c
-    float a0 = to_f<T>(u[us.row_off(g, ((i0 + 2) >> 2) - 1) + ((i0 + 2) & 3) * Cu + c]);
-    float a1 = to_f<T>(u[us.row_off(g, ((i1 + 2) >> 2) - 1) + ((i1 + 2) & 3) * Cu + c]);
+    float a0[VEC], a1[VEC], s0[VEC], s1[VEC], v[VEC];
+    VecIO<T, VEC>::load(u + us.row_off(g, ((i0 + 2) >> 2) - 1) + ((i0 + 2) & 3) * Cu + c, a0);
+    VecIO<T, VEC>::load(u + us.row_off(g, ((i1 + 2) >> 2) - 1) + ((i1 + 2) & 3) * Cu + c, a1);
     if (has_gn) {
       float mean = mr[2 * (g / G2)], rstd = mr[2 * (g / G2) + 1];
-      a0 = gelu_erf((a0 - mean) * rstd * gw[c] + gb[c]);
-      a1 = gelu_erf((a1 - mean) * rstd * gw[c] + gb[c]);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        float w = gw[c + k], bb = gb[c + k];
+        a0[k] = gelu_erf((a0[k] - mean) * rstd * w + bb);
+        a1[k] = gelu_erf((a1[k] - mean) * rstd * w + bb);
+      }
     }
-    float v = (1.f - lam) * a0 + lam * a1;
     int j0, j1; float mu;
     lerp_coords(d, ss.R, os.R, j0, j1, mu);
-    float s0 = to_f<T>(skip[ss.row_off(g, j0) + c]);
-    float s1 = to_f<T>(skip[ss.row_off(g, j1) + c]);
-    v += 0.1f * ((1.f - mu) * s0 + mu * s1);
-    out[os.row_off(g, d) + c] = from_f<T>(v);
+    VecIO<T, VEC>::load(skip + ss.row_off(g, j0) + c, s0);
+    VecIO<T, VEC>::load(skip + ss.row_off(g, j1) + c, s1);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = ((1.f - lam) * a0[k] + lam * a1[k]) + 0.1f * ((1.f - mu) * s0[k] + mu * s1[k]);
+    VecIO<T, VEC>::store(out + os.row_off(g, d) + c, v);
   }
 }
 template <typename T>
 void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace os, int G2, int has_gn,
                       const float* mr, const float* gw, const float* gb, const T* skip, RowSpace ss,
                       cudaStream_t st) {
-  long total = (long)os.G * os.R * os.C;
-  dec_apply_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(u, Uin, us, Cu, out, os, G2,
-                                                                                    has_gn, mr, gw, gb, skip, ss);
+  if (os.C % 8 == 0) {
+    long total = (long)os.G * os.R * (os.C / 8);
+    dec_apply_kernel<T, 8><<<(int)min((total + 255) / 256, (long)148 * 32), 256, 0, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw,
+                                                                                         gb, skip, ss);
+  } else {
+    long total = (long)os.G * os.R * (os.C / 4);
+    dec_apply_kernel<T, 4><<<(int)min((total + 255) / 256, (long)148 * 32), 256, 0, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw,
+                                                                                         gb, skip, ss);
+  }
 }
 
 // ------------------------------------------------------------------ weight packing (fp32 params -> T, GEMM layouts)

@@ -15,6 +15,9 @@ namespace athtd {
 
 enum { ACT_NONE = 0, ACT_GELU = 1 };
 enum { STAT_NONE = 0, STAT_PER_G1 = 1, STAT_PER_G1_M = 2 };
+// per-segment statistics are spread over STAT_SLOTS accumulator slots (slot = CTA index mod STAT_SLOTS) so that the
+// fp64 atomics of thousands of CTAs do not serialise on one L2 address; finalize_gn sums the slots.
+static constexpr int STAT_SLOTS = 64;
 
 struct GemmDesc {
   int G1, G2, Mg;

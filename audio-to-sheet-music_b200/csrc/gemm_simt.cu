@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
         if (g < 0) continue;
         if (g == gfirst) { s += red_s[r]; ss += red_ss[r]; }
         else {
-          atomicAdd(d.stats + 2 * (long)g, (double)red_s[r]);
-          atomicAdd(d.stats + 2 * (long)g + 1, (double)red_ss[r]);
+          atomicAdd(d.stats + 2 * ((long)g * STAT_SLOTS + blockIdx.x % STAT_SLOTS), (double)red_s[r]);
+          atomicAdd(d.stats + 2 * ((long)g * STAT_SLOTS + blockIdx.x % STAT_SLOTS) + 1, (double)red_ss[r]);
         }
       }
 #pragma unroll
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
         ss += __shfl_xor_sync(0xffffffffu, ss, o);
       }
       if (tid == 0 && gfirst >= 0) {
-        atomicAdd(d.stats + 2 * (long)gfirst, s);
-        atomicAdd(d.stats + 2 * (long)gfirst + 1, ss);
+        atomicAdd(d.stats + 2 * ((long)gfirst * STAT_SLOTS + blockIdx.x % STAT_SLOTS), s);
+        atomicAdd(d.stats + 2 * ((long)gfirst * STAT_SLOTS + blockIdx.x % STAT_SLOTS) + 1, ss);
       }
     }
   }

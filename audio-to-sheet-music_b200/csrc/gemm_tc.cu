@@ -222,9 +222,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (uniform) {
             float a = valid ? ssum : 0.f, c = valid ? ssq : 0.f;
             a = warp_sum(a); c = warp_sum(c);
-            if (lane == 0) { atomicAdd(p.stats + 2 * (long)key0, (double)a); atomicAdd(p.stats + 2 * (long)key0 + 1, (double)c); }
+            if (lane == 0) { double* sp = p.stats + 2 * ((long)key0 * STAT_SLOTS + (blockIdx.x + blockIdx.y) % STAT_SLOTS); atomicAdd(sp, (double)a); atomicAdd(sp + 1, (double)c); }
           } else if (valid) {
-            atomicAdd(p.stats + 2 * (long)b, (double)ssum); atomicAdd(p.stats + 2 * (long)b + 1, (double)ssq);
+            double* sp = p.stats + 2 * ((long)b * STAT_SLOTS + (blockIdx.x + blockIdx.y) % STAT_SLOTS); atomicAdd(sp, (double)ssum); atomicAdd(sp + 1, (double)ssq);
           }
         }
       }

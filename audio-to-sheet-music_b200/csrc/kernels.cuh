@@ -8,7 +8,7 @@ namespace athtd {
 
 // ---- elementwise.cu
 void launch_sum_sumsq(const float* x, int B, long n_per_sample, double* stats, cudaStream_t st);
-void launch_finalize_gn(const double* stats, double count, float* mr, long n, cudaStream_t st);
+void launch_finalize_gn(const double* stats, double count, float* mr, long n, int nslot, cudaStream_t st);
 void launch_finalize_meanstd(const double* stats, double n, float* out, int B, cudaStream_t st);
 template <typename T> void launch_pack_wav(const float* wav, const float* meanstd, T* out, RowSpace rs, int L, cudaStream_t st);
 template <typename T> void launch_pack_spec(const float* Z, const float* meanstd, T* out, RowSpace rs, int Tf, cudaStream_t st);

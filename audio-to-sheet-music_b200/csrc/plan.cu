@@ -106,10 +106,10 @@ void PlanT<T>::layout(char* base) {
     for (int d = 0; d < 2; ++d)
       for (int k = 0; k < 2; ++k) {
         st_df[i][d][k] = (double*)take(sizeof(double) * 2 * B * s.Fr[i + 1]);
-        st_dt[i][d][k] = (double*)take(sizeof(double) * 2 * B);
+        st_dt[i][d][k] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS);
       }
-  for (int l = 0; l < 5; ++l) { st_xf[l][0] = (double*)take(sizeof(double) * 2 * B); st_xf[l][1] = (double*)take(sizeof(double) * 2 * B); }
-  st_dec = (double*)take(sizeof(double) * 2 * B * 6 * s.P);
+  for (int l = 0; l < 5; ++l) { st_xf[l][0] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS); st_xf[l][1] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS); }
+  st_dec = (double*)take(sizeof(double) * 2 * B * 6 * s.P * STAT_SLOTS);
   stats_bytes = align_up(off, 256) - stats_begin;
   off = stats_begin + stats_bytes;
   // ---- plain scratch
@@ -313,14 +313,14 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
         o.dil = 1 << dd; o.bias = PA(q + ".0.bp"); o.stats = st_h; o.stat_mode = smode;
         conv(o, st);
       }
-      launch_finalize_gn(st_h, (double)H * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
+      launch_finalize_gn(st_h, (double)H * (freq ? s.Tf : R), mr, nstat, freq ? 1 : STAT_SLOTS, st); ++n_launches;
       launch_gn_gelu<T>(hbuf, hs, G2, freq ? 1 : 0, mr, PA(q + ".1.wp"), PA(q + ".1.bp"), st); ++n_launches;
       {
         ConvOp<T> o = conv_op<T>(CONV_ROWS, hbuf, hs, PW(q + ".3.wp"), 2 * C, y, ys);
         o.bias = PA(q + ".3.bi"); o.stats = st_e; o.stat_mode = smode; o.no_store = 1;
         conv(o, st);
       }
-      launch_finalize_gn(st_e, (double)2 * C * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
+      launch_finalize_gn(st_e, (double)2 * C * (freq ? s.Tf : R), mr, nstat, freq ? 1 : STAT_SLOTS, st); ++n_launches;
       {
         ConvOp<T> o = conv_op<T>(CONV_ROWS, hbuf, hs, PW(q + ".3.wp"), 2 * C, y, ys);
         o.bias = PA(q + ".3.bi"); o.gn_mr = mr; o.gn_w = PA(q + ".4.wi"); o.gn_b = PA(q + ".4.bi"); o.gn_mode = smode;
@@ -334,14 +334,14 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
       o.dil = 1 << dd; o.bias = P32(q + ".0.bias"); o.stats = st_h; o.stat_mode = smode;
       conv(o, st);
     }
-    launch_finalize_gn(st_h, (double)H * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
+    launch_finalize_gn(st_h, (double)H * (freq ? s.Tf : R), mr, nstat, freq ? 1 : STAT_SLOTS, st); ++n_launches;
     launch_gn_gelu<T>(hbuf, hs, G2, freq ? 1 : 0, mr, P32(q + ".1.weight"), P32(q + ".1.bias"), st); ++n_launches;
     {  // 1x1 expand C/8 -> 2C
       ConvOp<T> o = conv_op<T>(CONV_ROWS, hbuf, hs, PW(q + ".3.w"), 2 * C, ebuf, es);
       o.bias = P32(q + ".3.bias"); o.stats = st_e; o.stat_mode = smode;
       conv(o, st);
     }
-    launch_finalize_gn(st_e, (double)2 * C * (freq ? s.Tf : R), mr, nstat, st); ++n_launches;
+    launch_finalize_gn(st_e, (double)2 * C * (freq ? s.Tf : R), mr, nstat, freq ? 1 : STAT_SLOTS, st); ++n_launches;
     launch_gn_glu_res<T>(y, ys, ebuf, es, G2, freq ? 1 : 0, mr, P32(q + ".4.weight"), P32(q + ".4.bias"),
                          P32(q + ".6.scale"), st); ++n_launches;
   }
@@ -417,7 +417,7 @@ void PlanT<T>::xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x,
                       P32(p + "." + ffn_norm + ".bias"), nullptr, none, st); ++n_launches;
   linear(hn[0], S, 512, PW(p + ".linear1.w"), 2048, P32(p + ".linear1.bias"), ACT_GELU, ffn, st);
   linear_res(ffn, S, 2048, PW(p + ".linear2.w"), 512, P32(p + ".linear2.bias"), P32(p + ".gamma_2.scale"), x, stats, st);
-  launch_finalize_gn(stats, (double)S * 512, mr, sh.B, st); ++n_launches;
+  launch_finalize_gn(stats, (double)S * 512, mr, sh.B, STAT_SLOTS, st); ++n_launches;
   launch_norm_rows<T>(x, x, nullptr, rows, 512, S, mr, P32(p + ".norm_out.weight"), P32(p + ".norm_out.bias"), nullptr,
                       nullptr, nullptr, none, st); ++n_launches;
 }
@@ -555,13 +555,13 @@ void PlanT<T>::dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* ou
   const int G2 = xs.G2;
   const int Rin = xs.R;
   const std::string q = std::string(freq ? "freq_decoder" : "time_decoder") + ".layers." + std::to_string(i);
-  double* stt = st_dec + 2L * s.B * ((size_t)p * 6 + (freq ? 0 : 3) + (i < 3 ? i : 0));
+  double* stt = st_dec + 2L * s.B * STAT_SLOTS * ((size_t)p * 6 + (freq ? 0 : 3) + (i < 3 ? i : 0));
   RowSpace us = xs; us.C = 4 * Cout;
   ConvOp<T> o = conv_op<T>(CONV_T, x, xs, PW(q + ".0.w"), 4 * Cout, ubuf, us);
   o.bias = PA(q + ".0.b4");
   if (i < 3) { o.stats = stt; o.stat_mode = STAT_PER_G1; }
   conv(o, st);
-  if (i < 3) { launch_finalize_gn(stt, (double)Cout * 4.0 * Rin * G2, mr, s.B, st); ++n_launches; }
+  if (i < 3) { launch_finalize_gn(stt, (double)Cout * 4.0 * Rin * G2, mr, s.B, STAT_SLOTS, st); ++n_launches; }
   launch_dec_apply<T>(ubuf, 4 * Rin, us, Cout, out, os, G2, i < 3 ? 1 : 0, mr, i < 3 ? P32(q + ".1.weight") : nullptr,
                       i < 3 ? P32(q + ".1.bias") : nullptr, skip, ss, st); ++n_launches;
 }
