@@ -178,6 +178,8 @@ int athtd_gemm_test(const void* A_dev, const void* B_dev, const float* bias_dev,
     f.A = A_dev; f.a_rows = M; f.a_pitch = K; f.Ktap = K; f.ntaps = 1; f.B = B_dev; f.N = N; f.Mflat = M;
     f.RpA = M; f.G2p = 1; f.gpf = 0; f.G2 = 1; f.vlo = 0; f.vhi = M; f.oG2p = 1; f.ogsh = 0; f.oRp = M; f.orsh = 0;
     f.ldc = N; f.C = C_dev; f.alpha = 1.0f; f.bias = bias_dev;
+    if (use_tensor_cores == 2) f.no_store = 1;     // micro-benchmark variants (tools/gemm_bench.py)
+    if (use_tensor_cores == 3) { f.dbg = (void*)bias_dev; f.bias = nullptr; }   // bias_dev doubles as a long long[512*8] stamp buffer
     if (!tc_flat_supported(f)) return fail("athtd_gemm_test: shape not supported by the tcgen05 kernel");
     if (launch_gemm_tc_flat(f, (cudaStream_t)stream) != 0) return fail("athtd_gemm_test: cuTensorMapEncodeTiled failed");
   } else if (dtype == 0) launch_gemm_simt<float>(d, (cudaStream_t)stream);

@@ -65,6 +65,7 @@ struct TcFlat {
   int n_store;          // store only the first n_store output columns (0 = all): zero-padded hidden channels
   int no_store;         // statistics-only pass (the GroupNorm'd result is recomputed by a second pass instead of stored)
   const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;   // GroupNorm apply right after the bias
+  void* dbg;            // optional phase timestamps (micro-benchmark only)
 };
 bool tensor_map_api_available();              // cuTensorMapEncodeTiled reachable through the runtime's driver entry point
 bool tc_flat_supported(const TcFlat& f);

@@ -43,7 +43,10 @@ struct TcParams {
   double* stats; int stat_mode; int statR;
   const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;
   int convt_cout;
+  long long* dbg;      // optional per-CTA phase timestamps (tools/gemm_bench.py), nullptr in production
 };
+
+#define TC_STAMP(slot) do { if (p.dbg && blockIdx.y == 0 && blockIdx.x < 512) p.dbg[(long)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void store8(bf16* dst, const float* v) {
   uint32_t pk[4];
@@ -58,7 +61,25 @@ __device__ __forceinline__ void load8_add(const bf16* src, float* v) {
   for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
 }
 
+// epilogue feature flags (compile-time): unused stages must not cost issue slots
+enum { EF_GELU = 1, EF_GLU = 2, EF_GN = 4, EF_POST = 8, EF_STATS = 16 };
+
+// bf16 build only: exact-erf GELU / sigmoid evaluated with the SFU exponential.  erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below bf16 resolution); the fp32 build keeps erff()/expf() in its own kernels.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);       // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+
 // ------------------------------------------------------------------ kernel
+template <int EF>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -73,6 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TC_STAMP(0);
   const int row0 = blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * p.BN;
   const int nkb = p.ntaps * p.kb_per_tap;
@@ -95,6 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -110,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_load_2d(smem_u32(sA + s * stageA), &tmA, fb, kin, row0 + p.tapRow[tap]);
         tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
       }
+      TC_STAMP(2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -129,9 +153,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(smem_u32(&empty[s]));
       }
       umma_commit(smem_u32(tfull));
+      TC_STAMP(3);
     }
   } else {
-    // ---------------- epilogue: thread <-> accumulator row (TMEM lane)
+    // ---------------- epilogue: thread <-> accumulator row (TMEM lane).  EF compiles unused stages out: the
+    // if-converted generic version issued ~4400 instructions per 32-column chunk and dominated the kernel.
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const long rho = (long)row0 + row;
@@ -142,73 +168,88 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool valid = rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2;
     const long orow = ((long)b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
     const int m = fp - p.vlo;
-    const int Nout = p.glu ? p.N / 2 : p.N;
+    const int Nout = (EF & EF_GLU) ? p.N / 2 : p.N;
     float gmean = 0.f, grstd = 1.f;
-    if (p.gn_mr && valid) {
+    if ((EF & EF_GN) && valid) {
       const long gi = p.gn_mode == STAT_PER_G1_M ? (long)b * p.statR + m : (long)b;
       gmean = p.gn_mr[2 * gi]; grstd = p.gn_mr[2 * gi + 1];
     }
+    const bool edge_row = p.convt_cout > 0 && (m == 0 || m == p.vhi - p.vlo - 1);
     float ssum = 0.f, ssq = 0.f;
     mbar_wait(smem_u32(tfull), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (threadIdx.x == 64) TC_STAMP(4);
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int ncol = n0 + c0;
       const int nc = min(32, min(p.BN - c0, p.N - ncol));      // valid accumulator columns in this chunk (multiple of 8)
       if (!valid || nc <= 0) continue;
+      const int nlast = p.N - 1;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float x = 0.f;
-        if (j < nc) {
-          x = p.alpha * __uint_as_float(r[j]);
-          if (p.bias) x += p.bias[ncol + j];
-          if (p.gn_mr) x = (x - gmean) * grstd * p.gn_w[ncol + j] + p.gn_b[ncol + j];
-          if (p.act == ACT_GELU) x = gelu_erf(x);
-        }
+        const int n = min(ncol + j, nlast);                    // columns past N hold garbage and are never stored
+        float x = __uint_as_float(r[j]);
+        if (p.bias) x += __ldg(p.bias + n);
+        if (EF & EF_GN) x = (x - gmean) * grstd * __ldg(p.gn_w + n) + __ldg(p.gn_b + n);
+        if (EF & EF_GELU) x = gelu_fast(x);
         v[j] = x;
       }
       int no = ncol, nco = nc;             // output column base / count
-      if (p.glu) {
+      if (EF & EF_GLU) {
         no = ncol >> 1; nco = nc >> 1;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * sigmoid_acc(v[2 * j + 1]);
+        for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * sigmoid_fast(v[2 * j + 1]);
       }
-      if (p.colscale || p.rowtab) {
+      if (EF & EF_POST) {
+        const int olast = Nout - 1;
+        if (p.colscale) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nco) {
-            if (p.colscale) v[j] *= p.colscale[no + j];
-            if (p.rowtab) v[j] += p.rowtab_scale * p.rowtab[(long)m * Nout + no + j];
+          for (int j = 0; j < ((EF & EF_GLU) ? 16 : 32); ++j) v[j] *= __ldg(p.colscale + min(no + j, olast));
+        }
+        if (p.rowtab) {
+#pragma unroll
+          for (int j = 0; j < ((EF & EF_GLU) ? 16 : 32); ++j) v[j] += p.rowtab_scale * __ldg(p.rowtab + (long)m * Nout + min(no + j, olast));
+        }
+        if (p.res) {
+          const bf16* rp = (const bf16*)p.res + orow * p.ldc + no;
+#pragma unroll
+          for (int g = 0; g < ((EF & EF_GLU) ? 2 : 4); ++g)
+            if (8 * g < nco) load8_add(rp + 8 * g, v + 8 * g);
+        }
+      }
+      if (EF & EF_STATS) {
+        if (!edge_row && nco == ((EF & EF_GLU) ? 16 : 32)) {
+#pragma unroll
+          for (int j = 0; j < ((EF & EF_GLU) ? 16 : 32); ++j) { ssum += v[j]; ssq += v[j] * v[j]; }
+        } else {
+          // transposed conv: rows -2,-1 (q==0, phases 0,1) and 4F,4F+1 (last q, phases 2,3) are cropped
+          const int cout = max(p.convt_cout, 1);
+          const int ph0 = edge_row ? no / cout : 0;
+          const int rem0 = edge_row ? no - ph0 * cout : 0;
+#pragma unroll
+          for (int j = 0; j < ((EF & EF_GLU) ? 16 : 32); ++j) {
+            bool counted = j < nco;
+            if (edge_row) {
+              const int rem = rem0 + j;
+              const int phase = ph0 + (rem >= cout ? 1 : 0) + (rem >= 2 * cout ? 1 : 0) + (rem >= 3 * cout ? 1 : 0);
+              counted = counted && !((m == 0 && phase < 2) || (m != 0 && phase >= 2));
+            }
+            if (counted) { ssum += v[j]; ssq += v[j] * v[j]; }
           }
-      }
-      if (p.res) {
-        const bf16* rp = (const bf16*)p.res + orow * p.ldc + no;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (8 * g < nco) load8_add(rp + 8 * g, v + 8 * g);
-      }
-      if (p.stat_mode != STAT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          bool counted = j < nco;
-          if (p.convt_cout > 0) {
-            const int phase = (no + j) / p.convt_cout;
-            counted = counted && !((m == 0 && phase < 2) || (m == p.vhi - p.vlo - 1 && phase >= 2));
-          }
-          if (counted) { ssum += v[j]; ssq += v[j] * v[j]; }
         }
       }
       if (!p.no_store) {
         bf16* cp = (bf16*)p.C + orow * p.ldc + no;
         const int nst_cols = min(nco, p.n_store - no);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+        for (int g = 0; g < ((EF & EF_GLU) ? 2 : 4); ++g)
           if (8 * g < nst_cols) store8(cp + 8 * g, v + 8 * g);
       }
     }
-    if (p.stat_mode != STAT_NONE) {
+    if (threadIdx.x == 64) TC_STAMP(5);
+    if (EF & EF_STATS) {
       if (p.stat_mode == STAT_PER_G1_M) {
         if (valid) {
           double* st = p.stats + 2 * ((long)b * p.statR + m);
@@ -232,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -274,7 +316,6 @@ bool tensor_map_api_available() { return get_encode() != nullptr; }
 int tc_pick_bn(int N) {
   if (N % 16) return 0;
   if (N <= 256) return N;
-  if (N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
   if (N % 192 == 0) return 192;
   if (N % 64 == 0) return 64;
@@ -304,21 +345,43 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   p.no_store = f.no_store;
   p.colscale = f.colscale; p.res = f.res; p.rowtab = f.rowtab; p.rowtab_scale = f.rowtab_scale;
   p.stats = f.stats; p.stat_mode = f.stat_mode; p.statR = f.statR; p.convt_cout = f.convt_cout;
-  p.gn_mr = f.gn_mr; p.gn_w = f.gn_w; p.gn_b = f.gn_b; p.gn_mode = f.gn_mode;
+  p.gn_mr = f.gn_mr; p.gn_w = f.gn_w; p.gn_b = f.gn_b; p.gn_mode = f.gn_mode; p.dbg = (long long*)f.dbg;
   CUtensorMap tmA, tmB;
   if (!make_tensor_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
   if (!make_tensor_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
   p.stages = p.BN > 128 ? 4 : 3;      // <= 97 KB for BN <= 128: two CTAs per SM overlap epilogue and main loop
   const int stageB = ((p.BN * TC_BK * 2) + 1023) & ~1023;
   const size_t smem = 1024 + (size_t)p.stages * (TC_BM * TC_BK * 2 + stageB) + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + TC_MAX_STAGES * (16384 + 32768) + 256);
-    attr_set = true;
-  }
   dim3 grid((unsigned)((f.Mflat + TC_BM - 1) / TC_BM), (unsigned)((f.N + p.BN - 1) / p.BN));
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
-  return 0;
+  int ef = 0;
+  if (f.act == ACT_GELU) ef |= EF_GELU;
+  if (f.glu) ef |= EF_GLU;
+  if (f.gn_mr) ef |= EF_GN;
+  if (f.colscale || f.rowtab || f.res) ef |= EF_POST;
+  if (f.stat_mode != STAT_NONE) ef |= EF_STATS;
+#define TC_LAUNCH(E)                                                                                                      \
+  case E: {                                                                                                               \
+    static bool attr_set = false;                                                                                         \
+    if (!attr_set) {                                                                                                      \
+      cudaFuncSetAttribute(gemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,                                \
+                           1024 + TC_MAX_STAGES * (16384 + 32768) + 256);                                                 \
+      attr_set = true;                                                                                                    \
+    }                                                                                                                     \
+    gemm_tc_kernel<E><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);                                                       \
+    return 0;                                                                                                             \
+  }
+  switch (ef) {
+    TC_LAUNCH(0)
+    TC_LAUNCH(EF_GELU)
+    TC_LAUNCH(EF_STATS)
+    TC_LAUNCH(EF_POST)
+    TC_LAUNCH(EF_POST | EF_STATS)
+    TC_LAUNCH(EF_GLU)
+    TC_LAUNCH(EF_GLU | EF_POST)
+    TC_LAUNCH(EF_GLU | EF_GN | EF_POST)
+    default: return 5;     // unsupported epilogue combination
+  }
+#undef TC_LAUNCH
 }
 
 }  // namespace athtd
