@@ -5,3 +5,4 @@ from .model import AudioTextHTDemucsB200, HTDemucsParams, TextCrossAttention, Fr
 from .separation import (B200SeparationModel, SeparationModel, STEMS, segment_plan, OlaTables, gather_chunks,  # noqa: F401
                          chunk_ola)
 from .engine import Engine, Plan                                     # noqa: F401
+from . import distributed                                     # noqa: F401

@@ -146,25 +146,13 @@ def main():
     emb = emb.to(dev)
     plan = athtd_b200.segment_plan(T)
     n = len(plan.starts)
-    k0, k1 = rank * n // world, (rank + 1) * n // world
-    lo, hi = plan.starts[k0], (T if k1 == n else plan.starts[k1])
-    in_lo, in_hi = plan.starts[k0], min(T, plan.starts[k1 - 1] + plan.chunk_len)
+    k0, k1 = athtd_b200.distributed.partition_chunks(n, world)[rank]
+    lo, hi = athtd_b200.distributed.span_sample_range(plan.starts, T, (k0, k1))
+    in_lo, in_hi = athtd_b200.distributed.span_input_range(plan.starts, T, plan.chunk_len, (k0, k1))
     track_dev = track_host.to(dev)
     out_host = torch.empty(args.prompts, 2, hi - lo).pin_memory()
 
-    def halo_exchange(halo_out):
-        """one neighbour exchange: last chunk's raw output goes to rank+1"""
-        if world == 1:
-            return None
-        ops, recv = [], None
-        if rank + 1 < world:
-            ops.append(dist.P2POp(dist.isend, halo_out.contiguous(), rank + 1))
-        if rank > 0:
-            recv = torch.empty_like(halo_out)
-            ops.append(dist.P2POp(dist.irecv, recv, rank - 1))
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-        return recv
+    halo_exchange = athtd_b200.distributed.make_halo_exchange(rank, world)
 
     def step(track):
         # span outputs need the left neighbour's last chunk: run own chunks first, exchange, then overlap-add
