@@ -261,9 +261,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool uniform = __all_sync(0xffffffffu, key == key0 || key == -1);
         if (key0 >= 0) {
           if (uniform) {
-            float a = valid ? ssum : 0.f, c = valid ? ssq : 0.f;
-            a = warp_sum(a); c = warp_sum(c);
-            if (lane == 0) { double* sp = p.stats + 2 * ((long)key0 * STAT_SLOTS + (blockIdx.x + blockIdx.y) % STAT_SLOTS); atomicAdd(sp, (double)a); atomicAdd(sp + 1, (double)c); }
+            // rows are combined in fp64 so that the result does not depend on which rows share a warp / tile,
+            // i.e. on the position of a segment inside the batch (multi-GPU spans must reproduce one-GPU bits)
+            double a = valid ? (double)ssum : 0.0, c = valid ? (double)ssq : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+            if (lane == 0) { double* sp = p.stats + 2 * ((long)key0 * STAT_SLOTS + (blockIdx.x + blockIdx.y) % STAT_SLOTS); atomicAdd(sp, a); atomicAdd(sp + 1, c); }
           } else if (valid) {
             double* sp = p.stats + 2 * ((long)b * STAT_SLOTS + (blockIdx.x + blockIdx.y) % STAT_SLOTS); atomicAdd(sp, (double)ssum); atomicAdd(sp + 1, (double)ssq);
           }
