@@ -65,8 +65,10 @@ struct TcFlat {
   int n_store;          // store only the first n_store output columns (0 = all): zero-padded hidden channels
   int no_store;         // statistics-only pass (the GroupNorm'd result is recomputed by a second pass instead of stored)
   const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;   // GroupNorm apply right after the bias
-  void* dbg;            // optional phase timestamps (micro-benchmark only)
+  void* dbg;            // unused (kept for the micro-benchmark ABI)
+  int skip_lo, skip_hi; // output columns [skip_lo, skip_hi) feed the statistics but are not stored
 };
+void tc_set_bn_cap(int cap);   // 128 or 256: largest N tile (A/B tuning knob)
 bool tensor_map_api_available();              // cuTensorMapEncodeTiled reachable through the runtime's driver entry point
 bool tc_flat_supported(const TcFlat& f);
 int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st);   // bf16 in, fp32 accumulate; 0 = launched

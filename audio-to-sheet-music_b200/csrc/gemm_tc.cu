@@ -9,12 +9,16 @@
 // computed and discarded by the epilogue's validity decode.  Ktap need not be a multiple of the 64-element K block:
 // the TMA box is clipped by the tensor-map extent (zero fill) and only ceil(k/16) MMAs are issued.
 //
-// Structure (one 128 x BN tile per CTA, 192 threads, up to two CTAs per SM):
-//   warp 0      : TMA producer  - cp.async.bulk.tensor.2d (SWIZZLE_128B boxes 64 x 128 / 64 x BN) into a 3-4 stage ring
+// PERSISTENT, warp-specialised kernel: one CTA per SM loops over 128 x BN output tiles (n fastest, so the CTAs that
+// share an A tile run together and it is fetched from HBM once):
+//   warp 0      : TMA producer  - cp.async.bulk.tensor.2d (SWIZZLE_128B boxes 64 x 128 / 64 x BN) into a deep smem ring
+//                 that runs ahead ACROSS tiles (hides the ~1 us load latency of the short-K layers)
 //   warp 1      : TMEM allocator + MMA issuer - one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//                 (M=128, N=BN, K=16), tcgen05.commit releases the stage / signals the epilogue
-//   warps 2..5  : epilogue - tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused bias / GroupNorm apply /
-//                 GELU / GLU / LayerScale / residual / frequency-embedding / GroupNorm partial sums, 16-byte stores
+//                 (M=128, N=BN, K=16) into one of TWO TMEM accumulators; tcgen05.commit frees the smem stage /
+//                 hands the accumulator to the epilogue
+//   warps 2..9  : epilogue (2 warps per TMEM lane quarter, interleaved 32-column chunks) - tcgen05.ld, fused bias /
+//                 GroupNorm apply / GELU / GLU / LayerScale / residual / frequency-embedding / GroupNorm partial
+//                 sums, 16-byte stores; overlaps the next tile's main loop through the second accumulator
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
@@ -24,11 +28,13 @@ namespace athtd {
 
 static constexpr int TC_BM = 128;
 static constexpr int TC_BK = 64;
-static constexpr int TC_MAX_STAGES = 4;
-static constexpr int TC_THREADS = 192;
+static constexpr int TC_MAX_STAGES = 8;
+static constexpr int TC_THREADS = 320;
+static constexpr int TC_EPI_WARPS = 8;
 
 struct TcParams {
   int Mflat, N, BN, stages;
+  int m_tiles, n_tiles;
   int ntaps, kb_per_tap, Ktap;
   int tapRow[3];
   // flat row -> (b, t', f') decode and validity
@@ -37,16 +43,14 @@ struct TcParams {
   int oG2p, ogsh, oRp, orsh;
   long ldc;
   void* C; int n_store; int no_store;
-  float alpha; const float* bias; int act; int glu; const float* colscale;
+  const float* bias; const float* colscale;
   const void* res;
   const float* rowtab; float rowtab_scale;
   double* stats; int stat_mode; int statR;
   const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;
   int convt_cout;
-  long long* dbg;      // optional per-CTA phase timestamps (tools/gemm_bench.py), nullptr in production
+  int skip_lo, skip_hi;    // output columns [skip_lo, skip_hi) are computed (statistics) but not stored
 };
-
-#define TC_STAMP(slot) do { if (p.dbg && blockIdx.y == 0 && blockIdx.x < 512) p.dbg[(long)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void store8(bf16* dst, const float* v) {
   uint32_t pk[4];
@@ -61,7 +65,8 @@ __device__ __forceinline__ void load8_add(const bf16* src, float* v) {
   for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
 }
 
-// epilogue feature flags (compile-time): unused stages must not cost issue slots
+// epilogue feature flags (compile-time): unused stages must not cost issue slots (an if-converted generic epilogue
+// issued ~4400 instructions per 32-column chunk and dominated the kernel)
 enum { EF_GELU = 1, EF_GLU = 2, EF_GN = 4, EF_POST = 8, EF_STATS = 16 };
 
 // bf16 build only: exact-erf GELU / sigmoid evaluated with the SFU exponential.  erf by Abramowitz-Stegun 7.1.26
@@ -78,34 +83,112 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
+// per-row state of one epilogue thread for one tile
+struct EpiRow {
+  bool valid, edge_row;
+  long orow;
+  int b, m;
+  float gmean, grstd;
+};
+
+// One 32-column chunk of one accumulator row: r[] = raw fp32 accumulators of columns [ncol, ncol+32).
+template <int EF>
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& er, const uint32_t (&r)[32], int ncol, int nc,
+                                               float& ssum, float& ssq) {
+  constexpr int NV = (EF & EF_GLU) ? 16 : 32;
+  const int Nout = (EF & EF_GLU) ? p.N / 2 : p.N;
+  const int nlast = p.N - 1;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int n = min(ncol + j, nlast);                    // columns past N hold garbage and are never stored
+    float x = __uint_as_float(r[j]);
+    if (p.bias) x += __ldg(p.bias + n);
+    if (EF & EF_GN) x = (x - er.gmean) * er.grstd * __ldg(p.gn_w + n) + __ldg(p.gn_b + n);
+    if (EF & EF_GELU) x = gelu_fast(x);
+    v[j] = x;
+  }
+  int no = ncol, nco = nc;             // output column base / count
+  if (EF & EF_GLU) {
+    no = ncol >> 1; nco = nc >> 1;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * sigmoid_fast(v[2 * j + 1]);
+  }
+  if (EF & EF_POST) {
+    const int olast = Nout - 1;
+    if (p.colscale) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] *= __ldg(p.colscale + min(no + j, olast));
+    }
+    if (p.rowtab) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] += p.rowtab_scale * __ldg(p.rowtab + (long)er.m * Nout + min(no + j, olast));
+    }
+    if (p.res) {
+      const bf16* rp = (const bf16*)p.res + er.orow * p.ldc + no;
+#pragma unroll
+      for (int g = 0; g < NV / 8; ++g)
+        if (8 * g < nco) load8_add(rp + 8 * g, v + 8 * g);
+    }
+  }
+  if (EF & EF_STATS) {
+    if (!er.edge_row && nco == NV) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) { ssum += v[j]; ssq += v[j] * v[j]; }
+    } else {
+      // transposed conv: rows -2,-1 (q==0, phases 0,1) and 4F,4F+1 (last q, phases 2,3) are cropped
+      const int cout = max(p.convt_cout, 1);
+      const int ph0 = er.edge_row ? no / cout : 0;
+      const int rem0 = er.edge_row ? no - ph0 * cout : 0;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        bool counted = j < nco;
+        if (er.edge_row) {
+          const int rem = rem0 + j;
+          const int phase = ph0 + (rem >= cout ? 1 : 0) + (rem >= 2 * cout ? 1 : 0) + (rem >= 3 * cout ? 1 : 0);
+          counted = counted && !((er.m == 0 && phase < 2) || (er.m != 0 && phase >= 2));
+        }
+        if (counted) { ssum += v[j]; ssq += v[j] * v[j]; }
+      }
+    }
+  }
+  if (!p.no_store) {
+    bf16* cp = (bf16*)p.C + er.orow * p.ldc + no;
+    const int nst_cols = min(nco, p.n_store - no);
+#pragma unroll
+    for (int g = 0; g < NV / 8; ++g) {
+      const int c = no + 8 * g;
+      if (8 * g < nst_cols && !(c >= p.skip_lo && c < p.skip_hi)) store8(cp + 8 * g, v + 8 * g);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ kernel
 template <int EF>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stageA = TC_BM * TC_BK * 2;
-  const int stageB = ((p.BN * TC_BK * 2) + 1023) & ~1023;
+  const int stageB = p.BN * TC_BK * 2;             // BN multiple of 8 -> multiple of 1024 B
   const int nst = p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + nst * stageA;
   uint64_t* bars = (uint64_t*)(sB + nst * stageB);
-  uint64_t* full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_MAX_STAGES + 1);
+  uint64_t* full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES, *tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) TC_STAMP(0);
-  const int row0 = blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * p.BN;
   const int nkb = p.ntaps * p.kb_per_tap;
+  const int n_total_tiles = p.m_tiles * p.n_tiles;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(2 * p.BN)) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
     for (int s = 0; s < nst; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
-    mbar_init(smem_u32(tfull), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull[i]), 1); mbar_init(smem_u32(&tempty[i]), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -117,158 +200,115 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(stageA + p.BN * TC_BK * 2);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % nst;
-        const uint32_t ph = (uint32_t)(kb / nst) & 1u;
-        mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
-        const int tap = kb / p.kb_per_tap;
-        const int kin = (kb - tap * p.kb_per_tap) * TC_BK;
-        const uint32_t fb = smem_u32(&full[s]);
-        mbar_expect_tx(fb, bytes);
-        tma_load_2d(smem_u32(sA + s * stageA), &tmA, fb, kin, row0 + p.tapRow[tap]);
-        tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
+      const uint32_t bytes = (uint32_t)(stageA + stageB);
+      int it = 0;
+      for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x) {
+        const int row0 = (t / p.n_tiles) * TC_BM;
+        const int n0 = (t % p.n_tiles) * p.BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % nst;
+          const uint32_t ph = (uint32_t)(it / nst) & 1u;
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+          const int tap = kb / p.kb_per_tap;
+          const int kin = (kb - tap * p.kb_per_tap) * TC_BK;
+          const uint32_t fb = smem_u32(&full[s]);
+          mbar_expect_tx(fb, bytes);
+          tma_load_2d(smem_u32(sA + s * stageA), &tmA, fb, kin, row0 + p.tapRow[tap]);
+          tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
+        }
       }
-      TC_STAMP(2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % nst;
-        const uint32_t ph = (uint32_t)(kb / nst) & 1u;
-        mbar_wait(smem_u32(&full[s]), ph);
+      int it = 0, i = 0;
+      for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x, ++i) {
+        const int buf = i & 1;
+        mbar_wait(smem_u32(&tempty[buf]), ((uint32_t)(i >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = make_sw128_desc(smem_u32(sA + s * stageA));
-        const uint64_t db = make_sw128_desc(smem_u32(sB + s * stageB));
-        const int kin = (kb % p.kb_per_tap) * TC_BK;
-        const int nmma = (min(TC_BK, p.Ktap - kin) + 15) >> 4;     // columns past Ktap are zero-filled by TMA
-        for (int k = 0; k < nmma; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
-          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-        umma_commit(smem_u32(&empty[s]));
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % nst;
+          const uint32_t ph = (uint32_t)(it / nst) & 1u;
+          mbar_wait(smem_u32(&full[s]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_sw128_desc(smem_u32(sA + s * stageA));
+          const uint64_t db = make_sw128_desc(smem_u32(sB + s * stageB));
+          const int kin = (kb % p.kb_per_tap) * TC_BK;
+          const int nmma = (min(TC_BK, p.Ktap - kin) + 15) >> 4;     // columns past Ktap are zero-filled by TMA
+          for (int k = 0; k < nmma; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
+            umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(smem_u32(&empty[s]));
+        }
+        umma_commit(smem_u32(&tfull[buf]));
       }
-      umma_commit(smem_u32(tfull));
-      TC_STAMP(3);
     }
   } else {
-    // ---------------- epilogue: thread <-> accumulator row (TMEM lane).  EF compiles unused stages out: the
-    // if-converted generic version issued ~4400 instructions per 32-column chunk and dominated the kernel.
+    // ---------------- epilogue warps: thread <-> accumulator row (TMEM lane), two warps per lane quarter
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const long rho = (long)row0 + row;
-    int q2 = (int)(rho / p.RpA);
-    const int fp = (int)(rho - (long)q2 * p.RpA);
-    const int b = q2 / p.G2p;
-    const int tp = q2 - b * p.G2p;
-    const bool valid = rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2;
-    const long orow = ((long)b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
-    const int m = fp - p.vlo;
-    const int Nout = (EF & EF_GLU) ? p.N / 2 : p.N;
-    float gmean = 0.f, grstd = 1.f;
-    if ((EF & EF_GN) && valid) {
-      const long gi = p.gn_mode == STAT_PER_G1_M ? (long)b * p.statR + m : (long)b;
-      gmean = p.gn_mr[2 * gi]; grstd = p.gn_mr[2 * gi + 1];
-    }
-    const bool edge_row = p.convt_cout > 0 && (m == 0 || m == p.vhi - p.vlo - 1);
-    float ssum = 0.f, ssq = 0.f;
-    mbar_wait(smem_u32(tfull), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (threadIdx.x == 64) TC_STAMP(4);
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      const int ncol = n0 + c0;
-      const int nc = min(32, min(p.BN - c0, p.N - ncol));      // valid accumulator columns in this chunk (multiple of 8)
-      if (!valid || nc <= 0) continue;
-      const int nlast = p.N - 1;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = min(ncol + j, nlast);                    // columns past N hold garbage and are never stored
-        float x = __uint_as_float(r[j]);
-        if (p.bias) x += __ldg(p.bias + n);
-        if (EF & EF_GN) x = (x - gmean) * grstd * __ldg(p.gn_w + n) + __ldg(p.gn_b + n);
-        if (EF & EF_GELU) x = gelu_fast(x);
-        v[j] = x;
+    int i = 0;
+    for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x, ++i) {
+      const int buf = i & 1;
+      const int row0 = (t / p.n_tiles) * TC_BM;
+      const int n0 = (t % p.n_tiles) * p.BN;
+      EpiRow er;
+      const long rho = (long)row0 + row;
+      const int q2 = (int)(rho / p.RpA);
+      const int fp = (int)(rho - (long)q2 * p.RpA);
+      er.b = q2 / p.G2p;
+      const int tp = q2 - er.b * p.G2p;
+      er.valid = rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2;
+      er.orow = ((long)er.b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
+      er.m = fp - p.vlo;
+      er.gmean = 0.f; er.grstd = 1.f;
+      if ((EF & EF_GN) && er.valid) {
+        const long gi = p.gn_mode == STAT_PER_G1_M ? (long)er.b * p.statR + er.m : (long)er.b;
+        er.gmean = p.gn_mr[2 * gi]; er.grstd = p.gn_mr[2 * gi + 1];
       }
-      int no = ncol, nco = nc;             // output column base / count
-      if (EF & EF_GLU) {
-        no = ncol >> 1; nco = nc >> 1;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * sigmoid_fast(v[2 * j + 1]);
+      er.edge_row = p.convt_cout > 0 && (er.m == 0 || er.m == p.vhi - p.vlo - 1);
+      float ssum = 0.f, ssq = 0.f;
+      mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 32 * half; c0 < p.BN; c0 += 64) {
+        uint32_t r[32];
+        tmem_ld32(tacc + (uint32_t)c0, r);
+        const int ncol = n0 + c0;
+        const int nc = min(32, min(p.BN - c0, p.N - ncol));      // valid accumulator columns in this chunk (multiple of 8)
+        if (er.valid && nc > 0) epilogue_chunk<EF>(p, er, r, ncol, nc, ssum, ssq);
       }
-      if (EF & EF_POST) {
-        const int olast = Nout - 1;
-        if (p.colscale) {
-#pragma unroll
-          for (int j = 0; j < ((EF & EF_GLU) ? 16 : 32); ++j) v[j] *= __ldg(p.colscale + min(no + j, olast));
-        }
-        if (p.rowtab) {
-#pragma unroll
-          for (int j = 0; j < ((EF & EF_GLU) ? 16 : 32); ++j) v[j] += p.rowtab_scale * __ldg(p.rowtab + (long)m * Nout + min(no + j, olast));
-        }
-        if (p.res) {
-          const bf16* rp = (const bf16*)p.res + orow * p.ldc + no;
-#pragma unroll
-          for (int g = 0; g < ((EF & EF_GLU) ? 2 : 4); ++g)
-            if (8 * g < nco) load8_add(rp + 8 * g, v + 8 * g);
-        }
-      }
+      // this warp is done reading the accumulator: release it to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[buf])) : "memory");
       if (EF & EF_STATS) {
-        if (!edge_row && nco == ((EF & EF_GLU) ? 16 : 32)) {
-#pragma unroll
-          for (int j = 0; j < ((EF & EF_GLU) ? 16 : 32); ++j) { ssum += v[j]; ssq += v[j] * v[j]; }
-        } else {
-          // transposed conv: rows -2,-1 (q==0, phases 0,1) and 4F,4F+1 (last q, phases 2,3) are cropped
-          const int cout = max(p.convt_cout, 1);
-          const int ph0 = edge_row ? no / cout : 0;
-          const int rem0 = edge_row ? no - ph0 * cout : 0;
-#pragma unroll
-          for (int j = 0; j < ((EF & EF_GLU) ? 16 : 32); ++j) {
-            bool counted = j < nco;
-            if (edge_row) {
-              const int rem = rem0 + j;
-              const int phase = ph0 + (rem >= cout ? 1 : 0) + (rem >= 2 * cout ? 1 : 0) + (rem >= 3 * cout ? 1 : 0);
-              counted = counted && !((m == 0 && phase < 2) || (m != 0 && phase >= 2));
-            }
-            if (counted) { ssum += v[j]; ssq += v[j] * v[j]; }
+        if (p.stat_mode == STAT_PER_G1_M) {
+          if (er.valid) {
+            double* st = p.stats + 2 * ((long)er.b * p.statR + er.m);
+            atomicAdd(st, (double)ssum); atomicAdd(st + 1, (double)ssq);
           }
-        }
-      }
-      if (!p.no_store) {
-        bf16* cp = (bf16*)p.C + orow * p.ldc + no;
-        const int nst_cols = min(nco, p.n_store - no);
+        } else {
+          const int key = er.valid ? er.b : -1;
+          const int key0 = __reduce_max_sync(0xffffffffu, key);
+          const bool uniform = __all_sync(0xffffffffu, key == key0 || key == -1);
+          if (key0 >= 0) {
+            const int slot = (t + half) % STAT_SLOTS;
+            if (uniform) {
+              // rows are combined in fp64 so that the result does not depend on which rows share a warp / tile,
+              // i.e. on the position of a segment inside the batch (multi-GPU spans must reproduce one-GPU bits)
+              double a = er.valid ? (double)ssum : 0.0, c = er.valid ? (double)ssq : 0.0;
 #pragma unroll
-        for (int g = 0; g < ((EF & EF_GLU) ? 2 : 4); ++g)
-          if (8 * g < nst_cols) store8(cp + 8 * g, v + 8 * g);
-      }
-    }
-    if (threadIdx.x == 64) TC_STAMP(5);
-    if (EF & EF_STATS) {
-      if (p.stat_mode == STAT_PER_G1_M) {
-        if (valid) {
-          double* st = p.stats + 2 * ((long)b * p.statR + m);
-          atomicAdd(st, (double)ssum); atomicAdd(st + 1, (double)ssq);
-        }
-      } else {
-        const int key = valid ? b : -1;
-        int key0 = __reduce_max_sync(0xffffffffu, key);
-        const bool uniform = __all_sync(0xffffffffu, key == key0 || key == -1);
-        if (key0 >= 0) {
-          if (uniform) {
-            // rows are combined in fp64 so that the result does not depend on which rows share a warp / tile,
-            // i.e. on the position of a segment inside the batch (multi-GPU spans must reproduce one-GPU bits)
-            double a = valid ? (double)ssum : 0.0, c = valid ? (double)ssq : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
-            if (lane == 0) { double* sp = p.stats + 2 * ((long)key0 * STAT_SLOTS + (blockIdx.x + blockIdx.y) % STAT_SLOTS); atomicAdd(sp, a); atomicAdd(sp + 1, c); }
-          } else if (valid) {
-            double* sp = p.stats + 2 * ((long)b * STAT_SLOTS + (blockIdx.x + blockIdx.y) % STAT_SLOTS); atomicAdd(sp, (double)ssum); atomicAdd(sp + 1, (double)ssq);
+              for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+              if (lane == 0) { double* sp = p.stats + 2 * ((long)key0 * STAT_SLOTS + slot); atomicAdd(sp, a); atomicAdd(sp + 1, c); }
+            } else if (er.valid) {
+              double* sp = p.stats + 2 * ((long)er.b * STAT_SLOTS + slot); atomicAdd(sp, (double)ssum); atomicAdd(sp + 1, (double)ssq);
+            }
           }
         }
       }
@@ -276,7 +316,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -316,11 +355,15 @@ bool make_tensor_map_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint6
 
 bool tensor_map_api_available() { return get_encode() != nullptr; }
 
+static int g_tc_bn_cap = 256;
+void tc_set_bn_cap(int cap) { g_tc_bn_cap = cap; }
+
 int tc_pick_bn(int N) {
   if (N % 16) return 0;
-  if (N <= 256) return N;
+  if (N <= g_tc_bn_cap) return N;
+  if (g_tc_bn_cap >= 256 && N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
-  if (N % 192 == 0) return 192;
+  if (N % 192 == 0 && g_tc_bn_cap >= 192) return 192;
   if (N % 64 == 0) return 64;
   if (N % 32 == 0) return 32;
   return 16;
@@ -331,8 +374,19 @@ bool tc_flat_supported(const TcFlat& f) {
   if (tc_pick_bn(f.N) == 0) return false;
   if (f.glu && (f.N % 16)) return false;
   if ((f.a_pitch * 2) % 16 || ((uintptr_t)f.A % 16) || ((uintptr_t)f.B % 16)) return false;
-  if (f.ldc % 8 || f.c_is_f32) return false;
+  if (f.ldc % 8 || f.c_is_f32 || f.alpha != 1.0f) return false;
   return get_encode() != nullptr;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
@@ -343,19 +397,24 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   for (int i = 0; i < 3; ++i) p.tapRow[i] = f.tapRow[i];
   p.RpA = f.RpA; p.G2p = f.G2p; p.gpf = f.gpf; p.G2 = f.G2; p.vlo = f.vlo; p.vhi = f.vhi;
   p.oG2p = f.oG2p; p.ogsh = f.ogsh; p.oRp = f.oRp; p.orsh = f.orsh; p.ldc = f.ldc;
-  p.C = f.C; p.alpha = f.alpha; p.bias = f.bias; p.act = f.act; p.glu = f.glu;
+  p.C = f.C; p.bias = f.bias;
   p.n_store = f.n_store > 0 ? f.n_store : (f.glu ? f.N / 2 : f.N);
   p.no_store = f.no_store;
   p.colscale = f.colscale; p.res = f.res; p.rowtab = f.rowtab; p.rowtab_scale = f.rowtab_scale;
   p.stats = f.stats; p.stat_mode = f.stat_mode; p.statR = f.statR; p.convt_cout = f.convt_cout;
-  p.gn_mr = f.gn_mr; p.gn_w = f.gn_w; p.gn_b = f.gn_b; p.gn_mode = f.gn_mode; p.dbg = (long long*)f.dbg;
+  p.gn_mr = f.gn_mr; p.gn_w = f.gn_w; p.gn_b = f.gn_b; p.gn_mode = f.gn_mode;
+  p.skip_lo = f.skip_lo; p.skip_hi = f.skip_hi;
+  p.m_tiles = (int)((f.Mflat + TC_BM - 1) / TC_BM);
+  p.n_tiles = (f.N + p.BN - 1) / p.BN;
   CUtensorMap tmA, tmB;
   if (!make_tensor_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
   if (!make_tensor_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
-  p.stages = p.BN > 128 ? 4 : 3;      // <= 97 KB for BN <= 128: two CTAs per SM overlap epilogue and main loop
-  const int stageB = ((p.BN * TC_BK * 2) + 1023) & ~1023;
-  const size_t smem = 1024 + (size_t)p.stages * (TC_BM * TC_BK * 2 + stageB) + 256;
-  dim3 grid((unsigned)((f.Mflat + TC_BM - 1) / TC_BM), (unsigned)((f.N + p.BN - 1) / p.BN));
+  const int stage_bytes = TC_BM * TC_BK * 2 + p.BN * TC_BK * 2;
+  const int smem_budget = 227 * 1024 - 1024 - 512;
+  p.stages = std::min(TC_MAX_STAGES, std::max(2, smem_budget / stage_bytes));
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 512;
+  const long tiles = (long)p.m_tiles * p.n_tiles;
+  dim3 grid((unsigned)std::min<long>(tiles, num_sms()));
   int ef = 0;
   if (f.act == ACT_GELU) ef |= EF_GELU;
   if (f.glu) ef |= EF_GLU;
@@ -366,8 +425,7 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   case E: {                                                                                                               \
     static bool attr_set = false;                                                                                         \
     if (!attr_set) {                                                                                                      \
-      cudaFuncSetAttribute(gemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,                                \
-                           1024 + TC_MAX_STAGES * (16384 + 32768) + 256);                                                 \
+      cudaFuncSetAttribute(gemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                   \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
     gemm_tc_kernel<E><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);                                                       \

@@ -236,7 +236,7 @@ void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
     f.C = o.c; f.c_is_f32 = 0; f.bias = o.bias; f.act = o.act; f.glu = o.glu; f.colscale = o.colscale; f.res = o.res;
     f.rowtab = o.rowtab; f.rowtab_scale = o.rowtab_scale; f.stats = o.stats; f.stat_mode = o.stat_mode; f.statR = as.R;
     f.convt_cout = o.mode == CONV_T ? o.N / 4 : 0;
-    f.n_store = o.n_store; f.no_store = o.no_store; f.gn_mr = o.gn_mr; f.gn_w = o.gn_w; f.gn_b = o.gn_b; f.gn_mode = o.gn_mode;
+    f.n_store = o.n_store; f.no_store = o.no_store; f.skip_lo = o.skip_lo; f.skip_hi = o.skip_hi; f.gn_mr = o.gn_mr; f.gn_w = o.gn_w; f.gn_b = o.gn_b; f.gn_mode = o.gn_mode;
     const bool geom_ok = (o.mode != CONV_K8S4) || (as.Rp % 4 == 0 && as.pf == 2);
     if (geom_ok && tc_flat_supported(f)) {
       prof_begin(gflop, st);
@@ -560,6 +560,9 @@ void PlanT<T>::dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* ou
   ConvOp<T> o = conv_op<T>(CONV_T, x, xs, PW(q + ".0.w"), 4 * Cout, ubuf, us);
   o.bias = PA(q + ".0.b4");
   if (i < 3) { o.stats = stt; o.stat_mode = STAT_PER_G1; }
+  // exact 4:1 resize (4*Rin -> Rin rows) reads only rows 4d+1, 4d+2 = phases 3 and 0: phases 1, 2 feed the GroupNorm
+  // statistics but are never stored; tensor-core path only
+  if (sizeof(T) == 2 && use_tc && os.R == Rin) { o.skip_lo = Cout; o.skip_hi = 3 * Cout; }
   conv(o, st);
   if (i < 3) { launch_finalize_gn(stt, (double)Cout * 4.0 * Rin * G2, mr, s.B, STAT_SLOTS, st); ++n_launches; }
   launch_dec_apply<T>(ubuf, 4 * Rin, us, Cout, out, os, G2, i < 3 ? 1 : 0, mr, i < 3 ? P32(q + ".1.weight") : nullptr,

@@ -46,7 +46,7 @@ struct ConvOp {
   T* c; RowSpace cs;        // output buffer / space
   const float* bias; int act; int glu; const float* colscale; const T* res;
   const float* rowtab; float rowtab_scale; double* stats; int stat_mode;
-  int n_store, no_store; const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;   // tensor-core path only
+  int n_store, no_store, skip_lo, skip_hi; const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;   // tensor-core path only
 };
 
 struct PlanBase {
