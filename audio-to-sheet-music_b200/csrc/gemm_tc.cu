@@ -158,7 +158,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
 #pragma unroll
     for (int g = 0; g < NV / 8; ++g) {
       const int c = no + 8 * g;
-      if (8 * g < nst_cols && !(c >= p.skip_lo && c < p.skip_hi)) store8(cp + 8 * g, v + 8 * g);
+      if (8 * g < nst_cols && !(c >= p.skip_lo && c + 8 <= p.skip_hi)) store8(cp + 8 * g, v + 8 * g);
     }
   }
 }
