@@ -116,6 +116,7 @@ int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* 
 }
 int athtd_plan_set_tc(void* plan, int on) { ((PlanBase*)plan)->set_use_tc(on != 0); return 0; }
 int athtd_plan_set_flash(void* plan, int on) { ((PlanBase*)plan)->set_use_flash(on != 0); return 0; }
+int athtd_plan_set_fused_dconv(void* plan, int on) { ((PlanBase*)plan)->set_use_fused_dconv(on != 0); return 0; }
 int athtd_plan_tc_launches(void* plan) { return ((PlanBase*)plan)->tc_launches(); }
 
 int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* stream) {

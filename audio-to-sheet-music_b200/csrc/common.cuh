@@ -21,6 +21,21 @@ template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __flo
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// bf16 build: exact-erf GELU evaluated with the SFU exponential; erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below bf16 resolution).  The fp32 build keeps erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);       // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+template <typename T> __device__ __forceinline__ float gelu_act(float x);
+template <> __device__ __forceinline__ float gelu_act<float>(float x) { return gelu_erf(x); }
+template <> __device__ __forceinline__ float gelu_act<bf16>(float x) { return gelu_fast(x); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -44,6 +59,37 @@ __device__ __forceinline__ void stats_to_mean_rstd(const double* st, double coun
   mean = (float)m;
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
+
+// 16-byte (8 x bf16) / 32-byte (8 x fp32) vector access helpers
+template <typename T, int VEC> struct VecIO;
+template <int VEC> struct VecIO<float, VEC> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) { float4 t = *(const float4*)(p + i); v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) *(float4*)(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+};
+template <int VEC> struct VecIO<bf16, VEC> {
+  static __device__ __forceinline__ void load(const bf16* p, float* v) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+      uint2 t = *(const uint2*)(p + i);
+      float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&t.x), c = __bfloat1622float2(*(const __nv_bfloat162*)&t.y);
+      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = c.x; v[i + 3] = c.y;
+    }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[i], v[i + 1]), c = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+      uint2 t; t.x = *(uint32_t*)&a; t.y = *(uint32_t*)&c;
+      *(uint2*)(p + i) = t;
+    }
+  }
+};
 
 // A padded channels-last row space.  G = B*G2 interior groups (G2 groups per segment: frames on the
 // frequency branch, 1 on the time branch); every segment stores G2p >= G2 groups (gpf zero groups in front) and

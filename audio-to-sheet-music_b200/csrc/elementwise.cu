@@ -99,9 +99,27 @@ void launch_pack_spec(const float* Z, const float* meanstd, T* out, RowSpace rs,
 
 // ------------------------------------------------------------------ GroupNorm(1,C) + GELU, in place
 // stat index: per_row ? (g/G2)*R + r : g/G2 ; count given by the caller.
-template <typename T>
+template <typename T, int VEC>
 __global__ void gn_gelu_kernel(T* __restrict__ h, RowSpace rs, int G2, int per_row, const float* __restrict__ mr,
                                const float* __restrict__ w, const float* __restrict__ bvec) {
+  const int CV = rs.C / VEC;
+  long total = (long)rs.G * rs.R * CV;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * VEC; long row = i / CV;
+    int r = (int)(row % rs.R); int g = (int)(row / rs.R);
+    long si = per_row ? (long)(g / G2) * rs.R + r : (long)(g / G2);
+    float mean = mr[2 * si], rstd = mr[2 * si + 1];
+    long o = rs.row_off(g, r) + c;
+    float v[VEC];
+    VecIO<T, VEC>::load(h + o, v);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = gelu_act<T>((v[k] - mean) * rstd * w[c + k] + bvec[c + k]);
+    VecIO<T, VEC>::store(h + o, v);
+  }
+}
+template <typename T>
+__global__ void gn_gelu_scalar_kernel(T* __restrict__ h, RowSpace rs, int G2, int per_row, const float* __restrict__ mr,
+                                      const float* __restrict__ w, const float* __restrict__ bvec) {
   long total = (long)rs.G * rs.R * rs.C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int c = (int)(i % rs.C); long row = i / rs.C;
@@ -110,15 +128,19 @@ __global__ void gn_gelu_kernel(T* __restrict__ h, RowSpace rs, int G2, int per_r
     float mean = mr[2 * si], rstd = mr[2 * si + 1];
     long o = rs.row_off(g, r) + c;
     float v = (to_f<T>(h[o]) - mean) * rstd * w[c] + bvec[c];
-    h[o] = from_f<T>(gelu_erf(v));
+    h[o] = from_f<T>(gelu_act<T>(v));
   }
 }
 template <typename T>
 void launch_gn_gelu(T* h, RowSpace rs, int G2, int per_row, const float* mr, const float* w,
                     const float* b, cudaStream_t st) {
-  long total = (long)rs.G * rs.R * rs.C;
-  int blocks = (int)min((total + 255) / 256, (long)148 * 16);
-  gn_gelu_kernel<T><<<blocks, 256, 0, st>>>(h, rs, G2, per_row, mr, w, b);
+  if (rs.C % 8 == 0) {
+    long total = (long)rs.G * rs.R * (rs.C / 8);
+    gn_gelu_kernel<T, 8><<<(int)min((total + 255) / 256, (long)148 * 32), 256, 0, st>>>(h, rs, G2, per_row, mr, w, b);
+  } else {
+    long total = (long)rs.G * rs.R * rs.C;
+    gn_gelu_scalar_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 32), 256, 0, st>>>(h, rs, G2, per_row, mr, w, b);
+  }
 }
 
 // x <- x + scale[c] * ( GN(e)[c] * sigmoid(GN(e)[c+C]) )     DConv tail (demucs DConv layers 4..6)
@@ -157,35 +179,60 @@ __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, 
                                  const float* __restrict__ gmr, const float* __restrict__ gw,
                                  const float* __restrict__ gb, const float* __restrict__ lw, const float* __restrict__ lb,
                                  const float* __restrict__ pe, RowSpace yrs) {
+  // one warp per row; each lane owns up to two 8-channel chunks (C <= 512, C % 8 == 0): 16-byte loads / stores
   int lane = threadIdx.x & 31;
   long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* xr = x + row * C;
+  const int nchunk = C >> 3;
   float v[16];
-  int cnt = 0;
   float gm = 0.f, gr = 1.f;
   if (gmr) { gm = gmr[2 * (row / S)]; gr = gmr[2 * (row / S) + 1]; }
   float s = 0.f;
-  for (int c = lane; c < C; c += 32, ++cnt) {
-    float t = to_f<T>(xr[c]);
-    if (gmr) { t = (t - gm) * gr * gw[c] + gb[c]; xout[row * C + c] = from_f<T>(t); }
-    v[cnt] = t; s += t;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < nchunk) {
+      const int c = ch * 8;
+      VecIO<T, 8>::load(xr + c, v + 8 * i);
+      if (gmr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[8 * i + k] = (v[8 * i + k] - gm) * gr * gw[c + k] + gb[c + k];
+        VecIO<T, 8>::store(xout + row * C + c, v + 8 * i);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[8 * i + k];
+    }
   }
   if (!lw) return;
   s = warp_sum(s);
   float mean = s / C;
   float q = 0.f;
-  for (int i = 0; i < cnt; ++i) { float dlt = v[i] - mean; q += dlt * dlt; }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    if (lane + 32 * i < nchunk) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { float dlt = v[8 * i + k] - mean; q += dlt * dlt; }
+    }
   q = warp_sum(q);
   float rstd = rsqrtf(q / C + 1e-5f);
   long srow = row % S;
   long yoff = row * C;
   if (yrs.C > 0) yoff = yrs.row_off((int)(row / yrs.R), (int)(row % yrs.R));   // scatter into a padded row space
-  cnt = 0;
-  for (int c = lane; c < C; c += 32, ++cnt) {
-    float t = (v[cnt] - mean) * rstd * lw[c] + lb[c];
-    if (pe) t += pe[srow * C + c];
-    y[yoff + c] = from_f<T>(t);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < nchunk) {
+      const int c = ch * 8;
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float t = (v[8 * i + k] - mean) * rstd * lw[c + k] + lb[c + k];
+        if (pe) t += pe[srow * C + c + k];
+        o[k] = t;
+      }
+      VecIO<T, 8>::store(y + yoff + c, o);
+    }
   }
 }
 template <typename T>
@@ -257,36 +304,6 @@ __device__ __forceinline__ void lerp_coords(int d, int in, int out, int& i0, int
   i1 = i0 + (i0 < in - 1 ? 1 : 0);
   lam = src - (float)i0;
 }
-template <typename T, int VEC> struct VecIO;
-template <int VEC> struct VecIO<float, VEC> {
-  static __device__ __forceinline__ void load(const float* p, float* v) {
-#pragma unroll
-    for (int i = 0; i < VEC; i += 4) { float4 t = *(const float4*)(p + i); v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }
-  }
-  static __device__ __forceinline__ void store(float* p, const float* v) {
-#pragma unroll
-    for (int i = 0; i < VEC; i += 4) *(float4*)(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-  }
-};
-template <int VEC> struct VecIO<bf16, VEC> {
-  static __device__ __forceinline__ void load(const bf16* p, float* v) {
-#pragma unroll
-    for (int i = 0; i < VEC; i += 4) {
-      uint2 t = *(const uint2*)(p + i);
-      float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&t.x), c = __bfloat1622float2(*(const __nv_bfloat162*)&t.y);
-      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = c.x; v[i + 3] = c.y;
-    }
-  }
-  static __device__ __forceinline__ void store(bf16* p, const float* v) {
-#pragma unroll
-    for (int i = 0; i < VEC; i += 4) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[i], v[i + 1]), c = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-      uint2 t; t.x = *(uint32_t*)&a; t.y = *(uint32_t*)&c;
-      *(uint2*)(p + i) = t;
-    }
-  }
-};
-
 template <typename T, int VEC>
 __global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, int Cu, T* __restrict__ out,
                                  RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
@@ -308,8 +325,8 @@ __global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, 
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         float w = gw[c + k], bb = gb[c + k];
-        a0[k] = gelu_erf((a0[k] - mean) * rstd * w + bb);
-        a1[k] = gelu_erf((a1[k] - mean) * rstd * w + bb);
+        a0[k] = gelu_act<T>((a0[k] - mean) * rstd * w + bb);
+        a1[k] = gelu_act<T>((a1[k] - mean) * rstd * w + bb);
       }
     }
     int j0, j1; float mu;

@@ -69,18 +69,6 @@ __device__ __forceinline__ void load8_add(const bf16* src, float* v) {
 // issued ~4400 instructions per 32-column chunk and dominated the kernel)
 enum { EF_GELU = 1, EF_GLU = 2, EF_GN = 4, EF_POST = 8, EF_STATS = 16 };
 
-// bf16 build only: exact-erf GELU / sigmoid evaluated with the SFU exponential.  erf by Abramowitz-Stegun 7.1.26
-// (|error| <= 1.5e-7, far below bf16 resolution); the fp32 build keeps erff()/expf() in its own kernels.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = 1.0f - poly * t * __expf(-z * z);       // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
-}
 __device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 // per-row state of one epilogue thread for one tile

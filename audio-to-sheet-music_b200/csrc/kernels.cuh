@@ -27,6 +27,10 @@ template <typename T> void launch_dec_apply(const T* u, int Uin, RowSpace us, in
                                             RowSpace ss, cudaStream_t st);
 template <typename T> void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int d1, int d2, cudaStream_t st);
 
+// ---- dconv_row.cu (fused DConv residual branch of the frequency encoder layers)
+template <typename T> bool dconv_row_supported(int C, int Tn);
+template <typename T> void launch_dconv_row(T* y, RowSpace ys, const float* const* ptrs, cudaStream_t st);
+
 // ---- fft.cu
 void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
                      cudaStream_t st);

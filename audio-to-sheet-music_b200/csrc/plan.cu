@@ -298,6 +298,16 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
   const int Hp = hidden_pad(H);
   RowSpace hs = ys; hs.C = tc_dconv ? Hp : H;
   RowSpace es = ys; es.C = 2 * C;
+  if (freq && use_fused_dconv && dconv_row_supported<T>(C, s.Tf)) {
+    // frequency branch: GroupNorm statistics are per (segment, frequency row) -> one CTA per row, both layers fused
+    const float* ptrs[18];
+    for (int dd = 0; dd < 2; ++dd) {
+      const std::string q = p + ".dconv.layers." + std::to_string(dd);
+      const char* names[9] = {".0.weight", ".0.bias", ".1.weight", ".1.bias", ".3.weight", ".3.bias", ".4.weight", ".4.bias", ".6.scale"};
+      for (int k = 0; k < 9; ++k) ptrs[9 * dd + k] = P32(q + names[k]);
+    }
+    launch_dconv_row<T>(y, ys, ptrs, st); ++n_launches;
+  } else
   for (int dd = 0; dd < 2; ++dd) {
     const std::string q = p + ".dconv.layers." + std::to_string(dd);
     double* st_h = freq ? st_df[i][dd][0] : st_dt[i][dd][0];

@@ -61,6 +61,7 @@ struct PlanBase {
   virtual void set_profile(bool on) = 0;
   virtual void set_use_tc(bool on) = 0;
   virtual void set_use_flash(bool on) = 0;
+  virtual void set_use_fused_dconv(bool on) = 0;
   virtual int tc_launches() const = 0;
   virtual void get_profile(double* ms, double* gflop, int* n) = 0;
 };
@@ -76,7 +77,7 @@ struct PlanT : PlanBase {
   char* base_ = nullptr;
   size_t total_bytes = 0, zero_bytes = 0, stats_begin = 0, stats_bytes = 0;
   int n_launches = 0, n_tc = 0;
-  bool use_tc = true, use_flash = true;
+  bool use_tc = true, use_flash = true, use_fused_dconv = true;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
@@ -123,6 +124,7 @@ struct PlanT : PlanBase {
   void set_profile(bool on) override { profiling = on; prof_used = 0; prof_gflop = 0.0; }
   void set_use_tc(bool on) override { use_tc = on; }
   void set_use_flash(bool on) override { use_flash = on; }
+  void set_use_fused_dconv(bool on) override { use_fused_dconv = on; }
   int tc_launches() const override { return n_tc; }
   void get_profile(double* ms, double* gflop, int* n) override;
 };

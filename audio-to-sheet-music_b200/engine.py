@@ -125,6 +125,9 @@ class Plan:
     def tc_launches(self) -> int:
         return _lib.load().athtd_plan_tc_launches(self.handle)
 
+    def set_fused_dconv(self, on: bool) -> None:
+        _lib.load().athtd_plan_set_fused_dconv(self.handle, 1 if on else 0)
+
     def set_profile(self, on: bool) -> None:
         _lib.load().athtd_plan_set_profile(self.handle, 1 if on else 0)
 

@@ -35,6 +35,7 @@ SYMBOLS = [
     ("athtd_tap", _I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I), C.POINTER(_I * 8)]),
     ("athtd_plan_set_tc", _I, [_P, _I]),
     ("athtd_plan_set_flash", _I, [_P, _I]),
+    ("athtd_plan_set_fused_dconv", _I, [_P, _I]),
     ("athtd_plan_tc_launches", _I, [_P]),
     ("athtd_attention_test", _I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     ("athtd_memcpy_d2d", _I, [_P, _P, _L, _P]),

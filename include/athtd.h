@@ -65,6 +65,7 @@ int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* 
  * CUDA-core kernel (A/B measurements, kernel-level parity tests). */
 int athtd_plan_set_tc(void* plan, int on);
 int athtd_plan_set_flash(void* plan, int on);   /* fused tcgen05 attention (default on) vs GEMM-softmax-GEMM */
+int athtd_plan_set_fused_dconv(void* plan, int on);   /* per-row fused DConv kernel (default on) vs GEMM passes */
 int athtd_plan_tc_launches(void* plan);
 
 /* async device-to-device copy on `stream` (lets tests read taps without a second CUDA binding) */

@@ -126,3 +126,22 @@ def test_bf16_tensor_core_path_matches_cuda_core_path(models, state_dict):
     ref = athtd_oracle.forward(state_dict, wav, emb)
     assert athtd_oracle.snr_db(a, ref) >= 40.0 and athtd_oracle.snr_db(b, ref) >= 40.0
     assert athtd_oracle.snr_db(a, b) >= 40.0
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("bf16", None)])
+def test_fused_dconv_matches_gemm_passes(models, state_dict, prec, tol):
+    """Per-row fused DConv kernel (frequency encoder layers 0-1) vs the conv3 / GroupNorm / expand GEMM passes."""
+    wav, emb = weights.make_inputs(91, 2, 40000)
+    m = models[prec]
+    plan = m.engine().plan(2, 40000, 1)
+    plan.set_fused_dconv(True)
+    a = m(wav.cuda(), emb.cuda()).cpu()
+    n_fused = plan.launches
+    plan.set_fused_dconv(False)
+    b = m(wav.cuda(), emb.cuda()).cpu()
+    assert plan.launches > n_fused
+    plan.set_fused_dconv(True)
+    if tol is not None:
+        assert (a - b).abs().max() < tol
+    else:
+        assert athtd_oracle.snr_db(a, b) >= 40.0
