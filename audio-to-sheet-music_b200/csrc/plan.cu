@@ -179,6 +179,7 @@ void PlanT<T>::prof_begin(double gflop, cudaStream_t st) {
   if (!profiling) return;      // per-launch CUDA-event timing of the GEMM kernels (bench.py roofline pass only)
   while (prof_ev.size() < prof_used + 2) { cudaEvent_t e; cudaEventCreate(&e); prof_ev.push_back(e); }
   prof_gflop += gflop;
+  prof_items.push_back(gflop);
   cudaEventRecord(prof_ev[prof_used++], st);
 }
 template <typename T>
@@ -200,6 +201,12 @@ void PlanT<T>::get_profile(double* ms, double* gflop, int* n) {
   if (prof_used) cudaEventSynchronize(prof_ev[prof_used - 1]);
   for (size_t i = 0; i + 1 < prof_used; i += 2) { float t = 0.f; cudaEventElapsedTime(&t, prof_ev[i], prof_ev[i + 1]); total += t; }
   *ms = total; *gflop = prof_gflop; *n = (int)(prof_used / 2);
+  if (getenv("ATHTD_PROFILE_DUMP")) {      // per-launch list for tuning: index, GFLOP, us, TFLOP/s
+    for (size_t i = 0; i + 1 < prof_used; i += 2) {
+      float t = 0.f; cudaEventElapsedTime(&t, prof_ev[i], prof_ev[i + 1]);
+      fprintf(stderr, "gemm %3zu  %9.3f GFLOP  %8.1f us  %7.1f TFLOP/s\n", i / 2, prof_items[i / 2], t * 1e3, prof_items[i / 2] / t);
+    }
+  }
 }
 
 // ---- lower one convolution-shaped op either to the tcgen05 flat-row kernel (bf16 build, supported shapes) or to

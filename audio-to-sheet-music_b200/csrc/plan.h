@@ -82,6 +82,7 @@ struct PlanT : PlanBase {
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   double prof_gflop = 0.0;
+  std::vector<double> prof_items;
   // buffers
   RowSpace xf0_rs, xt0_rs, yf_rs[4], yt_rs[4], xc_rs, xtc_rs, df_rs[4], dt_rs[4];
   T *xf0, *xt0, *yf[4], *ef[4], *yt[4], *et[4], *xc, *xtc, *df[4], *dt[4];
@@ -121,7 +122,7 @@ struct PlanT : PlanBase {
   long workspace_bytes() const override { return (long)total_bytes; }
   long zero_region_bytes() const override { return (long)zero_bytes; }
   int launches() const override { return n_launches; }
-  void set_profile(bool on) override { profiling = on; prof_used = 0; prof_gflop = 0.0; }
+  void set_profile(bool on) override { profiling = on; prof_used = 0; prof_gflop = 0.0; prof_items.clear(); }
   void set_use_tc(bool on) override { use_tc = on; }
   void set_use_flash(bool on) override { use_flash = on; }
   void set_use_fused_dconv(bool on) override { use_fused_dconv = on; }
