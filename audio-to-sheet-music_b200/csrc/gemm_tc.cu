@@ -108,9 +108,15 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
 #pragma unroll
       for (int j = 0; j < NV; ++j) v[j] *= __ldg(p.colscale + min(no + j, olast));
     }
-    if (p.rowtab) {
+    if (p.rowtab) {      // per-row table (frequency embedding): Nout % 4 == 0, 16-byte gathers instead of scalar ones
+      const float4* tp = (const float4*)(p.rowtab + (long)er.m * Nout + no);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] += p.rowtab_scale * __ldg(p.rowtab + (long)er.m * Nout + min(no + j, olast));
+      for (int g = 0; g < NV / 4; ++g)
+        if (4 * g < nco) {
+          const float4 t4 = __ldg(tp + g);
+          v[4 * g] += p.rowtab_scale * t4.x; v[4 * g + 1] += p.rowtab_scale * t4.y;
+          v[4 * g + 2] += p.rowtab_scale * t4.z; v[4 * g + 3] += p.rowtab_scale * t4.w;
+        }
     }
     if (p.res) {
       const bf16* rp = (const bf16*)p.res + er.orow * p.ldc + no;
