@@ -24,6 +24,12 @@ struct FaParams {
 
 static constexpr int FA_TILE = 16384;   // 128 rows x 64 bf16
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
@@ -121,16 +127,26 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_wait(smem_u32(s_full), (uint32_t)(j & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float mx = -INFINITY;
+      if (nvalid == 128) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), r);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
       }
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
       const float mb = m_new * p.scale_log2;
       float l_tile = 0.f;
 #pragma unroll
@@ -138,13 +154,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint32_t r[32];
         tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), r);
         uint32_t pk[16];
+        if (nvalid == 128) {          // all but the last key tile: no masking
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < nvalid) ? exp2f(__uint_as_float(r[i]) * p.scale_log2 - mb) : 0.f;
-          float p1 = (c * 32 + i + 1 < nvalid) ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2 - mb) : 0.f;
-          l_tile += p0 + p1;
-          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *(uint32_t*)&t;
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -mb));
+            l_tile += p0 + p1;
+            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+            pk[i >> 1] = *(uint32_t*)&t;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c * 32 + i < nvalid) ? ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb)) : 0.f;
+            const float p1 = (c * 32 + i + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -mb)) : 0.f;
+            l_tile += p0 + p1;
+            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+            pk[i >> 1] = *(uint32_t*)&t;
+          }
         }
         // K-major SWIZZLE_128B: row pitch 128 B, 16-byte chunk index XOR (row & 7); keys [64a, 64a+64) in atom a
         uint8_t* prow = sP + (c >> 1) * FA_TILE + row * 128;

@@ -32,13 +32,27 @@ struct DconvRowParams {
   const float* w2[2]; const float* b2[2]; const float* g2w[2]; const float* g2b[2]; const float* scale[2];
 };
 
+template <typename T> struct Pair2;
+template <> struct Pair2<float> {
+  static __device__ __forceinline__ float2 ld(const float* p) { return *(const float2*)p; }
+  static __device__ __forceinline__ void st(float* p, float2 v) { *(float2*)p = v; }
+};
+template <> struct Pair2<bf16> {
+  static __device__ __forceinline__ float2 ld(const bf16* p) { return __bfloat1622float2(*(const __nv_bfloat162*)p); }
+  static __device__ __forceinline__ void st(bf16* p, float2 v) { *(__nv_bfloat162*)p = __floats2bfloat162_rn(v.x, v.y); }
+};
+
+static constexpr int DCONV_THREADS = 288;     // >= 259 frames of a 6 s segment: the k3 conv runs one frame per thread
+
 template <typename T, int C>
-__global__ void __launch_bounds__(256) dconv_row_kernel(T* __restrict__ y, RowSpace ys, DconvRowParams P) {
+__global__ void __launch_bounds__(DCONV_THREADS) dconv_row_kernel(T* __restrict__ y, RowSpace ys, DconvRowParams P) {
   constexpr int H = C / 8;
   constexpr int XP = C + 2;                       // padded slab pitch (elements): odd word stride -> no bank conflicts
+  constexpr int CB = 48 / H;                      // channels per thread in the statistics pass (48 weight registers)
+  constexpr int CC = 24 / H;                      // (value, gate) channel pairs per thread in the apply pass
   const int Tn = ys.G2;                           // frames
   extern __shared__ float smem_f[];
-  float* w1s = smem_f;                            // [H][3][C]   (tap-major inside a row)
+  float* w1s = smem_f;                            // [3][C][H]   (hidden channel fastest)
   float* w2s = w1s + H * 3 * C;                   // [2C][H]
   float* vec = w2s + 2 * C * H;                   // b1[H] g1w[H] g1b[H] b2[2C] g2w[2C] g2b[2C] scale[C]
   float* hs = vec + 3 * H + 7 * C;                // [Tn][H]
@@ -53,7 +67,7 @@ __global__ void __launch_bounds__(256) dconv_row_kernel(T* __restrict__ y, RowSp
     float v[8];
     VecIO<T, 8>::load(y + ys.row_off(b * Tn + t, f) + c, v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) xs[t * XP + c + k] = from_f<T>(v[k]);
+    for (int k = 0; k < 8; k += 2) Pair2<T>::st(xs + t * XP + c + k, make_float2(v[k], v[k + 1]));
   }
 
   for (int d = 0; d < 2; ++d) {
@@ -61,7 +75,7 @@ __global__ void __launch_bounds__(256) dconv_row_kernel(T* __restrict__ y, RowSp
     __syncthreads();
     // ---- stage this depth's weights (fp32) in shared memory
     for (int i = tid; i < H * 3 * C; i += blockDim.x) {
-      const int j = i / (3 * C), r = i % (3 * C), k = r / C, c = r % C;
+      const int j = i % H, r = i / H, c = r % C, k = r / C;       // dst [k][c][j]
       w1s[i] = P.w1[d][(j * C + c) * 3 + k];
     }
     for (int i = tid; i < 2 * C * H; i += blockDim.x) w2s[i] = P.w2[d][i];
@@ -74,25 +88,33 @@ __global__ void __launch_bounds__(256) dconv_row_kernel(T* __restrict__ y, RowSp
     const float* b1 = vec, *g1w = vec + H, *g1b = vec + 2 * H, *b2 = vec + 3 * H, *g2w = b2 + 2 * C, *g2b = b2 + 4 * C,
                *scl = b2 + 6 * C;
 
-    // ---- h = conv_k3_dil(x) + b1 ; partial sums for GroupNorm(1, H)
+    // ---- h = conv_k3_dil(x) + b1 : one frame per thread, all H hidden channels in registers
     float s1 = 0.f, q1 = 0.f;
-    for (int i = tid; i < Tn * (H / 3); i += blockDim.x) {          // 3 hidden channels per item
-      const int t = i % Tn, j0 = (i / Tn) * 3;
-      float a0 = b1[j0], a1 = b1[j0 + 1], a2 = b1[j0 + 2];
+    for (int t = tid; t < Tn; t += blockDim.x) {
+      float acc[H];
+#pragma unroll
+      for (int j = 0; j < H; ++j) acc[j] = b1[j];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int tt = t + (k - 1) * dil;
         if (tt < 0 || tt >= Tn) continue;
         const T* xr = xs + tt * XP;
-        const float* wa = w1s + (j0 * 3 + k) * C;
-#pragma unroll 8
-        for (int c = 0; c < C; ++c) {
-          const float xv = to_f<T>(xr[c]);
-          a0 = fmaf(wa[c], xv, a0); a1 = fmaf(wa[3 * C + c], xv, a1); a2 = fmaf(wa[6 * C + c], xv, a2);
+        const float4* wp = (const float4*)(w1s + k * C * H);
+#pragma unroll 4
+        for (int c = 0; c < C; c += 2) {
+          const float2 xv = Pair2<T>::ld(xr + c);
+          float w[2 * H];
+#pragma unroll
+          for (int g = 0; g < 2 * H / 4; ++g) {
+            const float4 t4 = wp[(c * H) / 4 + g];
+            w[4 * g] = t4.x; w[4 * g + 1] = t4.y; w[4 * g + 2] = t4.z; w[4 * g + 3] = t4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < H; ++j) { acc[j] = fmaf(w[j], xv.x, acc[j]); acc[j] = fmaf(w[H + j], xv.y, acc[j]); }
         }
       }
-      hs[t * H + j0] = a0; hs[t * H + j0 + 1] = a1; hs[t * H + j0 + 2] = a2;
-      s1 += a0 + a1 + a2; q1 += a0 * a0 + a1 * a1 + a2 * a2;
+#pragma unroll
+      for (int j = 0; j < H; ++j) { hs[t * H + j] = acc[j]; s1 += acc[j]; q1 += acc[j] * acc[j]; }
     }
     block_sum2(s1, q1, red);
     {
@@ -107,19 +129,33 @@ __global__ void __launch_bounds__(256) dconv_row_kernel(T* __restrict__ y, RowSp
     }
     __syncthreads();
 
-    // ---- e = W2 h + b2: statistics only (2C x T values), never stored
+    // ---- e = W2 h + b2: statistics only (2C x T values), never stored.  Thread = CB output channels (weights in
+    //      registers) x a strided set of frames.
     float s2 = 0.f, q2 = 0.f;
-    for (int i = tid; i < Tn * (C / 4); i += blockDim.x) {           // 8 of the 2C channels per item
-      const int t = i % Tn, c0 = (i / Tn) * 8;
-      float hv[H];
+    {
+      constexpr int NG = 2 * C / CB;
+      const int nslot = blockDim.x / NG;
+      const int cg = tid % NG, slot = tid / NG;
+      if (slot < nslot) {
+        float w[CB][H], bb[CB];
 #pragma unroll
-      for (int j = 0; j < H; ++j) hv[j] = hs[t * H + j];
+        for (int cc = 0; cc < CB; ++cc) {
+          bb[cc] = b2[cg * CB + cc];
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        float e = b2[c0 + cc];
+          for (int j = 0; j < H; ++j) w[cc][j] = w2s[(cg * CB + cc) * H + j];
+        }
+        for (int t = slot; t < Tn; t += nslot) {
+          float hv[H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) e = fmaf(w2s[(c0 + cc) * H + j], hv[j], e);
-        s2 += e; q2 += e * e;
+          for (int j = 0; j < H; j += 2) { const float2 h2 = *(const float2*)(hs + t * H + j); hv[j] = h2.x; hv[j + 1] = h2.y; }
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            float e = bb[cc];
+#pragma unroll
+            for (int j = 0; j < H; ++j) e = fmaf(w[cc][j], hv[j], e);
+            s2 += e; q2 = fmaf(e, e, q2);
+          }
+        }
       }
     }
     block_sum2(s2, q2, red);
@@ -127,22 +163,47 @@ __global__ void __launch_bounds__(256) dconv_row_kernel(T* __restrict__ y, RowSp
     const float mean2 = s2 / n2;
     const float rstd2 = rsqrtf(fmaxf(q2 / n2 - mean2 * mean2, 0.f) + 1e-5f);
 
-    // ---- x += scale * GN2(e)[c] * sigmoid(GN2(e)[c + C])      (e recomputed)
-    for (int i = tid; i < Tn * (C / 4); i += blockDim.x) {           // 4 channels per item
-      const int t = i % Tn, c0 = (i / Tn) * 4;
-      float hv[H];
+    // ---- x += scale * GN2(e)[c] * sigmoid(GN2(e)[c + C])      (e recomputed; CC (value, gate) pairs per thread)
+    {
+      constexpr int NG = C / CC;
+      const int nslot = blockDim.x / NG;
+      const int cg = tid % NG, slot = tid / NG;
+      if (slot < nslot) {
+        const int c0 = cg * CC;
+        float wa[CC][H], wg[CC][H], ba[CC], bg[CC], ga[CC], gb_[CC], gg[CC], gh[CC], sc[CC];
 #pragma unroll
-      for (int j = 0; j < H; ++j) hv[j] = hs[t * H + j];
+        for (int cc = 0; cc < CC; ++cc) {
+          const int c = c0 + cc;
+          // fold GroupNorm's affine into the recomputed dot product: GN(e) = (e - mean) * rstd * w + b
+          ga[cc] = rstd2 * g2w[c]; gb_[cc] = g2b[c] - mean2 * rstd2 * g2w[c];
+          gg[cc] = rstd2 * g2w[c + C]; gh[cc] = g2b[c + C] - mean2 * rstd2 * g2w[c + C];
+          ba[cc] = b2[c]; bg[cc] = b2[c + C]; sc[cc] = scl[c];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = c0 + cc;
-        float ea = b2[c], eg = b2[c + C];
+          for (int j = 0; j < H; ++j) { wa[cc][j] = w2s[c * H + j]; wg[cc][j] = w2s[(c + C) * H + j]; }
+        }
+        for (int t = slot; t < Tn; t += nslot) {
+          float hv[H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) { ea = fmaf(w2s[c * H + j], hv[j], ea); eg = fmaf(w2s[(c + C) * H + j], hv[j], eg); }
-        ea = (ea - mean2) * rstd2 * g2w[c] + g2b[c];
-        eg = (eg - mean2) * rstd2 * g2w[c + C] + g2b[c + C];
-        const float sg = sizeof(T) == 2 ? __frcp_rn(1.0f + __expf(-eg)) : sigmoid_acc(eg);
-        xs[t * XP + c] = from_f<T>(to_f<T>(xs[t * XP + c]) + scl[c] * (ea * sg));
+          for (int j = 0; j < H; j += 2) { const float2 h2 = *(const float2*)(hs + t * H + j); hv[j] = h2.x; hv[j + 1] = h2.y; }
+          float upd[CC];
+#pragma unroll
+          for (int cc = 0; cc < CC; ++cc) {
+            float ea = ba[cc], eg = bg[cc];
+#pragma unroll
+            for (int j = 0; j < H; ++j) { ea = fmaf(wa[cc][j], hv[j], ea); eg = fmaf(wg[cc][j], hv[j], eg); }
+            ea = fmaf(ea, ga[cc], gb_[cc]);
+            eg = fmaf(eg, gg[cc], gh[cc]);
+            const float sg = sizeof(T) == 2 ? __frcp_rn(1.0f + __expf(-eg)) : sigmoid_acc(eg);
+            upd[cc] = sc[cc] * (ea * sg);
+          }
+#pragma unroll
+          for (int cc = 0; cc < CC; cc += 2) {
+            T* xp = xs + t * XP + c0 + cc;
+            float2 xv = Pair2<T>::ld(xp);
+            xv.x += upd[cc]; xv.y += upd[cc + 1];
+            Pair2<T>::st(xp, xv);
+          }
+        }
       }
     }
   }
@@ -151,7 +212,7 @@ __global__ void __launch_bounds__(256) dconv_row_kernel(T* __restrict__ y, RowSp
     const int t = i / (C / 8), c = (i % (C / 8)) * 8;
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = to_f<T>(xs[t * XP + c + k]);
+    for (int k = 0; k < 8; k += 2) { const float2 p2 = Pair2<T>::ld(xs + t * XP + c + k); v[k] = p2.x; v[k + 1] = p2.y; }
     VecIO<T, 8>::store(y + ys.row_off(b * Tn + t, f) + c, v);
   }
 }
@@ -182,11 +243,11 @@ void launch_dconv_row(T* y, RowSpace ys, const float* const* ptrs, cudaStream_t 
   if (ys.C == 48) {
     const size_t smem = dconv_row_smem<T, 48>(Tn);
     cudaFuncSetAttribute(dconv_row_kernel<T, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dconv_row_kernel<T, 48><<<blocks, 256, smem, st>>>(y, ys, P);
+    dconv_row_kernel<T, 48><<<blocks, DCONV_THREADS, smem, st>>>(y, ys, P);
   } else {
     const size_t smem = dconv_row_smem<T, 96>(Tn);
     cudaFuncSetAttribute(dconv_row_kernel<T, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dconv_row_kernel<T, 96><<<blocks, 256, smem, st>>>(y, ys, P);
+    dconv_row_kernel<T, 96><<<blocks, DCONV_THREADS, smem, st>>>(y, ys, P);
   }
 }
 

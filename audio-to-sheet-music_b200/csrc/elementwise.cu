@@ -196,8 +196,10 @@ __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, 
       const int c = ch * 8;
       VecIO<T, 8>::load(xr + c, v + 8 * i);
       if (gmr) {
+        float w8[8], b8[8];
+        VecIO<float, 8>::load(gw + c, w8); VecIO<float, 8>::load(gb + c, b8);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[8 * i + k] = (v[8 * i + k] - gm) * gr * gw[c + k] + gb[c + k];
+        for (int k = 0; k < 8; ++k) v[8 * i + k] = (v[8 * i + k] - gm) * gr * w8[k] + b8[k];
         VecIO<T, 8>::store(xout + row * C + c, v + 8 * i);
       }
 #pragma unroll
@@ -224,12 +226,14 @@ __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, 
     const int ch = lane + 32 * i;
     if (ch < nchunk) {
       const int c = ch * 8;
-      float o[8];
+      float o[8], w8[8], b8[8];
+      VecIO<float, 8>::load(lw + c, w8); VecIO<float, 8>::load(lb + c, b8);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float t = (v[8 * i + k] - mean) * rstd * lw[c + k] + lb[c + k];
-        if (pe) t += pe[srow * C + c + k];
-        o[k] = t;
+      for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * w8[k] + b8[k];
+      if (pe) {
+        VecIO<float, 8>::load(pe + srow * C + c, w8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += w8[k];
       }
       VecIO<T, 8>::store(y + yoff + c, o);
     }
