@@ -45,11 +45,11 @@ template <> struct Pair2<bf16> {
 static constexpr int DCONV_THREADS = 288;     // >= 259 frames of a 6 s segment: the k3 conv runs one frame per thread
 
 template <typename T, int C>
-__global__ void __launch_bounds__(DCONV_THREADS) dconv_row_kernel(T* __restrict__ y, RowSpace ys, DconvRowParams P) {
+__global__ void __launch_bounds__(DCONV_THREADS, (C == 48 ? 3 : 2)) dconv_row_kernel(T* __restrict__ y, RowSpace ys, DconvRowParams P) {
   constexpr int H = C / 8;
   constexpr int XP = C + 2;                       // padded slab pitch (elements): odd word stride -> no bank conflicts
-  constexpr int CB = 48 / H;                      // channels per thread in the statistics pass (48 weight registers)
-  constexpr int CC = 24 / H;                      // (value, gate) channel pairs per thread in the apply pass
+  constexpr int CB = 24 / H;                      // channels per thread in the statistics pass (24 weight registers)
+  constexpr int CC = 2;                           // (value, gate) channel pairs per thread in the apply pass
   const int Tn = ys.G2;                           // frames
   extern __shared__ float smem_f[];
   float* w1s = smem_f;                            // [3][C][H]   (hidden channel fastest)

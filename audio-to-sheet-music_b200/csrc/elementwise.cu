@@ -313,48 +313,54 @@ __global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, 
                                  RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
                                  const float* __restrict__ gw, const float* __restrict__ gb, const T* __restrict__ skip,
                                  RowSpace ss) {
+  // blockIdx.y = group (segment x frame on the frequency branch, segment on the time branch): every per-group
+  // quantity (base offsets, GroupNorm mean / rstd) is computed once per thread, rows use 32-bit arithmetic
+  const int g = blockIdx.y;
   const int CV = os.C / VEC;
-  long total = (long)os.G * os.R * CV;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * VEC; long row = i / CV;
-    int d = (int)(row % os.R); int g = (int)(row / os.R);
+  const T* ug = u + us.row_off(g, 0);
+  T* og = out + os.row_off(g, 0);
+  const T* sg = skip + ss.row_off(g, 0);
+  const long urow = us.C, orow = os.C, srow = ss.C;
+  float mean = 0.f, rstd = 1.f;
+  if (has_gn) { mean = mr[2 * (g / G2)]; rstd = mr[2 * (g / G2) + 1]; }
+  const int total = os.R * CV;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = i % CV, d = i / CV, c = cv * VEC;
     int i0, i1; float lam;
     lerp_coords(d, Uin, os.R, i0, i1, lam);
     // phase layout: output row fo = 4q + r - 2 lives in the row of x[q-1] (us geometry), columns r*Cu + c
     float a0[VEC], a1[VEC], s0[VEC], s1[VEC], v[VEC];
-    VecIO<T, VEC>::load(u + us.row_off(g, ((i0 + 2) >> 2) - 1) + ((i0 + 2) & 3) * Cu + c, a0);
-    VecIO<T, VEC>::load(u + us.row_off(g, ((i1 + 2) >> 2) - 1) + ((i1 + 2) & 3) * Cu + c, a1);
+    VecIO<T, VEC>::load(ug + (long)(((i0 + 2) >> 2) - 1) * urow + ((i0 + 2) & 3) * Cu + c, a0);
+    VecIO<T, VEC>::load(ug + (long)(((i1 + 2) >> 2) - 1) * urow + ((i1 + 2) & 3) * Cu + c, a1);
     if (has_gn) {
-      float mean = mr[2 * (g / G2)], rstd = mr[2 * (g / G2) + 1];
+      float w[VEC], bb[VEC];
+      VecIO<float, VEC>::load(gw + c, w); VecIO<float, VEC>::load(gb + c, bb);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        float w = gw[c + k], bb = gb[c + k];
-        a0[k] = gelu_act<T>((a0[k] - mean) * rstd * w + bb);
-        a1[k] = gelu_act<T>((a1[k] - mean) * rstd * w + bb);
+        const float sc = rstd * w[k], sh = bb[k] - mean * sc;
+        a0[k] = gelu_act<T>(fmaf(a0[k], sc, sh));
+        a1[k] = gelu_act<T>(fmaf(a1[k], sc, sh));
       }
     }
     int j0, j1; float mu;
     lerp_coords(d, ss.R, os.R, j0, j1, mu);
-    VecIO<T, VEC>::load(skip + ss.row_off(g, j0) + c, s0);
-    VecIO<T, VEC>::load(skip + ss.row_off(g, j1) + c, s1);
+    VecIO<T, VEC>::load(sg + (long)j0 * srow + c, s0);
+    VecIO<T, VEC>::load(sg + (long)j1 * srow + c, s1);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) v[k] = ((1.f - lam) * a0[k] + lam * a1[k]) + 0.1f * ((1.f - mu) * s0[k] + mu * s1[k]);
-    VecIO<T, VEC>::store(out + os.row_off(g, d) + c, v);
+    VecIO<T, VEC>::store(og + (long)d * orow + c, v);
   }
 }
 template <typename T>
 void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace os, int G2, int has_gn,
                       const float* mr, const float* gw, const float* gb, const T* skip, RowSpace ss,
                       cudaStream_t st) {
-  if (os.C % 8 == 0) {
-    long total = (long)os.G * os.R * (os.C / 8);
-    dec_apply_kernel<T, 8><<<(int)min((total + 255) / 256, (long)148 * 32), 256, 0, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw,
-                                                                                         gb, skip, ss);
-  } else {
-    long total = (long)os.G * os.R * (os.C / 4);
-    dec_apply_kernel<T, 4><<<(int)min((total + 255) / 256, (long)148 * 32), 256, 0, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw,
-                                                                                         gb, skip, ss);
-  }
+  const int vec = os.C % 8 == 0 ? 8 : 4;
+  const long per_group = (long)os.R * (os.C / vec);
+  int bx = (int)min((per_group + 255) / 256, (long)max(1, (148 * 16) / os.G + 1));
+  dim3 grid(bx, os.G);
+  if (vec == 8) dec_apply_kernel<T, 8><<<grid, 256, 0, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw, gb, skip, ss);
+  else dec_apply_kernel<T, 4><<<grid, 256, 0, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw, gb, skip, ss);
 }
 
 // ------------------------------------------------------------------ weight packing (fp32 params -> T, GEMM layouts)
