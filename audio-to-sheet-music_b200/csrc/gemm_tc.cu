@@ -158,8 +158,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
 }
 
 // ------------------------------------------------------------------ kernel
-template <int EF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int EF, int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -350,7 +350,8 @@ bool make_tensor_map_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint6
 bool tensor_map_api_available() { return get_encode() != nullptr; }
 
 static int g_tc_bn_cap = 256;
-void tc_set_bn_cap(int cap) { g_tc_bn_cap = cap; }
+static bool g_tc_two_ctas = true;
+void tc_set_bn_cap(int cap) { g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); }
 
 int tc_pick_bn(int N) {
   if (N % 16) return 0;
@@ -404,11 +405,13 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   if (!make_tensor_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
   if (!make_tensor_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
   const int stage_bytes = TC_BM * TC_BK * 2 + p.BN * TC_BK * 2;
-  const int smem_budget = 227 * 1024 - 1024 - 512;
+  // narrow tiles are epilogue-bound: two CTAs per SM (2 x 8 epilogue warps, 2 x 2 accumulators <= 512 TMEM columns)
+  const int ctas_per_sm = (p.BN <= 128 && g_tc_two_ctas) ? 2 : 1;
+  const int smem_budget = (ctas_per_sm == 2 ? 112 : 227) * 1024 - 1024 - 512;
   p.stages = std::min(TC_MAX_STAGES, std::max(2, smem_budget / stage_bytes));
   const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 512;
   const long tiles = (long)p.m_tiles * p.n_tiles;
-  dim3 grid((unsigned)std::min<long>(tiles, num_sms()));
+  dim3 grid((unsigned)std::min<long>(tiles, (long)num_sms() * ctas_per_sm));
   int ef = 0;
   if (f.act == ACT_GELU) ef |= EF_GELU;
   if (f.glu) ef |= EF_GLU;
@@ -419,10 +422,12 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   case E: {                                                                                                               \
     static bool attr_set = false;                                                                                         \
     if (!attr_set) {                                                                                                      \
-      cudaFuncSetAttribute(gemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                   \
+      cudaFuncSetAttribute(gemm_tc_kernel<E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                \
+      cudaFuncSetAttribute(gemm_tc_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);                \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
-    gemm_tc_kernel<E><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);                                                       \
+    if (ctas_per_sm == 2) gemm_tc_kernel<E, 2><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);                              \
+    else gemm_tc_kernel<E, 1><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);                                               \
     return 0;                                                                                                             \
   }
   switch (ef) {
