@@ -190,7 +190,7 @@ class Engine:
         return self.plans[key]
 
     def gemm_kernel_name(self) -> str:
-        return "gemm_tc_kernel (tcgen05) + gemm_simt_kernel" if self.dtype == "bf16" else "gemm_simt_kernel (CUDA-core fp32)"
+        return "gemm_tc_kernel + flash_attn_kernel (tcgen05)" if self.dtype == "bf16" else "gemm_simt_kernel (CUDA-core fp32)"
 
     def drop_plans(self) -> None:
         self.plans.clear()

@@ -207,8 +207,15 @@ def main():
         except Exception:
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        traffic = None
+        try:      # DRAM bytes per launch of the GEMM + attention kernels from the committed ncu capture (B=32 forward)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = (tr["gemm_tc_kernel"]["dram_bytes_total"] + tr["flash_attn_kernel"]["dram_bytes_total"]) / (
+                tr["gemm_tc_kernel"]["launches"] + tr["flash_attn_kernel"]["launches"])
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": prof["kernel"], "achieved": prof["tflops"], "peak": peak, "unit": "TFLOP/s",
-                "frac": prof["tflops"] / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                "frac": prof["tflops"] / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, batch-32 forward, profiles/r01_traffic.json)", "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                 "launches_per_step": prof["launches"], "gemm_ms_per_step": prof["ms"], "share_of_step": prof["ms"] / (ms / args.steps),
                 "algorithmic_gflop_per_step": prof["gflop"]}
         line = {
