@@ -31,6 +31,11 @@ template <typename T> void launch_pack_weight(const float* src, T* dst, long n, 
 template <typename T> bool dconv_row_supported(int C, int Tn);
 template <typename T> void launch_dconv_row(T* y, RowSpace ys, const float* const* ptrs, cudaStream_t st);
 
+// ---- enc_row.cu (bf16: fused conv(level 0) + DConv + rewrite of a frequency encoder layer, warp-level MMA)
+bool enc_row_supported(int C, int Tn, bool fuse_conv);
+void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, RowSpace ys, const float* const* ptrs, float emb_scale,
+                    bool fuse_conv, cudaStream_t st);
+
 // ---- fft.cu
 void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
                      cudaStream_t st);

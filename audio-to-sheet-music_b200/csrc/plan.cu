@@ -285,6 +285,37 @@ static ConvOp<T> conv_op(int mode, const T* a, RowSpace as, const T* w, int N, T
   return o;
 }
 
+// bf16 only: fused per-row layer tail (enc_row.cu).  run=false just answers whether it applies.
+static bool enc_row_run(bool run, const ParamTable* pt, const float* params, int i, const bf16* x, RowSpace xin, const bf16* y, bf16* out,
+                        RowSpace ys, int Tf, cudaStream_t st) {
+  const int C = kCh[i];
+  if (!(C == 48 || C == 96) || !enc_row_supported(C, Tf, false)) return false;
+  if (!run) return true;
+  const bool fuse = i == 0 && enc_row_supported(C, Tf, true);
+  const std::string p = std::string("htdemucs.encoder.") + std::to_string(i);
+  const float* ptrs[23];
+  auto P = [&](const std::string& n) { return params + pt->off(n); };
+  ptrs[0] = P(p + ".conv.weight"); ptrs[1] = P(p + ".conv.bias");
+  for (int dd = 0; dd < 2; ++dd) {
+    const std::string q = p + ".dconv.layers." + std::to_string(dd);
+    const char* names[9] = {".0.weight", ".0.bias", ".1.weight", ".1.bias", ".3.weight", ".3.bias", ".4.weight", ".4.bias", ".6.scale"};
+    for (int k = 0; k < 9; ++k) ptrs[2 + 9 * dd + k] = P(q + names[k]);
+  }
+  ptrs[20] = P(p + ".rewrite.weight"); ptrs[21] = P(p + ".rewrite.bias");
+  ptrs[22] = i == 0 ? P("htdemucs.freq_emb.embedding.weight") : nullptr;
+  launch_enc_row(x, xin, y, out, ys, ptrs, 10.0f * 0.2f, fuse, st);
+  return true;
+}
+static bool enc_row_run(bool, const ParamTable*, const float*, int, const float*, RowSpace, const float*, float*, RowSpace, int, cudaStream_t) {
+  return false;      // fp32 build: SIMT kernels only
+}
+template <typename T>
+bool PlanT<T>::enc_row_dispatch(bool run, int i, const T* x, RowSpace xin, const T* y, T* out, RowSpace ys, cudaStream_t st) {
+  const bool ok = enc_row_run(run, pt, params, i, x, xin, y, out, ys, sh.Tf, st);
+  if (ok && run) ++n_launches;
+  return ok;
+}
+
 // ---- one HEncLayer (demucs hdemucs.py:HEncLayer) on a channels-last row space.
 //   x   : input activation (padded row space xin, C_in channels)
 //   y   : conv+GELU output, updated in place by the two DConv residual layers (space ys, C channels)
@@ -296,11 +327,16 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
   const std::string p = std::string("htdemucs.") + (freq ? "encoder." : "tencoder.") + std::to_string(i);
   const int G2 = ys.G2;
   const int R = ys.R;
-  {  // strided conv k8 s4 p2 (+ right zero pad to a multiple of 4 on the time branch) + GELU
+  // bf16 build, frequency levels 1-2: the whole layer tail (level 1: the k8s4 conv too) runs per (segment, frequency
+  // row) slab in shared memory -- input read once, output written once (enc_row.cu)
+  const bool row_fused = freq && use_fused_dconv && use_tc && enc_row_dispatch(false, i, nullptr, xin, nullptr, nullptr, ys, st);
+  const bool row_conv = row_fused && i == 0 && enc_row_supported(C, s.Tf, true);
+  if (!row_conv) {  // strided conv k8 s4 p2 (+ right zero pad to a multiple of 4 on the time branch) + GELU
     ConvOp<T> o = conv_op<T>(CONV_K8S4, x, xin, PW(p + ".conv.w"), C, y, ys);
     o.bias = P32(p + ".conv.bias"); o.act = ACT_GELU;
     conv(o, st);
   }
+  if (row_fused) { enc_row_dispatch(true, i, x, xin, y, out, ys, st); return; }
   const bool tc_dconv = sizeof(T) == 2 && use_tc && tensor_map_api_available();
   const int Hp = hidden_pad(H);
   RowSpace hs = ys; hs.C = tc_dconv ? Hp : H;

@@ -101,6 +101,7 @@ struct PlanT : PlanBase {
   void conv(const ConvOp<T>& o, cudaStream_t st);
   void prof_begin(double gflop, cudaStream_t st);
   void prof_end(cudaStream_t st);
+  bool enc_row_dispatch(bool run, int i, const T* x, RowSpace xin, const T* y, T* out, RowSpace ys, cudaStream_t st);
   void enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSpace ys, T* out, cudaStream_t st);
   void attention(const T* q, long ldq, const T* k, const T* v, long ldkv, int Sq, int Sk, T* o, cudaStream_t st);
   void linear(const T* a, int S, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st);
