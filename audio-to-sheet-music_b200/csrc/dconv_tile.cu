@@ -1,0 +1,386 @@
+// DConv residual branch (demucs demucs.py:DConv, depth 2, compress 8) for the layers whose
+// GroupNorm(1, .) statistics span more than one CTA can hold: the whole TIME branch (statistics per segment over
+// [C/8 | 2C, L_i]) and frequency levels 3-4 (per (segment, frequency row) over [., Tf], slabs too wide for one SM).
+//
+//   y += scale * GLU( GN2( W2 * GELU( GN1( conv_k3_dil(y) + b1 ) ) + b2 ) )
+//
+// runs as three bandwidth-bound passes; kernel boundaries are the two grid-wide reductions:
+//   A  h = conv_k3_dil(y) + b1              -> narrow hidden buffer (C/8 channels, bf16) + GN1 partial sums
+//   B  g = GELU(GN1(h)) in place            + GN2 partial sums of e = W2 g + b2 (e is never stored)
+//   C  y += scale * GLU(GN2(W2 g + b2))     e recomputed from the narrow g (K = 16..48), y tile staged in shared memory
+// The wide tensors move once in A (read y) and once in C (read + write y); the 2C-wide expand tensor never exists.
+// All contractions are warp-level mma.sync on 16-row tiles (K = 3C -> C/8 -> 2C is far too small / too epilogue-heavy
+// for a tcgen05 tile: the previous version ran them as three gemm_tc launches that were 5-10x off the HBM floor).
+//
+// Rows are addressed through a "logical row" space per segment: i = t * Rr + f, element offset
+// base + b*seg + t*fs + f*C; the k3 taps shift i by +-dil*Rr (time branch: Rr = 1, a row shift; frequency branch:
+// Rr = R rows per frame, a frame shift).  Out-of-range rows are zeros (the conv's zero padding).
+#include "kernels.cuh"
+#include "mma_sync.cuh"
+
+namespace athtd {
+
+struct DcGeom {
+  int nT, Rr, rows;      // rows = nT * Rr logical rows per segment
+  long seg, base, fs;
+};
+
+struct DcTileParams {
+  DcGeom g;
+  int dil, per_row;      // per_row: statistics per (segment, f) instead of per segment
+  bf16* y; bf16* h;
+  const bf16* w1; const float* b1; const float* g1w; const float* g1b;
+  const bf16* w2; const float* b2; const float* g2w; const float* g2b; const float* scale;
+  double* st1; double* st2;
+};
+
+template <int C> struct DcDims {
+  static constexpr int H = C / 8;
+  static constexpr int HN = (H + 7) / 8;                          // hidden n-tiles that hold real channels
+  static constexpr int HP = H <= 16 ? 16 : (H <= 32 ? 32 : 48);   // == hidden_pad(H), the packed K of the expand
+  static constexpr int KS = HP / 16;
+  static constexpr int XP = C + 8;                                // activation tile pitch (conflict-free ldmatrix)
+  static constexpr int K1 = 3 * C, K1P = K1 + 8;
+  static constexpr int K2P = HP + 8;
+};
+
+template <int C>
+__device__ __forceinline__ void dc_load_rows(bf16* dst, const bf16* __restrict__ yb, const DcGeom& g, int i_start, int n) {
+  constexpr int CV = C / 8, XP = C + 8;
+  for (int idx = threadIdx.x; idx < n * CV; idx += blockDim.x) {
+    const int row = idx / CV, cv = idx - row * CV;
+    const int i = i_start + row;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i >= 0 && i < g.rows) {
+      const int t = i / g.Rr, f = i - t * g.Rr;
+      v = *(const uint4*)(yb + (long)t * g.fs + (long)f * C + cv * 8);
+    }
+    *(uint4*)(dst + row * XP + cv * 8) = v;
+  }
+}
+
+// warp 0: (sum, sumsq) fp64 slots -> mean / rstd (biased variance, eps 1e-5)
+__device__ __forceinline__ void dc_mean_rstd(const double* st, int nslot, double count, float* out) {
+  const int lane = threadIdx.x & 31;
+  double a = 0.0, c = 0.0;
+  for (int s = lane; s < nslot; s += 32) { a += st[2 * s]; c += st[2 * s + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+  if (lane == 0) {
+    double tmp[2] = {a, c};
+    stats_to_mean_rstd(tmp, count, 1e-5f, out[0], out[1]);
+  }
+}
+// fills mr[2*f] for f < Rr (per_row) or mr[0..1] (per segment)
+__device__ __forceinline__ void dc_stage_mean_rstd(const double* st, int b, int per_row, int Rr, double count, float* mr) {
+  if (per_row) {
+    for (int f = threadIdx.x; f < Rr; f += blockDim.x) {
+      float m, r;
+      stats_to_mean_rstd(st + 2 * ((long)b * Rr + f), count, 1e-5f, m, r);
+      mr[2 * f] = m; mr[2 * f + 1] = r;
+    }
+  } else if (threadIdx.x < 32) {
+    dc_mean_rstd(st + 2 * (long)b * STAT_SLOTS, STAT_SLOTS, count, mr);
+  }
+}
+
+__device__ __forceinline__ void dc_block_sum2(float& a, float& b, float* red) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) { red[2 * w] = a; red[2 * w + 1] = b; }
+  __syncthreads();
+  float x = l < nw ? red[2 * l] : 0.f, y = l < nw ? red[2 * l + 1] : 0.f;
+  a = warp_sum(x); b = warp_sum(y);
+}
+
+// row-pair partial sums -> statistics accumulators
+__device__ __forceinline__ void dc_row_stats(double* st, int b, int Rr, int r_lo, int r_hi, bool v_lo, bool v_hi, float s_lo,
+                                             float q_lo, float s_hi, float q_hi) {
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    s_lo += __shfl_xor_sync(0xffffffffu, s_lo, o); q_lo += __shfl_xor_sync(0xffffffffu, q_lo, o);
+    s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o); q_hi += __shfl_xor_sync(0xffffffffu, q_hi, o);
+  }
+  if ((threadIdx.x & 3) == 0) {
+    if (v_lo) { double* sp = st + 2 * ((long)b * Rr + r_lo % Rr); atomicAdd(sp, (double)s_lo); atomicAdd(sp + 1, (double)q_lo); }
+    if (v_hi) { double* sp = st + 2 * ((long)b * Rr + r_hi % Rr); atomicAdd(sp, (double)s_hi); atomicAdd(sp + 1, (double)q_hi); }
+  }
+}
+
+// ------------------------------------------------------------------ pass A
+template <int C, int TM>
+__global__ void __launch_bounds__(256) dconv_a_kernel(const DcTileParams p) {
+  typedef DcDims<C> D;
+  constexpr int MW = TM / 16, NG = 8 / MW, NPW = (D::HN + NG - 1) / NG;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int halo = p.dil * p.g.Rr;
+  const int nload = TM + 2 * halo;
+  bf16* xs = (bf16*)smem_raw;                       // [nload][XP]: logical rows i0-halo .. i0+TM+halo
+  bf16* w1s = xs + (size_t)nload * D::XP;           // [8*HN][K1P]
+  float* red = (float*)(w1s + 8 * D::HN * D::K1P);  // 32 floats
+  const int b = blockIdx.y, i0 = blockIdx.x * TM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  dc_load_rows<C>(xs, p.y + p.g.base + (long)b * p.g.seg, p.g, i0 - halo, nload);
+  for (int idx = tid; idx < 8 * D::HN * (D::K1 / 8); idx += blockDim.x) {
+    const int n = idx / (D::K1 / 8), kc = idx - n * (D::K1 / 8);
+    *(uint4*)(w1s + n * D::K1P + kc * 8) = *(const uint4*)(p.w1 + (long)n * D::K1 + kc * 8);
+  }
+  __syncthreads();
+  const int mt = warp % MW, ng = warp / MW;
+  float acc[NPW][4];
+#pragma unroll
+  for (int j = 0; j < NPW; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 3; ++tap) {
+    const bf16* xr = xs + (size_t)tap * halo * D::XP;
+#pragma unroll 4
+    for (int kc = 0; kc < C / 16; ++kc) {
+      uint32_t a[4];
+      ldsm_a(xr, D::XP, mt * 16, kc * 16, lane, a);
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) {
+        const int nt = ng * NPW + j;
+        if (nt < D::HN) {
+          uint32_t bb[2];
+          frag_b(w1s, D::K1P, nt * 8, tap * C + kc * 16, lane, bb);
+          mma16816(acc[j], a, bb);
+        }
+      }
+    }
+  }
+  const int r_lo = i0 + mt * 16 + g, r_hi = r_lo + 8;
+  const bool v_lo = r_lo < p.g.rows, v_hi = r_hi < p.g.rows;
+  bf16* hb = p.h + (long)b * p.g.rows * D::HP;
+  float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+#pragma unroll
+  for (int j = 0; j < NPW; ++j) {
+    const int nt = ng * NPW + j;
+    if (nt < D::HN) {
+      const int c = nt * 8 + 2 * q;
+      const float b0 = p.b1[c], b1 = p.b1[c + 1];      // zero beyond H, like the packed weight rows: pad channels are exactly 0
+      const float x0 = acc[j][0] + b0, x1 = acc[j][1] + b1, x2 = acc[j][2] + b0, x3 = acc[j][3] + b1;
+      if (v_lo) { s_lo += x0 + x1; q_lo += x0 * x0 + x1 * x1; *(uint32_t*)(hb + (long)r_lo * D::HP + c) = pack_bf16x2(x0, x1); }
+      if (v_hi) { s_hi += x2 + x3; q_hi += x2 * x2 + x3 * x3; *(uint32_t*)(hb + (long)r_hi * D::HP + c) = pack_bf16x2(x2, x3); }
+    }
+  }
+  if (ng == 0) {
+    for (int c = 8 * D::HN + 2 * q; c < D::HP; c += 8) {   // K padding of the expand must be zero
+      if (v_lo) *(uint32_t*)(hb + (long)r_lo * D::HP + c) = 0u;
+      if (v_hi) *(uint32_t*)(hb + (long)r_hi * D::HP + c) = 0u;
+    }
+  }
+  if (p.per_row) {
+    dc_row_stats(p.st1, b, p.g.Rr, r_lo, r_hi, v_lo, v_hi, s_lo, q_lo, s_hi, q_hi);
+  } else {
+    float s = s_lo + s_hi, qq = q_lo + q_hi;
+    dc_block_sum2(s, qq, red);
+    if (tid == 0) {
+      double* sp = p.st1 + 2 * ((long)b * STAT_SLOTS + blockIdx.x % STAT_SLOTS);
+      atomicAdd(sp, (double)s); atomicAdd(sp + 1, (double)qq);
+    }
+  }
+}
+
+// GELU(GN1(.)) of one packed bf16 pair of the hidden buffer, written back in place; returns the packed result
+template <int C>
+__device__ __forceinline__ uint32_t dc_gn_gelu_pair(bf16* hp, int c, float mean, float rstd, const float* g1w, const float* g1b) {
+  const float2 x = unpack_bf16x2(*(const uint32_t*)hp);
+  // zero-padded affine beyond H: (x - m) * r * 0 + 0 = 0 and GELU(0) = 0, the K padding stays exactly zero
+  const float y0 = gelu_fast((x.x - mean) * rstd * g1w[c] + g1b[c]);
+  const float y1 = gelu_fast((x.y - mean) * rstd * g1w[c + 1] + g1b[c + 1]);
+  const uint32_t r = pack_bf16x2(y0, y1);
+  *(uint32_t*)hp = r;
+  return r;
+}
+
+// ------------------------------------------------------------------ pass B
+template <int C>
+__global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
+  typedef DcDims<C> D;
+  constexpr int NT2 = 2 * C / 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* w2s = (bf16*)smem_raw;                      // [2C][K2P]
+  float* b2s = (float*)(w2s + 2 * C * D::K2P);      // [2C]
+  float* g1ws = b2s + 2 * C;                        // [HP]
+  float* g1bs = g1ws + D::HP;                       // [HP]
+  float* mr = g1bs + D::HP;                         // [64]
+  float* red = mr + 64;                             // [32]
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  for (int idx = tid; idx < 2 * C * (D::HP / 8); idx += blockDim.x) {
+    const int n = idx / (D::HP / 8), kc = idx - n * (D::HP / 8);
+    *(uint4*)(w2s + n * D::K2P + kc * 8) = *(const uint4*)(p.w2 + (long)n * D::HP + kc * 8);
+  }
+  for (int i = tid; i < 2 * C; i += blockDim.x) b2s[i] = p.b2[i];
+  for (int i = tid; i < D::HP; i += blockDim.x) { g1ws[i] = p.g1w[i]; g1bs[i] = p.g1b[i]; }
+  dc_stage_mean_rstd(p.st1, b, p.per_row, p.g.Rr, (double)D::H * (p.per_row ? p.g.nT : p.g.rows), mr);
+  __syncthreads();
+  bf16* hb = p.h + (long)b * p.g.rows * D::HP;
+  float ts = 0.f, tq = 0.f;
+  for (int tile = blockIdx.x; tile * 128 < p.g.rows; tile += gridDim.x) {
+    const int r_lo = tile * 128 + warp * 16 + g, r_hi = r_lo + 8;
+    const bool v_lo = r_lo < p.g.rows, v_hi = r_hi < p.g.rows;
+    const int f_lo = p.per_row ? r_lo % p.g.Rr : 0, f_hi = p.per_row ? r_hi % p.g.Rr : 0;
+    const float m_lo = mr[2 * f_lo], rs_lo = mr[2 * f_lo + 1], m_hi = mr[2 * f_hi], rs_hi = mr[2 * f_hi + 1];
+    uint32_t a[D::KS][4];
+#pragma unroll
+    for (int ks = 0; ks < D::KS; ++ks) {
+      const int c0 = ks * 16 + 2 * q, c1 = c0 + 8;
+      a[ks][0] = v_lo ? dc_gn_gelu_pair<C>(hb + (long)r_lo * D::HP + c0, c0, m_lo, rs_lo, g1ws, g1bs) : 0u;
+      a[ks][1] = v_hi ? dc_gn_gelu_pair<C>(hb + (long)r_hi * D::HP + c0, c0, m_hi, rs_hi, g1ws, g1bs) : 0u;
+      a[ks][2] = v_lo ? dc_gn_gelu_pair<C>(hb + (long)r_lo * D::HP + c1, c1, m_lo, rs_lo, g1ws, g1bs) : 0u;
+      a[ks][3] = v_hi ? dc_gn_gelu_pair<C>(hb + (long)r_hi * D::HP + c1, c1, m_hi, rs_hi, g1ws, g1bs) : 0u;
+    }
+    float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+#pragma unroll 4
+    for (int nt = 0; nt < NT2; ++nt) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < D::KS; ++ks) {
+        uint32_t bb[2];
+        frag_b(w2s, D::K2P, nt * 8, ks * 16, lane, bb);
+        mma16816(d, a[ks], bb);
+      }
+      const int c = nt * 8 + 2 * q;
+      const float e0 = d[0] + b2s[c], e1 = d[1] + b2s[c + 1], e2 = d[2] + b2s[c], e3 = d[3] + b2s[c + 1];
+      s_lo += e0 + e1; q_lo += e0 * e0 + e1 * e1;
+      s_hi += e2 + e3; q_hi += e2 * e2 + e3 * e3;
+    }
+    if (p.per_row) {
+      dc_row_stats(p.st2, b, p.g.Rr, r_lo, r_hi, v_lo, v_hi, s_lo, q_lo, s_hi, q_hi);
+    } else {
+      if (v_lo) { ts += s_lo; tq += q_lo; }
+      if (v_hi) { ts += s_hi; tq += q_hi; }
+    }
+  }
+  if (!p.per_row) {
+    dc_block_sum2(ts, tq, red);
+    if (tid == 0) {
+      double* sp = p.st2 + 2 * ((long)b * STAT_SLOTS + blockIdx.x % STAT_SLOTS);
+      atomicAdd(sp, (double)ts); atomicAdd(sp + 1, (double)tq);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pass C
+template <int C, int TM>
+__global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
+  typedef DcDims<C> D;
+  constexpr int MW = TM / 16, NG = 8 / MW, CV = C / 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* ys = (bf16*)smem_raw;                       // [TM][XP]
+  bf16* w2s = ys + TM * D::XP;                      // [2C][K2P]
+  float* b2s = (float*)(w2s + 2 * C * D::K2P);      // [2C] interleaved (value, gate)
+  float* gws = b2s + 2 * C;                         // [2C]
+  float* gbs = gws + 2 * C;                         // [2C]
+  float* scs = gbs + 2 * C;                         // [C]
+  float* mr = scs + C;                              // [64]
+  const int b = blockIdx.y, i0 = blockIdx.x * TM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  bf16* yb = p.y + p.g.base + (long)b * p.g.seg;
+  dc_load_rows<C>(ys, yb, p.g, i0, TM);
+  for (int idx = tid; idx < 2 * C * (D::HP / 8); idx += blockDim.x) {
+    const int n = idx / (D::HP / 8), kc = idx - n * (D::HP / 8);
+    *(uint4*)(w2s + n * D::K2P + kc * 8) = *(const uint4*)(p.w2 + (long)n * D::HP + kc * 8);
+  }
+  for (int i = tid; i < 2 * C; i += blockDim.x) { b2s[i] = p.b2[i]; gws[i] = p.g2w[i]; gbs[i] = p.g2b[i]; }
+  for (int i = tid; i < C; i += blockDim.x) scs[i] = p.scale[i];
+  dc_stage_mean_rstd(p.st2, b, p.per_row, p.g.Rr, (double)(2 * C) * (p.per_row ? p.g.nT : p.g.rows), mr);
+  __syncthreads();
+  const int mt = warp % MW, ng = warp / MW;
+  const int r_lo = i0 + mt * 16 + g, r_hi = r_lo + 8;
+  const bool v_lo = r_lo < p.g.rows, v_hi = r_hi < p.g.rows;
+  const int f_lo = p.per_row ? r_lo % p.g.Rr : 0, f_hi = p.per_row ? r_hi % p.g.Rr : 0;
+  const float m_lo = mr[2 * f_lo], rs_lo = mr[2 * f_lo + 1], m_hi = mr[2 * f_hi], rs_hi = mr[2 * f_hi + 1];
+  const bf16* hb = p.h + (long)b * p.g.rows * D::HP;
+  uint32_t a[D::KS][4];
+#pragma unroll
+  for (int ks = 0; ks < D::KS; ++ks) {
+    const int c0 = ks * 16 + 2 * q, c1 = c0 + 8;
+    a[ks][0] = v_lo ? ld_b32(hb + (long)r_lo * D::HP + c0) : 0u;
+    a[ks][1] = v_hi ? ld_b32(hb + (long)r_hi * D::HP + c0) : 0u;
+    a[ks][2] = v_lo ? ld_b32(hb + (long)r_lo * D::HP + c1) : 0u;
+    a[ks][3] = v_hi ? ld_b32(hb + (long)r_hi * D::HP + c1) : 0u;
+  }
+  bf16* y_lo = ys + (mt * 16 + g) * D::XP, *y_hi = y_lo + 8 * D::XP;
+#pragma unroll 2
+  for (int nt = ng; nt < C / 4; nt += NG) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < D::KS; ++ks) {
+      uint32_t bb[2];
+      frag_b(w2s, D::K2P, nt * 8, ks * 16, lane, bb);
+      mma16816(d, a[ks], bb);
+    }
+    const int c = nt * 8 + 2 * q, j = nt * 4 + q;            // interleaved columns: (value_j, gate_j)
+    const float ba = b2s[c], bg = b2s[c + 1], wa = gws[c], wg = gws[c + 1], oa = gbs[c], og = gbs[c + 1], sc = scs[j];
+    const float ea_lo = (d[0] + ba - m_lo) * rs_lo * wa + oa, eg_lo = (d[1] + bg - m_lo) * rs_lo * wg + og;
+    const float ea_hi = (d[2] + ba - m_hi) * rs_hi * wa + oa, eg_hi = (d[3] + bg - m_hi) * rs_hi * wg + og;
+    y_lo[j] = __float2bfloat16_rn(__bfloat162float(y_lo[j]) + sc * (ea_lo * sigmoid_fast_(eg_lo)));
+    y_hi[j] = __float2bfloat16_rn(__bfloat162float(y_hi[j]) + sc * (ea_hi * sigmoid_fast_(eg_hi)));
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TM * CV; idx += blockDim.x) {
+    const int row = idx / CV, cv = idx - row * CV;
+    const int i = i0 + row;
+    if (i < p.g.rows) {
+      const int t = i / p.g.Rr, f = i - t * p.g.Rr;
+      *(uint4*)(yb + (long)t * p.g.fs + (long)f * C + cv * 8) = *(const uint4*)(ys + row * D::XP + cv * 8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+bool dconv_tile_supported(int C) { return C == 48 || C == 96 || C == 192 || C == 384; }
+
+template <int C, int TM>
+static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
+  typedef DcDims<C> D;
+  const int halo = p.dil * p.g.Rr;
+  const size_t smA = (size_t)(TM + 2 * halo) * D::XP * 2 + (size_t)8 * D::HN * D::K1P * 2 + 32 * 4 + 16;
+  const size_t smB = (size_t)2 * C * D::K2P * 2 + (size_t)(2 * C + 2 * D::HP + 64 + 32) * 4 + 16;
+  const size_t smC = (size_t)TM * D::XP * 2 + (size_t)2 * C * D::K2P * 2 + (size_t)(7 * C + 64) * 4 + 16;
+  if (smA > 227 * 1024 || smC > 227 * 1024) return 1;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dconv_a_kernel<C, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dconv_b_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dconv_c_kernel<C, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  const int tiles = (p.g.rows + TM - 1) / TM;
+  const int tiles_b = (p.g.rows + 127) / 128;
+  const int gb = std::min(tiles_b, std::max(1, (148 * 4 + B - 1) / B));
+  dconv_a_kernel<C, TM><<<dim3(tiles, B), 256, smA, st>>>(p);
+  dconv_b_kernel<C><<<dim3(gb, B), 256, smB, st>>>(p);
+  dconv_c_kernel<C, TM><<<dim3(tiles, B), 256, smC, st>>>(p);
+  return 0;
+}
+
+// ptrs: w1p [HP][3C] bf16, b1p, g1wp, g1bp [HP] fp32, w2p [2C][HP] bf16 (GLU-interleaved rows), b2i, g2wi, g2bi [2C] fp32
+// (interleaved), scale [C] fp32.  Three launches; returns 0 on success.
+int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
+                      const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
+                      double* st2, cudaStream_t st) {
+  DcTileParams p;
+  const bool freq = ys.G2 > 1;
+  p.g.nT = freq ? ys.G2 : ys.R; p.g.Rr = freq ? ys.R : 1; p.g.rows = p.g.nT * p.g.Rr;
+  p.g.seg = ys.g1_stride(); p.g.base = ys.origin(); p.g.fs = freq ? (long)ys.Rp * ys.C : ys.C;
+  p.dil = dil; p.per_row = freq ? 1 : 0;
+  p.y = y; p.h = h; p.w1 = w1p; p.b1 = b1p; p.g1w = g1wp; p.g1b = g1bp; p.w2 = w2p; p.b2 = b2i; p.g2w = g2wi; p.g2b = g2bi;
+  p.scale = scale; p.st1 = st1; p.st2 = st2;
+  const int B = ys.batch();
+  if (freq && ys.R > 32) return 1;
+  switch (ys.C) {
+    case 48: return dconv_tile_launch<48, 128>(p, B, st);
+    case 96: return dconv_tile_launch<96, 128>(p, B, st);
+    case 192: return dconv_tile_launch<192, 128>(p, B, st);
+    case 384: return dconv_tile_launch<384, 64>(p, B, st);
+  }
+  return 1;
+}
+
+}  // namespace athtd

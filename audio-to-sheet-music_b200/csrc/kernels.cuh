@@ -36,6 +36,12 @@ bool enc_row_supported(int C, int Tn, bool fuse_conv);
 void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, RowSpace ys, const float* const* ptrs, float emb_scale,
                     bool fuse_conv, cudaStream_t st);
 
+// ---- dconv_tile.cu (bf16: DConv residual branch as three tiled mma.sync passes; time branch + frequency levels 3-4)
+bool dconv_tile_supported(int C);
+int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
+                      const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
+                      double* st2, cudaStream_t st);
+
 // ---- fft.cu
 void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
                      cudaStream_t st);

@@ -309,6 +309,17 @@ static bool enc_row_run(bool run, const ParamTable* pt, const float* params, int
 static bool enc_row_run(bool, const ParamTable*, const float*, int, const float*, RowSpace, const float*, float*, RowSpace, int, cudaStream_t) {
   return false;      // fp32 build: SIMT kernels only
 }
+// bf16 only: one DConv residual layer as three tiled mma.sync passes (dconv_tile.cu)
+static int dconv_tile_run(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
+                          const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
+                          double* st2, cudaStream_t st) {
+  return launch_dconv_tile(y, ys, h, dil, w1p, b1p, g1wp, g1bp, w2p, b2i, g2wi, g2bi, scale, st1, st2, st);
+}
+static int dconv_tile_run(float*, RowSpace, float*, int, const float*, const float*, const float*, const float*, const float*,
+                          const float*, const float*, const float*, const float*, double*, double*, cudaStream_t) {
+  return 1;
+}
+
 template <typename T>
 bool PlanT<T>::enc_row_dispatch(bool run, int i, const T* x, RowSpace xin, const T* y, T* out, RowSpace ys, cudaStream_t st) {
   const bool ok = enc_row_run(run, pt, params, i, x, xin, y, out, ys, sh.Tf, st);
@@ -357,6 +368,14 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
     double* st_e = freq ? st_df[i][dd][1] : st_dt[i][dd][1];
     const long nstat = freq ? (long)s.B * R : s.B;
     const int smode = freq ? STAT_PER_G1_M : STAT_PER_G1;
+    if (tc_dconv && use_fused_dconv && dconv_tile_supported(C) && (!freq || R <= 32)) {
+      // three bandwidth-bound mma.sync passes (conv3 + stats | GN+GELU + expand stats | expand + GN + GLU + residual)
+      const int rc = dconv_tile_run(y, ys, hbuf, 1 << dd, PW(q + ".0.wp"), PA(q + ".0.bp"), PA(q + ".1.wp"), PA(q + ".1.bp"),
+                                    PW(q + ".3.wp"), PA(q + ".3.bi"), PA(q + ".4.wi"), PA(q + ".4.bi"), P32(q + ".6.scale"), st_h, st_e, st);
+      if (rc != 0) throw std::runtime_error("athtd: dconv_tile launch failed");
+      n_launches += 3;
+      continue;
+    }
     if (tc_dconv) {
       // DConv layer on tensor cores in three passes over a narrow hidden buffer (C/8 channels zero-padded to Hp):
       //   1. h = conv3(y) + GroupNorm partial sums     2. h <- GELU(GN(h))
