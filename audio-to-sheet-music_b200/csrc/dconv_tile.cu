@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
       const int c0 = ks * 16 + 2 * q, c1 = c0 + 8;
       a[ks][0] = v_lo ? dc_gn_gelu_pair<C>(hb + (long)r_lo * D::HP + c0, c0, m_lo, rs_lo, g1ws, g1bs) : 0u;
       a[ks][1] = v_hi ? dc_gn_gelu_pair<C>(hb + (long)r_hi * D::HP + c0, c0, m_hi, rs_hi, g1ws, g1bs) : 0u;
+      if (ks * 16 + 8 >= D::H) { a[ks][2] = 0u; a[ks][3] = 0u; continue; }     // pure K padding (zeros written by pass A)
       a[ks][2] = v_lo ? dc_gn_gelu_pair<C>(hb + (long)r_lo * D::HP + c1, c1, m_lo, rs_lo, g1ws, g1bs) : 0u;
       a[ks][3] = v_hi ? dc_gn_gelu_pair<C>(hb + (long)r_hi * D::HP + c1, c1, m_hi, rs_hi, g1ws, g1bs) : 0u;
     }
@@ -266,17 +267,27 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
 }
 
 // ------------------------------------------------------------------ pass C
-template <int C, int TM>
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// The GLU-interleaved packed expand rows (2j = value_j, 2j+1 = gate_j) are de-interleaved while they are staged
+// (rows [0,C) values, [C,2C) gates): a lane then owns two ADJACENT value channels and their gates (one value n-tile + one
+// gate n-tile per step) and updates the y tile with 4-byte accesses.  sigmoid(x) = 0.5 + 0.5 tanh(x/2) (one MUFU op).
+// Per-segment statistics (PER_ROW = false) fold GroupNorm into one per-column FMA: e = d * alpha + beta.
+template <int C, int TM, bool PER_ROW>
 __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
   typedef DcDims<C> D;
   constexpr int MW = TM / 16, NG = 8 / MW, CV = C / 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* ys = (bf16*)smem_raw;                       // [TM][XP]
-  bf16* w2s = ys + TM * D::XP;                      // [2C][K2P]
-  float* b2s = (float*)(w2s + 2 * C * D::K2P);      // [2C] interleaved (value, gate)
-  float* gws = b2s + 2 * C;                         // [2C]
-  float* gbs = gws + 2 * C;                         // [2C]
-  float* scs = gbs + 2 * C;                         // [C]
+  bf16* w2s = ys + TM * D::XP;                      // [2C][K2P] de-interleaved
+  float* al = (float*)(w2s + 2 * C * D::K2P);       // [2C] alpha (PER_ROW: GroupNorm weight)
+  float* be = al + 2 * C;                           // [2C] beta  (PER_ROW: GroupNorm bias)
+  float* b2s = be + 2 * C;                          // [2C] expand bias (PER_ROW only)
+  float* scs = b2s + 2 * C;                         // [C]
   float* mr = scs + C;                              // [64]
   const int b = blockIdx.y, i0 = blockIdx.x * TM;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -284,16 +295,27 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
   dc_load_rows<C>(ys, yb, p.g, i0, TM);
   for (int idx = tid; idx < 2 * C * (D::HP / 8); idx += blockDim.x) {
     const int n = idx / (D::HP / 8), kc = idx - n * (D::HP / 8);
-    *(uint4*)(w2s + n * D::K2P + kc * 8) = *(const uint4*)(p.w2 + (long)n * D::HP + kc * 8);
+    const int nd = (n & 1) * C + (n >> 1);
+    *(uint4*)(w2s + nd * D::K2P + kc * 8) = *(const uint4*)(p.w2 + (long)n * D::HP + kc * 8);
   }
-  for (int i = tid; i < 2 * C; i += blockDim.x) { b2s[i] = p.b2[i]; gws[i] = p.g2w[i]; gbs[i] = p.g2b[i]; }
   for (int i = tid; i < C; i += blockDim.x) scs[i] = p.scale[i];
-  dc_stage_mean_rstd(p.st2, b, p.per_row, p.g.Rr, (double)(2 * C) * (p.per_row ? p.g.nT : p.g.rows), mr);
+  dc_stage_mean_rstd(p.st2, b, PER_ROW ? 1 : 0, p.g.Rr, (double)(2 * C) * (PER_ROW ? p.g.nT : p.g.rows), mr);
+  __syncthreads();
+  for (int n = tid; n < 2 * C; n += blockDim.x) {
+    const int nd = (n & 1) * C + (n >> 1);
+    const float half = (n & 1) ? 0.5f : 1.0f;       // gates carry the x/2 of the tanh form
+    if (PER_ROW) {
+      al[nd] = half * p.g2w[n]; be[nd] = half * p.g2b[n]; b2s[nd] = p.b2[n];
+    } else {
+      const float a = mr[1] * p.g2w[n];
+      al[nd] = half * a; be[nd] = half * ((p.b2[n] - mr[0]) * a + p.g2b[n]);
+    }
+  }
   __syncthreads();
   const int mt = warp % MW, ng = warp / MW;
   const int r_lo = i0 + mt * 16 + g, r_hi = r_lo + 8;
   const bool v_lo = r_lo < p.g.rows, v_hi = r_hi < p.g.rows;
-  const int f_lo = p.per_row ? r_lo % p.g.Rr : 0, f_hi = p.per_row ? r_hi % p.g.Rr : 0;
+  const int f_lo = PER_ROW ? r_lo % p.g.Rr : 0, f_hi = PER_ROW ? r_hi % p.g.Rr : 0;
   const float m_lo = mr[2 * f_lo], rs_lo = mr[2 * f_lo + 1], m_hi = mr[2 * f_hi], rs_hi = mr[2 * f_hi + 1];
   const bf16* hb = p.h + (long)b * p.g.rows * D::HP;
   uint32_t a[D::KS][4];
@@ -302,25 +324,43 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
     const int c0 = ks * 16 + 2 * q, c1 = c0 + 8;
     a[ks][0] = v_lo ? ld_b32(hb + (long)r_lo * D::HP + c0) : 0u;
     a[ks][1] = v_hi ? ld_b32(hb + (long)r_hi * D::HP + c0) : 0u;
+    if (ks * 16 + 8 >= D::H) { a[ks][2] = 0u; a[ks][3] = 0u; continue; }
     a[ks][2] = v_lo ? ld_b32(hb + (long)r_lo * D::HP + c1) : 0u;
     a[ks][3] = v_hi ? ld_b32(hb + (long)r_hi * D::HP + c1) : 0u;
   }
   bf16* y_lo = ys + (mt * 16 + g) * D::XP, *y_hi = y_lo + 8 * D::XP;
 #pragma unroll 2
-  for (int nt = ng; nt < C / 4; nt += NG) {
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int vt = ng; vt < CV; vt += NG) {
+    float dv[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ks = 0; ks < D::KS; ++ks) {
       uint32_t bb[2];
-      frag_b(w2s, D::K2P, nt * 8, ks * 16, lane, bb);
-      mma16816(d, a[ks], bb);
+      frag_b(w2s, D::K2P, vt * 8, ks * 16, lane, bb);
+      mma16816(dv, a[ks], bb);
+      frag_b(w2s, D::K2P, C + vt * 8, ks * 16, lane, bb);
+      mma16816(dg, a[ks], bb);
     }
-    const int c = nt * 8 + 2 * q, j = nt * 4 + q;            // interleaved columns: (value_j, gate_j)
-    const float ba = b2s[c], bg = b2s[c + 1], wa = gws[c], wg = gws[c + 1], oa = gbs[c], og = gbs[c + 1], sc = scs[j];
-    const float ea_lo = (d[0] + ba - m_lo) * rs_lo * wa + oa, eg_lo = (d[1] + bg - m_lo) * rs_lo * wg + og;
-    const float ea_hi = (d[2] + ba - m_hi) * rs_hi * wa + oa, eg_hi = (d[3] + bg - m_hi) * rs_hi * wg + og;
-    y_lo[j] = __float2bfloat16_rn(__bfloat162float(y_lo[j]) + sc * (ea_lo * sigmoid_fast_(eg_lo)));
-    y_hi[j] = __float2bfloat16_rn(__bfloat162float(y_hi[j]) + sc * (ea_hi * sigmoid_fast_(eg_hi)));
+    const int j = vt * 8 + 2 * q;
+    const float2 av = *(const float2*)(al + j), bv = *(const float2*)(be + j);
+    const float2 ag = *(const float2*)(al + C + j), bg = *(const float2*)(be + C + j);
+    const float2 sc = *(const float2*)(scs + j);
+    float ev[4], eg[4];
+    if (PER_ROW) {
+      const float2 kv = *(const float2*)(b2s + j), kg = *(const float2*)(b2s + C + j);
+      ev[0] = fmaf((dv[0] + kv.x - m_lo) * rs_lo, av.x, bv.x); ev[1] = fmaf((dv[1] + kv.y - m_lo) * rs_lo, av.y, bv.y);
+      ev[2] = fmaf((dv[2] + kv.x - m_hi) * rs_hi, av.x, bv.x); ev[3] = fmaf((dv[3] + kv.y - m_hi) * rs_hi, av.y, bv.y);
+      eg[0] = fmaf((dg[0] + kg.x - m_lo) * rs_lo, ag.x, bg.x); eg[1] = fmaf((dg[1] + kg.y - m_lo) * rs_lo, ag.y, bg.y);
+      eg[2] = fmaf((dg[2] + kg.x - m_hi) * rs_hi, ag.x, bg.x); eg[3] = fmaf((dg[3] + kg.y - m_hi) * rs_hi, ag.y, bg.y);
+    } else {
+      ev[0] = fmaf(dv[0], av.x, bv.x); ev[1] = fmaf(dv[1], av.y, bv.y); ev[2] = fmaf(dv[2], av.x, bv.x); ev[3] = fmaf(dv[3], av.y, bv.y);
+      eg[0] = fmaf(dg[0], ag.x, bg.x); eg[1] = fmaf(dg[1], ag.y, bg.y); eg[2] = fmaf(dg[2], ag.x, bg.x); eg[3] = fmaf(dg[3], ag.y, bg.y);
+    }
+    float uo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) uo[e] = ev[e] * fmaf(0.5f, tanh_approx(eg[e]), 0.5f);
+    const float2 x0 = unpack_bf16x2(*(const uint32_t*)(y_lo + j)), x1 = unpack_bf16x2(*(const uint32_t*)(y_hi + j));
+    *(uint32_t*)(y_lo + j) = pack_bf16x2(fmaf(sc.x, uo[0], x0.x), fmaf(sc.y, uo[1], x0.y));
+    *(uint32_t*)(y_hi + j) = pack_bf16x2(fmaf(sc.x, uo[2], x1.x), fmaf(sc.y, uo[3], x1.y));
   }
   __syncthreads();
   for (int idx = tid; idx < TM * CV; idx += blockDim.x) {
@@ -348,15 +388,17 @@ static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
   if (!attr) {
     cudaFuncSetAttribute(dconv_a_kernel<C, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(dconv_b_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(dconv_c_kernel<C, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dconv_c_kernel<C, TM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dconv_c_kernel<C, TM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   const int tiles = (p.g.rows + TM - 1) / TM;
   const int tiles_b = (p.g.rows + 127) / 128;
-  const int gb = std::min(tiles_b, std::max(1, (148 * 4 + B - 1) / B));
+  const int gb = std::min(tiles_b, std::max(1, (148 * 16 + B - 1) / B));
   dconv_a_kernel<C, TM><<<dim3(tiles, B), 256, smA, st>>>(p);
   dconv_b_kernel<C><<<dim3(gb, B), 256, smB, st>>>(p);
-  dconv_c_kernel<C, TM><<<dim3(tiles, B), 256, smC, st>>>(p);
+  if (p.per_row) dconv_c_kernel<C, TM, true><<<dim3(tiles, B), 256, smC, st>>>(p);
+  else dconv_c_kernel<C, TM, false><<<dim3(tiles, B), 256, smC, st>>>(p);
   return 0;
 }
 

@@ -2,6 +2,7 @@
 // GLU/LayerScale residuals, softmax, decoder resize+skip, weight packing.
 // All activation tensors are channels-last inside padded row spaces (common.cuh: RowSpace).
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace athtd {
 
@@ -308,46 +309,139 @@ __device__ __forceinline__ void lerp_coords(int d, int in, int out, int& i0, int
   i1 = i0 + (i0 < in - 1 ? 1 : 0);
   lam = src - (float)i0;
 }
-template <typename T, int VEC>
-__global__ void dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, int Cu, T* __restrict__ out,
-                                 RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
-                                 const float* __restrict__ gw, const float* __restrict__ gb, const T* __restrict__ skip,
-                                 RowSpace ss) {
-  // blockIdx.y = group (segment x frame on the frequency branch, segment on the time branch): every per-group
-  // quantity (base offsets, GroupNorm mean / rstd) is computed once per thread, rows use 32-bit arithmetic
+// One block = one group (segment x frame on the frequency branch, segment on the time branch) x TD output rows.
+// Thread <-> fixed channel chunk x a contiguous RUN of output rows: GroupNorm scale / shift, the two interpolation
+// source rows and the two skip rows live in registers and are reloaded only when the source index moves (the resize
+// coordinates of the tile's rows are computed once per block into shared memory).
+// STAGE (every input row is used, i.e. up-sampling or ~1:1 resizes): GELU(GN(u)) of the input rows the tile needs is
+// evaluated ONCE into shared memory (fp32) and the outputs interpolate from there -- the direct form evaluated two GELUs
+// per output element (16x redundant on the 32 -> 259 layer) and was ALU-bound.  The exact 4:1 layers (only phases 0 / 3 of
+// the transposed conv are stored) keep the direct form: each stored row is used exactly once.
+struct LerpRow { int i0, i1; float lam; int j0, j1; float mu; };
+
+template <typename T, int VEC, bool STAGE>
+__global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, int Cu, T* __restrict__ out,
+                                                        RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
+                                                        const float* __restrict__ gw, const float* __restrict__ gb,
+                                                        const T* __restrict__ skip, RowSpace ss, int TD) {
+  extern __shared__ __align__(16) uint8_t dec_smem[];
+  LerpRow* tab = (LerpRow*)dec_smem;                                 // [TD]
+  float* act_s = (float*)(dec_smem + (((size_t)TD * sizeof(LerpRow) + 15) & ~(size_t)15));   // STAGE: [n_in][Cu]
   const int g = blockIdx.y;
   const int CV = os.C / VEC;
+  const int RW = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, rw = threadIdx.x / CV, c = cv * VEC;
+  const bool active = rw < RW;
+  const int d0 = blockIdx.x * TD, d1 = min(d0 + TD, os.R);
   const T* ug = u + us.row_off(g, 0);
   T* og = out + os.row_off(g, 0);
   const T* sg = skip + ss.row_off(g, 0);
   const long urow = us.C, orow = os.C, srow = ss.C;
-  float mean = 0.f, rstd = 1.f;
-  if (has_gn) { mean = mr[2 * (g / G2)]; rstd = mr[2 * (g / G2) + 1]; }
-  const int total = os.R * CV;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int cv = i % CV, d = i / CV, c = cv * VEC;
-    int i0, i1; float lam;
-    lerp_coords(d, Uin, os.R, i0, i1, lam);
-    // phase layout: output row fo = 4q + r - 2 lives in the row of x[q-1] (us geometry), columns r*Cu + c
-    float a0[VEC], a1[VEC], s0[VEC], s1[VEC], v[VEC];
-    VecIO<T, VEC>::load(ug + (long)(((i0 + 2) >> 2) - 1) * urow + ((i0 + 2) & 3) * Cu + c, a0);
-    VecIO<T, VEC>::load(ug + (long)(((i1 + 2) >> 2) - 1) * urow + ((i1 + 2) & 3) * Cu + c, a1);
-    if (has_gn) {
-      float w[VEC], bb[VEC];
-      VecIO<float, VEC>::load(gw + c, w); VecIO<float, VEC>::load(gb + c, bb);
+  for (int i = threadIdx.x; i < d1 - d0; i += blockDim.x) {
+    LerpRow lr;
+    lerp_coords(d0 + i, Uin, os.R, lr.i0, lr.i1, lr.lam);
+    lerp_coords(d0 + i, ss.R, os.R, lr.j0, lr.j1, lr.mu);
+    tab[i] = lr;
+  }
+  float sc[VEC], sh[VEC];
+  if (has_gn) {
+    const float mean = mr[2 * (g / G2)], rstd = mr[2 * (g / G2) + 1];
+    float w[VEC], bb[VEC];
+    VecIO<float, VEC>::load(gw + c, w); VecIO<float, VEC>::load(gb + c, bb);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        const float sc = rstd * w[k], sh = bb[k] - mean * sc;
-        a0[k] = gelu_act<T>(fmaf(a0[k], sc, sh));
-        a1[k] = gelu_act<T>(fmaf(a1[k], sc, sh));
+    for (int k = 0; k < VEC; ++k) { sc[k] = rstd * w[k]; sh[k] = bb[k] - mean * sc[k]; }
+  }
+  __syncthreads();
+  const int in_lo = tab[0].i0;
+  if (STAGE) {
+    const int n_in = tab[d1 - d0 - 1].i1 - in_lo + 1;
+    if (active)
+      for (int r = rw; r < n_in; r += RW) {
+        const int fo = in_lo + r;
+        float a[VEC];
+        // phase layout: output row fo = 4q + r - 2 lives in the row of x[q-1] (us geometry), columns r*Cu + c
+        VecIO<T, VEC>::load(ug + (long)(((fo + 2) >> 2) - 1) * urow + ((fo + 2) & 3) * Cu + c, a);
+        if (has_gn) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) a[k] = gelu_act<T>(fmaf(a[k], sc[k], sh[k]));
+        }
+        VecIO<float, VEC>::store(act_s + (long)r * Cu + c, a);
       }
-    }
-    int j0, j1; float mu;
-    lerp_coords(d, ss.R, os.R, j0, j1, mu);
-    VecIO<T, VEC>::load(sg + (long)j0 * srow + c, s0);
-    VecIO<T, VEC>::load(sg + (long)j1 * srow + c, s1);
+    __syncthreads();
+  }
+  if (!active) return;
+  if (!STAGE) {
+    // direct form: rows strided over the block, every iteration independent (two GELU'd source rows + two skip rows)
+    for (int d = d0 + rw; d < d1; d += RW) {
+      const LerpRow lr = tab[d - d0];
+      float a0[VEC], a1[VEC], s0[VEC], s1[VEC], v[VEC];
+      VecIO<T, VEC>::load(ug + (long)(((lr.i0 + 2) >> 2) - 1) * urow + ((lr.i0 + 2) & 3) * Cu + c, a0);
+      VecIO<T, VEC>::load(ug + (long)(((lr.i1 + 2) >> 2) - 1) * urow + ((lr.i1 + 2) & 3) * Cu + c, a1);
+      VecIO<T, VEC>::load(sg + (long)lr.j0 * srow + c, s0);
+      VecIO<T, VEC>::load(sg + (long)lr.j1 * srow + c, s1);
+      if (has_gn) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) v[k] = ((1.f - lam) * a0[k] + lam * a1[k]) + 0.1f * ((1.f - mu) * s0[k] + mu * s1[k]);
+        for (int k = 0; k < VEC; ++k) {
+          a0[k] = gelu_act<T>(fmaf(a0[k], sc[k], sh[k]));
+          a1[k] = gelu_act<T>(fmaf(a1[k], sc[k], sh[k]));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] = ((1.f - lr.lam) * a0[k] + lr.lam * a1[k]) + 0.1f * ((1.f - lr.mu) * s0[k] + lr.mu * s1[k]);
+      VecIO<T, VEC>::store(og + (long)d * orow + c, v);
+    }
+    return;
+  }
+  const int RL = (d1 - d0 + RW - 1) / RW;                // contiguous run of output rows per thread
+  const int da = d0 + rw * RL, db = min(da + RL, d1);
+  int ci0 = -1, ci1 = -1, cj0 = -1, cj1 = -1;
+  float a0[VEC], a1[VEC], s0[VEC], s1[VEC], v[VEC];
+  for (int d = da; d < db; ++d) {
+    const LerpRow lr = tab[d - d0];
+    if (lr.i0 != ci0 || lr.i1 != ci1) {
+      if (lr.i0 == ci1) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a0[k] = a1[k];
+      } else if (STAGE) {
+        VecIO<float, VEC>::load(act_s + (long)(lr.i0 - in_lo) * Cu + c, a0);
+      } else {
+        VecIO<T, VEC>::load(ug + (long)(((lr.i0 + 2) >> 2) - 1) * urow + ((lr.i0 + 2) & 3) * Cu + c, a0);
+        if (has_gn) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) a0[k] = gelu_act<T>(fmaf(a0[k], sc[k], sh[k]));
+        }
+      }
+      if (lr.i1 == lr.i0) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a1[k] = a0[k];
+      } else if (STAGE) {
+        VecIO<float, VEC>::load(act_s + (long)(lr.i1 - in_lo) * Cu + c, a1);
+      } else {
+        VecIO<T, VEC>::load(ug + (long)(((lr.i1 + 2) >> 2) - 1) * urow + ((lr.i1 + 2) & 3) * Cu + c, a1);
+        if (has_gn) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) a1[k] = gelu_act<T>(fmaf(a1[k], sc[k], sh[k]));
+        }
+      }
+      ci0 = lr.i0; ci1 = lr.i1;
+    }
+    if (lr.j0 != cj0 || lr.j1 != cj1) {
+      if (lr.j0 == cj1) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s0[k] = s1[k];
+      } else {
+        VecIO<T, VEC>::load(sg + (long)lr.j0 * srow + c, s0);
+      }
+      if (lr.j1 == lr.j0) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s1[k] = s0[k];
+      } else {
+        VecIO<T, VEC>::load(sg + (long)lr.j1 * srow + c, s1);
+      }
+      cj0 = lr.j0; cj1 = lr.j1;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = ((1.f - lr.lam) * a0[k] + lr.lam * a1[k]) + 0.1f * ((1.f - lr.mu) * s0[k] + lr.mu * s1[k]);
     VecIO<T, VEC>::store(og + (long)d * orow + c, v);
   }
 }
@@ -356,11 +450,22 @@ void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace
                       const float* mr, const float* gw, const float* gb, const T* skip, RowSpace ss,
                       cudaStream_t st) {
   const int vec = os.C % 8 == 0 ? 8 : 4;
-  const long per_group = (long)os.R * (os.C / vec);
-  int bx = (int)min((per_group + 255) / 256, (long)max(1, (148 * 16) / os.G + 1));
-  dim3 grid(bx, os.G);
-  if (vec == 8) dec_apply_kernel<T, 8><<<grid, 256, 0, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw, gb, skip, ss);
-  else dec_apply_kernel<T, 4><<<grid, 256, 0, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw, gb, skip, ss);
+  const bool stage = Uin <= os.R + 8 && Cu == os.C;       // all input rows are stored and used
+  const double ratio = (double)Uin / (double)os.R;
+  const int RW = 256 / (os.C / vec);
+  // staged: as many output rows per block as 40 KB of staged fp32 input rows allow (amortises the load -> GELU -> sync
+  // latency chain); direct: ~128 rows per block
+  int TD = stage ? (int)(((40 * 1024) / (4 * Cu) - 4) / ratio) : 256;
+  TD = std::max(1, std::min(std::min(TD, 1024), os.R));
+  const int tiles = (os.R + TD - 1) / TD;
+  TD = (os.R + tiles - 1) / tiles;                          // balanced tiles
+  size_t smem = (((size_t)TD * sizeof(LerpRow) + 15) & ~(size_t)15);
+  if (stage) smem += (size_t)((int)(TD * ratio) + 4) * Cu * sizeof(float);
+  dim3 grid(tiles, os.G);
+#define DEC_LAUNCH(V, S) dec_apply_kernel<T, V, S><<<grid, 256, smem, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw, gb, skip, ss, TD)
+  if (vec == 8) { if (stage) DEC_LAUNCH(8, true); else DEC_LAUNCH(8, false); }
+  else { if (stage) DEC_LAUNCH(4, true); else DEC_LAUNCH(4, false); }
+#undef DEC_LAUNCH
 }
 
 // ------------------------------------------------------------------ weight packing (fp32 params -> T, GEMM layouts)

@@ -42,6 +42,10 @@ int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, c
                       const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
                       double* st2, cudaStream_t st);
 
+// ---- small_conv.cu (bf16: time-branch level-0 conv + GELU fused with the waveform normalisation)
+void launch_tenc0_conv(const float* wav, const float* meanstd, int L, const bf16* w, const float* bias, bf16* y, RowSpace ys,
+                       cudaStream_t st);
+
 // ---- fft.cu
 void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
                      cudaStream_t st);

@@ -320,6 +320,13 @@ static int dconv_tile_run(float*, RowSpace, float*, int, const float*, const flo
   return 1;
 }
 
+// bf16 only: time-branch level-0 conv fused with the waveform normalisation (small_conv.cu)
+static bool tenc0_run(const float* wav, const float* ms, int L, const bf16* w, const float* bias, bf16* y, RowSpace ys, cudaStream_t st) {
+  launch_tenc0_conv(wav, ms, L, w, bias, y, ys, st);
+  return true;
+}
+static bool tenc0_run(const float*, const float*, int, const float*, const float*, float*, RowSpace, cudaStream_t) { return false; }
+
 template <typename T>
 bool PlanT<T>::enc_row_dispatch(bool run, int i, const T* x, RowSpace xin, const T* y, T* out, RowSpace ys, cudaStream_t st) {
   const bool ok = enc_row_run(run, pt, params, i, x, xin, y, out, ys, sh.Tf, st);
@@ -342,7 +349,10 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
   // row) slab in shared memory -- input read once, output written once (enc_row.cu)
   const bool row_fused = freq && use_fused_dconv && use_tc && enc_row_dispatch(false, i, nullptr, xin, nullptr, nullptr, ys, st);
   const bool row_conv = row_fused && i == 0 && enc_row_supported(C, s.Tf, true);
-  if (!row_conv) {  // strided conv k8 s4 p2 (+ right zero pad to a multiple of 4 on the time branch) + GELU
+  const bool wav_conv = !freq && i == 0 && use_tc && use_fused_dconv && sizeof(T) == 2 && cur_wav != nullptr &&
+                        tenc0_run(cur_wav, ms_wav, s.L, PW(p + ".conv.w"), P32(p + ".conv.bias"), y, ys, st);
+  if (wav_conv) ++n_launches;
+  if (!row_conv && !wav_conv) {  // strided conv k8 s4 p2 (+ right zero pad to a multiple of 4 on the time branch) + GELU
     ConvOp<T> o = conv_op<T>(CONV_K8S4, x, xin, PW(p + ".conv.w"), C, y, ys);
     o.bias = P32(p + ".conv.bias"); o.act = ACT_GELU;
     conv(o, st);
@@ -554,7 +564,8 @@ void PlanT<T>::encode(const float* wav, cudaStream_t st) {
   launch_finalize_meanstd(st_spec, 4.0 * 2048.0 * Tf, ms_spec, B, st); ++n_launches;
   launch_finalize_meanstd(st_wav, 2.0 * s.L, ms_wav, B, st); ++n_launches;
   launch_pack_spec<T>(Z, ms_spec, xf0, xf0_rs, Tf, st); ++n_launches;
-  launch_pack_wav<T>(wav, ms_wav, xt0, xt0_rs, s.L, st); ++n_launches;
+  cur_wav = wav;
+  if (!(use_tc && use_fused_dconv && sizeof(T) == 2)) { launch_pack_wav<T>(wav, ms_wav, xt0, xt0_rs, s.L, st); ++n_launches; }
   // interleaved encoders (ATHTDemucs_v2.py:196-217)
   const T* xf = xf0; RowSpace xfs = xf0_rs;
   const T* xt = xt0; RowSpace xts = xt0_rs;

@@ -79,6 +79,7 @@ struct PlanT : PlanBase {
   int n_launches = 0, n_tc = 0;
   bool use_tc = true, use_flash = true, use_fused_dconv = true;
   bool profiling = false;
+  const float* cur_wav = nullptr;   // waveform of the forward in flight (time-branch level 0 reads it directly)
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   double prof_gflop = 0.0;

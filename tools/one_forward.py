@@ -11,7 +11,11 @@ m.load_state_dict(weights.make_state_dict(0), strict=False)
 m = m.cuda().eval()
 wav = 0.1 * torch.randn(B, 2, 264600, device="cuda")
 emb = torch.nn.functional.normalize(torch.randn(B, 512, device="cuda"), dim=-1)
-for _ in range(reps):
+for _ in range(reps):          # warm-up (weight packing, plan creation)
     out = m(wav, emb)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()    # ncu --profile-from-start off captures exactly one forward
+out = m(wav, emb)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", tuple(out.shape), float(out.abs().mean()))
