@@ -31,10 +31,18 @@ template <typename T> void launch_pack_weight(const float* src, T* dst, long n, 
 template <typename T> bool dconv_row_supported(int C, int Tn);
 template <typename T> void launch_dconv_row(T* y, RowSpace ys, const float* const* ptrs, cudaStream_t st);
 
-// ---- enc_row.cu (bf16: fused conv(level 0) + DConv + rewrite of a frequency encoder layer, warp-level MMA)
+// ---- enc_row.cu (bf16: fused conv(level 0) + DConv + rewrite of a frequency encoder layer, warp-level MMA, persistent)
+// all weight pointers are entries of the packed blob (model.cuh build_pack_list): conv taps [C][32], conv3 [HP][3C],
+// expand [2C][HP] and rewrite [2C][C] with GLU-interleaved rows, fp32 vectors zero-padded / interleaved accordingly
+struct EncRowParams {
+  const bf16* cw; const float* cb;
+  const bf16* w1[2]; const float* b1[2]; const float* g1w[2]; const float* g1b[2];
+  const bf16* w2[2]; const float* b2[2]; const float* g2w[2]; const float* g2b[2]; const float* scale[2];
+  const bf16* rw; const float* rb; const float* emb; float emb_scale;
+};
 bool enc_row_supported(int C, int Tn, bool fuse_conv);
-void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, RowSpace ys, const float* const* ptrs, float emb_scale,
-                    bool fuse_conv, cudaStream_t st);
+void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, RowSpace ys, const EncRowParams& P, bool fuse_conv,
+                    cudaStream_t st);
 
 // ---- dconv_tile.cu (bf16: DConv residual branch as three tiled mma.sync passes; time branch + frequency levels 3-4)
 bool dconv_tile_supported(int C);

@@ -285,30 +285,6 @@ static ConvOp<T> conv_op(int mode, const T* a, RowSpace as, const T* w, int N, T
   return o;
 }
 
-// bf16 only: fused per-row layer tail (enc_row.cu).  run=false just answers whether it applies.
-static bool enc_row_run(bool run, const ParamTable* pt, const float* params, int i, const bf16* x, RowSpace xin, const bf16* y, bf16* out,
-                        RowSpace ys, int Tf, cudaStream_t st) {
-  const int C = kCh[i];
-  if (!(C == 48 || C == 96) || !enc_row_supported(C, Tf, false)) return false;
-  if (!run) return true;
-  const bool fuse = i == 0 && enc_row_supported(C, Tf, true);
-  const std::string p = std::string("htdemucs.encoder.") + std::to_string(i);
-  const float* ptrs[23];
-  auto P = [&](const std::string& n) { return params + pt->off(n); };
-  ptrs[0] = P(p + ".conv.weight"); ptrs[1] = P(p + ".conv.bias");
-  for (int dd = 0; dd < 2; ++dd) {
-    const std::string q = p + ".dconv.layers." + std::to_string(dd);
-    const char* names[9] = {".0.weight", ".0.bias", ".1.weight", ".1.bias", ".3.weight", ".3.bias", ".4.weight", ".4.bias", ".6.scale"};
-    for (int k = 0; k < 9; ++k) ptrs[2 + 9 * dd + k] = P(q + names[k]);
-  }
-  ptrs[20] = P(p + ".rewrite.weight"); ptrs[21] = P(p + ".rewrite.bias");
-  ptrs[22] = i == 0 ? P("htdemucs.freq_emb.embedding.weight") : nullptr;
-  launch_enc_row(x, xin, y, out, ys, ptrs, 10.0f * 0.2f, fuse, st);
-  return true;
-}
-static bool enc_row_run(bool, const ParamTable*, const float*, int, const float*, RowSpace, const float*, float*, RowSpace, int, cudaStream_t) {
-  return false;      // fp32 build: SIMT kernels only
-}
 // bf16 only: one DConv residual layer as three tiled mma.sync passes (dconv_tile.cu)
 static int dconv_tile_run(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
                           const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
@@ -327,11 +303,31 @@ static bool tenc0_run(const float* wav, const float* ms, int L, const bf16* w, c
 }
 static bool tenc0_run(const float*, const float*, int, const float*, const float*, float*, RowSpace, cudaStream_t) { return false; }
 
+// bf16 only: fused per-slab layer tail (enc_row.cu).  run=false just answers whether it applies.
 template <typename T>
 bool PlanT<T>::enc_row_dispatch(bool run, int i, const T* x, RowSpace xin, const T* y, T* out, RowSpace ys, cudaStream_t st) {
-  const bool ok = enc_row_run(run, pt, params, i, x, xin, y, out, ys, sh.Tf, st);
-  if (ok && run) ++n_launches;
-  return ok;
+  if constexpr (sizeof(T) == 2) {
+    const int C = kCh[i];
+    if (!(C == 48 || C == 96) || !enc_row_supported(C, sh.Tf, false)) return false;
+    if (!run) return true;
+    const bool fuse = i == 0 && enc_row_supported(C, sh.Tf, true);
+    const std::string p = std::string("htdemucs.encoder.") + std::to_string(i);
+    EncRowParams P;
+    P.cw = (const bf16*)PW(p + ".conv.w"); P.cb = P32(p + ".conv.bias");
+    for (int dd = 0; dd < 2; ++dd) {
+      const std::string q = p + ".dconv.layers." + std::to_string(dd);
+      P.w1[dd] = (const bf16*)PW(q + ".0.wp"); P.b1[dd] = PA(q + ".0.bp"); P.g1w[dd] = PA(q + ".1.wp"); P.g1b[dd] = PA(q + ".1.bp");
+      P.w2[dd] = (const bf16*)PW(q + ".3.wp"); P.b2[dd] = PA(q + ".3.bi"); P.g2w[dd] = PA(q + ".4.wi"); P.g2b[dd] = PA(q + ".4.bi");
+      P.scale[dd] = P32(q + ".6.scale");
+    }
+    P.rw = (const bf16*)PW(p + ".rewrite.w"); P.rb = PA(p + ".rewrite.b");
+    P.emb = i == 0 ? P32("htdemucs.freq_emb.embedding.weight") : nullptr; P.emb_scale = 10.0f * 0.2f;
+    launch_enc_row((const bf16*)x, xin, (const bf16*)y, (bf16*)out, ys, P, fuse, st);
+    ++n_launches;
+    return true;
+  } else {
+    return false;      // fp32 build: SIMT kernels only
+  }
 }
 
 // ---- one HEncLayer (demucs hdemucs.py:HEncLayer) on a channels-last row space.
