@@ -29,8 +29,14 @@ namespace athtd {
 static constexpr int TC_BM = 128;
 static constexpr int TC_BK = 64;
 static constexpr int TC_MAX_STAGES = 8;
-static constexpr int TC_THREADS = 320;
-static constexpr int TC_EPI_WARPS = 8;
+// epilogue warps per CTA: the epilogue is instruction-issue / latency bound (2 warps per scheduler reached ~60 % issue
+// utilisation and cost more than the MMAs of a K = 512 tile), so the one-CTA-per-SM variant runs 16 of them (4 per TMEM
+// lane quarter); the two-CTAs-per-SM variant keeps 8 per CTA (16 per SM)
+template <int MINB> struct TcCfg {
+  static constexpr int EPI_WARPS = MINB == 1 ? 16 : 8;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+};
+static constexpr int TC_VEC = 256;       // staged per-tile column vectors (bias, GroupNorm weight / bias, column scale)
 
 struct TcParams {
   int Mflat, N, BN, stages;
@@ -50,6 +56,7 @@ struct TcParams {
   const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;
   int convt_cout;
   int skip_lo, skip_hi;    // output columns [skip_lo, skip_hi) are computed (statistics) but not stored
+  int wide;                // 32-byte row accesses allowed (row pitch and base 32-byte aligned, skip range in 16-column units)
 };
 
 __device__ __forceinline__ void store8(bf16* dst, const float* v) {
@@ -57,6 +64,22 @@ __device__ __forceinline__ void store8(bf16* dst, const float* v) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); pk[i] = *(uint32_t*)&t; }
   *(uint4*)dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+// 32-byte (16 x bf16) accesses: one full sector per thread and instruction (sm_100 256-bit LDG / STG).  The row-per-thread
+// epilogue cannot coalesce across lanes, so wider per-thread accesses halve the L2 request count of the store-heavy GEMMs.
+__device__ __forceinline__ void store16(bf16* dst, const float* v) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); pk[i] = *(uint32_t*)&t; }
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+               "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+}
+__device__ __forceinline__ void load16_add(const bf16* src, float* v) {
+  uint32_t t[8];
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]),
+               "=r"(t[5]), "=r"(t[6]), "=r"(t[7]) : "l"(src));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { float2 f = __bfloat1622float2(*(const __nv_bfloat162*)&t[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
 }
 __device__ __forceinline__ void load8_add(const bf16* src, float* v) {
   uint4 t = *(const uint4*)src;
@@ -80,21 +103,26 @@ struct EpiRow {
 };
 
 // One 32-column chunk of one accumulator row: r[] = raw fp32 accumulators of columns [ncol, ncol+32).
+// sv: per-tile column vectors staged in shared memory, indexed relative to the tile's first column c0 = ncol - n0
+// ([0] bias, [1] GroupNorm weight, [2] GroupNorm bias: accumulator columns; [3] column scale: output columns)
 template <int EF>
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& er, const uint32_t (&r)[32], int ncol, int nc,
-                                               float& ssum, float& ssq) {
+                                               const float* __restrict__ sv, int c0, float& ssum, float& ssq) {
   constexpr int NV = (EF & EF_GLU) ? 16 : 32;
   const int Nout = (EF & EF_GLU) ? p.N / 2 : p.N;
-  const int nlast = p.N - 1;
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int n = min(ncol + j, nlast);                    // columns past N hold garbage and are never stored
-    float x = __uint_as_float(r[j]);
-    if (p.bias) x += __ldg(p.bias + n);
-    if (EF & EF_GN) x = (x - er.gmean) * er.grstd * __ldg(p.gn_w + n) + __ldg(p.gn_b + n);
-    if (EF & EF_GELU) x = gelu_fast(x);
-    v[j] = x;
+  for (int j4 = 0; j4 < 32; j4 += 4) {                     // columns past N hold garbage and are never stored
+    const float4 b4 = *(const float4*)(sv + c0 + j4);      // broadcast reads (every lane owns a row, same columns)
+    float x[4] = {__uint_as_float(r[j4]) + b4.x, __uint_as_float(r[j4 + 1]) + b4.y, __uint_as_float(r[j4 + 2]) + b4.z,
+                  __uint_as_float(r[j4 + 3]) + b4.w};
+    if (EF & EF_GN) {
+      const float4 w4 = *(const float4*)(sv + TC_VEC + c0 + j4), o4 = *(const float4*)(sv + 2 * TC_VEC + c0 + j4);
+      x[0] = (x[0] - er.gmean) * er.grstd * w4.x + o4.x; x[1] = (x[1] - er.gmean) * er.grstd * w4.y + o4.y;
+      x[2] = (x[2] - er.gmean) * er.grstd * w4.z + o4.z; x[3] = (x[3] - er.gmean) * er.grstd * w4.w + o4.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[j4 + e] = (EF & EF_GELU) ? gelu_fast(x[e]) : x[e];
   }
   int no = ncol, nco = nc;             // output column base / count
   if (EF & EF_GLU) {
@@ -103,10 +131,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
     for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * sigmoid_fast(v[2 * j + 1]);
   }
   if (EF & EF_POST) {
-    const int olast = Nout - 1;
     if (p.colscale) {
+      const float* cs = sv + 3 * TC_VEC + ((EF & EF_GLU) ? (c0 >> 1) : c0);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] *= __ldg(p.colscale + min(no + j, olast));
+      for (int j4 = 0; j4 < NV; j4 += 4) {
+        const float4 c4 = *(const float4*)(cs + j4);
+        v[j4] *= c4.x; v[j4 + 1] *= c4.y; v[j4 + 2] *= c4.z; v[j4 + 3] *= c4.w;
+      }
     }
     if (p.rowtab) {      // per-row table (frequency embedding): Nout % 4 == 0, 16-byte gathers instead of scalar ones
       const float4* tp = (const float4*)(p.rowtab + (long)er.m * Nout + no);
@@ -120,9 +151,17 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
     }
     if (p.res) {
       const bf16* rp = (const bf16*)p.res + er.orow * p.ldc + no;
+      if (p.wide) {
 #pragma unroll
-      for (int g = 0; g < NV / 8; ++g)
-        if (8 * g < nco) load8_add(rp + 8 * g, v + 8 * g);
+        for (int g = 0; g < NV / 16; ++g) {
+          if (16 * g + 16 <= nco) load16_add(rp + 16 * g, v + 16 * g);
+          else if (16 * g < nco) load8_add(rp + 16 * g, v + 16 * g);
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < NV / 8; ++g)
+          if (8 * g < nco) load8_add(rp + 8 * g, v + 8 * g);
+      }
     }
   }
   if (EF & EF_STATS) {
@@ -149,17 +188,29 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
   if (!p.no_store) {
     bf16* cp = (bf16*)p.C + er.orow * p.ldc + no;
     const int nst_cols = min(nco, p.n_store - no);
+    if (p.wide) {
 #pragma unroll
-    for (int g = 0; g < NV / 8; ++g) {
-      const int c = no + 8 * g;
-      if (8 * g < nst_cols && !(c >= p.skip_lo && c + 8 <= p.skip_hi)) store8(cp + 8 * g, v + 8 * g);
+      for (int g = 0; g < NV / 16; ++g) {
+        const int c = no + 16 * g;
+        if (16 * g + 16 <= nst_cols) {
+          if (!(c >= p.skip_lo && c + 16 <= p.skip_hi)) store16(cp + 16 * g, v + 16 * g);
+        } else if (16 * g < nst_cols) {
+          if (!(c >= p.skip_lo && c + 8 <= p.skip_hi)) store8(cp + 16 * g, v + 16 * g);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < NV / 8; ++g) {
+        const int c = no + 8 * g;
+        if (8 * g < nst_cols && !(c >= p.skip_lo && c + 8 <= p.skip_hi)) store8(cp + 8 * g, v + 8 * g);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------ kernel
 template <int EF, int MINB>
-__global__ void __launch_bounds__(TC_THREADS, MINB)
+__global__ void __launch_bounds__(TcCfg<MINB>::THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -171,6 +222,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* bars = (uint64_t*)(sB + nst * stageB);
   uint64_t* full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES, *tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* svec = (float*)(bars + 2 * TC_MAX_STAGES + 8);        // [2 tiles][4 vectors][TC_VEC]
+  constexpr int EPI_WARPS = TcCfg<MINB>::EPI_WARPS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.ntaps * p.kb_per_tap;
@@ -182,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
     for (int s = 0; s < nst; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull[i]), 1); mbar_init(smem_u32(&tempty[i]), TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull[i]), 1); mbar_init(smem_u32(&tempty[i]), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -242,15 +295,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ---------------- epilogue warps: thread <-> accumulator row (TMEM lane), two warps per lane quarter
+    // ---------------- epilogue warps: thread <-> accumulator row (TMEM lane), EPI_WARPS / 4 warps per lane quarter
+    // taking interleaved 32-column chunks
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    const int Nout_ = (EF & EF_GLU) ? p.N / 2 : p.N;
     int i = 0;
     for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
       const int row0 = (t / p.n_tiles) * TC_BM;
       const int n0 = (t % p.n_tiles) * p.BN;
+      // stage this tile's column vectors (clamped at the last column: columns past N are never stored)
+      float* sv = svec + buf * 4 * TC_VEC;
+      for (int c = etid; c < p.BN; c += EPI_WARPS * 32) {
+        const int n = min(n0 + c, p.N - 1);
+        sv[c] = p.bias ? __ldg(p.bias + n) : 0.f;
+        if (EF & EF_GN) { sv[TC_VEC + c] = __ldg(p.gn_w + n); sv[2 * TC_VEC + c] = __ldg(p.gn_b + n); }
+        if ((EF & EF_POST) && p.colscale) {
+          const int no = (EF & EF_GLU) ? (n0 >> 1) + c : n0 + c;
+          sv[3 * TC_VEC + c] = __ldg(p.colscale + min(no, Nout_ - 1));
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
       EpiRow er;
       const long rho = (long)row0 + row;
       const int q2 = (int)(rho / p.RpA);
@@ -270,12 +338,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 32 * half; c0 < p.BN; c0 += 64) {
+      for (int c0 = 32 * sub; c0 < p.BN; c0 += 8 * EPI_WARPS) {
         uint32_t r[32];
         tmem_ld32(tacc + (uint32_t)c0, r);
         const int ncol = n0 + c0;
         const int nc = min(32, min(p.BN - c0, p.N - ncol));      // valid accumulator columns in this chunk (multiple of 8)
-        if (er.valid && nc > 0) epilogue_chunk<EF>(p, er, r, ncol, nc, ssum, ssq);
+        if (er.valid && nc > 0) epilogue_chunk<EF>(p, er, r, ncol, nc, sv, c0, ssum, ssq);
       }
       // this warp is done reading the accumulator: release it to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -292,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int key0 = __reduce_max_sync(0xffffffffu, key);
           const bool uniform = __all_sync(0xffffffffu, key == key0 || key == -1);
           if (key0 >= 0) {
-            const int slot = (t + half) % STAT_SLOTS;
+            const int slot = (t + sub) % STAT_SLOTS;
             if (uniform) {
               // rows are combined in fp64 so that the result does not depend on which rows share a warp / tile,
               // i.e. on the position of a segment inside the batch (multi-GPU spans must reproduce one-GPU bits)
@@ -399,6 +467,8 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   p.stats = f.stats; p.stat_mode = f.stat_mode; p.statR = f.statR; p.convt_cout = f.convt_cout;
   p.gn_mr = f.gn_mr; p.gn_w = f.gn_w; p.gn_b = f.gn_b; p.gn_mode = f.gn_mode;
   p.skip_lo = f.skip_lo; p.skip_hi = f.skip_hi;
+  p.wide = (f.ldc % 16 == 0) && ((uintptr_t)f.C % 32 == 0) && (!f.res || (uintptr_t)f.res % 32 == 0) && (f.skip_lo % 16 == 0) &&
+           (f.skip_hi % 16 == 0);
   p.m_tiles = (int)((f.Mflat + TC_BM - 1) / TC_BM);
   p.n_tiles = (f.N + p.BN - 1) / p.BN;
   CUtensorMap tmA, tmB;
@@ -407,9 +477,10 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   const int stage_bytes = TC_BM * TC_BK * 2 + p.BN * TC_BK * 2;
   // narrow tiles are epilogue-bound: two CTAs per SM (2 x 8 epilogue warps, 2 x 2 accumulators <= 512 TMEM columns)
   const int ctas_per_sm = (p.BN <= 128 && g_tc_two_ctas) ? 2 : 1;
-  const int smem_budget = (ctas_per_sm == 2 ? 112 : 227) * 1024 - 1024 - 512;
+  const int tail_bytes = 512 + 2 * 4 * TC_VEC * 4;          // barriers + staged column vectors
+  const int smem_budget = (ctas_per_sm == 2 ? 112 : 227) * 1024 - 1024 - tail_bytes;
   p.stages = std::min(TC_MAX_STAGES, std::max(2, smem_budget / stage_bytes));
-  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 512;
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
   const long tiles = (long)p.m_tiles * p.n_tiles;
   dim3 grid((unsigned)std::min<long>(tiles, (long)num_sms() * ctas_per_sm));
   int ef = 0;
@@ -426,8 +497,8 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
       cudaFuncSetAttribute(gemm_tc_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);                \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
-    if (ctas_per_sm == 2) gemm_tc_kernel<E, 2><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);                              \
-    else gemm_tc_kernel<E, 1><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);                                               \
+    if (ctas_per_sm == 2) gemm_tc_kernel<E, 2><<<grid, TcCfg<2>::THREADS, smem, st>>>(tmA, tmB, p);                       \
+    else gemm_tc_kernel<E, 1><<<grid, TcCfg<1>::THREADS, smem, st>>>(tmA, tmB, p);                                        \
     return 0;                                                                                                             \
   }
   switch (ef) {
