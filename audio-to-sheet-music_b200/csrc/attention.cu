@@ -3,14 +3,18 @@
 // /root/reference/src/models/stem_separation/ATHTDemucs_v2.py:228).  Replaces the unfused
 // QK^T GEMM -> softmax -> PV GEMM sequence: scores never touch HBM.
 //
-// One CTA = one (segment, head, 128-query tile); 192 threads:
-//   warp 0     : TMA producer  (Q once; K double-buffered, V single-buffered 128-key tiles, SWIZZLE_128B)
-//   warp 1     : TMEM allocator + MMA issuer: S = Q K^T (M128 N128 K64) into TMEM cols [0,128),
-//                PV = P V (M128 N64 K128, V consumed MN-major straight from its [key][d] tile) into cols [128,192)
-//   warps 2..5 : online softmax, one query row per thread: tcgen05.ld S, running max / sum in fp32 with exp2,
-//                P written as bf16 into a swizzled K-major smem tile, O accumulated in registers
-// TMEM use is 256 columns and shared memory 97 KB, so two CTAs share an SM and one CTA's softmax
-// overlaps the other's MMAs.
+// One CTA = one (segment, head, 128-query tile); 192 threads; keys in tiles of 64:
+//   warp 0     : TMA producer  (Q once; K and V rings of three 64-key tiles each, SWIZZLE_128B)
+//   warp 1     : TMEM allocator + MMA issuer.  S(j) = Q K_j^T (M128 N64 K64) alternates between TWO TMEM buffers and is
+//                issued two tiles ahead of the softmax; O += P_j V_j (M128 N64 K64, V consumed MN-major from its [key][d]
+//                tile) accumulates IN TMEM across all key tiles.
+//   warps 2..5 : softmax, one query row per thread: the 64 scores of a tile are read from TMEM once, the row maximum is
+//                a register tree, P = exp2((s - m) * scale) goes as bf16 into one of two swizzled K-major smem tiles.
+//                The reference maximum m only moves when the tile maximum exceeds it by more than 2^8 (softmax is
+//                invariant to m; P <= 256 is exact in fp32 / bf16 range): then -- rarely, mostly in the first tiles --
+//                the warp rescales its O rows in TMEM (tcgen05.ld / st) before publishing P.  No per-tile O traffic.
+// TMEM use is 192 (256 allocated) columns and shared memory 98 KB, so two CTAs share an SM and one CTA's softmax overlaps
+// the other's MMAs; inside a CTA the double-buffered S / P let the tensor core run one tile ahead of the softmax.
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 
@@ -22,12 +26,39 @@ struct FaParams {
   bf16* O; long ldo;     // output rows [B*Sq, ldo], head h at columns h*64
 };
 
-static constexpr int FA_TILE = 16384;   // 128 rows x 64 bf16
+static constexpr int FA_QB = 16384;     // Q tile: 128 rows x 64 bf16
+static constexpr int FA_KB = 8192;      // K / V tile: 64 keys x 64 bf16
+static constexpr int FA_PB = 16384;     // P tile: 128 rows x 64 keys bf16
+static constexpr int FA_NK = 3, FA_NV = 3;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// 32 TMEM columns of one lane without the trailing wait (the caller waits once for several loads)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
 }
 
 __global__ void __launch_bounds__(192, 2)
@@ -36,26 +67,26 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + FA_TILE;            // 2 buffers
-  uint8_t* sV = smem + 3 * FA_TILE;
-  uint8_t* sP = smem + 4 * FA_TILE;        // 128 x 128 bf16 = two 64-key K-major atoms
-  uint64_t* bars = (uint64_t*)(smem + 6 * FA_TILE);
-  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 6,
-           *s_full = bars + 7, *p_ready = bars + 8, *pv_full = bars + 9;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+  uint8_t* sK = sQ + FA_QB;                       // FA_NK tiles
+  uint8_t* sV = sK + FA_NK * FA_KB;               // FA_NV tiles
+  uint8_t* sP = sV + FA_NV * FA_KB;               // 2 tiles
+  uint64_t* bars = (uint64_t*)(sP + 2 * FA_PB);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = k_full + FA_NK, *v_full = k_empty + FA_NK, *v_empty = v_full + FA_NV,
+           *s_full = v_empty + FA_NV, *p_ready = s_full + 2, *pv_done = p_ready + 2;
+  uint32_t* tmem_slot = (uint32_t*)(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nkv = (p.Sk + 127) / 128;
+  const int nkv = (p.Sk + 63) / 64;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQ) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmV) : "memory");
     mbar_init(smem_u32(q_full), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&k_full[i]), 1); mbar_init(smem_u32(&k_empty[i]), 1); }
-    mbar_init(smem_u32(v_full), 1); mbar_init(smem_u32(v_empty), 1);
-    mbar_init(smem_u32(s_full), 1); mbar_init(smem_u32(p_ready), 128); mbar_init(smem_u32(pv_full), 1);
+    for (int i = 0; i < FA_NK; ++i) { mbar_init(smem_u32(&k_full[i]), 1); mbar_init(smem_u32(&k_empty[i]), 1); }
+    for (int i = 0; i < FA_NV; ++i) { mbar_init(smem_u32(&v_full[i]), 1); mbar_init(smem_u32(&v_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&p_ready[i]), 128); mbar_init(smem_u32(&pv_done[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -66,151 +97,164 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;     // S buffers at columns [0,64) and [64,128)
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(smem_u32(q_full), FA_TILE);
+      mbar_expect_tx(smem_u32(q_full), FA_QB);
       tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(q_full), h * 64, b * p.Sq + q0);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(smem_u32(&k_empty[s]), (uint32_t)((j >> 1) & 1) ^ 1u);
-        mbar_expect_tx(smem_u32(&k_full[s]), FA_TILE);
-        tma_load_2d(smem_u32(sK + s * FA_TILE), &tmK, smem_u32(&k_full[s]), h * 64, b * p.Sk + j * 128);
-        mbar_wait(smem_u32(v_empty), (uint32_t)(j & 1) ^ 1u);
-        mbar_expect_tx(smem_u32(v_full), FA_TILE);
-        tma_load_2d(smem_u32(sV), &tmV, smem_u32(v_full), h * 64, b * p.Sk + j * 128);
+        const int sk = j % FA_NK, sv = j % FA_NV;
+        mbar_wait(smem_u32(&k_empty[sk]), (uint32_t)((j / FA_NK) & 1) ^ 1u);
+        mbar_expect_tx(smem_u32(&k_full[sk]), FA_KB);
+        tma_load_2d(smem_u32(sK + sk * FA_KB), &tmK, smem_u32(&k_full[sk]), h * 64, b * p.Sk + j * 64);
+        mbar_wait(smem_u32(&v_empty[sv]), (uint32_t)((j / FA_NV) & 1) ^ 1u);
+        mbar_expect_tx(smem_u32(&v_full[sv]), FA_KB);
+        tma_load_2d(smem_u32(sV + sv * FA_KB), &tmV, smem_u32(&v_full[sv]), h * 64, b * p.Sk + j * 64);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // S: M128 N128, A and B K-major.  PV: M128 N64, A K-major (P), B MN-major (V tile is [key][d], d contiguous)
-      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // S: M128 N64, A and B K-major.  PV: M128 N64, A K-major (P), B MN-major (V tile is [key][d], d contiguous)
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_pv = idesc_s | (1u << 16);
       const uint64_t dq = make_sw128_desc(smem_u32(sQ));
-      const uint64_t dp = make_sw128_desc(smem_u32(sP));
-      const uint64_t dv = make_sw128_desc(smem_u32(sV));
+      auto issue_s = [&](int j) {
+        const int sk = j % FA_NK;
+        mbar_wait(smem_u32(&k_full[sk]), (uint32_t)((j / FA_NK) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dk = make_sw128_desc(smem_u32(sK + sk * FA_KB));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S + (uint32_t)((j & 1) * 64), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+        umma_commit(smem_u32(&k_empty[sk]));
+        umma_commit(smem_u32(&s_full[j & 1]));
+      };
       mbar_wait(smem_u32(q_full), 0);
+      issue_s(0);
+      if (nkv > 1) issue_s(1);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(smem_u32(&k_full[s]), (uint32_t)((j >> 1) & 1));
+        const int sv = j % FA_NV;
+        mbar_wait(smem_u32(&p_ready[j & 1]), (uint32_t)((j >> 1) & 1));
+        mbar_wait(smem_u32(&v_full[sv]), (uint32_t)((j / FA_NV) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dk = make_sw128_desc(smem_u32(sK + s * FA_TILE));
+        const uint64_t dp = make_sw128_desc(smem_u32(sP + (j & 1) * FA_PB));
+        const uint64_t dv = make_sw128_desc(smem_u32(sV + sv * FA_KB));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
-        umma_commit(smem_u32(&k_empty[s]));
-        umma_commit(smem_u32(s_full));
-        mbar_wait(smem_u32(p_ready), (uint32_t)(j & 1));
-        mbar_wait(smem_u32(v_full), (uint32_t)(j & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // A: 16 keys = 32 B inside the (k/4)-th 64-key atom of P;  B: 16 key rows of V = 2048 B further
-          const uint64_t da = dp + (uint64_t)((k >> 2) * (FA_TILE >> 4) + (k & 3) * 2);
-          const uint64_t db = dv + (uint64_t)(k * (2048 >> 4));
-          umma_bf16(tmem_PV, da, db, idesc_pv, k ? 1u : 0u);
-        }
-        umma_commit(smem_u32(v_empty));
-        umma_commit(smem_u32(pv_full));
+        for (int k = 0; k < 4; ++k)   // A: 16 keys = 32 B inside the P atom;  B: 16 key rows of V = 2048 B further
+          umma_bf16(tmem_O, dp + (uint64_t)(2 * k), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j | k) ? 1u : 0u);
+        umma_commit(smem_u32(&v_empty[sv]));
+        umma_commit(smem_u32(&pv_done[j & 1]));
+        if (j + 2 < nkv) issue_s(j + 2);      // S buffer (j & 1) was drained before p_ready(j)
       }
     }
   } else {
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    const float cs = p.scale_log2;
+    const float tau = 8.0f / cs;               // the reference maximum moves only for jumps > 2^8 in the exp2 domain
+    float m_used = -INFINITY;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      const int nvalid = min(128, p.Sk - j * 128);
-      mbar_wait(smem_u32(s_full), (uint32_t)(j & 1));
+      const int nvalid = min(64, p.Sk - j * 64);
+      mbar_wait(smem_u32(&s_full[j & 1]), (uint32_t)((j >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float mx = -INFINITY;
-      if (nvalid == 128) {
+      uint32_t r0[32], r1[32];
+      const uint32_t ts = tmem_S + (uint32_t)((j & 1) * 64) + lane_addr;
+      tmem_ld32_nowait(ts, r0);
+      tmem_ld32_nowait(ts + 32u, r1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (nvalid < 64) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (i >= nvalid) r0[i] = 0xff800000u;            // -inf: exp2 -> 0, ignored by the maximum
+          if (32 + i >= nvalid) r1[i] = 0xff800000u;
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
-      const float mb = m_new * p.scale_log2;
-      float l_tile = 0.f;
+      float mx[8];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), r);
-        uint32_t pk[16];
-        if (nvalid == 128) {          // all but the last key tile: no masking
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(fmaxf(__uint_as_float(r0[i]), __uint_as_float(r0[8 + i])),
+                                                 fmaxf(__uint_as_float(r0[16 + i]), __uint_as_float(r0[24 + i])));
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -mb));
-            l_tile += p0 + p1;
-            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *(uint32_t*)&t;
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], fmaxf(fmaxf(__uint_as_float(r1[i]), __uint_as_float(r1[8 + i])),
+                                                              fmaxf(__uint_as_float(r1[16 + i]), __uint_as_float(r1[24 + i]))));
+      const float tmax = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      const bool need = tmax > m_used + tau;              // always true on the first tile (m_used = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? tmax : m_used;
+        const float alpha = (j == 0 || !need) ? 1.0f : ex2_approx((m_used - m_new) * cs);
+        if (j > 0) {
+          // O rows of this warp are rescaled in TMEM: PV(j-1) must have landed, PV(j) cannot start before p_ready(j)
+          mbar_wait(smem_u32(&pv_done[(j - 1) & 1]), (uint32_t)(((j - 1) >> 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_addr + (uint32_t)(c * 32), o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_addr + (uint32_t)(c * 32), o);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c * 32 + i < nvalid) ? ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb)) : 0.f;
-            const float p1 = (c * 32 + i + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -mb)) : 0.f;
-            l_tile += p0 + p1;
-            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *(uint32_t*)&t;
-          }
+          l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
         }
-        // K-major SWIZZLE_128B: row pitch 128 B, 16-byte chunk index XOR (row & 7); keys [64a, 64a+64) in atom a
-        uint8_t* prow = sP + (c >> 1) * FA_TILE + row * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = ((c & 1) * 4 + g) ^ (row & 7);
-          *(uint4*)(prow + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        }
+        m_used = m_new;
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the MMA (async proxy)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(p_ready)) : "memory");
-      l_run = l_run * alpha + l_tile;
-      m_run = m_new;
-      mbar_wait(smem_u32(pv_full), (uint32_t)(j & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (j >= 2) mbar_wait(smem_u32(&pv_done[j & 1]), (uint32_t)(((j - 2) >> 1) & 1));      // P buffer (j & 1) consumed by PV(j-2)
+      const float mb = m_used * cs;
+      uint8_t* prow = sP + (j & 1) * FA_PB + row * 128;
+      // K-major SWIZZLE_128B: row pitch 128 B, 16-byte chunk index XOR (row & 7)
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_PV + lane_addr + (uint32_t)(c * 32), r);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
-    if (q0 + row < p.Sq) {
-      const float inv = 1.0f / l_run;
-      bf16* dst = p.O + ((long)b * p.Sq + q0 + row) * p.ldo + h * 64;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 t = __floats2bfloat162_rn(o[8 * g + 2 * i] * inv, o[8 * g + 2 * i + 1] * inv);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r0[8 * g + 2 * i]), cs, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r0[8 * g + 2 * i + 1]), cs, -mb));
+          if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
+          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
           pk[i] = *(uint32_t*)&t;
         }
-        *(uint4*)(dst + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *(uint4*)(prow + ((g ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r1[8 * g + 2 * i]), cs, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r1[8 * g + 2 * i + 1]), cs, -mb));
+          if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
+          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+          pk[i] = *(uint32_t*)&t;
+        }
+        *(uint4*)(prow + (((4 + g) ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the MMA (async proxy)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[j & 1])) : "memory");
+    }
+    mbar_wait(smem_u32(&pv_done[(nkv - 1) & 1]), (uint32_t)(((nkv - 1) >> 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
+    bf16* dst = p.O + ((long)b * p.Sq + q0 + row) * p.ldo + h * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_addr + (uint32_t)(c * 32), o);
+      if (q0 + row < p.Sq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(o[8 * g + 2 * i]) * inv, __uint_as_float(o[8 * g + 2 * i + 1]) * inv);
+            pk[i] = *(uint32_t*)&t;
+          }
+          *(uint4*)(dst + c * 32 + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -228,11 +272,11 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
                       long ldo, cudaStream_t st) {
   CUtensorMap tmQ, tmK, tmV;
   if (!make_tensor_map_2d(&tmQ, q, 512, (uint64_t)B * Sq, (uint64_t)ldq * 2, 64, 128)) return 2;
-  if (!make_tensor_map_2d(&tmK, k, 512, (uint64_t)B * Sk, (uint64_t)ldkv * 2, 64, 128)) return 3;
-  if (!make_tensor_map_2d(&tmV, v, 512, (uint64_t)B * Sk, (uint64_t)ldkv * 2, 64, 128)) return 4;
+  if (!make_tensor_map_2d(&tmK, k, 512, (uint64_t)B * Sk, (uint64_t)ldkv * 2, 64, 64)) return 3;
+  if (!make_tensor_map_2d(&tmV, v, 512, (uint64_t)B * Sk, (uint64_t)ldkv * 2, 64, 64)) return 4;
   FaParams p;
   p.Sq = Sq; p.Sk = Sk; p.scale_log2 = 0.125f * 1.4426950408889634f; p.O = o; p.ldo = ldo;
-  const size_t smem = 1024 + 6 * FA_TILE + 128;
+  const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 2 * FA_PB + 256;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   dim3 grid((Sq + 127) / 128, 8, B);
