@@ -67,6 +67,18 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
     for (int b = a + 1; b < 4; ++b) { float2 t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
 }
 
+// w[k] = W^(base*k), k = 1..15, from FOUR table loads (k = 1, 2, 4, 8) and eleven complex products (product depth <= 3,
+// relative error <= 4e-7).  Loading all fifteen entries made the kernel L1-wavefront bound: the strided gathers
+// tw[base*k] touch ~240 cache lines per warp and pass, three times the shared-memory traffic of the transform itself.
+template <bool INV>
+__device__ __forceinline__ void twiddle_powers(const float2* __restrict__ tw, int base, float2 (&w)[16]) {
+  w[1] = tw[base]; w[2] = tw[2 * base]; w[4] = tw[4 * base]; w[8] = tw[8 * base];
+  if (INV) { w[1].y = -w[1].y; w[2].y = -w[2].y; w[4].y = -w[4].y; w[8].y = -w[8].y; }
+  w[3] = cmul(w[1], w[2]); w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]);
+#pragma unroll
+  for (int k = 1; k < 8; ++k) w[8 + k] = cmul(w[8], w[k]);
+}
+
 // Passes 2 and 3 plus the natural-order write-back; on entry v holds pass-1 outputs V[k1]
 // (already multiplied by W4096^(t*k1)) of thread t.  On exit sr/si hold X[k] at index k + (k>>4).
 template <bool INV>
@@ -81,11 +93,11 @@ __device__ __forceinline__ void fft4096_tail(float2 (&v)[16], float* sr, float* 
     v[m1].x = sr[hi * FFT_PITCH + 16 * m1 + lo]; v[m1].y = si[hi * FFT_PITCH + 16 * m1 + lo];
   }
   dft16<INV>(v);
+  {
+    float2 w[16];
+    twiddle_powers<INV>(tw, 16 * lo, w);
 #pragma unroll
-  for (int j1 = 1; j1 < 16; ++j1) {
-    float2 w = tw[16 * lo * j1];
-    if (INV) w.y = -w.y;
-    v[j1] = cmul(v[j1], w);
+    for (int j1 = 1; j1 < 16; ++j1) v[j1] = cmul(v[j1], w[j1]);
   }
   __syncthreads();
 #pragma unroll
@@ -127,8 +139,12 @@ __global__ void __launch_bounds__(256) stft_cac_kernel(const float* __restrict__
     v[n1] = make_float2(wl[idx] * w, wr[idx] * w);
   }
   dft16<false>(v);
+  {
+    float2 w[16];
+    twiddle_powers<false>(tw, t, w);
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tw[t * k1]);
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], w[k1]);
+  }
   fft4096_tail<false>(v, sr, si, tw);
   float s = 0.f, ss = 0.f;
   float4* zo = Z + ((long)b * Tf + frame) * 2048;
@@ -230,8 +246,12 @@ __global__ void __launch_bounds__(256) mask_istft_kernel(const float4* __restric
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) { v[n1].x = sr[256 * n1 + t]; v[n1].y = si[256 * n1 + t]; }
   dft16<true>(v);
+  {
+    float2 w[16];
+    twiddle_powers<true>(tw, t, w);
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) { float2 w = tw[t * k1]; w.y = -w.y; v[k1] = cmul(v[k1], w); }
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], w[k1]);
+  }
   __syncthreads();
   fft4096_tail<true>(v, sr, si, tw);
   float* fl = frames + (((long)bo * 2 + 0) * Tf + frame) * FFT_N;
