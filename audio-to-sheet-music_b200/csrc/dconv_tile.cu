@@ -44,18 +44,26 @@ template <int C> struct DcDims {
   static constexpr int K2P = HP + 8;
 };
 
-template <int C>
-__device__ __forceinline__ void dc_load_rows(bf16* dst, const bf16* __restrict__ yb, const DcGeom& g, int i_start, int n) {
-  constexpr int CV = C / 8, XP = C + 8;
+// 16-byte asynchronous global -> shared copies (LDGSTS): every thread issues all its copies back to back, so a tile load is
+// bounded by bandwidth instead of by (copies per thread) x (global latency) as with register-staged loops.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;                                     // src-size 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// logical rows [i_start, i_start + n) x CW channels starting at channel c0 of rows with C channels -> dst[n][CW + 8]
+template <int C, int CW>
+__device__ __forceinline__ void dc_load_rows(bf16* dst, const bf16* __restrict__ yb, const DcGeom& g, int i_start, int n, int c0 = 0) {
+  constexpr int CV = CW / 8, XP = CW + 8;
   for (int idx = threadIdx.x; idx < n * CV; idx += blockDim.x) {
     const int row = idx / CV, cv = idx - row * CV;
     const int i = i_start + row;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (i >= 0 && i < g.rows) {
-      const int t = i / g.Rr, f = i - t * g.Rr;
-      v = *(const uint4*)(yb + (long)t * g.fs + (long)f * C + cv * 8);
-    }
-    *(uint4*)(dst + row * XP + cv * 8) = v;
+    const bool valid = i >= 0 && i < g.rows;
+    const int t = valid ? i / g.Rr : 0, f = valid ? i - t * g.Rr : 0;
+    cp_async16(dst + row * XP + cv * 8, yb + (long)t * g.fs + (long)f * C + c0 + cv * 8, valid);
   }
 }
 
@@ -121,11 +129,13 @@ __global__ void __launch_bounds__(256) dconv_a_kernel(const DcTileParams p) {
   float* red = (float*)(w1s + 8 * D::HN * D::K1P);  // 32 floats
   const int b = blockIdx.y, i0 = blockIdx.x * TM;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  dc_load_rows<C>(xs, p.y + p.g.base + (long)b * p.g.seg, p.g, i0 - halo, nload);
+  dc_load_rows<C, C>(xs, p.y + p.g.base + (long)b * p.g.seg, p.g, i0 - halo, nload);
   for (int idx = tid; idx < 8 * D::HN * (D::K1 / 8); idx += blockDim.x) {
     const int n = idx / (D::K1 / 8), kc = idx - n * (D::K1 / 8);
-    *(uint4*)(w1s + n * D::K1P + kc * 8) = *(const uint4*)(p.w1 + (long)n * D::K1 + kc * 8);
+    cp_async16(w1s + n * D::K1P + kc * 8, p.w1 + (long)n * D::K1 + kc * 8, true);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   const int mt = warp % MW, ng = warp / MW;
   float acc[NPW][4];
@@ -212,11 +222,13 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   for (int idx = tid; idx < 2 * C * (D::HP / 8); idx += blockDim.x) {
     const int n = idx / (D::HP / 8), kc = idx - n * (D::HP / 8);
-    *(uint4*)(w2s + n * D::K2P + kc * 8) = *(const uint4*)(p.w2 + (long)n * D::HP + kc * 8);
+    cp_async16(w2s + n * D::K2P + kc * 8, p.w2 + (long)n * D::HP + kc * 8, true);
   }
+  cp_async_commit();
   for (int i = tid; i < 2 * C; i += blockDim.x) b2s[i] = p.b2[i];
   for (int i = tid; i < D::HP; i += blockDim.x) { g1ws[i] = p.g1w[i]; g1bs[i] = p.g1b[i]; }
   dc_stage_mean_rstd(p.st1, b, p.per_row, p.g.Rr, (double)D::H * (p.per_row ? p.g.nT : p.g.rows), mr);
+  cp_async_wait<0>();
   __syncthreads();
   bf16* hb = p.h + (long)b * p.g.rows * D::HP;
   float ts = 0.f, tq = 0.f;
@@ -277,33 +289,39 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // (rows [0,C) values, [C,2C) gates): a lane then owns two ADJACENT value channels and their gates (one value n-tile + one
 // gate n-tile per step) and updates the y tile with 4-byte accesses.  sigmoid(x) = 0.5 + 0.5 tanh(x/2) (one MUFU op).
 // Per-segment statistics (PER_ROW = false) fold GroupNorm into one per-column FMA: e = d * alpha + beta.
-template <int C, int TM, bool PER_ROW>
+// blockIdx.z selects a slice of CS value channels (and their gates): the wide layers run as several small CTAs per row tile
+// (occupancy instead of one 150 KB CTA per SM).  The y tile arrives through cp.async while the expand is evaluated; the
+// residual update happens after it has landed.
+template <int C, int CS, int TM, bool PER_ROW>
 __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
   typedef DcDims<C> D;
-  constexpr int MW = TM / 16, NG = 8 / MW, CV = C / 8;
+  constexpr int MW = TM / 16, NG = 8 / MW, CV = CS / 8, XPS = CS + 8;
+  constexpr int NVT = (CV + NG - 1) / NG;           // value n-tiles per warp
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* ys = (bf16*)smem_raw;                       // [TM][XP]
-  bf16* w2s = ys + TM * D::XP;                      // [2C][K2P] de-interleaved
-  float* al = (float*)(w2s + 2 * C * D::K2P);       // [2C] alpha (PER_ROW: GroupNorm weight)
-  float* be = al + 2 * C;                           // [2C] beta  (PER_ROW: GroupNorm bias)
-  float* b2s = be + 2 * C;                          // [2C] expand bias (PER_ROW only)
-  float* scs = b2s + 2 * C;                         // [C]
-  float* mr = scs + C;                              // [64]
-  const int b = blockIdx.y, i0 = blockIdx.x * TM;
+  bf16* ys = (bf16*)smem_raw;                       // [TM][XPS]
+  bf16* w2s = ys + TM * XPS;                        // [2CS][K2P] de-interleaved: rows [0,CS) values, [CS,2CS) gates
+  float* al = (float*)(w2s + 2 * CS * D::K2P);      // [2CS] alpha (PER_ROW: GroupNorm weight)
+  float* be = al + 2 * CS;                          // [2CS] beta  (PER_ROW: GroupNorm bias)
+  float* b2s = be + 2 * CS;                         // [2CS] expand bias (PER_ROW only)
+  float* scs = b2s + 2 * CS;                        // [CS]
+  float* mr = scs + CS;                             // [64]
+  const int b = blockIdx.y, i0 = blockIdx.x * TM, ch0 = blockIdx.z * CS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   bf16* yb = p.y + p.g.base + (long)b * p.g.seg;
-  dc_load_rows<C>(ys, yb, p.g, i0, TM);
-  for (int idx = tid; idx < 2 * C * (D::HP / 8); idx += blockDim.x) {
-    const int n = idx / (D::HP / 8), kc = idx - n * (D::HP / 8);
-    const int nd = (n & 1) * C + (n >> 1);
-    *(uint4*)(w2s + nd * D::K2P + kc * 8) = *(const uint4*)(p.w2 + (long)n * D::HP + kc * 8);
+  for (int idx = tid; idx < 2 * CS * (D::HP / 8); idx += blockDim.x) {
+    const int nd = idx / (D::HP / 8), kc = idx - nd * (D::HP / 8);
+    const int n = nd < CS ? 2 * (ch0 + nd) : 2 * (ch0 + nd - CS) + 1;     // packed rows are GLU-interleaved
+    cp_async16(w2s + nd * D::K2P + kc * 8, p.w2 + (long)n * D::HP + kc * 8, true);
   }
-  for (int i = tid; i < C; i += blockDim.x) scs[i] = p.scale[i];
+  cp_async_commit();
+  dc_load_rows<C, CS>(ys, yb, p.g, i0, TM, ch0);
+  cp_async_commit();
+  for (int i = tid; i < CS; i += blockDim.x) scs[i] = p.scale[ch0 + i];
   dc_stage_mean_rstd(p.st2, b, PER_ROW ? 1 : 0, p.g.Rr, (double)(2 * C) * (PER_ROW ? p.g.nT : p.g.rows), mr);
   __syncthreads();
-  for (int n = tid; n < 2 * C; n += blockDim.x) {
-    const int nd = (n & 1) * C + (n >> 1);
-    const float half = (n & 1) ? 0.5f : 1.0f;       // gates carry the x/2 of the tanh form
+  for (int nd = tid; nd < 2 * CS; nd += blockDim.x) {
+    const int n = nd < CS ? 2 * (ch0 + nd) : 2 * (ch0 + nd - CS) + 1;
+    const float half = nd < CS ? 1.0f : 0.5f;       // gates carry the x/2 of the tanh form
     if (PER_ROW) {
       al[nd] = half * p.g2w[n]; be[nd] = half * p.g2b[n]; b2s[nd] = p.b2[n];
     } else {
@@ -311,6 +329,7 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
       al[nd] = half * a; be[nd] = half * ((p.b2[n] - mr[0]) * a + p.g2b[n]);
     }
   }
+  cp_async_wait<1>();                               // expand weights have landed (the y tile may still be in flight)
   __syncthreads();
   const int mt = warp % MW, ng = warp / MW;
   const int r_lo = i0 + mt * 16 + g, r_hi = r_lo + 8;
@@ -328,39 +347,53 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
     a[ks][2] = v_lo ? ld_b32(hb + (long)r_lo * D::HP + c1) : 0u;
     a[ks][3] = v_hi ? ld_b32(hb + (long)r_hi * D::HP + c1) : 0u;
   }
-  bf16* y_lo = ys + (mt * 16 + g) * D::XP, *y_hi = y_lo + 8 * D::XP;
-#pragma unroll 2
-  for (int vt = ng; vt < CV; vt += NG) {
-    float dv[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
+  float uo[NVT][4];
 #pragma unroll
-    for (int ks = 0; ks < D::KS; ++ks) {
-      uint32_t bb[2];
-      frag_b(w2s, D::K2P, vt * 8, ks * 16, lane, bb);
-      mma16816(dv, a[ks], bb);
-      frag_b(w2s, D::K2P, C + vt * 8, ks * 16, lane, bb);
-      mma16816(dg, a[ks], bb);
-    }
-    const int j = vt * 8 + 2 * q;
-    const float2 av = *(const float2*)(al + j), bv = *(const float2*)(be + j);
-    const float2 ag = *(const float2*)(al + C + j), bg = *(const float2*)(be + C + j);
-    const float2 sc = *(const float2*)(scs + j);
-    float ev[4], eg[4];
-    if (PER_ROW) {
-      const float2 kv = *(const float2*)(b2s + j), kg = *(const float2*)(b2s + C + j);
-      ev[0] = fmaf((dv[0] + kv.x - m_lo) * rs_lo, av.x, bv.x); ev[1] = fmaf((dv[1] + kv.y - m_lo) * rs_lo, av.y, bv.y);
-      ev[2] = fmaf((dv[2] + kv.x - m_hi) * rs_hi, av.x, bv.x); ev[3] = fmaf((dv[3] + kv.y - m_hi) * rs_hi, av.y, bv.y);
-      eg[0] = fmaf((dg[0] + kg.x - m_lo) * rs_lo, ag.x, bg.x); eg[1] = fmaf((dg[1] + kg.y - m_lo) * rs_lo, ag.y, bg.y);
-      eg[2] = fmaf((dg[2] + kg.x - m_hi) * rs_hi, ag.x, bg.x); eg[3] = fmaf((dg[3] + kg.y - m_hi) * rs_hi, ag.y, bg.y);
-    } else {
-      ev[0] = fmaf(dv[0], av.x, bv.x); ev[1] = fmaf(dv[1], av.y, bv.y); ev[2] = fmaf(dv[2], av.x, bv.x); ev[3] = fmaf(dv[3], av.y, bv.y);
-      eg[0] = fmaf(dg[0], ag.x, bg.x); eg[1] = fmaf(dg[1], ag.y, bg.y); eg[2] = fmaf(dg[2], ag.x, bg.x); eg[3] = fmaf(dg[3], ag.y, bg.y);
-    }
-    float uo[4];
+  for (int iv = 0; iv < NVT; ++iv) {
+    const int vt = ng + iv * NG;
+    if (vt < CV) {
+      float dv[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) uo[e] = ev[e] * fmaf(0.5f, tanh_approx(eg[e]), 0.5f);
-    const float2 x0 = unpack_bf16x2(*(const uint32_t*)(y_lo + j)), x1 = unpack_bf16x2(*(const uint32_t*)(y_hi + j));
-    *(uint32_t*)(y_lo + j) = pack_bf16x2(fmaf(sc.x, uo[0], x0.x), fmaf(sc.y, uo[1], x0.y));
-    *(uint32_t*)(y_hi + j) = pack_bf16x2(fmaf(sc.x, uo[2], x1.x), fmaf(sc.y, uo[3], x1.y));
+      for (int ks = 0; ks < D::KS; ++ks) {
+        uint32_t bb[2];
+        frag_b(w2s, D::K2P, vt * 8, ks * 16, lane, bb);
+        mma16816(dv, a[ks], bb);
+        frag_b(w2s, D::K2P, CS + vt * 8, ks * 16, lane, bb);
+        mma16816(dg, a[ks], bb);
+      }
+      const int j = vt * 8 + 2 * q;
+      const float2 av = *(const float2*)(al + j), bv = *(const float2*)(be + j);
+      const float2 ag = *(const float2*)(al + CS + j), bg = *(const float2*)(be + CS + j);
+      const float2 sc = *(const float2*)(scs + j);
+      float ev[4], eg[4];
+      if (PER_ROW) {
+        const float2 kv = *(const float2*)(b2s + j), kg = *(const float2*)(b2s + CS + j);
+        ev[0] = fmaf((dv[0] + kv.x - m_lo) * rs_lo, av.x, bv.x); ev[1] = fmaf((dv[1] + kv.y - m_lo) * rs_lo, av.y, bv.y);
+        ev[2] = fmaf((dv[2] + kv.x - m_hi) * rs_hi, av.x, bv.x); ev[3] = fmaf((dv[3] + kv.y - m_hi) * rs_hi, av.y, bv.y);
+        eg[0] = fmaf((dg[0] + kg.x - m_lo) * rs_lo, ag.x, bg.x); eg[1] = fmaf((dg[1] + kg.y - m_lo) * rs_lo, ag.y, bg.y);
+        eg[2] = fmaf((dg[2] + kg.x - m_hi) * rs_hi, ag.x, bg.x); eg[3] = fmaf((dg[3] + kg.y - m_hi) * rs_hi, ag.y, bg.y);
+      } else {
+        ev[0] = fmaf(dv[0], av.x, bv.x); ev[1] = fmaf(dv[1], av.y, bv.y); ev[2] = fmaf(dv[2], av.x, bv.x); ev[3] = fmaf(dv[3], av.y, bv.y);
+        eg[0] = fmaf(dg[0], ag.x, bg.x); eg[1] = fmaf(dg[1], ag.y, bg.y); eg[2] = fmaf(dg[2], ag.x, bg.x); eg[3] = fmaf(dg[3], ag.y, bg.y);
+      }
+      uo[iv][0] = sc.x * (ev[0] * fmaf(0.5f, tanh_approx(eg[0]), 0.5f));
+      uo[iv][1] = sc.y * (ev[1] * fmaf(0.5f, tanh_approx(eg[1]), 0.5f));
+      uo[iv][2] = sc.x * (ev[2] * fmaf(0.5f, tanh_approx(eg[2]), 0.5f));
+      uo[iv][3] = sc.y * (ev[3] * fmaf(0.5f, tanh_approx(eg[3]), 0.5f));
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  bf16* y_lo = ys + (mt * 16 + g) * XPS, *y_hi = y_lo + 8 * XPS;
+#pragma unroll
+  for (int iv = 0; iv < NVT; ++iv) {
+    const int vt = ng + iv * NG;
+    if (vt < CV) {
+      const int j = vt * 8 + 2 * q;
+      const float2 x0 = unpack_bf16x2(*(const uint32_t*)(y_lo + j)), x1 = unpack_bf16x2(*(const uint32_t*)(y_hi + j));
+      *(uint32_t*)(y_lo + j) = pack_bf16x2(x0.x + uo[iv][0], x0.y + uo[iv][1]);
+      *(uint32_t*)(y_hi + j) = pack_bf16x2(x1.x + uo[iv][2], x1.y + uo[iv][3]);
+    }
   }
   __syncthreads();
   for (int idx = tid; idx < TM * CV; idx += blockDim.x) {
@@ -368,7 +401,7 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
     const int i = i0 + row;
     if (i < p.g.rows) {
       const int t = i / p.g.Rr, f = i - t * p.g.Rr;
-      *(uint4*)(yb + (long)t * p.g.fs + (long)f * C + cv * 8) = *(const uint4*)(ys + row * D::XP + cv * 8);
+      *(uint4*)(yb + (long)t * p.g.fs + (long)f * C + ch0 + cv * 8) = *(const uint4*)(ys + row * XPS + cv * 8);
     }
   }
 }
@@ -376,29 +409,30 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
 // ------------------------------------------------------------------ host side
 bool dconv_tile_supported(int C) { return C == 48 || C == 96 || C == 192 || C == 384; }
 
-template <int C, int TM>
+template <int C, int TM, int CS, int TMC>
 static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
   typedef DcDims<C> D;
   const int halo = p.dil * p.g.Rr;
   const size_t smA = (size_t)(TM + 2 * halo) * D::XP * 2 + (size_t)8 * D::HN * D::K1P * 2 + 32 * 4 + 16;
   const size_t smB = (size_t)2 * C * D::K2P * 2 + (size_t)(2 * C + 2 * D::HP + 64 + 32) * 4 + 16;
-  const size_t smC = (size_t)TM * D::XP * 2 + (size_t)2 * C * D::K2P * 2 + (size_t)(7 * C + 64) * 4 + 16;
+  const size_t smC = (size_t)TMC * (CS + 8) * 2 + (size_t)2 * CS * D::K2P * 2 + (size_t)(7 * CS + 64) * 4 + 16;
   if (smA > 227 * 1024 || smC > 227 * 1024) return 1;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(dconv_a_kernel<C, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(dconv_b_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(dconv_c_kernel<C, TM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(dconv_c_kernel<C, TM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   const int tiles = (p.g.rows + TM - 1) / TM;
+  const int tiles_c = (p.g.rows + TMC - 1) / TMC;
   const int tiles_b = (p.g.rows + 127) / 128;
   const int gb = std::min(tiles_b, std::max(1, (148 * 16 + B - 1) / B));
   dconv_a_kernel<C, TM><<<dim3(tiles, B), 256, smA, st>>>(p);
   dconv_b_kernel<C><<<dim3(gb, B), 256, smB, st>>>(p);
-  if (p.per_row) dconv_c_kernel<C, TM, true><<<dim3(tiles, B), 256, smC, st>>>(p);
-  else dconv_c_kernel<C, TM, false><<<dim3(tiles, B), 256, smC, st>>>(p);
+  if (p.per_row) dconv_c_kernel<C, CS, TMC, true><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);
+  else dconv_c_kernel<C, CS, TMC, false><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);
   return 0;
 }
 
@@ -417,10 +451,10 @@ int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, c
   const int B = ys.batch();
   if (freq && ys.R > 32) return 1;
   switch (ys.C) {
-    case 48: return dconv_tile_launch<48, 128>(p, B, st);
-    case 96: return dconv_tile_launch<96, 128>(p, B, st);
-    case 192: return dconv_tile_launch<192, 128>(p, B, st);
-    case 384: return dconv_tile_launch<384, 64>(p, B, st);
+    case 48: return dconv_tile_launch<48, 128, 48, 128>(p, B, st);
+    case 96: return dconv_tile_launch<96, 128, 96, 64>(p, B, st);
+    case 192: return dconv_tile_launch<192, 128, 96, 64>(p, B, st);
+    case 384: return dconv_tile_launch<384, 64, 96, 64>(p, B, st);
   }
   return 1;
 }

@@ -425,7 +425,7 @@ int tc_pick_bn(int N) {
   if (N % 16) return 0;
   if (N <= g_tc_bn_cap) return N;
   if (g_tc_bn_cap >= 256 && N % 256 == 0) return 256;
-  if (N % 128 == 0) return 128;
+  if (N % 128 == 0) return 128;      // (measured: two 128-wide CTAs per SM beat one 192-wide tile for N = 384)
   if (N % 192 == 0 && g_tc_bn_cap >= 192) return 192;
   if (N % 64 == 0) return 64;
   if (N % 32 == 0) return 32;
