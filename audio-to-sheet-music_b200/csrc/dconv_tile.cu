@@ -63,7 +63,14 @@ __device__ __forceinline__ void dc_load_rows(bf16* dst, const bf16* __restrict__
     const int i = i_start + row;
     const bool valid = i >= 0 && i < g.rows;
     const int t = valid ? i / g.Rr : 0, f = valid ? i - t * g.Rr : 0;
-    cp_async16(dst + row * XP + cv * 8, yb + (long)t * g.fs + (long)f * C + c0 + cv * 8, valid);
+    const bf16* src = yb + (long)t * g.fs + (long)f * C + c0 + cv * 8;
+    if (C <= 96) {      // few copies per thread: register-staged loads are faster than LDGSTS + wait (measured)
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) v = *(const uint4*)src;
+      *(uint4*)(dst + row * XP + cv * 8) = v;
+    } else {
+      cp_async16(dst + row * XP + cv * 8, src, valid);
+    }
   }
 }
 

@@ -179,7 +179,8 @@ template <typename T>
 __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, T* __restrict__ y, long rows, int C, int S,
                                  const float* __restrict__ gmr, const float* __restrict__ gw,
                                  const float* __restrict__ gb, const float* __restrict__ lw, const float* __restrict__ lb,
-                                 const float* __restrict__ pe, RowSpace yrs) {
+                                 const float* __restrict__ pe, RowSpace yrs, T* __restrict__ y2,
+                                 const float* __restrict__ lw2, const float* __restrict__ lb2) {
   // one warp per row; each lane owns up to two 8-channel chunks (C <= 512, C % 8 == 0): 16-byte loads / stores
   int lane = threadIdx.x & 31;
   long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -237,16 +238,22 @@ __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, 
         for (int k = 0; k < 8; ++k) o[k] += w8[k];
       }
       VecIO<T, 8>::store(y + yoff + c, o);
+      if (y2) {      // a second LayerNorm of the same row (same statistics, other affine): the next layer's other consumer
+        VecIO<float, 8>::load(lw2 + c, w8); VecIO<float, 8>::load(lb2 + c, b8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * w8[k] + b8[k];
+        VecIO<T, 8>::store(y2 + row * C + c, o);
+      }
     }
   }
 }
 template <typename T>
 void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const float* gmr,
                       const float* gw, const float* gb, const float* lw, const float* lb, const float* pe,
-                      RowSpace yrs, cudaStream_t st) {
+                      RowSpace yrs, cudaStream_t st, T* y2, const float* lw2, const float* lb2) {
   int wpb = 8;
   norm_rows_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, xout, y, rows, C, S, gmr,
-                                                                                gw, gb, lw, lb, pe, yrs);
+                                                                                gw, gb, lw, lb, pe, yrs, y2, lw2, lb2);
 }
 
 // ------------------------------------------------------------------ row softmax, in place (fp32 math)
@@ -517,7 +524,7 @@ void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int 
   template void launch_gn_glu_res<T>(T*, RowSpace, const T*, RowSpace, int, int, const float*, const float*,            \
                                      const float*, const float*, cudaStream_t);                                         \
   template void launch_norm_rows<T>(const T*, T*, T*, long, int, int, const float*, const float*, const float*,         \
-                                    const float*, const float*, const float*, RowSpace, cudaStream_t);                            \
+                                    const float*, const float*, const float*, RowSpace, cudaStream_t, T*, const float*, const float*); \
   template void launch_softmax_rows<T>(T*, long, int, cudaStream_t);                                                    \
   template void launch_add_rowvec<T>(const T*, T*, long, int, int, const float*, long, cudaStream_t);                   \
   template void launch_dec_apply<T>(const T*, int, RowSpace, int, T*, RowSpace, int, int, const float*,                     \

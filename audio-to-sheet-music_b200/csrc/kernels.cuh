@@ -18,7 +18,8 @@ template <typename T> void launch_gn_glu_res(T* x, RowSpace xs, const T* e, RowS
                                              const float* w, const float* b, const float* scale, cudaStream_t st);
 template <typename T> void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const float* gmr,
                                             const float* gw, const float* gb, const float* lw, const float* lb,
-                                            const float* pe, RowSpace yrs, cudaStream_t st);
+                                            const float* pe, RowSpace yrs, cudaStream_t st, T* y2 = nullptr,
+                                            const float* lw2 = nullptr, const float* lb2 = nullptr);
 template <typename T> void launch_softmax_rows(T* s, long rows, int n, cudaStream_t st);
 template <typename T> void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const float* vec, long vstride,
                                              cudaStream_t st);

@@ -128,7 +128,7 @@ void PlanT<T>::layout(char* base) {
   const size_t Smax = std::max(s.Sf, s.St);
   tokf = (T*)take((size_t)B * s.Sf * 512 * sizeof(T));
   tokt = (T*)take((size_t)B * s.St * 512 * sizeof(T));
-  for (int i = 0; i < 4; ++i) hn[i] = (T*)take((size_t)B * Smax * 512 * sizeof(T));
+  for (int i = 0; i < 5; ++i) hn[i] = (T*)take((size_t)B * Smax * 512 * sizeof(T));
   qkv = (T*)take((size_t)B * Smax * 1536 * sizeof(T));
   kvb = (T*)take((size_t)B * Smax * 1024 * sizeof(T));
   obuf = (T*)take((size_t)B * Smax * 512 * sizeof(T));
@@ -487,17 +487,21 @@ void PlanT<T>::linear_res(const T* a, int S, int K, const T* w, int N, const flo
   conv(o, st);
 }
 
+// FFN half of a transformer layer + norm_out (MyGroupNorm over all tokens of the segment).  The norm_out apply pass also
+// emits the LayerNorm(s) the NEXT layer starts with (same row statistics, the next layer's affine): n1 = next layer's norm1
+// of this branch, n2 = the other branch's next-layer norm2 applied to this branch (cross-attention keys / values).
 template <typename T>
-void PlanT<T>::xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, cudaStream_t st) {
+void PlanT<T>::xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, T* n1, const float* n1w,
+                               const float* n1b, T* n2, const float* n2w, const float* n2b, cudaStream_t st) {
   const long rows = (long)sh.B * S;
   const RowSpace none{};
-  launch_norm_rows<T>(x, nullptr, hn[0], rows, 512, S, nullptr, nullptr, nullptr, P32(p + "." + ffn_norm + ".weight"),
+  launch_norm_rows<T>(x, nullptr, hn[4], rows, 512, S, nullptr, nullptr, nullptr, P32(p + "." + ffn_norm + ".weight"),
                       P32(p + "." + ffn_norm + ".bias"), nullptr, none, st); ++n_launches;
-  linear(hn[0], S, 512, PW(p + ".linear1.w"), 2048, P32(p + ".linear1.bias"), ACT_GELU, ffn, st);
+  linear(hn[4], S, 512, PW(p + ".linear1.w"), 2048, P32(p + ".linear1.bias"), ACT_GELU, ffn, st);
   linear_res(ffn, S, 2048, PW(p + ".linear2.w"), 512, P32(p + ".linear2.bias"), P32(p + ".gamma_2.scale"), x, stats, st);
   launch_finalize_gn(stats, (double)S * 512, mr, sh.B, STAT_SLOTS, st); ++n_launches;
-  launch_norm_rows<T>(x, x, nullptr, rows, 512, S, mr, P32(p + ".norm_out.weight"), P32(p + ".norm_out.bias"), nullptr,
-                      nullptr, nullptr, none, st); ++n_launches;
+  launch_norm_rows<T>(x, x, n1, rows, 512, S, mr, P32(p + ".norm_out.weight"), P32(p + ".norm_out.bias"), n1w, n1b,
+                      nullptr, none, st, n2, n2w, n2b); ++n_launches;
 }
 
 template <typename T>
@@ -509,40 +513,53 @@ void PlanT<T>::cross_transformer(cudaStream_t st) {
   T* X[2] = {tokf, tokt};
   const int S[2] = {s.Sf, s.St};
   const char* stacks[2] = {".layers.", ".layers_t."};
+  // hn[br] = this branch's next-layer norm1 output, hn[2 + br] = LayerNorm of this branch with the OTHER stack's norm2 (read
+  // by the other branch's cross-attention), hn[4] = scratch.  Both are written by the previous layer's norm_out pass.
+  auto next_norms = [&](int l, int br, T*& n1, const float*& n1w, const float*& n1b, T*& n2, const float*& n2w, const float*& n2b) {
+    n1 = nullptr; n1w = n1b = nullptr; n2 = nullptr; n2w = n2b = nullptr;
+    if (l + 1 >= 5) return;
+    const std::string pn = xp + stacks[br] + std::to_string(l + 1);
+    n1 = hn[br]; n1w = P32(pn + ".norm1.weight"); n1b = P32(pn + ".norm1.bias");
+    if ((l + 1) % 2 == 1) {      // next layer is a cross layer: the other stack normalises this branch with its norm2
+      const std::string po = xp + stacks[1 - br] + std::to_string(l + 1);
+      n2 = hn[2 + br]; n2w = P32(po + ".norm2.weight"); n2b = P32(po + ".norm2.bias");
+    }
+  };
   for (int l = 0; l < 5; ++l) {
     if (l % 2 == 0) {
       for (int br = 0; br < 2; ++br) {
         const std::string p = xp + stacks[br] + std::to_string(l);
         const long rows = (long)B * S[br];
-        launch_norm_rows<T>(X[br], nullptr, hn[0], rows, 512, S[br], nullptr, nullptr, nullptr, P32(p + ".norm1.weight"),
-                            P32(p + ".norm1.bias"), nullptr, none, st); ++n_launches;
-        linear(hn[0], S[br], 512, PW(p + ".in_proj.w"), 1536, P32(p + ".self_attn.in_proj_bias"), ACT_NONE, qkv, st);
+        const T* h1 = hn[br];
+        if (l == 0) {
+          launch_norm_rows<T>(X[br], nullptr, hn[4], rows, 512, S[br], nullptr, nullptr, nullptr, P32(p + ".norm1.weight"),
+                              P32(p + ".norm1.bias"), nullptr, none, st); ++n_launches;
+          h1 = hn[4];
+        }
+        linear(h1, S[br], 512, PW(p + ".in_proj.w"), 1536, P32(p + ".self_attn.in_proj_bias"), ACT_NONE, qkv, st);
         attention(qkv, 1536, qkv + 512, qkv + 1024, 1536, S[br], S[br], obuf, st);
         linear_res(obuf, S[br], 512, PW(p + ".out_proj.w"), 512, P32(p + ".self_attn.out_proj.bias"),
                    P32(p + ".gamma_1.scale"), X[br], nullptr, st);
-        xf_ffn_and_norm(p, "norm2", X[br], S[br], st_xf[l][br], st);
+        T *n1, *n2; const float *n1w, *n1b, *n2w, *n2b;
+        next_norms(l, br, n1, n1w, n1b, n2, n2w, n2b);
+        xf_ffn_and_norm(p, "norm2", X[br], S[br], st_xf[l][br], n1, n1w, n1b, n2, n2w, n2b, st);
       }
     } else {
-      // both branches read the PRE-update other branch (old_x, demucs transformer.py) -> normalise first
-      for (int br = 0; br < 2; ++br) {
-        const std::string p = xp + stacks[br] + std::to_string(l);
-        const int o = 1 - br;
-        launch_norm_rows<T>(X[br], nullptr, hn[2 * br], (long)B * S[br], 512, S[br], nullptr, nullptr, nullptr,
-                            P32(p + ".norm1.weight"), P32(p + ".norm1.bias"), nullptr, none, st); ++n_launches;
-        launch_norm_rows<T>(X[o], nullptr, hn[2 * br + 1], (long)B * S[o], 512, S[o], nullptr, nullptr, nullptr,
-                            P32(p + ".norm2.weight"), P32(p + ".norm2.bias"), nullptr, none, st); ++n_launches;
-      }
+      // both branches read the PRE-update other branch (old_x, demucs transformer.py): hn[0..3] were all written by the
+      // previous (self-attention) layer, before any update of this layer
       for (int br = 0; br < 2; ++br) {
         const std::string p = xp + stacks[br] + std::to_string(l);
         const int o = 1 - br;
         const T* w_in = PW(p + ".in_proj.w");
         const float* b_in = P32(p + ".cross_attn.in_proj_bias");
-        linear(hn[2 * br], S[br], 512, w_in, 512, b_in, ACT_NONE, qkv, st);
-        linear(hn[2 * br + 1], S[o], 512, w_in + 512L * 512, 1024, b_in + 512, ACT_NONE, kvb, st);
+        linear(hn[br], S[br], 512, w_in, 512, b_in, ACT_NONE, qkv, st);
+        linear(hn[2 + o], S[o], 512, w_in + 512L * 512, 1024, b_in + 512, ACT_NONE, kvb, st);
         attention(qkv, 512, kvb, kvb + 512, 1024, S[br], S[o], obuf, st);
         linear_res(obuf, S[br], 512, PW(p + ".out_proj.w"), 512, P32(p + ".cross_attn.out_proj.bias"),
                    P32(p + ".gamma_1.scale"), X[br], nullptr, st);
-        xf_ffn_and_norm(p, "norm3", X[br], S[br], st_xf[l][br], st);
+        T *n1, *n2; const float *n1w, *n1b, *n2w, *n2b;
+        next_norms(l, br, n1, n1w, n1b, n2, n2w, n2b);
+        xf_ffn_and_norm(p, "norm3", X[br], S[br], st_xf[l][br], n1, n1w, n1b, n2, n2w, n2b, st);
       }
     }
   }

@@ -89,7 +89,7 @@ struct PlanT : PlanBase {
   T *xf0, *xt0, *yf[4], *ef[4], *yt[4], *et[4], *xc, *xtc, *df[4], *dt[4];
   double *st_spec, *st_wav, *st_df[4][2][2], *st_dt[4][2][2], *st_xf[5][2], *st_dec;
   float *mr, *ms_spec, *ms_wav, *Z, *cvec, *frames;
-  T *hbuf, *ebuf, *tokf, *tokt, *hn[4], *qkv, *kvb, *obuf, *ffn, *scores, *xenc, *xtenc, *t1, *t2, *ubuf;
+  T *hbuf, *ebuf, *tokf, *tokt, *hn[5], *qkv, *kvb, *obuf, *ffn, *scores, *xenc, *xtenc, *t1, *t2, *ubuf;
 
   PlanT(int B, int L, int P, const ParamTable* pt, const PackLayout* pl, const float* params, const void* packed,
         void* workspace, const PlanConsts& c);
@@ -108,7 +108,8 @@ struct PlanT : PlanBase {
   void linear(const T* a, int S, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st);
   void linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x, double* stats,
                   cudaStream_t st);
-  void xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, cudaStream_t st);
+  void xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, T* n1, const float* n1w,
+                       const float* n1b, T* n2, const float* n2w, const float* n2b, cudaStream_t st);
   void cross_transformer(cudaStream_t st);
   void encode(const float* wav, cudaStream_t st);
   void text_vectors(const float* emb, cudaStream_t st);
