@@ -32,6 +32,8 @@ struct DcTileParams {
   const bf16* w1; const float* b1; const float* g1w; const float* g1b;
   const bf16* w2; const float* b2; const float* g2w; const float* g2b; const float* scale;
   double* st1; double* st2;
+  // optional HEncLayer tail fused into pass C of the second residual layer (C <= 96): out = GLU(rewrite_1x1(y) + rb)
+  const bf16* rw; const float* rb; bf16* out;      // rw [2C][C], rb [2C]: GLU-interleaved rows like the expand
 };
 
 template <int C> struct DcDims {
@@ -55,7 +57,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // logical rows [i_start, i_start + n) x CW channels starting at channel c0 of rows with C channels -> dst[n][CW + 8]
-template <int C, int CW>
+template <int C, int CW, bool ASYNC>
 __device__ __forceinline__ void dc_load_rows(bf16* dst, const bf16* __restrict__ yb, const DcGeom& g, int i_start, int n, int c0 = 0) {
   constexpr int CV = CW / 8, XP = CW + 8;
   for (int idx = threadIdx.x; idx < n * CV; idx += blockDim.x) {
@@ -64,7 +66,7 @@ __device__ __forceinline__ void dc_load_rows(bf16* dst, const bf16* __restrict__
     const bool valid = i >= 0 && i < g.rows;
     const int t = valid ? i / g.Rr : 0, f = valid ? i - t * g.Rr : 0;
     const bf16* src = yb + (long)t * g.fs + (long)f * C + c0 + cv * 8;
-    if (C <= 96) {      // few copies per thread: register-staged loads are faster than LDGSTS + wait (measured)
+    if (!ASYNC) {       // few copies per thread (C = 48 conv pass): register-staged loads beat LDGSTS + wait (measured)
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (valid) v = *(const uint4*)src;
       *(uint4*)(dst + row * XP + cv * 8) = v;
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(256) dconv_a_kernel(const DcTileParams p) {
   float* red = (float*)(w1s + 8 * D::HN * D::K1P);  // 32 floats
   const int b = blockIdx.y, i0 = blockIdx.x * TM;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  dc_load_rows<C, C>(xs, p.y + p.g.base + (long)b * p.g.seg, p.g, i0 - halo, nload);
+  dc_load_rows<C, C, (C >= 96)>(xs, p.y + p.g.base + (long)b * p.g.seg, p.g, i0 - halo, nload);
   for (int idx = tid; idx < 8 * D::HN * (D::K1 / 8); idx += blockDim.x) {
     const int n = idx / (D::K1 / 8), kc = idx - n * (D::K1 / 8);
     cp_async16(w1s + n * D::K1P + kc * 8, p.w1 + (long)n * D::K1 + kc * 8, true);
@@ -299,15 +301,18 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // blockIdx.z selects a slice of CS value channels (and their gates): the wide layers run as several small CTAs per row tile
 // (occupancy instead of one 150 KB CTA per SM).  The y tile arrives through cp.async while the expand is evaluated; the
 // residual update happens after it has landed.
-template <int C, int CS, int TM, bool PER_ROW>
+template <int C, int CS, int TM, bool PER_ROW, bool REWRITE>
 __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
   typedef DcDims<C> D;
   constexpr int MW = TM / 16, NG = 8 / MW, CV = CS / 8, XPS = CS + 8;
   constexpr int NVT = (CV + NG - 1) / NG;           // value n-tiles per warp
+  static_assert(!REWRITE || CS == C, "the fused rewrite needs all channels of a row in one CTA");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* ys = (bf16*)smem_raw;                       // [TM][XPS]
   bf16* w2s = ys + TM * XPS;                        // [2CS][K2P] de-interleaved: rows [0,CS) values, [CS,2CS) gates
-  float* al = (float*)(w2s + 2 * CS * D::K2P);      // [2CS] alpha (PER_ROW: GroupNorm weight)
+  bf16* wrs = w2s + 2 * CS * D::K2P;                // REWRITE: [2C][XPS] de-interleaved rewrite rows, then out tile [TM][XPS]
+  bf16* os = wrs + (REWRITE ? 2 * C * XPS : 0);
+  float* al = (float*)(os + (REWRITE ? TM * XPS : 0));   // [2CS] alpha (PER_ROW: GroupNorm weight)
   float* be = al + 2 * CS;                          // [2CS] beta  (PER_ROW: GroupNorm bias)
   float* b2s = be + 2 * CS;                         // [2CS] expand bias (PER_ROW only)
   float* scs = b2s + 2 * CS;                        // [CS]
@@ -321,7 +326,14 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
     cp_async16(w2s + nd * D::K2P + kc * 8, p.w2 + (long)n * D::HP + kc * 8, true);
   }
   cp_async_commit();
-  dc_load_rows<C, CS>(ys, yb, p.g, i0, TM, ch0);
+  dc_load_rows<C, CS, true>(ys, yb, p.g, i0, TM, ch0);
+  if (REWRITE) {
+    for (int idx = tid; idx < 2 * C * (C / 8); idx += blockDim.x) {
+      const int nd = idx / (C / 8), kc = idx - nd * (C / 8);
+      const int n = nd < C ? 2 * nd : 2 * (nd - C) + 1;
+      cp_async16(wrs + nd * XPS + kc * 8, p.rw + (long)n * C + kc * 8, true);
+    }
+  }
   cp_async_commit();
   for (int i = tid; i < CS; i += blockDim.x) scs[i] = p.scale[ch0 + i];
   dc_stage_mean_rstd(p.st2, b, PER_ROW ? 1 : 0, p.g.Rr, (double)(2 * C) * (PER_ROW ? p.g.nT : p.g.rows), mr);
@@ -403,12 +415,42 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
     }
   }
   __syncthreads();
+  if (REWRITE) {
+    // HEncLayer tail on the updated tile: out = GLU(Wr y + rb); y itself is not needed again and is not written back
+    uint32_t ar[C / 16][4];
+#pragma unroll
+    for (int kc = 0; kc < C / 16; ++kc) ldsm_a(ys, XPS, mt * 16, kc * 16, lane, ar[kc]);
+#pragma unroll
+    for (int iv = 0; iv < NVT; ++iv) {
+      const int vt = ng + iv * NG;
+      if (vt < CV) {
+        float dv[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kc = 0; kc < C / 16; ++kc) {
+          uint32_t bb[2];
+          frag_b(wrs, XPS, vt * 8, kc * 16, lane, bb); mma16816(dv, ar[kc], bb);
+          frag_b(wrs, XPS, C + vt * 8, kc * 16, lane, bb); mma16816(dg, ar[kc], bb);
+        }
+        const int j = vt * 8 + 2 * q;
+        const float rv0 = p.rb[2 * j], rg0 = 0.5f * p.rb[2 * j + 1], rv1 = p.rb[2 * j + 2], rg1 = 0.5f * p.rb[2 * j + 3];
+        const float o0 = (dv[0] + rv0) * fmaf(0.5f, tanh_approx(fmaf(dg[0], 0.5f, rg0)), 0.5f);
+        const float o1 = (dv[1] + rv1) * fmaf(0.5f, tanh_approx(fmaf(dg[1], 0.5f, rg1)), 0.5f);
+        const float o2 = (dv[2] + rv0) * fmaf(0.5f, tanh_approx(fmaf(dg[2], 0.5f, rg0)), 0.5f);
+        const float o3 = (dv[3] + rv1) * fmaf(0.5f, tanh_approx(fmaf(dg[3], 0.5f, rg1)), 0.5f);
+        *(uint32_t*)(os + (mt * 16 + g) * XPS + j) = pack_bf16x2(o0, o1);
+        *(uint32_t*)(os + (mt * 16 + g + 8) * XPS + j) = pack_bf16x2(o2, o3);
+      }
+    }
+    __syncthreads();
+  }
+  const bf16* src_tile = REWRITE ? os : ys;
+  bf16* dstb = REWRITE ? p.out + p.g.base + (long)b * p.g.seg : yb;
   for (int idx = tid; idx < TM * CV; idx += blockDim.x) {
     const int row = idx / CV, cv = idx - row * CV;
     const int i = i0 + row;
     if (i < p.g.rows) {
       const int t = i / p.g.Rr, f = i - t * p.g.Rr;
-      *(uint4*)(yb + (long)t * p.g.fs + (long)f * C + ch0 + cv * 8) = *(const uint4*)(ys + row * XPS + cv * 8);
+      *(uint4*)(dstb + (long)t * p.g.fs + (long)f * C + ch0 + cv * 8) = *(const uint4*)(src_tile + row * XPS + cv * 8);
     }
   }
 }
@@ -422,14 +464,18 @@ static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
   const int halo = p.dil * p.g.Rr;
   const size_t smA = (size_t)(TM + 2 * halo) * D::XP * 2 + (size_t)8 * D::HN * D::K1P * 2 + 32 * 4 + 16;
   const size_t smB = (size_t)2 * C * D::K2P * 2 + (size_t)(2 * C + 2 * D::HP + 64 + 32) * 4 + 16;
-  const size_t smC = (size_t)TMC * (CS + 8) * 2 + (size_t)2 * CS * D::K2P * 2 + (size_t)(7 * CS + 64) * 4 + 16;
+  const bool rewrite = p.rw != nullptr && CS == C;
+  const size_t smC = (size_t)TMC * (CS + 8) * 2 + (size_t)2 * CS * D::K2P * 2 + (size_t)(7 * CS + 64) * 4 + 16 +
+                     (rewrite ? (size_t)(2 * C + TMC) * (CS + 8) * 2 : 0);
   if (smA > 227 * 1024 || smC > 227 * 1024) return 1;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(dconv_a_kernel<C, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(dconv_b_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if constexpr (CS == C)
+      cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   const int tiles = (p.g.rows + TM - 1) / TM;
@@ -438,17 +484,22 @@ static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
   const int gb = std::min(tiles_b, std::max(1, (148 * 16 + B - 1) / B));
   dconv_a_kernel<C, TM><<<dim3(tiles, B), 256, smA, st>>>(p);
   dconv_b_kernel<C><<<dim3(gb, B), 256, smB, st>>>(p);
-  if (p.per_row) dconv_c_kernel<C, CS, TMC, true><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);
-  else dconv_c_kernel<C, CS, TMC, false><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);
+  if (p.per_row) dconv_c_kernel<C, CS, TMC, true, false><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);
+  else if (rewrite) {
+    if constexpr (CS == C) dconv_c_kernel<C, CS, TMC, false, true><<<dim3(tiles_c, B, 1), 256, smC, st>>>(p);
+  } else dconv_c_kernel<C, CS, TMC, false, false><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);
   return 0;
 }
 
 // ptrs: w1p [HP][3C] bf16, b1p, g1wp, g1bp [HP] fp32, w2p [2C][HP] bf16 (GLU-interleaved rows), b2i, g2wi, g2bi [2C] fp32
-// (interleaved), scale [C] fp32.  Three launches; returns 0 on success.
+// (interleaved), scale [C] fp32.  rw / rb / out (optional, time branch with C <= 96): fuse out = GLU(rewrite(y)) into pass C.
+// Three launches; returns 0 on success.
+bool dconv_tile_can_rewrite(int C, bool freq) { return !freq && (C == 48 || C == 96); }
 int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
                       const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
-                      double* st2, cudaStream_t st) {
+                      double* st2, const bf16* rw, const float* rb, bf16* out, cudaStream_t st) {
   DcTileParams p;
+  p.rw = rw; p.rb = rb; p.out = out;
   const bool freq = ys.G2 > 1;
   p.g.nT = freq ? ys.G2 : ys.R; p.g.Rr = freq ? ys.R : 1; p.g.rows = p.g.nT * p.g.Rr;
   p.g.seg = ys.g1_stride(); p.g.base = ys.origin(); p.g.fs = freq ? (long)ys.Rp * ys.C : ys.C;

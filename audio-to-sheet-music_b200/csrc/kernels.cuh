@@ -49,7 +49,8 @@ void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, R
 bool dconv_tile_supported(int C);
 int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
                       const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
-                      double* st2, cudaStream_t st);
+                      double* st2, const bf16* rw, const float* rb, bf16* out, cudaStream_t st);
+bool dconv_tile_can_rewrite(int C, bool freq);
 
 // ---- small_conv.cu (bf16: time-branch level-0 conv + GELU fused with the waveform normalisation)
 void launch_tenc0_conv(const float* wav, const float* meanstd, int L, const bf16* w, const float* bias, bf16* y, RowSpace ys,

@@ -288,11 +288,12 @@ static ConvOp<T> conv_op(int mode, const T* a, RowSpace as, const T* w, int N, T
 // bf16 only: one DConv residual layer as three tiled mma.sync passes (dconv_tile.cu)
 static int dconv_tile_run(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
                           const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
-                          double* st2, cudaStream_t st) {
-  return launch_dconv_tile(y, ys, h, dil, w1p, b1p, g1wp, g1bp, w2p, b2i, g2wi, g2bi, scale, st1, st2, st);
+                          double* st2, const bf16* rw, const float* rb, bf16* out, cudaStream_t st) {
+  return launch_dconv_tile(y, ys, h, dil, w1p, b1p, g1wp, g1bp, w2p, b2i, g2wi, g2bi, scale, st1, st2, rw, rb, out, st);
 }
 static int dconv_tile_run(float*, RowSpace, float*, int, const float*, const float*, const float*, const float*, const float*,
-                          const float*, const float*, const float*, const float*, double*, double*, cudaStream_t) {
+                          const float*, const float*, const float*, const float*, double*, double*, const float*, const float*, float*,
+                          cudaStream_t) {
   return 1;
 }
 
@@ -376,10 +377,15 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
     const int smode = freq ? STAT_PER_G1_M : STAT_PER_G1;
     if (tc_dconv && use_fused_dconv && dconv_tile_supported(C) && (!freq || R <= 32)) {
       // three bandwidth-bound mma.sync passes (conv3 + stats | GN+GELU + expand stats | expand + GN + GLU + residual)
+      // second residual layer of a narrow time-branch level: the 1x1 rewrite + GLU runs on the updated tile inside pass C
+      const bool fuse_rw = dd == 1 && dconv_tile_can_rewrite(C, freq);
       const int rc = dconv_tile_run(y, ys, hbuf, 1 << dd, PW(q + ".0.wp"), PA(q + ".0.bp"), PA(q + ".1.wp"), PA(q + ".1.bp"),
-                                    PW(q + ".3.wp"), PA(q + ".3.bi"), PA(q + ".4.wi"), PA(q + ".4.bi"), P32(q + ".6.scale"), st_h, st_e, st);
+                                    PW(q + ".3.wp"), PA(q + ".3.bi"), PA(q + ".4.wi"), PA(q + ".4.bi"), P32(q + ".6.scale"), st_h, st_e,
+                                    fuse_rw ? PW(p + ".rewrite.w") : nullptr, fuse_rw ? PA(p + ".rewrite.b") : nullptr,
+                                    fuse_rw ? out : nullptr, st);
       if (rc != 0) throw std::runtime_error("athtd: dconv_tile launch failed");
       n_launches += 3;
+      if (fuse_rw) return;
       continue;
     }
     if (tc_dconv) {
