@@ -184,6 +184,108 @@ class B200SeparationModel(SeparationModel):
         self._last_seg_out = seg_out
         return out
 
+    @torch.no_grad()
+    def separate_span_host(self, track_host: torch.Tensor, emb: torch.Tensor, span, out_host: torch.Tensor,
+                           halo_exchange=None, halo_in: Optional[torch.Tensor] = None):
+        """Host-staged variant of ``separate_span`` (the step either side of the path: app.py:230-231,
+        benchmark.py:207/211 move the whole track with ``.to(device)`` / ``.cpu()`` around the loop).
+
+        track_host : [2, T] float32 in PINNED host memory (the whole track); out_host : [P, 2, t_end - t_begin] pinned.
+        Inputs are uploaded batch by batch on a copy stream while the previous batch computes; every batch is
+        overlap-added as soon as its chunks (and the chunk before them) are done and its output range is downloaded
+        while the next batch computes.  Results are bit-identical to ``separate_span`` (same kernels, same order of
+        operations per sample).  The device work is ordered on the current stream; the call returns after the last
+        download has completed."""
+        T = track_host.shape[-1]
+        P = emb.shape[0]
+        plan = segment_plan(T, self.segment_seconds, self.overlap, self.model.sample_rate)
+        n = len(plan.starts)
+        k0, k1 = span
+        key = (T, str(self.device))
+        if getattr(self, "_tables_key", None) != key:
+            self._tables, self._tables_key = OlaTables(plan, self.device), key
+        tables = self._tables
+        L = plan.chunk_len
+        nk = k1 - k0
+        in_lo, in_hi = plan.starts[k0], min(T, plan.starts[k1 - 1] + L)
+        t_begin = plan.starts[k0]
+        t_end = plan.T if k1 == n else plan.starts[k1]
+        dev = self.device
+        comp = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cps = self._copy_stream
+        track = torch.empty(2, in_hi - in_lo, dtype=torch.float32, device=dev)
+        seg_out = torch.empty(nk + 1, P, 2, L, dtype=torch.float32, device=dev)      # slot 0 = halo chunk k0-1
+        segs = torch.empty(min(self.batch, nk), 2, L, dtype=torch.float32, device=dev)
+        local_starts = (tables.starts[k0:k1] - in_lo).contiguous()
+        eng = self.model.engine(dev)
+        batches = [(b0, min(b0 + self.batch, nk)) for b0 in range(0, nk, self.batch)]
+        cps.wait_stream(comp)                       # buffers above are allocated on the compute stream
+
+        def upload(i, done_to):
+            b0, b1 = batches[i]
+            hi = min(T, plan.starts[k0 + b1 - 1] + L)
+            with torch.cuda.stream(cps):
+                for c in range(2):
+                    track[c, done_to - in_lo:hi - in_lo].copy_(track_host[c, done_to:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cps)
+            return ev, hi
+
+        launches = 0
+        up_ev, up_to = upload(0, in_lo)
+        pending_first = None
+        for i, (b0, b1) in enumerate(batches):
+            comp.wait_event(up_ev)
+            if i + 1 < len(batches):
+                up_ev, up_to = upload(i + 1, up_to)
+            st = comp.cuda_stream
+            _lib.check(_lib.load().athtd_gather_chunks(track.data_ptr(), track.shape[-1], 2, local_starts[b0:].data_ptr(), b1 - b0, L,
+                                                       segs.data_ptr(), st), "athtd_gather_chunks")
+            e = emb.unsqueeze(0).expand(b1 - b0, P, 512).contiguous()
+            fplan = eng.plan(b1 - b0, L, P)
+            fplan.forward(segs[:b1 - b0], e, seg_out[1 + b0:1 + b1])
+            launches += fplan.launches + 1
+            if i == len(batches) - 1 and halo_exchange is not None:
+                halo_in = halo_exchange(seg_out[nk])
+            # output samples that are complete now: [starts[k0+b0], starts[k0+b1]) (to the span end for the last batch)
+            ra = plan.starts[k0 + b0]
+            rb = t_end if b1 == nk else plan.starts[k0 + b1]
+            if b0 == 0 and k0 > 0 and halo_in is None and halo_exchange is not None:
+                pending_first = (ra, rb)             # needs the left neighbour's last chunk: finished after the exchange
+                continue
+            if b0 == 0 and k0 > 0:
+                if halo_in is None:
+                    raise ValueError("span starts inside the track: the left neighbour's last chunk output is required")
+                seg_out[0].copy_(halo_in)
+            self._ola_and_download(seg_out, tables, k0, P, L, ra, rb, t_begin, out_host, comp, cps)
+            launches += P
+        if pending_first is not None:
+            if halo_in is None:
+                raise ValueError("span starts inside the track: the left neighbour's last chunk output is required")
+            seg_out[0].copy_(halo_in)
+            self._ola_and_download(seg_out, tables, k0, P, L, pending_first[0], pending_first[1], t_begin, out_host, comp, cps)
+            launches += P
+        cps.synchronize()
+        comp.wait_stream(cps)
+        self.last_launches = launches
+        self._last_seg_out = seg_out
+        return out_host
+
+    def _ola_and_download(self, seg_out, tables, k0, P, L, ra, rb, t_begin, out_host, comp, cps):
+        piece = torch.empty(P, 2, rb - ra, dtype=torch.float32, device=self.device)
+        for p in range(P):
+            chunk_ola(seg_out[:, p], P * 2 * L, k0 - 1, tables, ra, rb, piece[p])
+        ev = torch.cuda.Event()
+        ev.record(comp)
+        with torch.cuda.stream(cps):
+            cps.wait_event(ev)
+            for p in range(P):
+                for c in range(2):
+                    out_host[p, c, ra - t_begin:rb - t_begin].copy_(piece[p, c], non_blocking=True)
+        piece.record_stream(cps)
+
     def separate_many(self, mixture: torch.Tensor, emb: torch.Tensor, span=None, halo_in: Optional[torch.Tensor] = None):
         """mixture [2,T], emb [P,512] -> ([P,2,T'], raw output [P,2,chunk_len] of the span's last chunk)."""
         mixture = mixture.to(self.device, torch.float32).contiguous()

@@ -187,10 +187,9 @@ def main():
     launches = sep.last_launches
 
     def e2e_step():
-        t = track_host[:, in_lo:in_hi].to(dev, non_blocking=True)       # H2D of this rank's input span (pinned)
-        o = sep.separate_span(t, emb, (k0, k1), halo_exchange, track_offset=in_lo, track_len=T)
-        out_host.copy_(o, non_blocking=True)                             # D2H of the separated span
-        torch.cuda.current_stream().synchronize()
+        # pinned host track -> batch-wise H2D on a copy stream -> separate -> per-batch overlap-add -> D2H of finished
+        # output ranges while the next batch computes (B200SeparationModel.separate_span_host); returns after the last copy
+        sep.separate_span_host(track_host, emb, (k0, k1), out_host, halo_exchange)
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
