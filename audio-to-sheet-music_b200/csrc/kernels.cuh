@@ -56,6 +56,12 @@ bool dconv_tile_can_rewrite(int C, bool freq);
 void launch_tenc0_conv(const float* wav, const float* meanstd, int L, const bf16* w, const float* bias, bf16* y, RowSpace ys,
                        cudaStream_t st);
 
+// last decoder layers (48 -> 4 channels, no norm): transposed conv + resize + skip in one kernel (bf16)
+void launch_dec_last_freq(const bf16* x, RowSpace xs, const float* w, const float* bias, const bf16* skip, RowSpace ss, bf16* out,
+                          RowSpace os, cudaStream_t st);
+void launch_dec_last_time(const bf16* x, RowSpace xs, const bf16* w, const float* bias4, const bf16* skip, RowSpace ss, bf16* out,
+                          RowSpace os, cudaStream_t st);
+
 // ---- fft.cu
 void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
                      cudaStream_t st);

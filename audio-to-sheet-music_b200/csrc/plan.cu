@@ -297,6 +297,17 @@ static int dconv_tile_run(float*, RowSpace, float*, int, const float*, const flo
   return 1;
 }
 
+// bf16 only: last decoder layer (transposed conv 48 -> 4 + resize + skip) in one kernel (small_conv.cu)
+static bool dec_last_run(bool freq, const bf16* x, RowSpace xs, const float* w32, const bf16* wp, const float* b, const float* b4,
+                         const bf16* skip, RowSpace ss, bf16* out, RowSpace os, cudaStream_t st) {
+  if (xs.C != 48 || os.C != 4) return false;
+  if (freq) { if (os.R != xs.R) return false; launch_dec_last_freq(x, xs, w32, b, skip, ss, out, os, st); }
+  else { if (os.R != 4 * xs.R) return false; launch_dec_last_time(x, xs, wp, b4, skip, ss, out, os, st); }
+  return true;
+}
+static bool dec_last_run(bool, const float*, RowSpace, const float*, const float*, const float*, const float*, const float*, RowSpace,
+                         float*, RowSpace, cudaStream_t) { return false; }
+
 // bf16 only: time-branch level-0 conv fused with the waveform normalisation (small_conv.cu)
 static bool tenc0_run(const float* wav, const float* ms, int L, const bf16* w, const float* bias, bf16* y, RowSpace ys, cudaStream_t st) {
   launch_tenc0_conv(wav, ms, L, w, bias, y, ys, st);
@@ -657,6 +668,11 @@ void PlanT<T>::dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* ou
   const int G2 = xs.G2;
   const int Rin = xs.R;
   const std::string q = std::string(freq ? "freq_decoder" : "time_decoder") + ".layers." + std::to_string(i);
+  if (i == 3 && use_tc && use_fused_dconv &&
+      dec_last_run(freq, x, xs, P32(q + ".0.weight"), PW(q + ".0.w"), P32(q + ".0.bias"), PA(q + ".0.b4"), skip, ss, out, os, st)) {
+    ++n_launches;
+    return;
+  }
   double* stt = st_dec + 2L * s.B * STAT_SLOTS * ((size_t)p * 6 + (freq ? 0 : 3) + (i < 3 ? i : 0));
   RowSpace us = xs; us.C = 4 * Cout;
   ConvOp<T> o = conv_op<T>(CONV_T, x, xs, PW(q + ".0.w"), 4 * Cout, ubuf, us);
