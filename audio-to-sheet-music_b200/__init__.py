@@ -6,3 +6,4 @@ from .separation import (B200SeparationModel, SeparationModel, STEMS, segment_pl
                          chunk_ola)
 from .engine import Engine, Plan                                     # noqa: F401
 from . import distributed                                     # noqa: F401
+from . import metrics                                         # noqa: F401

@@ -125,6 +125,12 @@ int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* strea
   return 0;
 }
 
+int athtd_sdr_sums(const float* est_dev, const float* tgt_dev, int items, long n, double* sums_dev, void* stream) {
+  if (items <= 0 || n <= 0) return fail("athtd_sdr_sums: items and n must be positive");
+  launch_sdr_sums(est_dev, tgt_dev, items, n, sums_dev, (cudaStream_t)stream);
+  return check_cuda("athtd_sdr_sums");
+}
+
 int athtd_stft_cac(const float* wav_dev, int B, int L, float* Z_dev, double* stats_dev, const float* tw_dev,
                    const float* win_dev, void* stream) {
   if (L < 4096) return fail("athtd_stft_cac: L must be >= 4096");

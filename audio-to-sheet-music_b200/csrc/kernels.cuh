@@ -85,4 +85,7 @@ void launch_chunk_ola(const float* seg_out, long seg_stride, int k_base, int chu
                       const float* ramp_up, const float* ramp_down, const int* ramp_off, float* out, int C, long t_begin,
                       long t_end, cudaStream_t st);
 
+// ---- metrics.cu  (sums behind sdr_loss / sisdr_loss / new_sdr_metric, src/loss.py:9-87)
+void launch_sdr_sums(const float* est, const float* tgt, int items, long n, double* sums, cudaStream_t st);
+
 }  // namespace athtd

@@ -39,6 +39,7 @@ SYMBOLS = [
     ("athtd_plan_tc_launches", _I, [_P]),
     ("athtd_attention_test", _I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     ("athtd_memcpy_d2d", _I, [_P, _P, _L, _P]),
+    ("athtd_sdr_sums", _I, [_P, _P, _I, _L, _P, _P]),
     ("athtd_stft_cac", _I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     ("athtd_istft", _I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     ("athtd_gather_chunks", _I, [_P, _L, _I, _P, _I, _I, _P, _P]),

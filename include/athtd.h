@@ -90,6 +90,11 @@ int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int c
                     const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
                     long t_begin, long t_end, void* stream);
 
+/* ---- evaluation metrics on the device (src/loss.py:9-87 sdr_loss / sisdr_loss / new_sdr_metric; benchmark.py:555-588).
+ * est / tgt: [items, n] fp32 rows; sums_dev: double[items][6] = {sum t, sum e, sum t^2, sum e^2, sum e*t, sum (t-e)^2}
+ * (zeroed by the call).  The dB values are closed forms of these sums (audio-to-sheet-music_b200/metrics.py). */
+int athtd_sdr_sums(const float* est_dev, const float* tgt_dev, int items, long n, double* sums_dev, void* stream);
+
 /* kernel-level parity test of the fused attention: q [B*Sq,512], k/v [B*Sk,512] bf16 (8 heads x 64) -> o [B*Sq,512] */
 int athtd_attention_test(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev, int B, int Sq, int Sk,
                          void* stream);
