@@ -110,6 +110,41 @@ def test_track_separation_matches_reference_loop(models, state_dict):
     assert torch.equal(torch.cat([left, right], dim=-1), out)
 
 
+def test_silent_and_constant_segments_match_oracle(models, state_dict):
+    """Edge inputs of the reference's normalisation (ATHTDemucs_v2.py:268-275): an all-zero segment (std = 0, the 1e-5
+    guard decides) and a DC-only segment, batched with a normal one; fp32 build vs oracle."""
+    wav, emb = weights.make_inputs(81, 3, 20000)
+    wav[0].zero_()
+    wav[1].fill_(0.25)
+    ref = athtd_oracle.forward(state_dict, wav, emb)
+    out = models["fp32"](wav.cuda(), emb.cuda()).cpu()
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max() < 1e-3
+
+
+def test_full_track_properties_bf16(models):
+    """BASELINE config-3 shape at a size the CPU oracle cannot reach (bf16, 90 s track, 21 chunks): size-independent
+    properties instead of an oracle -- (1) the result does not depend on the batch size (7 vs 16 segments per launch:
+    every statistic is per segment), (2) the track output equals the reference overlap-add
+    (oracle/ola.py, the restated benchmark.py loop) applied to the per-chunk model outputs, bit for bit,
+    (3) linearity of the track loop: separating with two prompts at once == one prompt at a time."""
+    m = models["bf16"]
+    T = 44100 * 90 + 1234
+    wav, emb = weights.make_inputs(91, 1, T)
+    embs = torch.stack([emb[0], weights.make_inputs(92, 1, 4096)[1][0]]).cuda()
+    mix = wav[0].cuda()
+    a, _ = athtd_b200.B200SeparationModel(m, "cuda", batch=7).separate_many(mix, embs)
+    sep16 = athtd_b200.B200SeparationModel(m, "cuda", batch=16)
+    b, _ = sep16.separate_many(mix, embs)
+    assert torch.equal(a, b)
+    seg_out = sep16._last_seg_out[1:, 0].cpu()              # [n_chunks, 2, L] raw model outputs for prompt 0
+    it = iter(range(seg_out.shape[0]))
+    ref = ola.chunked_inference(lambda c: seg_out[next(it)].unsqueeze(0), wav[0])
+    assert torch.equal(b[0].cpu(), ref)
+    c, _ = sep16.separate_many(mix, embs[1:])
+    assert torch.equal(c[0], b[1])
+
+
 def test_host_staged_pipeline_matches_device_path(models):
     """separate_span_host (batch-wise H2D / per-batch overlap-add / D2H on a copy stream) == separate_span, bit for bit,
     including a span that starts inside the track (halo chunk supplied by the left neighbour)."""
