@@ -29,12 +29,14 @@ __device__ __forceinline__ float er_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void er_block_sum2(float& a, float& b, float* red) {
+// barrier of one 9-warp slab group (named barrier 1 + group; a CTA runs one or two groups that share the staged weights)
+__device__ __forceinline__ void er_gsync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(ER_THREADS) : "memory"); }
+__device__ __forceinline__ void er_block_sum2(float& a, float& b, float* red, int grp, int tid) {
   a = warp_sum(a); b = warp_sum(b);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
-  __syncthreads();
+  const int w = tid >> 5, l = tid & 31, nw = ER_THREADS >> 5;
+  er_gsync(grp);
   if (l == 0) { red[2 * w] = a; red[2 * w + 1] = b; }
-  __syncthreads();
+  er_gsync(grp);
   float x = l < nw ? red[2 * l] : 0.f, y = l < nw ? red[2 * l + 1] : 0.f;
   a = warp_sum(x); b = warp_sum(y);
 }
@@ -53,80 +55,87 @@ template <int C> struct ErDims {
   static constexpr int VD = 48 + 7 * C;           // fp32 vectors per depth: b1 g1w g1b [16] | b2 g2w g2b [2C] | scale [C]
 };
 
-template <int C, bool FUSE_CONV>
-__global__ void __launch_bounds__(ER_THREADS, (C == 48 ? 2 : 1))
+template <int C, bool FUSE_CONV, int G>
+__global__ void __launch_bounds__(ER_THREADS * G, (C == 48 ? 2 : 1))
 enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restrict__ yin, bf16* __restrict__ out, RowSpace ys,
                const EncRowParams P) {
   typedef ErDims<C> D;
   const int Tn = ys.G2;
   const int MT = (Tn + 15) / 16;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* xs = (bf16*)smem_raw;                               // [(MT*16 + 4)][XP], rows shifted by +2 (zero halo)
-  bf16* hb = xs + (MT * 16 + 4) * D::XP;                    // [MT*16][K2P]
-  bf16* w1t = hb + MT * 16 * D::K2P;                        // [2][8*HN][K1P]
+  // shared by all slab groups of the CTA: every weight of the layer
+  bf16* w1t = (bf16*)smem_raw;                              // [2][8*HN][K1P]
   bf16* w2t = w1t + 2 * 8 * D::HN * D::K1P;                 // [2][2C][K2P]  rows [0,C) values, [C,2C) gates
   bf16* wrt = w2t + 2 * 2 * C * D::K2P;                     // [2C][KRP]     same split
-  bf16* pst = wrt + 2 * C * D::KRP;                         // FUSE_CONV: patch [MT*16][PP], conv weights [C][PP]
-  bf16* cwt = pst + (FUSE_CONV ? MT * 16 * D::PP : 0);
+  bf16* cwt = wrt + 2 * C * D::KRP;                         // FUSE_CONV: conv weights [C][PP]
   float* vec = (float*)(cwt + (FUSE_CONV ? C * D::PP : 0)); // [2][VD] | rb [2C] (gate half pre-scaled by 0.5) | cb [C]
   float* rbs = vec + 2 * D::VD;
   float* cbs = rbs + 2 * C;
-  float* al = cbs + C;                                      // [2C] per-slab GroupNorm-2 alpha (gate half x 0.5)
+  // per slab group (9 warps): activation tiles and per-slab vectors
+  constexpr int GF = 4 * C + C + 64;                        // al [2C] be [2C] embv [C] red [64]
+  const int slab_elems = (MT * 16 + 4) * D::XP + MT * 16 * D::K2P + (FUSE_CONV ? MT * 16 * D::PP : 0);
+  const int btid = threadIdx.x;
+  const int grp = btid / ER_THREADS;
+  const int tid = btid - grp * ER_THREADS, lane = tid & 31, warp = tid >> 5, nwarp = ER_THREADS >> 5;
+  float* gvec = cbs + C + grp * GF;
+  float* al = gvec;                                         // [2C] per-slab GroupNorm-2 alpha (gate half x 0.5)
   float* be = al + 2 * C;                                   // [2C] beta
   float* embv = be + 2 * C;                                 // [C]
   float* red = embv + C;                                    // 64 floats
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  bf16* xs = (bf16*)(cbs + C + G * GF) + (size_t)grp * slab_elems;   // [(MT*16 + 4)][XP], rows shifted by +2 (zero halo)
+  bf16* hb = xs + (MT * 16 + 4) * D::XP;                    // [MT*16][K2P]
+  bf16* pst = hb + MT * 16 * D::K2P;                        // FUSE_CONV: patch [MT*16][PP]
   const int g = lane >> 2, q = lane & 3;
   bf16* xsi = xs + 2 * D::XP;                               // interior row 0
 
   // ---- once per CTA: zero the activation tiles, stage every weight of the layer
-  for (int i = tid; i < ((MT * 16 + 4) * D::XP) / 2; i += blockDim.x) ((uint32_t*)xs)[i] = 0u;
-  for (int i = tid; i < (MT * 16 * D::K2P) / 2; i += blockDim.x) ((uint32_t*)hb)[i] = 0u;
+  for (int i = tid; i < ((MT * 16 + 4) * D::XP) / 2; i += ER_THREADS) ((uint32_t*)xs)[i] = 0u;
+  for (int i = tid; i < (MT * 16 * D::K2P) / 2; i += ER_THREADS) ((uint32_t*)hb)[i] = 0u;
   if (FUSE_CONV) {
-    for (int i = tid; i < (MT * 16 * D::PP) / 2; i += blockDim.x) ((uint32_t*)pst)[i] = 0u;
-    for (int i = tid; i < C * 4; i += blockDim.x) {         // conv taps [C][32] -> [C][PP]
+    for (int i = tid; i < (MT * 16 * D::PP) / 2; i += ER_THREADS) ((uint32_t*)pst)[i] = 0u;
+    for (int i = btid; i < C * 4; i += blockDim.x) {         // conv taps [C][32] -> [C][PP]
       const int n = i >> 2, kc = i & 3;
       *(uint4*)(cwt + n * D::PP + kc * 8) = *(const uint4*)(P.cw + n * 32 + kc * 8);
     }
-    for (int i = tid; i < C; i += blockDim.x) cbs[i] = P.cb[i];
+    for (int i = btid; i < C; i += blockDim.x) cbs[i] = P.cb[i];
   }
   for (int dd = 0; dd < 2; ++dd) {
     bf16* w1 = w1t + dd * 8 * D::HN * D::K1P;
-    for (int i = tid; i < 8 * D::HN * (D::K1 / 8); i += blockDim.x) {
+    for (int i = btid; i < 8 * D::HN * (D::K1 / 8); i += blockDim.x) {
       const int n = i / (D::K1 / 8), kc = i - n * (D::K1 / 8);
       *(uint4*)(w1 + n * D::K1P + kc * 8) = *(const uint4*)(P.w1[dd] + (long)n * D::K1 + kc * 8);
     }
     bf16* w2 = w2t + dd * 2 * C * D::K2P;
-    for (int i = tid; i < 2 * C * 2; i += blockDim.x) {      // packed rows are GLU-interleaved (2j value, 2j+1 gate)
+    for (int i = btid; i < 2 * C * 2; i += blockDim.x) {      // packed rows are GLU-interleaved (2j value, 2j+1 gate)
       const int n = i >> 1, kc = i & 1, nd = (n & 1) * C + (n >> 1);
       *(uint4*)(w2 + nd * D::K2P + kc * 8) = *(const uint4*)(P.w2[dd] + (long)n * D::HP + kc * 8);
     }
     float* v = vec + dd * D::VD;
-    for (int i = tid; i < 16; i += blockDim.x) { v[i] = P.b1[dd][i]; v[16 + i] = P.g1w[dd][i]; v[32 + i] = P.g1b[dd][i]; }
-    for (int n = tid; n < 2 * C; n += blockDim.x) {
+    for (int i = btid; i < 16; i += blockDim.x) { v[i] = P.b1[dd][i]; v[16 + i] = P.g1w[dd][i]; v[32 + i] = P.g1b[dd][i]; }
+    for (int n = btid; n < 2 * C; n += blockDim.x) {
       const int nd = (n & 1) * C + (n >> 1);
       v[48 + nd] = P.b2[dd][n]; v[48 + 2 * C + nd] = P.g2w[dd][n]; v[48 + 4 * C + nd] = P.g2b[dd][n];
     }
-    for (int i = tid; i < C; i += blockDim.x) v[48 + 6 * C + i] = P.scale[dd][i];
+    for (int i = btid; i < C; i += blockDim.x) v[48 + 6 * C + i] = P.scale[dd][i];
   }
-  for (int i = tid; i < 2 * C * (C / 8); i += blockDim.x) {
+  for (int i = btid; i < 2 * C * (C / 8); i += blockDim.x) {
     const int n = i / (C / 8), kc = i - n * (C / 8), nd = (n & 1) * C + (n >> 1);
     *(uint4*)(wrt + nd * D::KRP + kc * 8) = *(const uint4*)(P.rw + (long)n * C + kc * 8);
   }
-  for (int n = tid; n < 2 * C; n += blockDim.x) rbs[(n & 1) * C + (n >> 1)] = (n & 1) ? 0.5f * P.rb[n] : P.rb[n];
+  for (int n = btid; n < 2 * C; n += blockDim.x) rbs[(n & 1) * C + (n >> 1)] = (n & 1) ? 0.5f * P.rb[n] : P.rb[n];
   __syncthreads();
 
   const int n_slabs = ys.batch() * ys.R;
-  for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+  for (int slab = blockIdx.x * G + grp; slab < n_slabs; slab += gridDim.x * G) {
     const int f = slab % ys.R, b = slab / ys.R;
-    if (P.emb) for (int i = tid; i < C; i += blockDim.x) embv[i] = P.emb_scale * P.emb[f * C + i];
+    if (P.emb) for (int i = tid; i < C; i += ER_THREADS) embv[i] = P.emb_scale * P.emb[f * C + i];
     if (FUSE_CONV) {
       // level 0: y = GELU(conv_k8s4(x)): patch [T x 32] = 8 padded frequency rows x 4 channels, contiguous in xin
-      for (int i = tid; i < Tn * 4; i += blockDim.x) {        // 4 x 16-byte chunks per frame
+      for (int i = tid; i < Tn * 4; i += ER_THREADS) {        // 4 x 16-byte chunks per frame
         const int t = i >> 2, ch = i & 3;
         *(uint4*)(pst + t * D::PP + ch * 8) = *(const uint4*)(xin + xis.row_off(b * Tn + t, 4 * f - 2) + ch * 8);
       }
-      __syncthreads();
+      er_gsync(grp);
       for (int mt = warp; mt < MT; mt += nwarp) {
         uint32_t a[2][4];
         ldsm_a(pst, D::PP, mt * 16, 0, lane, a[0]);
@@ -145,7 +154,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
         }
       }
     } else {
-      for (int i = tid; i < Tn * (C / 8); i += blockDim.x) {
+      for (int i = tid; i < Tn * (C / 8); i += ER_THREADS) {
         const int t = i / (C / 8), c = (i - t * (C / 8)) * 8;
         *(uint4*)(xsi + t * D::XP + c) = *(const uint4*)(yin + ys.row_off(b * Tn + t, f) + c);
       }
@@ -157,7 +166,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
       const bf16* w2 = w2t + dd * 2 * C * D::K2P;
       const float* v = vec + dd * D::VD;
       const float* b1 = v, *g1w = v + 16, *g1b = v + 32, *b2 = v + 48, *g2w = b2 + 2 * C, *g2b = b2 + 4 * C, *scl = b2 + 6 * C;
-      __syncthreads();
+      er_gsync(grp);
       // ---- h = conv_k3_dil(y) + b1 (taps = row-shifted A fragments of the resident slab); GroupNorm(1,H) partial sums
       float hacc[2][D::HN][4];
       float s1 = 0.f, q1 = 0.f;
@@ -196,7 +205,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
           }
         }
       }
-      er_block_sum2(s1, q1, red);
+      er_block_sum2(s1, q1, red, grp, tid);
       {
         const float n = (float)(Tn * D::H);
         const float mean = s1 / n;
@@ -220,7 +229,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
           }
         }
       }
-      __syncthreads();
+      er_gsync(grp);
 
       // ---- e = W2 h + b2 : statistics pass (nothing stored), then GroupNorm + GLU + LayerScale + residual pass
       float s2 = 0.f, q2 = 0.f;
@@ -244,18 +253,18 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
         if (v0) { s2 += sl; q2 += ql; }
         if (v1) { s2 += sh; q2 += qh; }
       }
-      er_block_sum2(s2, q2, red);
+      er_block_sum2(s2, q2, red, grp, tid);
       {
         const float n2 = (float)(Tn * 2 * C);
         const float mean2 = s2 / n2;
         const float rstd2 = rsqrtf(fmaxf(q2 / n2 - mean2 * mean2, 0.f) + 1e-5f);
-        for (int n = tid; n < 2 * C; n += blockDim.x) {       // e_norm = d * alpha + beta (gate half carries the x/2 of tanh)
+        for (int n = tid; n < 2 * C; n += ER_THREADS) {       // e_norm = d * alpha + beta (gate half carries the x/2 of tanh)
           const float half = n >= C ? 0.5f : 1.0f;
           const float a_ = rstd2 * g2w[n];
           al[n] = half * a_; be[n] = half * ((b2[n] - mean2) * a_ + g2b[n]);
         }
       }
-      __syncthreads();
+      er_gsync(grp);
       for (int mt = warp; mt < MT; mt += nwarp) {
         uint32_t a[4];
         ldsm_a(hb, D::K2P, mt * 16, 0, lane, a);
@@ -285,7 +294,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
         }
       }
     }
-    __syncthreads();
+    er_gsync(grp);
 
     // ---- rewrite 1x1 (C -> 2C) + GLU (+ frequency embedding): result overwrites the slab rows of the owning warp
     for (int mt = warp; mt < MT; mt += nwarp) {
@@ -315,28 +324,28 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
         if (r0 + 8 < Tn) sts_pair(xsi + (r0 + 8) * D::XP + c, o2, o3);
       }
     }
-    __syncthreads();
-    for (int i = tid; i < Tn * (C / 8); i += blockDim.x) {
+    er_gsync(grp);
+    for (int i = tid; i < Tn * (C / 8); i += ER_THREADS) {
       const int t = i / (C / 8), c = (i - t * (C / 8)) * 8;
       *(uint4*)(out + ys.row_off(b * Tn + t, f) + c) = *(const uint4*)(xsi + t * D::XP + c);
     }
-    __syncthreads();
+    er_gsync(grp);
   }
 }
 
 template <int C>
-static size_t enc_row_smem(int Tn, bool fuse) {
+static size_t enc_row_smem(int Tn, bool fuse, int G) {
   typedef ErDims<C> D;
   const int MT = (Tn + 15) / 16;
-  size_t bf = (size_t)(MT * 16 + 4) * D::XP + (size_t)MT * 16 * D::K2P + (size_t)2 * 8 * D::HN * D::K1P + (size_t)2 * 2 * C * D::K2P +
-              (size_t)2 * C * D::KRP + (fuse ? (size_t)MT * 16 * D::PP + (size_t)C * D::PP : 0);
-  return bf * 2 + sizeof(float) * (2 * D::VD + 2 * C + C + 4 * C + C + 64) + 32;
+  const size_t wbf = (size_t)2 * 8 * D::HN * D::K1P + (size_t)2 * 2 * C * D::K2P + (size_t)2 * C * D::KRP + (fuse ? (size_t)C * D::PP : 0);
+  const size_t slab = (size_t)(MT * 16 + 4) * D::XP + (size_t)MT * 16 * D::K2P + (fuse ? (size_t)MT * 16 * D::PP : 0);
+  return wbf * 2 + sizeof(float) * (2 * D::VD + 2 * C + C + (size_t)G * (4 * C + C + 64)) + (size_t)G * slab * 2 + 32;
 }
 
 bool enc_row_supported(int C, int Tn, bool fuse_conv) {
   if (Tn > 16 * 2 * (ER_THREADS / 32)) return false;          // two row tiles per warp
-  if (C == 48) return enc_row_smem<48>(Tn, fuse_conv) <= 113 * 1024;
-  if (C == 96) return !fuse_conv && enc_row_smem<96>(Tn, false) <= 226 * 1024;
+  if (C == 48) return enc_row_smem<48>(Tn, fuse_conv, 1) <= 113 * 1024;
+  if (C == 96) return !fuse_conv && enc_row_smem<96>(Tn, false, 1) <= 226 * 1024;
   return false;
 }
 
@@ -356,20 +365,27 @@ void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, R
   const int Tn = ys.G2;
   const int slabs = ys.batch() * ys.R;
   if (ys.C == 48) {
-    const size_t smem = enc_row_smem<48>(Tn, fuse_conv);
+    const size_t smem = enc_row_smem<48>(Tn, fuse_conv, 1);
     const int grid = std::min(slabs, 2 * er_num_sms());
     if (fuse_conv) {
-      cudaFuncSetAttribute(enc_row_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      enc_row_kernel<48, true><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+      cudaFuncSetAttribute(enc_row_kernel<48, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      enc_row_kernel<48, true, 1><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
     } else {
-      cudaFuncSetAttribute(enc_row_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      enc_row_kernel<48, false><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+      cudaFuncSetAttribute(enc_row_kernel<48, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      enc_row_kernel<48, false, 1><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
     }
   } else {
-    const size_t smem = enc_row_smem<96>(Tn, false);
-    const int grid = std::min(slabs, er_num_sms());
-    cudaFuncSetAttribute(enc_row_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    enc_row_kernel<96, false><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+    // C = 96: the weights alone are 77 KB, so one CTA per SM; two 9-warp slab groups share them (18 warps per SM)
+    const int G = enc_row_smem<96>(Tn, false, 2) <= 226 * 1024 ? 2 : 1;
+    const size_t smem = enc_row_smem<96>(Tn, false, G);
+    const int grid = std::min((slabs + G - 1) / G, er_num_sms());
+    if (G == 2) {
+      cudaFuncSetAttribute(enc_row_kernel<96, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      enc_row_kernel<96, false, 2><<<grid, 2 * ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+    } else {
+      cudaFuncSetAttribute(enc_row_kernel<96, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      enc_row_kernel<96, false, 1><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+    }
   }
 }
 
