@@ -56,7 +56,7 @@ template <int C> struct ErDims {
 };
 
 template <int C, bool FUSE_CONV, int G>
-__global__ void __launch_bounds__(ER_THREADS * G, (C == 48 ? 2 : 1))
+__global__ void __launch_bounds__(ER_THREADS * G, (C == 48 && G == 1 ? 2 : 1))
 enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restrict__ yin, bf16* __restrict__ out, RowSpace ys,
                const EncRowParams P) {
   typedef ErDims<C> D;
@@ -73,7 +73,8 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
   float* cbs = rbs + 2 * C;
   // per slab group (9 warps): activation tiles and per-slab vectors
   constexpr int GF = 4 * C + C + 64;                        // al [2C] be [2C] embv [C] red [64]
-  const int slab_elems = (MT * 16 + 4) * D::XP + MT * 16 * D::K2P + (FUSE_CONV ? MT * 16 * D::PP : 0);
+  // FUSE_CONV: the hidden operand tile hb aliases the (larger) level-0 patch tile, which is dead after the strided conv
+  const int slab_elems = (MT * 16 + 4) * D::XP + (FUSE_CONV ? MT * 16 * D::PP : MT * 16 * D::K2P);
   const int btid = threadIdx.x;
   const int grp = btid / ER_THREADS;
   const int tid = btid - grp * ER_THREADS, lane = tid & 31, warp = tid >> 5, nwarp = ER_THREADS >> 5;
@@ -84,15 +85,15 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
   float* red = embv + C;                                    // 64 floats
   bf16* xs = (bf16*)(cbs + C + G * GF) + (size_t)grp * slab_elems;   // [(MT*16 + 4)][XP], rows shifted by +2 (zero halo)
   bf16* hb = xs + (MT * 16 + 4) * D::XP;                    // [MT*16][K2P]
-  bf16* pst = hb + MT * 16 * D::K2P;                        // FUSE_CONV: patch [MT*16][PP]
+  bf16* pst = hb;                                           // FUSE_CONV: patch [MT*16][PP] (aliases hb)
   const int g = lane >> 2, q = lane & 3;
   bf16* xsi = xs + 2 * D::XP;                               // interior row 0
 
   // ---- once per CTA: zero the activation tiles, stage every weight of the layer
   for (int i = tid; i < ((MT * 16 + 4) * D::XP) / 2; i += ER_THREADS) ((uint32_t*)xs)[i] = 0u;
-  for (int i = tid; i < (MT * 16 * D::K2P) / 2; i += ER_THREADS) ((uint32_t*)hb)[i] = 0u;
+  if (!FUSE_CONV)
+    for (int i = tid; i < (MT * 16 * D::K2P) / 2; i += ER_THREADS) ((uint32_t*)hb)[i] = 0u;
   if (FUSE_CONV) {
-    for (int i = tid; i < (MT * 16 * D::PP) / 2; i += ER_THREADS) ((uint32_t*)pst)[i] = 0u;
     for (int i = btid; i < C * 4; i += blockDim.x) {         // conv taps [C][32] -> [C][PP]
       const int n = i >> 2, kc = i & 3;
       *(uint4*)(cwt + n * D::PP + kc * 8) = *(const uint4*)(P.cw + n * 32 + kc * 8);
@@ -131,9 +132,11 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
     if (P.emb) for (int i = tid; i < C; i += ER_THREADS) embv[i] = P.emb_scale * P.emb[f * C + i];
     if (FUSE_CONV) {
       // level 0: y = GELU(conv_k8s4(x)): patch [T x 32] = 8 padded frequency rows x 4 channels, contiguous in xin
-      for (int i = tid; i < Tn * 4; i += ER_THREADS) {        // 4 x 16-byte chunks per frame
+      for (int i = tid; i < MT * 16 * 4; i += ER_THREADS) {   // 4 x 16-byte chunks per frame; frames >= Tn are zero
         const int t = i >> 2, ch = i & 3;
-        *(uint4*)(pst + t * D::PP + ch * 8) = *(const uint4*)(xin + xis.row_off(b * Tn + t, 4 * f - 2) + ch * 8);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (t < Tn) v = *(const uint4*)(xin + xis.row_off(b * Tn + t, 4 * f - 2) + ch * 8);
+        *(uint4*)(pst + t * D::PP + ch * 8) = v;
       }
       er_gsync(grp);
       for (int mt = warp; mt < MT; mt += nwarp) {
@@ -160,6 +163,12 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
       }
     }
 
+    if (FUSE_CONV) {
+      // the patch tile becomes the hidden operand tile: its K padding (columns >= 8*HN of 16) must read as zero
+      er_gsync(grp);
+      for (int i = tid; i < MT * 16; i += ER_THREADS)
+        for (int c = 8 * D::HN; c < 16; c += 8) *(uint4*)(hb + i * D::K2P + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
     for (int dd = 0; dd < 2; ++dd) {
       const int dil = 1 << dd;
       const bf16* w1 = w1t + dd * 8 * D::HN * D::K1P;
@@ -338,7 +347,7 @@ static size_t enc_row_smem(int Tn, bool fuse, int G) {
   typedef ErDims<C> D;
   const int MT = (Tn + 15) / 16;
   const size_t wbf = (size_t)2 * 8 * D::HN * D::K1P + (size_t)2 * 2 * C * D::K2P + (size_t)2 * C * D::KRP + (fuse ? (size_t)C * D::PP : 0);
-  const size_t slab = (size_t)(MT * 16 + 4) * D::XP + (size_t)MT * 16 * D::K2P + (fuse ? (size_t)MT * 16 * D::PP : 0);
+  const size_t slab = (size_t)(MT * 16 + 4) * D::XP + (fuse ? (size_t)MT * 16 * D::PP : (size_t)MT * 16 * D::K2P);
   return wbf * 2 + sizeof(float) * (2 * D::VD + 2 * C + C + (size_t)G * (4 * C + C + 64)) + (size_t)G * slab * 2 + 32;
 }
 
@@ -365,6 +374,14 @@ void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, R
   const int Tn = ys.G2;
   const int slabs = ys.batch() * ys.R;
   if (ys.C == 48) {
+    // level 0 (fused conv): three 9-warp slab groups in one CTA per SM (27 warps) if they fit, else two CTAs of one group
+    const bool g3 = fuse_conv && enc_row_smem<48>(Tn, true, 3) <= 226 * 1024;
+    if (g3) {
+      const size_t smem = enc_row_smem<48>(Tn, true, 3);
+      cudaFuncSetAttribute(enc_row_kernel<48, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      enc_row_kernel<48, true, 3><<<std::min((slabs + 2) / 3, er_num_sms()), 3 * ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+      return;
+    }
     const size_t smem = enc_row_smem<48>(Tn, fuse_conv, 1);
     const int grid = std::min(slabs, 2 * er_num_sms());
     if (fuse_conv) {
