@@ -383,6 +383,215 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// Two CTAs of a cluster (two SMs) share one 256 x BN tile: each loads ITS 128 rows of A and HALF of the B tile (BN / 2
+// weight rows), the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256) which reads both halves of B from both
+// CTAs' shared memory and writes each CTA's 128 accumulator rows into its own TMEM.  Per CTA and k-block that is 16 + 16 KB
+// of operands instead of 16 + 32 KB: the K = 512 transformer GEMMs are bound by L2 -> SM operand traffic.
+// Barriers: full[s] lives in the leader (armed with the bytes of both CTAs; both CTAs' TMA loads complete_tx on it), the
+// leader's MMA commits arrive on empty[s] / tfull[buf] of BOTH CTAs (multicast), both CTAs' epilogue warps arrive on the
+// leader's tempty[buf].
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {   // arrive on the same barrier of cluster rank 0
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(local_bar));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int EF>
+__global__ void __launch_bounds__(TcCfg<1>::THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stageA = TC_BM * TC_BK * 2;
+  const int stageB = (p.BN / 2) * TC_BK * 2;        // this CTA's half of the B tile
+  const int nst = p.stages;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + nst * stageA;
+  uint64_t* bars = (uint64_t*)(sB + nst * stageB);
+  uint64_t* full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES, *tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* svec = (float*)(bars + 2 * TC_MAX_STAGES + 8);
+  constexpr int EPI_WARPS = TcCfg<1>::EPI_WARPS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int nkb = p.ntaps * p.kb_per_tap;
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int n_pair_tiles = m_pairs * p.n_tiles;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * p.BN)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < nst; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull[i]), 1); mbar_init(smem_u32(&tempty[i]), 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();        // both CTAs' barriers exist before any remote arrive / complete_tx
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(2 * (stageA + stageB));      // both CTAs' shares land on the leader's barrier
+      int it = 0;
+      for (int u = cid; u < n_pair_tiles; u += ncl) {
+        const int row0 = (2 * (u / p.n_tiles) + (int)rank) * TC_BM;
+        const int nb0 = (u % p.n_tiles) * p.BN + (int)rank * (p.BN / 2);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % nst;
+          const uint32_t ph = (uint32_t)(it / nst) & 1u;
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+          const int tap = kb / p.kb_per_tap;
+          const int kin = (kb - tap * p.kb_per_tap) * TC_BK;
+          const uint32_t fb = smem_u32(&full[s]);
+          if (leader) mbar_expect_tx(fb, bytes);
+          const uint32_t fbl = fb & 0xFEFFFFFFu;                       // the leader CTA's copy of this barrier
+          tma_load_2d_pair(smem_u32(sA + s * stageA), &tmA, fbl, kin, row0 + p.tapRow[tap]);
+          tma_load_2d_pair(smem_u32(sB + s * stageB), &tmB, fbl, tap * p.Ktap + kin, nb0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 across the pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int it = 0, i = 0;
+      for (int u = cid; u < n_pair_tiles; u += ncl, ++i) {
+        const int buf = i & 1;
+        mbar_wait(smem_u32(&tempty[buf]), ((uint32_t)(i >> 1) & 1u) ^ 1u);     // both CTAs' epilogues drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % nst;
+          const uint32_t ph = (uint32_t)(it / nst) & 1u;
+          mbar_wait(smem_u32(&full[s]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_sw128_desc(smem_u32(sA + s * stageA));
+          const uint64_t db = make_sw128_desc(smem_u32(sB + s * stageB));
+          const int kin = (kb % p.kb_per_tap) * TC_BK;
+          const int nmma = (min(TC_BK, p.Ktap - kin) + 15) >> 4;
+          for (int k = 0; k < nmma; ++k)
+            umma_bf16_pair(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit_pair(smem_u32(&empty[s]));
+        }
+        umma_commit_pair(smem_u32(&tfull[buf]));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    const int Nout_ = (EF & EF_GLU) ? p.N / 2 : p.N;
+    int i = 0;
+    for (int u = cid; u < n_pair_tiles; u += ncl, ++i) {
+      const int buf = i & 1;
+      const int row0 = (2 * (u / p.n_tiles) + (int)rank) * TC_BM;
+      const int n0 = (u % p.n_tiles) * p.BN;
+      float* sv = svec + buf * 4 * TC_VEC;
+      for (int c = etid; c < p.BN; c += EPI_WARPS * 32) {
+        const int n = min(n0 + c, p.N - 1);
+        sv[c] = p.bias ? __ldg(p.bias + n) : 0.f;
+        if (EF & EF_GN) { sv[TC_VEC + c] = __ldg(p.gn_w + n); sv[2 * TC_VEC + c] = __ldg(p.gn_b + n); }
+        if ((EF & EF_POST) && p.colscale) {
+          const int no = (EF & EF_GLU) ? (n0 >> 1) + c : n0 + c;
+          sv[3 * TC_VEC + c] = __ldg(p.colscale + min(no, Nout_ - 1));
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+      EpiRow er;
+      const long rho = (long)row0 + row;
+      const int q2 = (int)(rho / p.RpA);
+      const int fp = (int)(rho - (long)q2 * p.RpA);
+      er.b = q2 / p.G2p;
+      const int tp = q2 - er.b * p.G2p;
+      er.valid = rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2;
+      er.orow = ((long)er.b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
+      er.m = fp - p.vlo;
+      er.gmean = 0.f; er.grstd = 1.f;
+      if ((EF & EF_GN) && er.valid) {
+        const long gi = p.gn_mode == STAT_PER_G1_M ? (long)er.b * p.statR + er.m : (long)er.b;
+        er.gmean = p.gn_mr[2 * gi]; er.grstd = p.gn_mr[2 * gi + 1];
+      }
+      er.edge_row = p.convt_cout > 0 && (er.m == 0 || er.m == p.vhi - p.vlo - 1);
+      float ssum = 0.f, ssq = 0.f;
+      mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 32 * sub; c0 < p.BN; c0 += 8 * EPI_WARPS) {
+        uint32_t r[32];
+        tmem_ld32(tacc + (uint32_t)c0, r);
+        const int ncol = n0 + c0;
+        const int nc = min(32, min(p.BN - c0, p.N - ncol));
+        if (er.valid && nc > 0) epilogue_chunk<EF>(p, er, r, ncol, nc, sv, c0, ssum, ssq);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[buf])) : "memory");
+        else mbar_arrive_leader(smem_u32(&tempty[buf]));
+      }
+      if (EF & EF_STATS) {      // per-segment sums only (the pair kernel is used for the transformer linears)
+        const int key = er.valid ? er.b : -1;
+        const int key0 = __reduce_max_sync(0xffffffffu, key);
+        const bool uniform = __all_sync(0xffffffffu, key == key0 || key == -1);
+        if (key0 >= 0) {
+          const int slot = (2 * u + (int)rank + sub) % STAT_SLOTS;
+          if (uniform) {
+            double a = er.valid ? (double)ssum : 0.0, c = er.valid ? (double)ssq : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+            if (lane == 0) { double* sp = p.stats + 2 * ((long)key0 * STAT_SLOTS + slot); atomicAdd(sp, a); atomicAdd(sp + 1, c); }
+          } else if (er.valid) {
+            double* sp = p.stats + 2 * ((long)er.b * STAT_SLOTS + slot); atomicAdd(sp, (double)ssum); atomicAdd(sp + 1, (double)ssq);
+          }
+        }
+      }
+    }
+  }
+  // the peer's shared memory and TMEM are read / written by the leader's MMAs: nobody leaves before everything has drained
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -419,6 +628,8 @@ bool tensor_map_api_available() { return get_encode() != nullptr; }
 
 static int g_tc_bn_cap = 256;
 static bool g_tc_two_ctas = true;
+static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide tiles: env ATHTD_TC_PAIR=1 (default off: measured
+                                // 5-8 % slower than the single-CTA kernel on the K = 512 / 2048 transformer shapes, profiles/r01_summary.md)
 void tc_set_bn_cap(int cap) { g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); }
 
 int tc_pick_bn(int N) {
@@ -483,6 +694,19 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
   const long tiles = (long)p.m_tiles * p.n_tiles;
   dim3 grid((unsigned)std::min<long>(tiles, (long)num_sms() * ctas_per_sm));
+  if (g_tc_pair < 0) { const char* e = getenv("ATHTD_TC_PAIR"); g_tc_pair = e ? atoi(e) : 0; }
+  // CTA pairs for the 256-wide tiles of long-M problems (transformer linears): 256 x 256 tile per cluster
+  const bool pair = g_tc_pair > 0 && p.BN == 256 && f.N % 256 == 0 && p.m_tiles >= 2 * num_sms() && f.stat_mode != STAT_PER_G1_M &&
+                    (num_sms() % 2 == 0);
+  CUtensorMap tmBh;
+  int pair_stages = 0;
+  size_t pair_smem = 0;
+  if (pair) {
+    if (!make_tensor_map_2d(&tmBh, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN / 2)) return 3;
+    const int sb = TC_BM * TC_BK * 2 + (p.BN / 2) * TC_BK * 2;
+    pair_stages = std::min(TC_MAX_STAGES, (227 * 1024 - 1024 - tail_bytes) / sb);
+    pair_smem = 1024 + (size_t)pair_stages * sb + tail_bytes;
+  }
   int ef = 0;
   if (f.act == ACT_GELU) ef |= EF_GELU;
   if (f.glu) ef |= EF_GLU;
@@ -495,7 +719,21 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
     if (!attr_set) {                                                                                                      \
       cudaFuncSetAttribute(gemm_tc_kernel<E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                \
       cudaFuncSetAttribute(gemm_tc_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);                \
+      cudaFuncSetAttribute(gemm_tc_pair_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);              \
       attr_set = true;                                                                                                    \
+    }                                                                                                                     \
+    if (pair) {                                                                                                           \
+      TcParams pp = p;                                                                                                    \
+      pp.stages = pair_stages;                                                                                            \
+      cudaLaunchConfig_t cfg;                                                                                             \
+      memset(&cfg, 0, sizeof(cfg));                                                                                       \
+      cfg.gridDim = dim3((unsigned)num_sms()); cfg.blockDim = dim3(TcCfg<1>::THREADS); cfg.dynamicSmemBytes = pair_smem;  \
+      cfg.stream = st;                                                                                                    \
+      cudaLaunchAttribute at[1];                                                                                          \
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1;             \
+      at[0].val.clusterDim.z = 1;                                                                                         \
+      cfg.attrs = at; cfg.numAttrs = 1;                                                                                   \
+      return cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<E>, tmA, tmBh, pp) == cudaSuccess ? 0 : 6;                      \
     }                                                                                                                     \
     if (ctas_per_sm == 2) gemm_tc_kernel<E, 2><<<grid, TcCfg<2>::THREADS, smem, st>>>(tmA, tmB, p);                       \
     else gemm_tc_kernel<E, 1><<<grid, TcCfg<1>::THREADS, smem, st>>>(tmA, tmB, p);                                        \
