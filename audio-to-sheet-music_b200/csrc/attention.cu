@@ -9,14 +9,17 @@
 //                issued two tiles ahead of the softmax; O += P_j V_j (M128 N64 K64, V consumed MN-major from its [key][d]
 //                tile) accumulates IN TMEM across all key tiles.
 //   warps 2..5 : softmax, one query row per thread: the 64 scores of a tile are read from TMEM once, the row maximum is
-//                a register tree, P = exp2((s - m) * scale) goes as bf16 into one of two swizzled K-major smem tiles.
+//                a register tree, P = exp2((s - m) * scale) goes as bf16 pairs into one of two 32-column TMEM buffers
+//                (one tcgen05.st per row) and is consumed by the PV MMA as its TMEM A operand: no shared-memory round
+//                trip and no generic -> async proxy fence on the critical path.
 //                The reference maximum m only moves when the tile maximum exceeds it by more than 2^8 (softmax is
 //                invariant to m; P <= 256 is exact in fp32 / bf16 range): then -- rarely, mostly in the first tiles --
 //                the warp rescales its O rows in TMEM (tcgen05.ld / st) before publishing P.  No per-tile O traffic.
-// TMEM use is 192 (256 allocated) columns and shared memory 98 KB, so two CTAs share an SM and one CTA's softmax overlaps
+// TMEM use is 256 columns and shared memory 66 KB, so two CTAs share an SM and one CTA's softmax overlaps
 // the other's MMAs; inside a CTA the double-buffered S / P let the tensor core run one tile ahead of the softmax.
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace athtd {
 
@@ -36,6 +39,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// tcgen05.mma with the A operand in TMEM (P never leaves the tensor-memory / register domain): D[tmem] += A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -48,6 +60,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// MODE 0 = product kernel; 1 / 2 = measurement-only variants (ATHTD_FA_MODE): 1 replaces exp2 by a multiply (no SFU work),
+// 2 also drops the per-element arithmetic (pipeline floor: MMAs, TMEM loads, P stores, barriers).  Results are wrong for != 0.
+template <int MODE>
 __global__ void __launch_bounds__(192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
@@ -56,8 +71,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + FA_QB;                       // FA_NK tiles
   uint8_t* sV = sK + FA_NK * FA_KB;               // FA_NV tiles
-  uint8_t* sP = sV + FA_NV * FA_KB;               // 2 tiles
-  uint64_t* bars = (uint64_t*)(sP + 2 * FA_PB);
+  uint64_t* bars = (uint64_t*)(sV + FA_NV * FA_KB);
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = k_full + FA_NK, *v_full = k_empty + FA_NK, *v_empty = v_full + FA_NV,
            *s_full = v_empty + FA_NV, *p_ready = s_full + 2, *pv_done = p_ready + 2;
   uint32_t* tmem_slot = (uint32_t*)(pv_done + 2);
@@ -84,7 +98,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;     // S buffers at columns [0,64) and [64,128)
+  // columns: S buffers [0,64) [64,128), O [128,192), P buffers (bf16 pairs: 64 keys = 32 columns) [192,224) [224,256)
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -124,11 +139,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_wait(smem_u32(&p_ready[j & 1]), (uint32_t)((j >> 1) & 1));
         mbar_wait(smem_u32(&v_full[sv]), (uint32_t)((j / FA_NV) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dp = make_sw128_desc(smem_u32(sP + (j & 1) * FA_PB));
+        const uint32_t tp = tmem_P + (uint32_t)((j & 1) * 32);
         const uint64_t dv = make_sw128_desc(smem_u32(sV + sv * FA_KB));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // A: 16 keys = 32 B inside the P atom;  B: 16 key rows of V = 2048 B further
-          umma_bf16(tmem_O, dp + (uint64_t)(2 * k), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j | k) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)   // A: 16 keys = 8 TMEM columns of P;  B: 16 key rows of V = 2048 B further
+          umma_bf16_ts(tmem_O, tp + (uint32_t)(8 * k), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j | k) ? 1u : 0u);
         umma_commit(smem_u32(&v_empty[sv]));
         umma_commit(smem_u32(&pv_done[j & 1]));
         if (j + 2 < nkv) issue_s(j + 2);      // S buffer (j & 1) was drained before p_ready(j)
@@ -188,35 +203,48 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       if (j >= 2) mbar_wait(smem_u32(&pv_done[j & 1]), (uint32_t)(((j - 2) >> 1) & 1));      // P buffer (j & 1) consumed by PV(j-2)
       const float mb = m_used * cs;
-      uint8_t* prow = sP + (j & 1) * FA_PB + row * 128;
-      // K-major SWIZZLE_128B: row pitch 128 B, 16-byte chunk index XOR (row & 7)
+      uint32_t pk32[32];                              // P row as bf16 pairs: one TMEM column per two keys
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint32_t pk[4];
+        uint32_t* pk = pk32 + 4 * g;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(r0[8 * g + 2 * i]), cs, -mb));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(r0[8 * g + 2 * i + 1]), cs, -mb));
+          float p0, p1;
+          if (MODE == 0) {
+            p0 = ex2_approx(fmaf(__uint_as_float(r0[8 * g + 2 * i]), cs, -mb));
+            p1 = ex2_approx(fmaf(__uint_as_float(r0[8 * g + 2 * i + 1]), cs, -mb));
+          } else if (MODE == 1) {
+            p0 = fmaf(__uint_as_float(r0[8 * g + 2 * i]), cs, -mb) * 1e-3f;
+            p1 = fmaf(__uint_as_float(r0[8 * g + 2 * i + 1]), cs, -mb) * 1e-3f;
+          } else {
+            p0 = __uint_as_float(r0[8 * g + 2 * i]); p1 = __uint_as_float(r0[8 * g + 2 * i + 1]);
+          }
           if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
           __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
           pk[i] = *(uint32_t*)&t;
         }
-        *(uint4*)(prow + ((g ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint32_t pk[4];
+        uint32_t* pk = pk32 + 16 + 4 * g;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(r1[8 * g + 2 * i]), cs, -mb));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(r1[8 * g + 2 * i + 1]), cs, -mb));
+          float p0, p1;
+          if (MODE == 0) {
+            p0 = ex2_approx(fmaf(__uint_as_float(r1[8 * g + 2 * i]), cs, -mb));
+            p1 = ex2_approx(fmaf(__uint_as_float(r1[8 * g + 2 * i + 1]), cs, -mb));
+          } else if (MODE == 1) {
+            p0 = fmaf(__uint_as_float(r1[8 * g + 2 * i]), cs, -mb) * 1e-3f;
+            p1 = fmaf(__uint_as_float(r1[8 * g + 2 * i + 1]), cs, -mb) * 1e-3f;
+          } else {
+            p0 = __uint_as_float(r1[8 * g + 2 * i]); p1 = __uint_as_float(r1[8 * g + 2 * i + 1]);
+          }
           if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
           __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
           pk[i] = *(uint32_t*)&t;
         }
-        *(uint4*)(prow + (((4 + g) ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the MMA (async proxy)
+      tmem_st32(tmem_P + (uint32_t)((j & 1) * 32) + lane_addr, pk32);      // includes tcgen05.wait::st
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[j & 1])) : "memory");
     }
@@ -263,11 +291,19 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
   if (!make_tensor_map_2d(&tmV, v, 512, (uint64_t)B * Sk, (uint64_t)ldkv * 2, 64, 64)) return 4;
   FaParams p;
   p.Sq = Sq; p.Sk = Sk; p.scale_log2 = 0.125f * 1.4426950408889634f; p.O = o; p.ldo = ldo;
-  const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 2 * FA_PB + 256;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 256;
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ATHTD_FA_MODE");
+    mode = e ? atoi(e) : 0;
+    cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   dim3 grid((Sq + 127) / 128, 8, B);
-  flash_attn_kernel<<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
+  if (mode == 1) flash_attn_kernel<1><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
+  else if (mode == 2) flash_attn_kernel<2><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
+  else flash_attn_kernel<0><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
   return 0;
 }
 
