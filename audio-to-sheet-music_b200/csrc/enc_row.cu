@@ -132,6 +132,28 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
     if (P.emb) for (int i = tid; i < C; i += ER_THREADS) embv[i] = P.emb_scale * P.emb[f * C + i];
     if (FUSE_CONV) {
       // level 0: y = GELU(conv_k8s4(x)): patch [T x 32] = 8 padded frequency rows x 4 channels, contiguous in xin
+      if (P.zspec) {
+        // straight from the fp32 spectrogram: chunk ch = patch rows 2ch, 2ch+1 (4 CaC channels each), normalised + rounded
+        // exactly like the packed copy was (bf16((z - mean) * inv)); rows outside [0, zrows) are the conv's zero padding
+        const float mean = P.ms_spec[2 * b], inv = 1.0f / (1e-5f + P.ms_spec[2 * b + 1]);
+        for (int i = tid; i < MT * 16 * 4; i += ER_THREADS) {
+          const int t = i >> 2, ch = i & 3;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (t < Tn) {
+            const int r0 = 4 * f - 2 + 2 * ch;
+            const float4* zp = (const float4*)P.zspec + ((long)(b * Tn + t) * P.zrows + r0);
+            float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0;
+            const bool in0 = r0 >= 0 && r0 < P.zrows, in1 = r0 + 1 >= 0 && r0 + 1 < P.zrows;
+            if (in0) z0 = zp[0];
+            if (in1) z1 = zp[1];
+            v.x = in0 ? pack_bf16x2((z0.x - mean) * inv, (z0.y - mean) * inv) : 0u;
+            v.y = in0 ? pack_bf16x2((z0.z - mean) * inv, (z0.w - mean) * inv) : 0u;
+            v.z = in1 ? pack_bf16x2((z1.x - mean) * inv, (z1.y - mean) * inv) : 0u;
+            v.w = in1 ? pack_bf16x2((z1.z - mean) * inv, (z1.w - mean) * inv) : 0u;
+          }
+          *(uint4*)(pst + t * D::PP + ch * 8) = v;
+        }
+      } else
       for (int i = tid; i < MT * 16 * 4; i += ER_THREADS) {   // 4 x 16-byte chunks per frame; frames >= Tn are zero
         const int t = i >> 2, ch = i & 3;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);

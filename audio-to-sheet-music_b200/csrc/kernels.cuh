@@ -40,6 +40,9 @@ struct EncRowParams {
   const bf16* w1[2]; const float* b1[2]; const float* g1w[2]; const float* g1b[2];
   const bf16* w2[2]; const float* b2[2]; const float* g2w[2]; const float* g2b[2]; const float* scale[2];
   const bf16* rw; const float* rb; const float* emb; float emb_scale;
+  // level 0 with fused conv: read the fp32 spectrogram Z [B, Tf, 2048, 4] directly and normalise on the fly
+  // ((z - mean) / (1e-5 + std), ATHTDemucs_v2.py:268-270) instead of reading a packed bf16 copy; nullptr = read xin
+  const float* zspec; const float* ms_spec; int zrows;
 };
 bool enc_row_supported(int C, int Tn, bool fuse_conv);
 void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, RowSpace ys, const EncRowParams& P, bool fuse_conv,

@@ -334,6 +334,7 @@ bool PlanT<T>::enc_row_dispatch(bool run, int i, const T* x, RowSpace xin, const
     }
     P.rw = (const bf16*)PW(p + ".rewrite.w"); P.rb = PA(p + ".rewrite.b");
     P.emb = i == 0 ? P32("htdemucs.freq_emb.embedding.weight") : nullptr; P.emb_scale = 10.0f * 0.2f;
+    P.zspec = fuse ? Z : nullptr; P.ms_spec = ms_spec; P.zrows = 2048;
     launch_enc_row((const bf16*)x, xin, (const bf16*)y, (bf16*)out, ys, P, fuse, st);
     ++n_launches;
     return true;
@@ -593,7 +594,10 @@ void PlanT<T>::encode(const float* wav, cudaStream_t st) {
   launch_sum_sumsq(wav, B, 2L * s.L, st_wav, st); ++n_launches;
   launch_finalize_meanstd(st_spec, 4.0 * 2048.0 * Tf, ms_spec, B, st); ++n_launches;
   launch_finalize_meanstd(st_wav, 2.0 * s.L, ms_wav, B, st); ++n_launches;
-  launch_pack_spec<T>(Z, ms_spec, xf0, xf0_rs, Tf, st); ++n_launches;
+  // the packed bf16 copy of the normalised spectrogram is only needed when level 0 does not read Z itself (enc_row.cu)
+  const bool z_direct = sizeof(T) == 2 && use_tc && use_fused_dconv && enc_row_dispatch(false, 0, nullptr, xf0_rs, nullptr, nullptr, yf_rs[0], st) &&
+                        enc_row_supported(kCh[0], Tf, true);
+  if (!z_direct) { launch_pack_spec<T>(Z, ms_spec, xf0, xf0_rs, Tf, st); ++n_launches; }
   cur_wav = wav;
   if (!(use_tc && use_fused_dconv && sizeof(T) == 2)) { launch_pack_wav<T>(wav, ms_wav, xt0, xt0_rs, s.L, st); ++n_launches; }
   // interleaved encoders (ATHTDemucs_v2.py:196-217)
