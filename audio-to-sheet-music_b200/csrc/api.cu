@@ -161,8 +161,18 @@ int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int c
                     long t_begin, long t_end, void* stream) {
   if (C < 1 || C > 2) return fail("athtd_chunk_ola: C must be 1 or 2");
   launch_chunk_ola(seg_out_dev, seg_stride, k_base, chunk_len, starts_dev, actual_len_dev, fade_len_dev, flags_dev, n_chunks,
-                   stride, ramp_up_dev, ramp_down_dev, ramp_off_dev, out_dev, C, t_begin, t_end, (cudaStream_t)stream);
+                   stride, ramp_up_dev, ramp_down_dev, ramp_off_dev, out_dev, C, t_begin, t_end, 1, (cudaStream_t)stream);
   return check_cuda("athtd_chunk_ola");
+}
+
+int athtd_chunk_fade_add(const float* seg_out_dev, long seg_stride, int k_base, int chunk_len, const long* starts_dev,
+                         const int* actual_len_dev, const int* fade_len_dev, const int* flags_dev, int n_chunks, long stride,
+                         const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
+                         long t_begin, long t_end, void* stream) {
+  if (C < 1 || C > 2) return fail("athtd_chunk_fade_add: C must be 1 or 2");
+  launch_chunk_ola(seg_out_dev, seg_stride, k_base, chunk_len, starts_dev, actual_len_dev, fade_len_dev, flags_dev, n_chunks,
+                   stride, ramp_up_dev, ramp_down_dev, ramp_off_dev, out_dev, C, t_begin, t_end, 0, (cudaStream_t)stream);
+  return check_cuda("athtd_chunk_fade_add");
 }
 
 int athtd_attention_test(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev, int B, int Sq, int Sk, void* stream) {

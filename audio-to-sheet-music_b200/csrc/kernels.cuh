@@ -86,7 +86,7 @@ void launch_gather_chunks(const float* track, long T, int C, const long* starts,
 void launch_chunk_ola(const float* seg_out, long seg_stride, int k_base, int chunk_len, const long* starts,
                       const int* actual_len, const int* fade_len, const int* flags, int n_chunks, long stride,
                       const float* ramp_up, const float* ramp_down, const int* ramp_off, float* out, int C, long t_begin,
-                      long t_end, cudaStream_t st);
+                      long t_end, int normalize, cudaStream_t st);
 
 // ---- metrics.cu  (sums behind sdr_loss / sisdr_loss / new_sdr_metric, src/loss.py:9-87)
 void launch_sdr_sums(const float* est, const float* tgt, int items, long n, double* sums, cudaStream_t st);

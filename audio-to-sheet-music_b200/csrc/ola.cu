@@ -27,10 +27,12 @@ void launch_gather_chunks(const float* track, long T, int C, const long* starts,
 
 __device__ __forceinline__ float chunk_w(int i, int actual, int fade, int flags, const float* __restrict__ up,
                                          const float* __restrict__ down) {
-  float w = 1.0f;
-  if ((flags & 1) && i < fade) w = up[i];
-  if ((flags & 2) && i >= actual - fade) w = down[i - (actual - fade)];
-  return w;
+  // fade-in mask x fade-out mask (torchaudio Fade order; identical to the reference's slice assignments whenever the two ramps do not
+  // overlap, which benchmark.py:185 guarantees with fade_len = min(overlap, actual_len // 2); a factor 1.0f is exact)
+  float w_in = 1.0f, w_out = 1.0f;
+  if ((flags & 1) && i < fade) w_in = up[i];
+  if ((flags & 2) && i >= actual - fade) w_out = down[i - (actual - fade)];
+  return __fmul_rn(w_in, w_out);
 }
 
 // seg_out: model output of global chunk k at seg_out + (k - k_base)*seg_stride, layout [C, chunk_len].
@@ -40,7 +42,7 @@ __global__ void chunk_ola_kernel(const float* __restrict__ seg_out, long seg_str
                                  const int* __restrict__ fade_len, const int* __restrict__ flags, int n_chunks, long stride,
                                  const float* __restrict__ ramp_up, const float* __restrict__ ramp_down,
                                  const int* __restrict__ ramp_off, float* __restrict__ out, long out_pitch, int C,
-                                 long t_begin, long t_end) {
+                                 long t_begin, long t_end, int normalize) {
   for (long s = t_begin + (long)blockIdx.x * blockDim.x + threadIdx.x; s < t_end; s += (long)gridDim.x * blockDim.x) {
     int k_hi = (int)(s / stride); if (k_hi > n_chunks - 1) k_hi = n_chunks - 1;
     int k_lo = k_hi;
@@ -56,19 +58,20 @@ __global__ void chunk_ola_kernel(const float* __restrict__ seg_out, long seg_str
       wsum = __fadd_rn(wsum, w);
     }
     wsum = fmaxf(wsum, 1e-8f);
-    for (int c = 0; c < C; ++c) out[(long)c * out_pitch + (s - t_begin)] = __fdiv_rn(acc[c], wsum);
+    // normalize = 0: plain weighted sum (test_inference.py:113-141: faded chunks are added, never divided)
+    for (int c = 0; c < C; ++c) out[(long)c * out_pitch + (s - t_begin)] = normalize ? __fdiv_rn(acc[c], wsum) : acc[c];
   }
 }
 void launch_chunk_ola(const float* seg_out, long seg_stride, int k_base, int chunk_len, const long* starts,
                       const int* actual_len, const int* fade_len, const int* flags, int n_chunks, long stride,
                       const float* ramp_up, const float* ramp_down, const int* ramp_off, float* out, int C, long t_begin,
-                      long t_end, cudaStream_t st) {
+                      long t_end, int normalize, cudaStream_t st) {
   long n = t_end - t_begin;
   if (n <= 0) return;
   chunk_ola_kernel<<<(int)min((n + 255) / 256, (long)148 * 16), 256, 0, st>>>(seg_out, seg_stride, k_base, chunk_len, starts,
                                                                               actual_len, fade_len, flags, n_chunks, stride,
                                                                               ramp_up, ramp_down, ramp_off, out, n, C,
-                                                                              t_begin, t_end);
+                                                                              t_begin, t_end, normalize);
 }
 
 }  // namespace athtd

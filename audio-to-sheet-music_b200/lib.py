@@ -44,6 +44,7 @@ SYMBOLS = [
     ("athtd_istft", _I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     ("athtd_gather_chunks", _I, [_P, _L, _I, _P, _I, _I, _P, _P]),
     ("athtd_chunk_ola", _I, [_P, _L, _I, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _L, _L, _P]),
+    ("athtd_chunk_fade_add", _I, [_P, _L, _I, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _L, _L, _P]),
     ("athtd_gemm_test", _I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 ]
 

@@ -25,6 +25,69 @@ class SeparationModel(ABC):
     """Same contract as benchmark.py:81-115."""
 
     @abstractmethod
+    @torch.no_grad()
+    def separate_fade(self, mixture: torch.Tensor, emb: torch.Tensor, segment_seconds: Optional[float] = None,
+                      overlap_seconds: float = 0.1) -> torch.Tensor:
+        """The chunk loop of test_inference.py:96-141 (the reference's older inference script): stride chunk_len - overlap,
+        the last chunk is NOT zero-padded (the model runs on its true length), every chunk is multiplied by a
+        ``torchaudio.transforms.Fade(fade_in, fade_out, "linear")`` mask (fade-in iff start > 0, fade-out iff end < T, both of
+        ``int(overlap * sr)`` samples) and added into the output; there is no weight normalisation.
+        mixture [2, T], emb [P, 512] -> [P, 2, T].  Chunks of equal length share one batched launch sequence."""
+        mixture = mixture.to(self.device, torch.float32).contiguous()
+        emb = emb.to(self.device, torch.float32).contiguous()
+        sr = self.model.sample_rate
+        seg = self.segment_seconds if segment_seconds is None else segment_seconds
+        T = mixture.shape[-1]
+        P = emb.shape[0]
+        L = int(sr * seg)
+        ov = int(overlap_seconds * sr)
+        stride = L - ov
+        if stride <= 0 or 2 * stride <= L:
+            raise ValueError("overlap must be smaller than half a segment")
+        starts = list(range(0, T, stride))
+        ends = [min(s + L, T) for s in starts]
+        actual = [e - s for s, e in zip(starts, ends)]
+        flags = [(1 if s > 0 else 0) | (2 if e < T else 0) for s, e in zip(starts, ends)]
+        for a, f in zip(actual, flags):
+            if f and a < ov:       # torchaudio's Fade would fail on torch.ones(negative)
+                raise ValueError(f"a faded chunk of {a} samples is shorter than the fade ({ov}): the reference loop fails here too")
+            if a < 4096:
+                raise ValueError(f"chunk of {a} samples is shorter than one STFT window")
+        n = len(starts)
+        seg_out = torch.zeros(n, P, 2, L, dtype=torch.float32, device=self.device)
+        eng = self.model.engine(self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        full = [k for k in range(n) if actual[k] == L]
+        for b0 in range(0, len(full), self.batch):
+            ks = full[b0:b0 + self.batch]                       # consecutive chunk indices
+            segs = torch.empty(len(ks), 2, L, dtype=torch.float32, device=self.device)
+            st_dev = torch.tensor([starts[k] for k in ks], dtype=torch.int64, device=self.device)
+            _lib.check(_lib.load().athtd_gather_chunks(mixture.data_ptr(), T, 2, st_dev.data_ptr(), len(ks), L, segs.data_ptr(), st),
+                       "athtd_gather_chunks")
+            e = emb.unsqueeze(0).expand(len(ks), P, 512).contiguous()
+            eng.plan(len(ks), L, P).forward(segs, e, seg_out[ks[0]:ks[0] + len(ks)])
+        for k in range(n):
+            if actual[k] != L:                                  # ragged tail chunk(s): the model sees the true length
+                chunk = mixture[:, starts[k]:ends[k]].unsqueeze(0).contiguous()
+                o = torch.empty(1, P, 2, actual[k], dtype=torch.float32, device=self.device)
+                eng.plan(1, actual[k], P).forward(chunk, emb.unsqueeze(0).contiguous(), o)
+                seg_out[k, :, :, :actual[k]] = o[0]
+        up = torch.linspace(0, 1, ov).clamp_(0, 1) if ov > 0 else torch.zeros(1)          # Fade._fade_in (linear)
+        down = (-torch.linspace(0, 1, ov) + 1).clamp_(0, 1) if ov > 0 else torch.zeros(1)  # Fade._fade_out (linear)
+        dev = self.device
+        t_starts = torch.tensor(starts, dtype=torch.int64, device=dev)
+        t_actual = torch.tensor(actual, dtype=torch.int32, device=dev)
+        t_fade = torch.full((n,), ov, dtype=torch.int32, device=dev)
+        t_flags = torch.tensor(flags if ov > 0 else [0] * n, dtype=torch.int32, device=dev)
+        t_off = torch.zeros(n, dtype=torch.int32, device=dev)
+        up, down = up.float().to(dev), down.float().to(dev)
+        out = torch.empty(P, 2, T, dtype=torch.float32, device=dev)
+        for p in range(P):
+            _lib.check(_lib.load().athtd_chunk_fade_add(seg_out[:, p].data_ptr(), P * 2 * L, 0, L, t_starts.data_ptr(), t_actual.data_ptr(),
+                                                        t_fade.data_ptr(), t_flags.data_ptr(), n, stride, up.data_ptr(), down.data_ptr(),
+                                                        t_off.data_ptr(), out[p].data_ptr(), 2, 0, T, st), "athtd_chunk_fade_add")
+        return out
+
     def separate(self, mixture: torch.Tensor, stem_name: str) -> torch.Tensor: ...
 
     @abstractmethod
@@ -313,6 +376,69 @@ class B200SeparationModel(SeparationModel):
             ms, gf, n = ms + a, gf + b, n + c
             pl.set_profile(False)
         return {"kernel": eng.gemm_kernel_name(), "ms": ms, "gflop": gf, "launches": n, "tflops": gf / ms if ms > 0 else 0.0}
+
+    @torch.no_grad()
+    def separate_fade(self, mixture: torch.Tensor, emb: torch.Tensor, segment_seconds: Optional[float] = None,
+                      overlap_seconds: float = 0.1) -> torch.Tensor:
+        """The chunk loop of test_inference.py:96-141 (the reference's older inference script): stride chunk_len - overlap,
+        the last chunk is NOT zero-padded (the model runs on its true length), every chunk is multiplied by a
+        ``torchaudio.transforms.Fade(fade_in, fade_out, "linear")`` mask (fade-in iff start > 0, fade-out iff end < T, both of
+        ``int(overlap * sr)`` samples) and added into the output; there is no weight normalisation.
+        mixture [2, T], emb [P, 512] -> [P, 2, T].  Chunks of equal length share one batched launch sequence."""
+        mixture = mixture.to(self.device, torch.float32).contiguous()
+        emb = emb.to(self.device, torch.float32).contiguous()
+        sr = self.model.sample_rate
+        seg = self.segment_seconds if segment_seconds is None else segment_seconds
+        T = mixture.shape[-1]
+        P = emb.shape[0]
+        L = int(sr * seg)
+        ov = int(overlap_seconds * sr)
+        stride = L - ov
+        if stride <= 0 or 2 * stride <= L:
+            raise ValueError("overlap must be smaller than half a segment")
+        starts = list(range(0, T, stride))
+        ends = [min(s + L, T) for s in starts]
+        actual = [e - s for s, e in zip(starts, ends)]
+        flags = [(1 if s > 0 else 0) | (2 if e < T else 0) for s, e in zip(starts, ends)]
+        for a, f in zip(actual, flags):
+            if f and a < ov:       # torchaudio's Fade would fail on torch.ones(negative)
+                raise ValueError(f"a faded chunk of {a} samples is shorter than the fade ({ov}): the reference loop fails here too")
+            if a < 4096:
+                raise ValueError(f"chunk of {a} samples is shorter than one STFT window")
+        n = len(starts)
+        seg_out = torch.zeros(n, P, 2, L, dtype=torch.float32, device=self.device)
+        eng = self.model.engine(self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        full = [k for k in range(n) if actual[k] == L]
+        for b0 in range(0, len(full), self.batch):
+            ks = full[b0:b0 + self.batch]                       # consecutive chunk indices
+            segs = torch.empty(len(ks), 2, L, dtype=torch.float32, device=self.device)
+            st_dev = torch.tensor([starts[k] for k in ks], dtype=torch.int64, device=self.device)
+            _lib.check(_lib.load().athtd_gather_chunks(mixture.data_ptr(), T, 2, st_dev.data_ptr(), len(ks), L, segs.data_ptr(), st),
+                       "athtd_gather_chunks")
+            e = emb.unsqueeze(0).expand(len(ks), P, 512).contiguous()
+            eng.plan(len(ks), L, P).forward(segs, e, seg_out[ks[0]:ks[0] + len(ks)])
+        for k in range(n):
+            if actual[k] != L:                                  # ragged tail chunk(s): the model sees the true length
+                chunk = mixture[:, starts[k]:ends[k]].unsqueeze(0).contiguous()
+                o = torch.empty(1, P, 2, actual[k], dtype=torch.float32, device=self.device)
+                eng.plan(1, actual[k], P).forward(chunk, emb.unsqueeze(0).contiguous(), o)
+                seg_out[k, :, :, :actual[k]] = o[0]
+        up = torch.linspace(0, 1, ov).clamp_(0, 1) if ov > 0 else torch.zeros(1)          # Fade._fade_in (linear)
+        down = (-torch.linspace(0, 1, ov) + 1).clamp_(0, 1) if ov > 0 else torch.zeros(1)  # Fade._fade_out (linear)
+        dev = self.device
+        t_starts = torch.tensor(starts, dtype=torch.int64, device=dev)
+        t_actual = torch.tensor(actual, dtype=torch.int32, device=dev)
+        t_fade = torch.full((n,), ov, dtype=torch.int32, device=dev)
+        t_flags = torch.tensor(flags if ov > 0 else [0] * n, dtype=torch.int32, device=dev)
+        t_off = torch.zeros(n, dtype=torch.int32, device=dev)
+        up, down = up.float().to(dev), down.float().to(dev)
+        out = torch.empty(P, 2, T, dtype=torch.float32, device=dev)
+        for p in range(P):
+            _lib.check(_lib.load().athtd_chunk_fade_add(seg_out[:, p].data_ptr(), P * 2 * L, 0, L, t_starts.data_ptr(), t_actual.data_ptr(),
+                                                        t_fade.data_ptr(), t_flags.data_ptr(), n, stride, up.data_ptr(), down.data_ptr(),
+                                                        t_off.data_ptr(), out[p].data_ptr(), 2, 0, T, st), "athtd_chunk_fade_add")
+        return out
 
     def separate(self, mixture: torch.Tensor, stem_name: str) -> torch.Tensor:
         out, _ = self.separate_many(mixture, self.prompt_embeddings([stem_name]))

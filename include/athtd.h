@@ -90,6 +90,13 @@ int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int c
                     const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
                     long t_begin, long t_end, void* stream);
 
+/* test_inference.py:113-141 variant of the loop: chunks are multiplied by torchaudio-Fade masks (ramp tables supplied by the
+ * caller: linspace(0,1,n) and -linspace(0,1,n)+1) and ADDED, never divided by a weight sum; same arguments as athtd_chunk_ola. */
+int athtd_chunk_fade_add(const float* seg_out_dev, long seg_stride, int k_base, int chunk_len, const long* starts_dev,
+                         const int* actual_len_dev, const int* fade_len_dev, const int* flags_dev, int n_chunks, long stride,
+                         const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
+                         long t_begin, long t_end, void* stream);
+
 /* ---- evaluation metrics on the device (src/loss.py:9-87 sdr_loss / sisdr_loss / new_sdr_metric; benchmark.py:555-588).
  * est / tgt: [items, n] fp32 rows; sums_dev: double[items][6] = {sum t, sum e, sum t^2, sum e^2, sum e*t, sum (t-e)^2}
  * (zeroed by the call).  The dB values are closed forms of these sums (audio-to-sheet-music_b200/metrics.py). */

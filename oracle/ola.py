@@ -76,6 +76,36 @@ def chunked_inference(model_fn: Callable[[torch.Tensor], torch.Tensor], mixture:
     return output / weight
 
 
+def fade_mask(length: int, fade_in_len: int, fade_out_len: int) -> torch.Tensor:
+    """torchaudio.transforms.Fade(fade_in_len, fade_out_len, "linear") applied to ones(length):
+    cat(linspace(0,1,n_in), ones).clamp(0,1) * cat(ones, -linspace(0,1,n_out)+1).clamp(0,1)
+    (torchaudio/transforms/_transforms.py Fade._fade_in / _fade_out / forward)."""
+    fin = torch.cat((torch.linspace(0, 1, fade_in_len), torch.ones(length - fade_in_len))).clamp_(0, 1)
+    fout = torch.cat((torch.ones(length - fade_out_len), -torch.linspace(0, 1, fade_out_len) + 1)).clamp_(0, 1)
+    return fin * fout
+
+
+def fade_inference(model_fn: Callable[[torch.Tensor], torch.Tensor], mixture: torch.Tensor,
+                   segment_seconds: float = 6.0, overlap_seconds: float = 0.1, sample_rate: int = SAMPLE_RATE) -> torch.Tensor:
+    """test_inference.py:96-141 for one stem: no zero padding of the last chunk (``model_fn`` sees its true length),
+    Fade(fade_in = overlap iff start > 0, fade_out = overlap iff end < T), ``final[:, start:end] += out``, no normalisation."""
+    C, length = mixture.shape
+    chunk_len = int(sample_rate * segment_seconds)
+    overlap_frames = int(overlap_seconds * sample_rate)
+    final = torch.zeros(C, length)
+    start = 0
+    while start < length:
+        end = min(start + chunk_len, length)
+        chunk = mixture[:, start:end].unsqueeze(0)
+        out = model_fn(chunk)
+        fade_in = 0 if start == 0 else overlap_frames
+        fade_out = overlap_frames if end < length else 0
+        out = fade_mask(out.shape[-1], fade_in, fade_out) * out
+        final[:, start:end] += out.squeeze(0)
+        start += chunk_len - overlap_frames
+    return final
+
+
 def separate_all(model_fn_for: Callable[[str], Callable], mixture: torch.Tensor) -> Dict[str, torch.Tensor]:
     """benchmark.py:210-215: one complete chunked pass per stem prompt."""
     return {stem: chunked_inference(model_fn_for(stem), mixture) for stem in STEMS}

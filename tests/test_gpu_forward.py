@@ -145,6 +145,19 @@ def test_full_track_properties_bf16(models):
     assert torch.equal(c[0], b[1])
 
 
+def test_fade_loop_matches_test_inference_semantics(models, state_dict):
+    """separate_fade == the restated test_inference.py:96-141 loop (ragged last chunk at its true length, torchaudio Fade
+    masks, plain accumulation) driving the oracle forward; fp32 build, 1 s segments to keep the CPU oracle fast."""
+    m = models["fp32"]
+    sep = athtd_b200.B200SeparationModel(m, "cuda", segment_seconds=1.0, overlap_seconds=0.25, batch=2)
+    T = 44100 * 3 + 9000                          # 3 full chunks + a ragged one (stride 39690)
+    wav, emb = weights.make_inputs(73, 1, T)
+    ref = ola.fade_inference(lambda c: athtd_oracle.forward(state_dict, c, emb), wav[0], 1.0, 0.1)
+    out = sep.separate_fade(wav[0], emb, 1.0, 0.1)
+    assert out.shape == (1, 2, T)
+    assert (out[0].cpu() - ref).abs().max() < 1e-3
+
+
 def test_host_staged_pipeline_matches_device_path(models):
     """separate_span_host (batch-wise H2D / per-batch overlap-add / D2H on a copy stream) == separate_span, bit for bit,
     including a span that starts inside the track (halo chunk supplied by the left neighbour)."""

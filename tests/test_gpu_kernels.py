@@ -99,6 +99,39 @@ def test_chunk_gather_and_ola_bit_exact(T):
         assert torch.equal(torch.cat([left, right], dim=1).cpu(), ref)
 
 
+@pytest.mark.parametrize("T,ov", [(600000, 4410), (264600 * 2 + 17, 66150), (300000, 0)])
+def test_fade_add_kernel_bit_exact(T, ov):
+    """athtd_chunk_fade_add vs the restated test_inference.py loop (oracle/ola.fade_inference) with an element-wise stand-in
+    model (so ragged chunks are well defined): bit-exact fp32."""
+    g = torch.Generator().manual_seed(T + ov)
+    mix = torch.randn(2, T, generator=g)
+    fn = lambda c: torch.tanh(c * 3.0) + 0.25 * c
+    sr, L = 44100, 264600
+    ref = ola.fade_inference(fn, mix, 6.0, ov / sr)
+    stride = L - int((ov / sr) * sr)
+    assert stride == L - ov
+    starts = list(range(0, T, stride))
+    ends = [min(s + L, T) for s in starts]
+    n = len(starts)
+    seg_out = torch.zeros(n, 2, L)
+    for k in range(n):
+        seg_out[k, :, :ends[k] - starts[k]] = fn(mix[:, starts[k]:ends[k]])
+    dev = "cuda"
+    so = seg_out.to(dev)
+    t_starts = torch.tensor(starts, dtype=torch.int64, device=dev)
+    t_actual = torch.tensor([e - s for s, e in zip(starts, ends)], dtype=torch.int32, device=dev)
+    t_fade = torch.full((n,), ov, dtype=torch.int32, device=dev)
+    t_flags = torch.tensor([((1 if s > 0 else 0) | (2 if e < T else 0)) if ov > 0 else 0 for s, e in zip(starts, ends)], dtype=torch.int32, device=dev)
+    t_off = torch.zeros(n, dtype=torch.int32, device=dev)
+    up = (torch.linspace(0, 1, ov).clamp_(0, 1) if ov > 0 else torch.zeros(1)).to(dev)
+    down = ((-torch.linspace(0, 1, ov) + 1).clamp_(0, 1) if ov > 0 else torch.zeros(1)).to(dev)
+    out = torch.empty(2, T, device=dev)
+    alib.check(alib.load().athtd_chunk_fade_add(so.data_ptr(), 2 * L, 0, L, t_starts.data_ptr(), t_actual.data_ptr(), t_fade.data_ptr(),
+                                                t_flags.data_ptr(), n, stride, up.data_ptr(), down.data_ptr(), t_off.data_ptr(),
+                                                out.data_ptr(), 2, 0, T, _stream()))
+    assert torch.equal(out.cpu(), ref)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 128), (1000, 512, 384), (777, 96, 1536), (4144, 2048, 512),
                                    (2072, 192, 96), (515, 64, 72), (1000, 96, 48), (1000, 48, 32), (700, 48, 16),
                                    (300, 16, 144), (260, 192, 16), (130, 384, 8)])

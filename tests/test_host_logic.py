@@ -98,3 +98,24 @@ def test_positional_tables_match_oracle():
     assert torch.equal(sin_embedding_2d(512, 8, 40), ref2)
     ref1 = create_sin_embedding(157, 512).permute(1, 0, 2)[0]
     assert torch.equal(sin_embedding_1d(157, 512), ref1)
+
+
+def test_fade_mask_matches_torchaudio_fade():
+    """oracle/ola.fade_mask restates torchaudio.transforms.Fade(..., "linear") (the transform test_inference.py:126-134
+    applies); pinned against the real transform when torchaudio is importable."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from torchaudio.transforms import Fade
+    from oracle import ola
+    for (L, a, b) in [(1000, 0, 100), (1000, 100, 0), (5000, 441, 441), (300, 100, 250), (264600, 4410, 4410)]:
+        x = torch.randn(2, L)
+        assert torch.equal(Fade(a, b, "linear")(x), ola.fade_mask(L, a, b) * x)
+
+
+def test_fade_inference_identity_model_reconstructs_interior():
+    """With an identity model the faded chunks of test_inference.py sum to the input wherever fade-in + fade-out = 1
+    up to fp32 rounding (the loop has no weight normalisation)."""
+    from oracle import ola
+    T = 44100 * 3 + 5000
+    x = torch.randn(2, T)
+    y = ola.fade_inference(lambda c: c, x, 1.0, 0.1)
+    assert (y - x).abs().max() < 1e-5
