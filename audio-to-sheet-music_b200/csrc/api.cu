@@ -125,6 +125,24 @@ int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* strea
   return 0;
 }
 
+static const ParamTable& clap_table() { static ParamTable t = build_clap_param_table(); return t; }
+int athtd_clap_param_count(void) { return (int)clap_table().items.size(); }
+const char* athtd_clap_param_name(int i) { return clap_table().items[i].name.c_str(); }
+long athtd_clap_param_numel(int i) { return clap_table().items[i].numel; }
+long athtd_clap_param_offset(int i) { return clap_table().items[i].offset; }
+long athtd_clap_params_total(void) { return clap_table().total; }
+long athtd_clap_workspace_bytes(int P, int S) { return clap_workspace_bytes(P, S); }
+int athtd_clap_text_forward(const float* params_dev, const long* input_ids_dev, const long* attention_mask_dev, int P, int S,
+                            void* workspace_dev, float* out_dev, int normalize, void* stream) {
+  if (P <= 0 || S <= 0 || S > 512) return fail("athtd_clap_text_forward: need 1 <= S <= 512 tokens and P >= 1 prompts");
+  try {
+    int rc = clap_text_forward(clap_table(), params_dev, input_ids_dev, attention_mask_dev, P, S, workspace_dev, out_dev, normalize,
+                               (cudaStream_t)stream);
+    if (rc != 0) return fail(std::string("athtd_clap_text_forward: ") + cudaGetErrorString((cudaError_t)rc));
+  } catch (const std::exception& e) { return fail(e.what()); }
+  return 0;
+}
+
 int athtd_sdr_sums(const float* est_dev, const float* tgt_dev, int items, long n, double* sums_dev, void* stream) {
   if (items <= 0 || n <= 0) return fail("athtd_sdr_sums: items and n must be positive");
   launch_sdr_sums(est_dev, tgt_dev, items, n, sums_dev, (cudaStream_t)stream);

@@ -92,3 +92,12 @@ void launch_chunk_ola(const float* seg_out, long seg_stride, int k_base, int chu
 void launch_sdr_sums(const float* est, const float* tgt, int items, long n, double* sums, cudaStream_t st);
 
 }  // namespace athtd
+
+// ---- clap_text.cu (CLAP text tower: RoBERTa-base + pooler + projection; ATHTDemucs_v2.py:238-248)
+#include "model.cuh"
+namespace athtd {
+ParamTable build_clap_param_table();
+long clap_workspace_bytes(int P, int S);
+int clap_text_forward(const ParamTable& pt, const float* params, const long* ids, const long* mask, int P, int S, void* workspace,
+                      float* out, int normalize, cudaStream_t st);
+}  // namespace athtd

@@ -44,6 +44,13 @@ SYMBOLS = [
     ("athtd_istft", _I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     ("athtd_gather_chunks", _I, [_P, _L, _I, _P, _I, _I, _P, _P]),
     ("athtd_chunk_ola", _I, [_P, _L, _I, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _L, _L, _P]),
+    ("athtd_clap_param_count", _I, []),
+    ("athtd_clap_param_name", C.c_char_p, [_I]),
+    ("athtd_clap_param_numel", _L, [_I]),
+    ("athtd_clap_param_offset", _L, [_I]),
+    ("athtd_clap_params_total", _L, []),
+    ("athtd_clap_workspace_bytes", _L, [_I, _I]),
+    ("athtd_clap_text_forward", _I, [_P, _P, _P, _I, _I, _P, _P, _I, _P]),
     ("athtd_chunk_fade_add", _I, [_P, _L, _I, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _L, _L, _P]),
     ("athtd_gemm_test", _I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 ]

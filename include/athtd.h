@@ -90,6 +90,19 @@ int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int c
                     const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
                     long t_begin, long t_end, void* stream);
 
+/* ---- CLAP text tower (ATHTDemucs_v2.py:238-248: tokenizer output -> ClapTextModelWithProjection(...).text_embeds, or
+ * ClapModel.get_text_features with normalize = 1).  Parameters: the "text_model.*" / "text_projection.*" tensors of the HF
+ * state_dict copied by name into one flat fp32 device buffer at athtd_clap_param_offset(i) (like athtd_param_*).
+ * input_ids / attention_mask: int64 [P, S] (the tokenizer's padded batch); out: fp32 [P, 512]; fp32 throughout. */
+int athtd_clap_param_count(void);
+const char* athtd_clap_param_name(int i);
+long athtd_clap_param_numel(int i);
+long athtd_clap_param_offset(int i);
+long athtd_clap_params_total(void);
+long athtd_clap_workspace_bytes(int P, int S);
+int athtd_clap_text_forward(const float* params_dev, const long* input_ids_dev, const long* attention_mask_dev, int P, int S,
+                            void* workspace_dev, float* out_dev, int normalize, void* stream);
+
 /* test_inference.py:113-141 variant of the loop: chunks are multiplied by torchaudio-Fade masks (ramp tables supplied by the
  * caller: linspace(0,1,n) and -linspace(0,1,n)+1) and ADDED, never divided by a weight sum; same arguments as athtd_chunk_ola. */
 int athtd_chunk_fade_add(const float* seg_out_dev, long seg_stride, int k_base, int chunk_len, const long* starts_dev,
