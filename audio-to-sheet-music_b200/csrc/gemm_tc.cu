@@ -96,7 +96,7 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f +
 
 // per-row state of one epilogue thread for one tile
 struct EpiRow {
-  bool valid, edge_row;
+  bool valid, edge_lo, edge_hi;      // edge_*: first / last input row of a transposed conv
   long orow;
   int b, m;
   float gmean, grstd;
@@ -165,24 +165,20 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
     }
   }
   if (EF & EF_STATS) {
-    if (!er.edge_row && nco == NV) {
+    // 16-column groups (N, the chunk starts and the transposed conv's C_out are multiples of 16, so a group never straddles
+    // a phase).  Transposed conv: output rows -2, -1 (q == 0, phases 0, 1) and 4F, 4F+1 (last q, phases 2, 3) are cropped and
+    // do not count; the phase of a group is uniform across the warp, so this is two selects per group, no divergence.
 #pragma unroll
-      for (int j = 0; j < NV; ++j) { ssum += v[j]; ssq += v[j] * v[j]; }
-    } else {
-      // transposed conv: rows -2,-1 (q==0, phases 0,1) and 4F,4F+1 (last q, phases 2,3) are cropped
-      const int cout = max(p.convt_cout, 1);
-      const int ph0 = er.edge_row ? no / cout : 0;
-      const int rem0 = er.edge_row ? no - ph0 * cout : 0;
+    for (int g = 0; g < NV / 16; ++g) {
+      float s = 0.f, q = 0.f;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        bool counted = j < nco;
-        if (er.edge_row) {
-          const int rem = rem0 + j;
-          const int phase = ph0 + (rem >= cout ? 1 : 0) + (rem >= 2 * cout ? 1 : 0) + (rem >= 3 * cout ? 1 : 0);
-          counted = counted && !((er.m == 0 && phase < 2) || (er.m != 0 && phase >= 2));
-        }
-        if (counted) { ssum += v[j]; ssq += v[j] * v[j]; }
+      for (int j = 0; j < 16; ++j) {
+        const float x = (16 * g + 16 <= nco || 16 * g + j < nco) ? v[16 * g + j] : 0.f;     // ragged last group (N % 32 == 8 / GLU)
+        s += x; q += x * x;
       }
+      bool counted = 16 * g < nco;
+      if (p.convt_cout > 0) counted = counted && !((no + 16 * g < 2 * p.convt_cout) ? er.edge_lo : er.edge_hi);
+      if (counted) { ssum += s; ssq += q; }
     }
   }
   if (!p.no_store) {
@@ -302,27 +298,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;
     const int etid = threadIdx.x - 64;
     const int Nout_ = (EF & EF_GLU) ? p.N / 2 : p.N;
+    // Per-tile column vectors (bias, GroupNorm weight / bias, column scale; clamped at the last column: columns past N are
+    // never stored) are staged in shared memory ONE TILE AHEAD: the global loads of tile i+1 are issued before tile i's
+    // accumulator is processed and stashed after it, so their latency is off the epilogue's per-tile dependency chain (that
+    // chain, not the MMAs, bounds every short-K layer).  BN <= TC_VEC <= epilogue threads: one column per thread.
+    float vr0 = 0.f, vr1 = 0.f, vr2 = 0.f, vr3 = 0.f;
+    auto fetch_vecs = [&](int n0) {
+      if (etid < p.BN) {
+        const int n = min(n0 + etid, p.N - 1);
+        vr0 = p.bias ? __ldg(p.bias + n) : 0.f;
+        if (EF & EF_GN) { vr1 = __ldg(p.gn_w + n); vr2 = __ldg(p.gn_b + n); }
+        if ((EF & EF_POST) && p.colscale) {
+          const int no = (EF & EF_GLU) ? (n0 >> 1) + etid : n0 + etid;
+          vr3 = __ldg(p.colscale + min(no, Nout_ - 1));
+        }
+      }
+    };
+    auto stash_vecs = [&](float* sv) {
+      if (etid < p.BN) {
+        sv[etid] = vr0;
+        if (EF & EF_GN) { sv[TC_VEC + etid] = vr1; sv[2 * TC_VEC + etid] = vr2; }
+        if ((EF & EF_POST) && p.colscale) sv[3 * TC_VEC + etid] = vr3;
+      }
+    };
+    if ((int)blockIdx.x < n_total_tiles) { fetch_vecs(((int)blockIdx.x % p.n_tiles) * p.BN); stash_vecs(svec); }
     int i = 0;
     for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
       const int row0 = (t / p.n_tiles) * TC_BM;
       const int n0 = (t % p.n_tiles) * p.BN;
-      // stage this tile's column vectors (clamped at the last column: columns past N are never stored)
-      float* sv = svec + buf * 4 * TC_VEC;
-      for (int c = etid; c < p.BN; c += EPI_WARPS * 32) {
-        const int n = min(n0 + c, p.N - 1);
-        sv[c] = p.bias ? __ldg(p.bias + n) : 0.f;
-        if (EF & EF_GN) { sv[TC_VEC + c] = __ldg(p.gn_w + n); sv[2 * TC_VEC + c] = __ldg(p.gn_b + n); }
-        if ((EF & EF_POST) && p.colscale) {
-          const int no = (EF & EF_GLU) ? (n0 >> 1) + c : n0 + c;
-          sv[3 * TC_VEC + c] = __ldg(p.colscale + min(no, Nout_ - 1));
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+      const float* sv = svec + buf * 4 * TC_VEC;
       EpiRow er;
-      const long rho = (long)row0 + row;
-      const int q2 = (int)(rho / p.RpA);
-      const int fp = (int)(rho - (long)q2 * p.RpA);
+      const int rho = row0 + row;                   // Mflat < 2^31: 32-bit row decode
+      const int q2 = rho / p.RpA;
+      const int fp = rho - q2 * p.RpA;
       er.b = q2 / p.G2p;
       const int tp = q2 - er.b * p.G2p;
       er.valid = rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2;
@@ -333,7 +342,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long gi = p.gn_mode == STAT_PER_G1_M ? (long)er.b * p.statR + er.m : (long)er.b;
         er.gmean = p.gn_mr[2 * gi]; er.grstd = p.gn_mr[2 * gi + 1];
       }
-      er.edge_row = p.convt_cout > 0 && (er.m == 0 || er.m == p.vhi - p.vlo - 1);
+      // tile i's vectors (stashed during tile i-1) become visible; every warp is done reading the other buffer
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+      const int tn = t + (int)gridDim.x;
+      if (tn < n_total_tiles) fetch_vecs((tn % p.n_tiles) * p.BN);
+      er.edge_lo = er.m == 0; er.edge_hi = er.m == p.vhi - p.vlo - 1;
       float ssum = 0.f, ssq = 0.f;
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -349,6 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[buf])) : "memory");
+      if (tn < n_total_tiles) stash_vecs(svec + (buf ^ 1) * 4 * TC_VEC);
       if (EF & EF_STATS) {
         if (p.stat_mode == STAT_PER_G1_M) {
           if (er.valid) {
@@ -547,7 +561,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long gi = p.gn_mode == STAT_PER_G1_M ? (long)er.b * p.statR + er.m : (long)er.b;
         er.gmean = p.gn_mr[2 * gi]; er.grstd = p.gn_mr[2 * gi + 1];
       }
-      er.edge_row = p.convt_cout > 0 && (er.m == 0 || er.m == p.vhi - p.vlo - 1);
+      er.edge_lo = er.m == 0; er.edge_hi = er.m == p.vhi - p.vlo - 1;
       float ssum = 0.f, ssq = 0.f;
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
