@@ -697,7 +697,17 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   p.m_tiles = (int)((f.Mflat + TC_BM - 1) / TC_BM);
   p.n_tiles = (f.N + p.BN - 1) / p.BN;
   CUtensorMap tmA, tmB;
-  if (!make_tensor_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
+  // Two taps on ADJACENT rows of a dense activation buffer (row pitch == channels: the transposed-conv layers) are one
+  // K = 2 * C view with overlapping rows [x[r], x[r+1]] (row stride C): no half-empty K blocks when C is not a multiple of 64
+  // (C = 96: 3 full K blocks per tile instead of 4 half-padded ones).  The packed weights are already [tap0 | tap1] along K.
+  bool merged = false;
+  if (f.ntaps == 2 && f.tapRow[0] == 0 && f.tapRow[1] == 1 && f.a_pitch == f.Ktap && (f.Ktap % TC_BK) != 0 && f.a_rows > 1 &&
+      make_tensor_map_2d(&tmA, f.A, (uint64_t)2 * f.Ktap, (uint64_t)f.a_rows - 1, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) {
+    merged = true;
+    p.ntaps = 1; p.Ktap = 2 * f.Ktap; p.kb_per_tap = (p.Ktap + TC_BK - 1) / TC_BK; p.tapRow[1] = 0;
+  }
+  if (!merged &&
+      !make_tensor_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
   if (!make_tensor_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
   const int stage_bytes = TC_BM * TC_BK * 2 + p.BN * TC_BK * 2;
   // narrow tiles are epilogue-bound: two CTAs per SM (2 x 8 epilogue warps, 2 x 2 accumulators <= 512 TMEM columns)
