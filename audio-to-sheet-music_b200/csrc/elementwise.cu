@@ -36,13 +36,25 @@ void launch_sum_sumsq(const float* x, int B, long n_per_sample, double* stats, c
 __global__ void finalize_gn_kernel(const double* __restrict__ stats, double count, float* __restrict__ mr, long n, int nslot) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    double st[2] = {0.0, 0.0};
-    for (int s = 0; s < nslot; ++s) { st[0] += stats[2 * (i * nslot + s)]; st[1] += stats[2 * (i * nslot + s) + 1]; }
+    double st[2] = {stats[2 * i], stats[2 * i + 1]};
     float m, r; stats_to_mean_rstd(st, count, 1e-5f, m, r); mr[2 * i] = m; mr[2 * i + 1] = r;
   }
 }
+// slotted accumulators (nslot > 1): one warp per group, lanes over slots, fixed-order tree (a single thread walking the
+// 64 slots was a 10 us dependent-load chain, 16 times per forward)
+__global__ void finalize_gn_slots_kernel(const double* __restrict__ stats, double count, float* __restrict__ mr, long n, int nslot) {
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  double st[2] = {0.0, 0.0};
+  for (int s = lane; s < nslot; s += 32) { st[0] += stats[2 * (i * nslot + s)]; st[1] += stats[2 * (i * nslot + s) + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { st[0] += __shfl_xor_sync(0xffffffffu, st[0], o); st[1] += __shfl_xor_sync(0xffffffffu, st[1], o); }
+  if (lane == 0) { float m, r; stats_to_mean_rstd(st, count, 1e-5f, m, r); mr[2 * i] = m; mr[2 * i + 1] = r; }
+}
 void launch_finalize_gn(const double* stats, double count, float* mr, long n, int nslot, cudaStream_t st) {
-  finalize_gn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stats, count, mr, n, nslot);
+  if (nslot == 1) finalize_gn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stats, count, mr, n, nslot);
+  else finalize_gn_slots_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(stats, count, mr, n, nslot);
 }
 
 // torch.std default (unbiased) and the reference guard (x - mean) / (1e-5 + std)   ATHTDemucs_v2.py:268-275
@@ -294,10 +306,81 @@ __global__ void add_rowvec_kernel(const T* __restrict__ x, T* __restrict__ y, lo
     y[i] = from_f<T>(to_f<T>(x[i]) + vec[b * vstride + c]);
   }
 }
+// 16-byte form (C % VEC == 0, 16-byte aligned buffers): one vector of one row per thread and iteration
+template <typename T>
+__global__ void add_rowvec_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long rows_per_b, int C, int B,
+                                      const float* __restrict__ vec, long vstride) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const int cv = C / VEC;
+  const long total = (long)B * rows_per_b * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long row = i / cv;
+    const int c = (int)(i - row * cv) * VEC;
+    const long b = row / rows_per_b;
+    uint4 raw = *(const uint4*)(x + i * VEC);
+    T* e = (T*)&raw;
+    const float* vp = vec + b * vstride + c;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) e[k] = from_f<T>(to_f<T>(e[k]) + __ldg(vp + k));
+    *(uint4*)(y + i * VEC) = raw;
+  }
+}
 template <typename T>
 void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const float* vec, long vstride, cudaStream_t st) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  if (C % VEC == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {
+    long total = (long)B * rows_per_b * (C / VEC);
+    add_rowvec_vec_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(x, y, rows_per_b, C, B, vec, vstride);
+    return;
+  }
   long total = (long)B * rows_per_b * C;
   add_rowvec_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(x, y, rows_per_b, C, B, vec, vstride);
+}
+
+// ------------------------------------------------------------------ text conditioning vector
+// cvec[row] = out_proj(in_proj_v(v_proj(emb[row]))): three chained fp32 linears of one 512-vector (TextCrossAttention with a
+// single key: softmax == 1, ATHTDemucs_v2.py:38-58).  One block per (segment, prompt) row, a warp per
+// output feature (coalesced float4 weight reads, shuffle reduction), the intermediates stay in shared memory: three
+// latency-bound M = B*P GEMM launches (~55 us each) become one ~10 us launch.
+__device__ __forceinline__ void tv_layer(const float* __restrict__ x, int K, const float* __restrict__ W, const float* __restrict__ b,
+                                         float* __restrict__ y, int N) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // four outputs per warp pass: 4 x K/128 independent 16-byte weight loads in flight per lane (the loop is L2-latency bound)
+  for (int n0 = 4 * warp; n0 < N; n0 += 4 * nw) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+      const float4 v = *(const float4*)(x + 4 * k4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = __ldg((const float4*)(W + (long)min(n0 + j, N - 1) * K) + k4);
+        acc[j] = fmaf(w.x, v.x, acc[j]); acc[j] = fmaf(w.y, v.y, acc[j]); acc[j] = fmaf(w.z, v.z, acc[j]); acc[j] = fmaf(w.w, v.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      if (lane == 0 && n0 + j < N) y[n0 + j] = acc[j] + b[n0 + j];
+    }
+  }
+}
+__global__ void __launch_bounds__(1024) text_vectors_kernel(const float* __restrict__ emb, const float* __restrict__ W1,
+                                                           const float* __restrict__ b1, const float* __restrict__ W2,
+                                                           const float* __restrict__ b2, const float* __restrict__ W3,
+                                                           const float* __restrict__ b3, float* __restrict__ out) {
+  __shared__ __align__(16) float s0[512], s1[384], s2[384];
+  const long row = blockIdx.x;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s0[i] = emb[row * 512 + i];
+  __syncthreads();
+  tv_layer(s0, 512, W1, b1, s1, 384);
+  __syncthreads();
+  tv_layer(s1, 384, W2, b2, s2, 384);
+  __syncthreads();
+  tv_layer(s2, 384, W3, b3, out + row * 384, 384);
+}
+void launch_text_vectors(const float* emb, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                         const float* b3, float* out, int rows, cudaStream_t st) {
+  text_vectors_kernel<<<rows, 1024, 0, st>>>(emb, W1, b1, W2, b2, W3, b3, out);
 }
 
 // ------------------------------------------------------------------ decoder layer tail

@@ -21,6 +21,8 @@ template <typename T> void launch_norm_rows(const T* x, T* xout, T* y, long rows
                                             const float* pe, RowSpace yrs, cudaStream_t st, T* y2 = nullptr,
                                             const float* lw2 = nullptr, const float* lb2 = nullptr);
 template <typename T> void launch_softmax_rows(T* s, long rows, int n, cudaStream_t st);
+void launch_text_vectors(const float* emb, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                         const float* b3, float* out, int rows, cudaStream_t st);
 template <typename T> void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const float* vec, long vstride,
                                              cudaStream_t st);
 template <typename T> void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace os, int G2,

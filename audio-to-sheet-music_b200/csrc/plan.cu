@@ -633,17 +633,10 @@ void PlanT<T>::encode(const float* wav, cudaStream_t st) {
 // softmax is exactly 1, so attn_out is one 384-vector per (segment, prompt) -- SURVEY.md quirk Q3.
 template <typename T>
 void PlanT<T>::text_vectors(const float* emb, cudaStream_t st) {
-  const int rows = sh.B * sh.P;
-  float* v1 = cvec + (size_t)rows * 384, *v2 = cvec + (size_t)rows * 768;
-  auto lin32 = [&](const float* a, int K, const float* w, const float* b, float* c) {
-    GemmDesc d = gemm_desc_zero();
-    d.Mg = rows; d.N = 384; d.K = K; d.Ktap = K; d.A = a; d.sAm = K; d.B = w; d.sBn = K; d.sBk = 1;
-    d.C = c; d.sCm = 384; d.bias = b;
-    launch_gemm_simt<float>(d, st); ++n_launches;
-  };
-  lin32(emb, 512, P32("text_attn.v_proj.weight"), P32("text_attn.v_proj.bias"), v1);
-  lin32(v1, 384, P32("text_attn.attn.in_proj_weight") + 768L * 384, P32("text_attn.attn.in_proj_bias") + 768, v2);
-  lin32(v2, 384, P32("text_attn.attn.out_proj.weight"), P32("text_attn.attn.out_proj.bias"), cvec);
+  launch_text_vectors(emb, P32("text_attn.v_proj.weight"), P32("text_attn.v_proj.bias"),
+                      P32("text_attn.attn.in_proj_weight") + 768L * 384, P32("text_attn.attn.in_proj_bias") + 768,
+                      P32("text_attn.attn.out_proj.weight"), P32("text_attn.attn.out_proj.bias"), cvec, sh.B * sh.P, st);
+  ++n_launches;
 }
 
 template <typename T>

@@ -10,6 +10,7 @@ for row in csv.DictReader(lines):
     a = agg[name]; a["launches"].add(row["ID"])
     if m.startswith("dram__bytes"): a["dram_bytes_total"] += v * scale.get(u, 1.0)
     elif m.startswith("gpu__time"): a["time_us"] += v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v
-out = {k: {"launches": len(v["launches"]), "dram_bytes_total": v["dram_bytes_total"], "time_us": v["time_us"]} for k, v in agg.items()}
+out = {k: {"launches": len(v["launches"]), "dram_bytes_total": v["dram_bytes_total"], "time_us": v["time_us"],
+           "dram_gbs": round(v["dram_bytes_total"] / max(v["time_us"], 1e-9) / 1e3, 1)} for k, v in agg.items()}
 out["_note"] = "one batch-32 bf16 forward (6 s segments), ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, summed per kernel"
 print(json.dumps(out, indent=1))
