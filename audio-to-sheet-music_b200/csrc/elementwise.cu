@@ -187,85 +187,204 @@ void launch_gn_glu_res(T* x, RowSpace xs, const T* e, RowSpace es, int G2, int p
 // One warp per token row of C <= 512 channels.  x: [rows, C] contiguous.
 //   if gstats: x' = (x-mu_b)*rstd_b*gw + gb  is written to xout (MyGroupNorm over all tokens of a sample)
 //   if lw:     y  = LN(x')*lw + lb (+ pe[row % S])   is written to y
-template <typename T>
+template <typename T, int RPW>
 __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, T* __restrict__ y, long rows, int C, int S,
                                  const float* __restrict__ gmr, const float* __restrict__ gw,
                                  const float* __restrict__ gb, const float* __restrict__ lw, const float* __restrict__ lb,
                                  const float* __restrict__ pe, RowSpace yrs, T* __restrict__ y2,
                                  const float* __restrict__ lw2, const float* __restrict__ lb2) {
-  // one warp per row; each lane owns up to two 8-channel chunks (C <= 512, C % 8 == 0): 16-byte loads / stores
-  int lane = threadIdx.x & 31;
-  long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const T* xr = x + row * C;
+  // one warp per RPW consecutive rows; each lane owns up to two 8-channel chunks (C <= 512, C % 8 == 0): 16-byte loads /
+  // stores, all RPW rows' loads in flight together, and every affine vector is fetched once per RPW rows (fetched per row,
+  // the fp32 parameters were 4-6x the bf16 payload in L1 traffic)
+  const int lane = threadIdx.x & 31;
+  const long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
   const int nchunk = C >> 3;
-  float v[16];
-  float gm = 0.f, gr = 1.f;
-  if (gmr) { gm = gmr[2 * (row / S)]; gr = gmr[2 * (row / S) + 1]; }
-  float s = 0.f;
+  float v[RPW][16];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int ch = lane + 32 * i;
-    if (ch < nchunk) {
-      const int c = ch * 8;
-      VecIO<T, 8>::load(xr + c, v + 8 * i);
-      if (gmr) {
+  for (int r = 0; r < RPW; ++r) {
+    const long row = min(row0 + r, rows - 1);          // tail rows recompute the last row and are not stored
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (lane + 32 * i < nchunk) VecIO<T, 8>::load(x + row * C + (lane + 32 * i) * 8, v[r] + 8 * i);
+  }
+  if (gmr) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (lane + 32 * i < nchunk) {
         float w8[8], b8[8];
         VecIO<float, 8>::load(gw + c, w8); VecIO<float, 8>::load(gb + c, b8);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[8 * i + k] = (v[8 * i + k] - gm) * gr * w8[k] + b8[k];
-        VecIO<T, 8>::store(xout + row * C + c, v + 8 * i);
-      }
+        for (int r = 0; r < RPW; ++r) {
+          const long row = row0 + r;
+          const long rc = min(row, rows - 1);
+          const float gm = gmr[2 * (rc / S)], gr = gmr[2 * (rc / S) + 1];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s += v[8 * i + k];
+          for (int k = 0; k < 8; ++k) v[r][8 * i + k] = (v[r][8 * i + k] - gm) * gr * w8[k] + b8[k];
+          if (row < rows) VecIO<T, 8>::store(xout + row * C + c, v[r] + 8 * i);
+        }
+      }
     }
   }
   if (!lw) return;
-  s = warp_sum(s);
-  float mean = s / C;
-  float q = 0.f;
+  float mean[RPW], rstd[RPW];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-    if (lane + 32 * i < nchunk) {
+  for (int r = 0; r < RPW; ++r) {
+    float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { float dlt = v[8 * i + k] - mean; q += dlt * dlt; }
-    }
-  q = warp_sum(q);
-  float rstd = rsqrtf(q / C + 1e-5f);
-  long srow = row % S;
-  long yoff = row * C;
-  if (yrs.C > 0) yoff = yrs.row_off((int)(row / yrs.R), (int)(row % yrs.R));   // scatter into a padded row space
+    for (int i = 0; i < 2; ++i)
+      if (lane + 32 * i < nchunk) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[r][8 * i + k];
+      }
+    mean[r] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    mean[r] = mean[r] / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (lane + 32 * i < nchunk) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { float dlt = v[r][8 * i + k] - mean[r]; q += dlt * dlt; }
+      }
+    rstd[r] = q;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) rstd[r] = rsqrtf(rstd[r] / C + 1e-5f);
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int ch = lane + 32 * i;
     if (ch < nchunk) {
       const int c = ch * 8;
-      float o[8], w8[8], b8[8];
+      float w8[8], b8[8];
       VecIO<float, 8>::load(lw + c, w8); VecIO<float, 8>::load(lb + c, b8);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * w8[k] + b8[k];
-      if (pe) {
-        VecIO<float, 8>::load(pe + srow * C + c, w8);
+      for (int r = 0; r < RPW; ++r) {
+        const long row = row0 + r;
+        if (row < rows) {
+          float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += w8[k];
+          for (int k = 0; k < 8; ++k) o[k] = (v[r][8 * i + k] - mean[r]) * rstd[r] * w8[k] + b8[k];
+          if (pe) {
+            float p8[8];
+            VecIO<float, 8>::load(pe + (row % S) * C + c, p8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] += p8[k];
+          }
+          long yoff = row * C;
+          if (yrs.C > 0) yoff = yrs.row_off((int)(row / yrs.R), (int)(row % yrs.R));   // scatter into a padded row space
+          VecIO<T, 8>::store(y + yoff + c, o);
+        }
       }
-      VecIO<T, 8>::store(y + yoff + c, o);
-      if (y2) {      // a second LayerNorm of the same row (same statistics, other affine): the next layer's other consumer
+      if (y2) {      // a second LayerNorm of the same rows (same statistics, other affine): the next layer's other consumer
         VecIO<float, 8>::load(lw2 + c, w8); VecIO<float, 8>::load(lb2 + c, b8);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * w8[k] + b8[k];
-        VecIO<T, 8>::store(y2 + row * C + c, o);
+        for (int r = 0; r < RPW; ++r) {
+          const long row = row0 + r;
+          if (row < rows) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = (v[r][8 * i + k] - mean[r]) * rstd[r] * w8[k] + b8[k];
+            VecIO<T, 8>::store(y2 + row * C + c, o);
+          }
+        }
       }
     }
   }
 }
+// LayerNorm-only form for C == 512 (every transformer norm): the affine vectors of a lane's two fixed 8-channel chunks live in
+// registers and the warp walks rows grid-stride with the next row's 2 x 16 B already in flight.  The generic kernel re-read
+// 4 KB of fp32 affine parameters from L1 per 1 KB row (4x the payload) and ran at ~2.5 TB/s.  Same operation order as the
+// generic kernel (bit-identical results).
+template <typename T, bool HAS2>
+__global__ void __launch_bounds__(256) ln512_rows_kernel(const T* __restrict__ x, T* __restrict__ y, long rows, int S,
+                                                         const float* __restrict__ lw, const float* __restrict__ lb,
+                                                         const float* __restrict__ pe, RowSpace yrs, T* __restrict__ y2,
+                                                         const float* __restrict__ lw2, const float* __restrict__ lb2) {
+  constexpr int C = 512;
+  const int lane = threadIdx.x & 31;
+  const long nw = (long)gridDim.x * (blockDim.x >> 5);
+  long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float w[16], b[16], w2[HAS2 ? 16 : 1], b2[HAS2 ? 16 : 1];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    VecIO<float, 8>::load(lw + c, w + 8 * i); VecIO<float, 8>::load(lb + c, b + 8 * i);
+    if (HAS2) { VecIO<float, 8>::load(lw2 + c, w2 + 8 * i); VecIO<float, 8>::load(lb2 + c, b2 + 8 * i); }
+  }
+  float v[16];
+  VecIO<T, 8>::load(x + row * C + lane * 8, v); VecIO<T, 8>::load(x + row * C + (lane + 32) * 8, v + 8);
+  for (; row < rows; row += nw) {
+    float nx[16];
+    const long rn = row + nw;
+    if (rn < rows) { VecIO<T, 8>::load(x + rn * C + lane * 8, nx); VecIO<T, 8>::load(x + rn * C + (lane + 32) * 8, nx + 8); }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += v[k];
+    s = warp_sum(s);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { float dlt = v[k] - mean; q += dlt * dlt; }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / C + 1e-5f);
+    long yoff = row * C;
+    if (yrs.C > 0) yoff = yrs.row_off((int)(row / yrs.R), (int)(row % yrs.R));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * w[8 * i + k] + b[8 * i + k];
+      if (pe) {
+        float p8[8];
+        VecIO<float, 8>::load(pe + (row % S) * C + c, p8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += p8[k];
+      }
+      VecIO<T, 8>::store(y + yoff + c, o);
+      if (HAS2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * w2[8 * i + k] + b2[8 * i + k];
+        VecIO<T, 8>::store(y2 + row * C + c, o);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = nx[k];
+  }
+}
+
 template <typename T>
 void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const float* gmr,
                       const float* gw, const float* gb, const float* lw, const float* lb, const float* pe,
                       RowSpace yrs, cudaStream_t st, T* y2, const float* lw2, const float* lb2) {
-  int wpb = 8;
-  norm_rows_kernel<T><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, xout, y, rows, C, S, gmr,
-                                                                                gw, gb, lw, lb, pe, yrs, y2, lw2, lb2);
+  if (C == 512 && !gmr && lw && sizeof(T) == 2) {
+    const unsigned grid = (unsigned)std::min<long>((rows + 7) / 8, 148L * 4);
+    if (y2) ln512_rows_kernel<T, true><<<grid, 256, 0, st>>>(x, y, rows, S, lw, lb, pe, yrs, y2, lw2, lb2);
+    else ln512_rows_kernel<T, false><<<grid, 256, 0, st>>>(x, y, rows, S, lw, lb, pe, yrs, y2, lw2, lb2);
+    return;
+  }
+  constexpr int wpb = 8;
+  if (C == 512)      // (measured: two rows per warp help the 512-channel GroupNorm + LayerNorm passes, not the narrower ones)
+    norm_rows_kernel<T, 2><<<(unsigned)((rows + wpb * 2 - 1) / (wpb * 2)), wpb * 32, 0, st>>>(x, xout, y, rows, C, S, gmr, gw, gb, lw,
+                                                                                              lb, pe, yrs, y2, lw2, lb2);
+  else
+    norm_rows_kernel<T, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, xout, y, rows, C, S, gmr, gw, gb, lw, lb, pe,
+                                                                                    yrs, y2, lw2, lb2);
 }
 
 // ------------------------------------------------------------------ row softmax, in place (fp32 math)
