@@ -131,7 +131,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
+        # NCCL_DEBUG stays unset (level NONE): at VERSION / WARN / INFO NCCL writes its banner to stdout next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
 
