@@ -121,6 +121,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: everything else that libraries write to file descriptor 1 (NCCL prints its
+    # version banner there) goes to stderr; the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch.distributed as dist
     import athtd_b200
     from oracle import weights          # seeded synthetic weights / inputs only (not on the measured path)
@@ -131,7 +137,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL_DEBUG stays unset (level NONE): at VERSION / WARN / INFO NCCL writes its banner to stdout next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
 
@@ -237,7 +242,8 @@ def main():
             rate, per_chunk, nch = cpu_reference_rate(3, 1, 1, args.seconds)
             line["cpu_baseline"] = {"value": rate, "unit": "x realtime", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"3 timed 6 s chunks (batch 1, {per_chunk * 1e3:.0f} ms each) after 1 warm-up, extrapolated to {nch} chunks"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
