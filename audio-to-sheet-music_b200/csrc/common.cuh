@@ -35,6 +35,37 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): exact fp32 arithmetic, two lanes per issue slot.  The elementwise kernels
+// of this path are instruction-issue bound (ncu: 62-77 % issue-active, no unit saturated), not FP32-pipe bound.
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b), "l"(*(unsigned long long*)&c));
+  return *(float2*)&d;
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b));
+  return *(float2*)&d;
+}
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b));
+  return *(float2*)&d;
+}
+__device__ __forceinline__ float2 f2splat(float a) { return make_float2(a, a); }
+// gelu_fast on a pair: the same operation sequence per lane (bit-identical to two scalar calls)
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  float2 x2 = f2mul(x, x);
+  x2.x = fminf(x2.x, 32.0f); x2.y = fminf(x2.y, 32.0f);
+  float2 p = f2fma(f2splat(-3.5471127794746665e-4f), x2, f2splat(3.702029975737703e-2f));
+  p = f2fma(p, x2, f2splat(7.975055041244574e-1f));
+  const float2 u = f2mul(x, p);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hx = f2mul(f2splat(0.5f), x);
+  return f2fma(hx, t, hx);
+}
 template <typename T> __device__ __forceinline__ float gelu_act(float x);
 template <> __device__ __forceinline__ float gelu_act<float>(float x) { return gelu_erf(x); }
 template <> __device__ __forceinline__ float gelu_act<bf16>(float x) { return gelu_fast(x); }

@@ -208,9 +208,9 @@ template <int C>
 __device__ __forceinline__ uint32_t dc_gn_gelu_pair(bf16* hp, int c, float mean, float rstd, const float* g1w, const float* g1b) {
   const float2 x = unpack_bf16x2(*(const uint32_t*)hp);
   // zero-padded affine beyond H: (x - m) * r * 0 + 0 = 0 and GELU(0) = 0, the K padding stays exactly zero
-  const float y0 = gelu_fast((x.x - mean) * rstd * g1w[c] + g1b[c]);
-  const float y1 = gelu_fast((x.y - mean) * rstd * g1w[c + 1] + g1b[c + 1]);
-  const uint32_t r = pack_bf16x2(y0, y1);
+  const float2 y = gelu_fast2(f2fma(f2mul(f2add(x, f2splat(-mean)), f2splat(rstd)), make_float2(g1w[c], g1w[c + 1]),
+                                     make_float2(g1b[c], g1b[c + 1])));
+  const uint32_t r = pack_bf16x2(y.x, y.y);
   *(uint32_t*)hp = r;
   return r;
 }

@@ -527,6 +527,39 @@ __device__ __forceinline__ void lerp_coords(int d, int in, int out, int& i0, int
 // per output element (16x redundant on the 32 -> 259 layer) and was ALU-bound.  The exact 4:1 layers (only phases 0 / 3 of
 // the transposed conv are stored) keep the direct form: each stored row is used exactly once.
 struct LerpRow { int i0, i1; float lam; int j0, j1; float mu; };
+// a[k] = GELU(a[k] * sc[k] + sh[k]); bf16 build: packed pairs
+template <typename T, int VEC>
+__device__ __forceinline__ void dec_gn_gelu(float (&a)[VEC], const float (&sc)[VEC], const float (&sh)[VEC]) {
+  if constexpr (sizeof(T) == 2 && VEC % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < VEC; k += 2) {
+      const float2 r = gelu_fast2(f2fma(make_float2(a[k], a[k + 1]), make_float2(sc[k], sc[k + 1]), make_float2(sh[k], sh[k + 1])));
+      a[k] = r.x; a[k + 1] = r.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) a[k] = gelu_act<T>(fmaf(a[k], sc[k], sh[k]));
+  }
+}
+// v = lerp(a0, a1; lam) + 0.1 * lerp(s0, s1; mu)
+template <typename T, int VEC>
+__device__ __forceinline__ void dec_blend(float (&v)[VEC], const float (&a0)[VEC], const float (&a1)[VEC], const float (&s0)[VEC],
+                                          const float (&s1)[VEC], float lam, float mu) {
+  if constexpr (sizeof(T) == 2 && VEC % 2 == 0) {
+    const float2 l0 = f2splat(1.f - lam), l1 = f2splat(lam), m0 = f2splat(0.1f * (1.f - mu)), m1 = f2splat(0.1f * mu);
+#pragma unroll
+    for (int k = 0; k < VEC; k += 2) {
+      float2 r = f2mul(l0, make_float2(a0[k], a0[k + 1]));
+      r = f2fma(l1, make_float2(a1[k], a1[k + 1]), r);
+      r = f2fma(m0, make_float2(s0[k], s0[k + 1]), r);
+      r = f2fma(m1, make_float2(s1[k], s1[k + 1]), r);
+      v[k] = r.x; v[k + 1] = r.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = ((1.f - lam) * a0[k] + lam * a1[k]) + 0.1f * ((1.f - mu) * s0[k] + mu * s1[k]);
+  }
+}
 
 template <typename T, int VEC, bool STAGE>
 __global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, int Cu, T* __restrict__ out,
@@ -570,10 +603,7 @@ __global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u,
         float a[VEC];
         // phase layout: output row fo = 4q + r - 2 lives in the row of x[q-1] (us geometry), columns r*Cu + c
         VecIO<T, VEC>::load(ug + (long)(((fo + 2) >> 2) - 1) * urow + ((fo + 2) & 3) * Cu + c, a);
-        if (has_gn) {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) a[k] = gelu_act<T>(fmaf(a[k], sc[k], sh[k]));
-        }
+        if (has_gn) dec_gn_gelu<T, VEC>(a, sc, sh);
         VecIO<float, VEC>::store(act_s + (long)r * Cu + c, a);
       }
     __syncthreads();
@@ -588,15 +618,8 @@ __global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u,
       VecIO<T, VEC>::load(ug + (long)(((lr.i1 + 2) >> 2) - 1) * urow + ((lr.i1 + 2) & 3) * Cu + c, a1);
       VecIO<T, VEC>::load(sg + (long)lr.j0 * srow + c, s0);
       VecIO<T, VEC>::load(sg + (long)lr.j1 * srow + c, s1);
-      if (has_gn) {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          a0[k] = gelu_act<T>(fmaf(a0[k], sc[k], sh[k]));
-          a1[k] = gelu_act<T>(fmaf(a1[k], sc[k], sh[k]));
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) v[k] = ((1.f - lr.lam) * a0[k] + lr.lam * a1[k]) + 0.1f * ((1.f - lr.mu) * s0[k] + lr.mu * s1[k]);
+      if (has_gn) { dec_gn_gelu<T, VEC>(a0, sc, sh); dec_gn_gelu<T, VEC>(a1, sc, sh); }
+      dec_blend<T, VEC>(v, a0, a1, s0, s1, lr.lam, lr.mu);
       VecIO<T, VEC>::store(og + (long)d * orow + c, v);
     }
     return;
@@ -615,10 +638,7 @@ __global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u,
         VecIO<float, VEC>::load(act_s + (long)(lr.i0 - in_lo) * Cu + c, a0);
       } else {
         VecIO<T, VEC>::load(ug + (long)(((lr.i0 + 2) >> 2) - 1) * urow + ((lr.i0 + 2) & 3) * Cu + c, a0);
-        if (has_gn) {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) a0[k] = gelu_act<T>(fmaf(a0[k], sc[k], sh[k]));
-        }
+        if (has_gn) dec_gn_gelu<T, VEC>(a0, sc, sh);
       }
       if (lr.i1 == lr.i0) {
 #pragma unroll
@@ -627,10 +647,7 @@ __global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u,
         VecIO<float, VEC>::load(act_s + (long)(lr.i1 - in_lo) * Cu + c, a1);
       } else {
         VecIO<T, VEC>::load(ug + (long)(((lr.i1 + 2) >> 2) - 1) * urow + ((lr.i1 + 2) & 3) * Cu + c, a1);
-        if (has_gn) {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) a1[k] = gelu_act<T>(fmaf(a1[k], sc[k], sh[k]));
-        }
+        if (has_gn) dec_gn_gelu<T, VEC>(a1, sc, sh);
       }
       ci0 = lr.i0; ci1 = lr.i1;
     }
@@ -649,8 +666,7 @@ __global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u,
       }
       cj0 = lr.j0; cj1 = lr.j1;
     }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) v[k] = ((1.f - lr.lam) * a0[k] + lr.lam * a1[k]) + 0.1f * ((1.f - lr.mu) * s0[k] + lr.mu * s1[k]);
+    dec_blend<T, VEC>(v, a0, a1, s0, s1, lr.lam, lr.mu);
     VecIO<T, VEC>::store(og + (long)d * orow + c, v);
   }
 }

@@ -174,8 +174,8 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
           mma16816(d, a[1], b1);
           const int c = nt * 8 + 2 * q, r0 = mt * 16 + g;
           const float2 cb = *(const float2*)(cbs + c);
-          if (r0 < Tn) sts_pair(xsi + r0 * D::XP + c, gelu_fast(d[0] + cb.x), gelu_fast(d[1] + cb.y));
-          if (r0 + 8 < Tn) sts_pair(xsi + (r0 + 8) * D::XP + c, gelu_fast(d[2] + cb.x), gelu_fast(d[3] + cb.y));
+          if (r0 < Tn) { const float2 g2 = gelu_fast2(f2add(make_float2(d[0], d[1]), make_float2(cb.x, cb.y))); sts_pair(xsi + r0 * D::XP + c, g2.x, g2.y); }
+          if (r0 + 8 < Tn) { const float2 g2 = gelu_fast2(f2add(make_float2(d[2], d[3]), make_float2(cb.x, cb.y))); sts_pair(xsi + (r0 + 8) * D::XP + c, g2.x, g2.y); }
         }
       }
     } else {

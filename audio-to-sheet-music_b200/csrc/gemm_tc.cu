@@ -114,15 +114,17 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
 #pragma unroll
   for (int j4 = 0; j4 < 32; j4 += 4) {                     // columns past N hold garbage and are never stored
     const float4 b4 = *(const float4*)(sv + c0 + j4);      // broadcast reads (every lane owns a row, same columns)
-    float x[4] = {__uint_as_float(r[j4]) + b4.x, __uint_as_float(r[j4 + 1]) + b4.y, __uint_as_float(r[j4 + 2]) + b4.z,
-                  __uint_as_float(r[j4 + 3]) + b4.w};
+    // packed fp32 pairs (FADD2 / FFMA2): the epilogue is issue-bound, the accumulator registers already come in pairs
+    float2 x01 = f2add(make_float2(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1])), make_float2(b4.x, b4.y));
+    float2 x23 = f2add(make_float2(__uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3])), make_float2(b4.z, b4.w));
     if (EF & EF_GN) {
       const float4 w4 = *(const float4*)(sv + TC_VEC + c0 + j4), o4 = *(const float4*)(sv + 2 * TC_VEC + c0 + j4);
-      x[0] = (x[0] - er.gmean) * er.grstd * w4.x + o4.x; x[1] = (x[1] - er.gmean) * er.grstd * w4.y + o4.y;
-      x[2] = (x[2] - er.gmean) * er.grstd * w4.z + o4.z; x[3] = (x[3] - er.gmean) * er.grstd * w4.w + o4.w;
+      const float2 nm = f2splat(-er.gmean), rs = f2splat(er.grstd);
+      x01 = f2fma(f2mul(f2add(x01, nm), rs), make_float2(w4.x, w4.y), make_float2(o4.x, o4.y));
+      x23 = f2fma(f2mul(f2add(x23, nm), rs), make_float2(w4.z, w4.w), make_float2(o4.z, o4.w));
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[j4 + e] = (EF & EF_GELU) ? gelu_fast(x[e]) : x[e];
+    if (EF & EF_GELU) { x01 = gelu_fast2(x01); x23 = gelu_fast2(x23); }
+    v[j4] = x01.x; v[j4 + 1] = x01.y; v[j4 + 2] = x23.x; v[j4 + 3] = x23.y;
   }
   int no = ncol, nco = nc;             // output column base / count
   if (EF & EF_GLU) {
@@ -136,7 +138,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
 #pragma unroll
       for (int j4 = 0; j4 < NV; j4 += 4) {
         const float4 c4 = *(const float4*)(cs + j4);
-        v[j4] *= c4.x; v[j4 + 1] *= c4.y; v[j4 + 2] *= c4.z; v[j4 + 3] *= c4.w;
+        const float2 a = f2mul(make_float2(v[j4], v[j4 + 1]), make_float2(c4.x, c4.y));
+        const float2 b = f2mul(make_float2(v[j4 + 2], v[j4 + 3]), make_float2(c4.z, c4.w));
+        v[j4] = a.x; v[j4 + 1] = a.y; v[j4 + 2] = b.x; v[j4 + 3] = b.y;
       }
     }
     if (p.rowtab) {      // per-row table (frequency embedding): Nout % 4 == 0, 16-byte gathers instead of scalar ones
@@ -170,12 +174,14 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
     // do not count; the phase of a group is uniform across the warp, so this is two selects per group, no divergence.
 #pragma unroll
     for (int g = 0; g < NV / 16; ++g) {
-      float s = 0.f, q = 0.f;
+      float2 s2 = f2splat(0.f), q2 = f2splat(0.f);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x = (16 * g + 16 <= nco || 16 * g + j < nco) ? v[16 * g + j] : 0.f;     // ragged last group (N % 32 == 8 / GLU)
-        s += x; q += x * x;
+      for (int j = 0; j < 16; j += 2) {
+        const bool full = 16 * g + 16 <= nco;                                               // ragged last group (N % 32 == 8 / GLU)
+        const float2 x = make_float2(full || 16 * g + j < nco ? v[16 * g + j] : 0.f, full || 16 * g + j + 1 < nco ? v[16 * g + j + 1] : 0.f);
+        s2 = f2add(s2, x); q2 = f2fma(x, x, q2);
       }
+      const float s = s2.x + s2.y, q = q2.x + q2.y;
       bool counted = 16 * g < nco;
       if (p.convt_cout > 0) counted = counted && !((no + 16 * g < 2 * p.convt_cout) ? er.edge_lo : er.edge_hi);
       if (counted) { ssum += s; ssq += q; }

@@ -36,8 +36,10 @@ __global__ void __launch_bounds__(256) tenc0_conv_kernel(const float* __restrict
     mma16816(d, a, bb);
     const int c = nt * 8 + 2 * q;
     const float b0 = bias[c], b1 = bias[c + 1];
-    *(uint32_t*)&stage[warp][g][c] = pack_bf16x2(gelu_fast(d[0] + b0), gelu_fast(d[1] + b1));
-    *(uint32_t*)&stage[warp][g + 8][c] = pack_bf16x2(gelu_fast(d[2] + b0), gelu_fast(d[3] + b1));
+    const float2 ga = gelu_fast2(f2add(make_float2(d[0], d[1]), make_float2(b0, b1)));
+    const float2 gb = gelu_fast2(f2add(make_float2(d[2], d[3]), make_float2(b0, b1)));
+    *(uint32_t*)&stage[warp][g][c] = pack_bf16x2(ga.x, ga.y);
+    *(uint32_t*)&stage[warp][g + 8][c] = pack_bf16x2(gb.x, gb.y);
   }
   __syncwarp();
   bf16* dst = y + ys.row_off(b, t0);
