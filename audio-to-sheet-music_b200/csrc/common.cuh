@@ -52,6 +52,11 @@ __device__ __forceinline__ float2 f2add(float2 a, float2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b));
   return *(float2*)&d;
 }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b));
+  return *(float2*)&d;
+}
 __device__ __forceinline__ float2 f2splat(float a) { return make_float2(a, a); }
 // gelu_fast on a pair: the same operation sequence per lane (bit-identical to two scalar calls)
 __device__ __forceinline__ float2 gelu_fast2(float2 x) {

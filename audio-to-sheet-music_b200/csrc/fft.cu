@@ -22,21 +22,29 @@ namespace athtd {
 #define FFT_PITCH 272          // 256 + 16: half-warps land on disjoint banks
 #define FFT_SMEM (16 * FFT_PITCH)
 
+// Complex arithmetic on packed fp32 pairs (re, im) = one 64-bit register pair: FADD2 / FMUL2 / FFMA2 (ptxas folds the
+// scalar broadcasts and the re <-> im swaps into operand modifiers).  The transform is instruction-issue bound (~1600 SASS
+// instructions per thread and frame, 850 of them fp32 arithmetic in the scalar form), not HBM bound.
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  // (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+  return f2fma(f2splat(a.y), make_float2(-b.y, b.x), f2mul(f2splat(a.x), b));
+}
+// v * (wr + i wi) with compile-time wr, wi: v * (wr, wr) + swap(v) * (-wi, wi)
+__device__ __forceinline__ float2 cmul_const(float2 v, float wr, float wi) {
+  return f2fma(make_float2(v.y, v.x), make_float2(-wi, wi), f2mul(v, f2splat(wr)));
 }
 
 // 4-point DFT, forward uses W4 = -i, inverse +i
 template <bool INV>
 __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
-  float2 s0 = make_float2(a.x + c.x, a.y + c.y), s1 = make_float2(a.x - c.x, a.y - c.y);
-  float2 s2 = make_float2(b.x + d.x, b.y + d.y), s3 = make_float2(b.x - d.x, b.y - d.y);
-  // forward: y1 = s1 - i*s3 ; y3 = s1 + i*s3.   (-i)*(x+iy) = y - ix
-  float2 is3 = INV ? make_float2(-s3.y, s3.x) : make_float2(s3.y, -s3.x);
-  a = make_float2(s0.x + s2.x, s0.y + s2.y);
-  c = make_float2(s0.x - s2.x, s0.y - s2.y);
-  b = make_float2(s1.x + is3.x, s1.y + is3.y);
-  d = make_float2(s1.x - is3.x, s1.y - is3.y);
+  const float2 s0 = f2add(a, c), s1 = f2sub(a, c), s2 = f2add(b, d), s3 = f2sub(b, d);
+  // forward: y1 = s1 - i*s3 ; y3 = s1 + i*s3.   (-i)*(x+iy) = (y, -x): swap(s3) * (1, -1)
+  const float2 sw = make_float2(s3.y, s3.x);
+  const float2 pm = INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f), mp = INV ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f);
+  a = f2add(s0, s2);
+  c = f2sub(s0, s2);
+  b = f2fma(sw, pm, s1);
+  d = f2fma(sw, mp, s1);
 }
 
 // 16-point DFT in registers, natural order in and out.
@@ -55,7 +63,7 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 #pragma unroll
     for (int n2 = 1; n2 < 4; ++n2) {
       const int m = k1 * n2;
-      v[4 * k1 + n2] = cmul(v[4 * k1 + n2], make_float2(cs[m], sg * sn[m]));
+      v[4 * k1 + n2] = cmul_const(v[4 * k1 + n2], cs[m], sg * sn[m]);
     }
   // step 3: for each k1, DFT4 over n2 -> X[k1 + 4*k2] ; currently at v[4*k1 + n2]
 #pragma unroll
@@ -129,14 +137,25 @@ __global__ void __launch_bounds__(256) stft_cac_kernel(const float* __restrict__
   const float* wl = wav + (long)b * 2 * L;
   const float* wr = wl + L;
   float2 v[16];
+  const int base = frame * 1024 - 1536;        // kept frame `frame` of _spec == stft frame frame+2
+  if (base >= 0 && base + FFT_N <= L) {        // interior frame (all but 2 + 3 per segment): no reflection, constant offsets
+    const float* pl = wl + base + t;
+    const float* pr = wr + base + t;
 #pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) {
-    int n = 256 * n1 + t;
-    int idx = frame * 1024 - 1536 + n;       // kept frame `frame` of _spec == stft frame frame+2
-    if (idx < 0) idx = -idx;
-    if (idx >= L) idx = 2 * (L - 1) - idx;
-    float w = win[n];
-    v[n1] = make_float2(wl[idx] * w, wr[idx] * w);
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const float w = win[256 * n1 + t];
+      v[n1] = make_float2(pl[256 * n1] * w, pr[256 * n1] * w);
+    }
+  } else {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      int n = 256 * n1 + t;
+      int idx = base + n;
+      if (idx < 0) idx = -idx;
+      if (idx >= L) idx = 2 * (L - 1) - idx;
+      float w = win[n];
+      v[n1] = make_float2(wl[idx] * w, wr[idx] * w);
+    }
   }
   dft16<false>(v);
   {
@@ -217,19 +236,32 @@ __global__ void __launch_bounds__(256) mask_istft_kernel(const float4* __restric
     if (use_mask) {
       int i0, i1; float lam;
       lerp_coords_f(k, ds.R, 2048, i0, i1, lam);
-      const T* r0 = dec + ds.row_off(g, i0);
-      const T* r1 = dec + ds.row_off(g, i1);
-      float a0 = to_f<T>(r0[0]), a1 = to_f<T>(r0[1]), a2 = to_f<T>(r0[2]), a3 = to_f<T>(r0[3]);
-      float c0 = to_f<T>(r1[0]), c1 = to_f<T>(r1[1]), c2 = to_f<T>(r1[2]), c3 = to_f<T>(r1[3]);
+      float a0, a1, a2, a3, c0, c1, c2, c3;
+      if constexpr (sizeof(T) == 2) {      // the 4 decoder channels of a row are one 8-byte load
+        const uint2 ra = *(const uint2*)(dec + ds.row_off(g, i0)), rc = *(const uint2*)(dec + ds.row_off(g, i1));
+        const float2 ra0 = __bfloat1622float2(*(const __nv_bfloat162*)&ra.x), ra1 = __bfloat1622float2(*(const __nv_bfloat162*)&ra.y);
+        const float2 rc0 = __bfloat1622float2(*(const __nv_bfloat162*)&rc.x), rc1 = __bfloat1622float2(*(const __nv_bfloat162*)&rc.y);
+        a0 = ra0.x; a1 = ra0.y; a2 = ra1.x; a3 = ra1.y; c0 = rc0.x; c1 = rc0.y; c2 = rc1.x; c3 = rc1.y;
+      } else {
+        const float4 ra = *(const float4*)(dec + ds.row_off(g, i0)), rc = *(const float4*)(dec + ds.row_off(g, i1));
+        a0 = ra.x; a1 = ra.y; a2 = ra.z; a3 = ra.w; c0 = rc.x; c1 = rc.y; c2 = rc.z; c3 = rc.w;
+      }
       float l0a = w00 * a0 + w01 * a1 + w02 * a2 + w03 * a3 + b0;
       float l1a = w10 * a0 + w11 * a1 + w12 * a2 + w13 * a3 + b1;
       float l0b = w00 * c0 + w01 * c1 + w02 * c2 + w03 * c3 + b0;
       float l1b = w10 * c0 + w11 * c1 + w12 * c2 + w13 * c3 + b1;
-      float m0 = sigmoid_acc((1.f - lam) * l0a + lam * l0b);
-      float m1 = sigmoid_acc((1.f - lam) * l1a + lam * l1b);
+      const float q0 = (1.f - lam) * l0a + lam * l0b, q1 = (1.f - lam) * l1a + lam * l1b;
+      float m0, m1, inv0, inv1;
+      if constexpr (sizeof(T) == 2) {      // bf16 build: MUFU exp / reciprocal (relative error ~1e-6, far below the bf16 activations)
+        m0 = __frcp_rn(1.0f + __expf(-q0)); m1 = __frcp_rn(1.0f + __expf(-q1));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(z.x + 1e-8f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(z.y + 1e-8f));
+      } else {
+        m0 = sigmoid_acc(q0); m1 = sigmoid_acc(q1);
+        inv0 = 1.0f / (z.x + 1e-8f); inv1 = 1.0f / (z.y + 1e-8f);
+      }
       // quirk Q4 (ATHTDemucs_v2.py:303-309): "magnitudes" are the signed CaC planes L.re and L.im
       float ms0 = z.x * m0, ms1 = z.y * m1;
-      float inv0 = 1.0f / (z.x + 1e-8f), inv1 = 1.0f / (z.y + 1e-8f);
       xl = make_float2(ms0 * (z.x * inv0), ms0 * (z.y * inv0));
       xr = make_float2(ms1 * (z.z * inv1), ms1 * (z.w * inv1));
     } else {
