@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
       a[ks][2] = v_lo ? dc_gn_gelu_pair<C>(hb + (long)r_lo * D::HP + c1, c1, m_lo, rs_lo, g1ws, g1bs) : 0u;
       a[ks][3] = v_hi ? dc_gn_gelu_pair<C>(hb + (long)r_hi * D::HP + c1, c1, m_hi, rs_hi, g1ws, g1bs) : 0u;
     }
-    float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+    float2 sl2 = f2splat(0.f), ql2 = f2splat(0.f), sh2 = f2splat(0.f), qh2 = f2splat(0.f);     // packed (even, odd column) partials
 #pragma unroll 4
     for (int nt = 0; nt < NT2; ++nt) {
       float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -266,11 +266,12 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
         frag_b(w2s, D::K2P, nt * 8, ks * 16, lane, bb);
         mma16816(d, a[ks], bb);
       }
-      const int c = nt * 8 + 2 * q;
-      const float e0 = d[0] + b2s[c], e1 = d[1] + b2s[c + 1], e2 = d[2] + b2s[c], e3 = d[3] + b2s[c + 1];
-      s_lo += e0 + e1; q_lo += e0 * e0 + e1 * e1;
-      s_hi += e2 + e3; q_hi += e2 * e2 + e3 * e3;
+      const float2 bv = *(const float2*)(b2s + nt * 8 + 2 * q);
+      const float2 e01 = f2add(make_float2(d[0], d[1]), bv), e23 = f2add(make_float2(d[2], d[3]), bv);
+      sl2 = f2add(sl2, e01); ql2 = f2fma(e01, e01, ql2);
+      sh2 = f2add(sh2, e23); qh2 = f2fma(e23, e23, qh2);
     }
+    const float s_lo = sl2.x + sl2.y, q_lo = ql2.x + ql2.y, s_hi = sh2.x + sh2.y, q_hi = qh2.x + qh2.y;
     if (p.per_row) {
       dc_row_stats(p.st2, b, p.g.Rr, r_lo, r_hi, v_lo, v_hi, s_lo, q_lo, s_hi, q_hi);
     } else {
@@ -392,13 +393,17 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
         eg[0] = fmaf((dg[0] + kg.x - m_lo) * rs_lo, ag.x, bg.x); eg[1] = fmaf((dg[1] + kg.y - m_lo) * rs_lo, ag.y, bg.y);
         eg[2] = fmaf((dg[2] + kg.x - m_hi) * rs_hi, ag.x, bg.x); eg[3] = fmaf((dg[3] + kg.y - m_hi) * rs_hi, ag.y, bg.y);
       } else {
-        ev[0] = fmaf(dv[0], av.x, bv.x); ev[1] = fmaf(dv[1], av.y, bv.y); ev[2] = fmaf(dv[2], av.x, bv.x); ev[3] = fmaf(dv[3], av.y, bv.y);
-        eg[0] = fmaf(dg[0], ag.x, bg.x); eg[1] = fmaf(dg[1], ag.y, bg.y); eg[2] = fmaf(dg[2], ag.x, bg.x); eg[3] = fmaf(dg[3], ag.y, bg.y);
+        const float2 v01 = f2fma(make_float2(dv[0], dv[1]), av, bv), v23 = f2fma(make_float2(dv[2], dv[3]), av, bv);
+        const float2 g01 = f2fma(make_float2(dg[0], dg[1]), ag, bg), g23 = f2fma(make_float2(dg[2], dg[3]), ag, bg);
+        ev[0] = v01.x; ev[1] = v01.y; ev[2] = v23.x; ev[3] = v23.y; eg[0] = g01.x; eg[1] = g01.y; eg[2] = g23.x; eg[3] = g23.y;
       }
-      uo[iv][0] = sc.x * (ev[0] * fmaf(0.5f, tanh_approx(eg[0]), 0.5f));
-      uo[iv][1] = sc.y * (ev[1] * fmaf(0.5f, tanh_approx(eg[1]), 0.5f));
-      uo[iv][2] = sc.x * (ev[2] * fmaf(0.5f, tanh_approx(eg[2]), 0.5f));
-      uo[iv][3] = sc.y * (ev[3] * fmaf(0.5f, tanh_approx(eg[3]), 0.5f));
+      {
+        const float2 h2 = f2splat(0.5f);
+        const float2 s01 = f2fma(h2, make_float2(tanh_approx(eg[0]), tanh_approx(eg[1])), h2);
+        const float2 s23 = f2fma(h2, make_float2(tanh_approx(eg[2]), tanh_approx(eg[3])), h2);
+        const float2 u01 = f2mul(sc, f2mul(make_float2(ev[0], ev[1]), s01)), u23 = f2mul(sc, f2mul(make_float2(ev[2], ev[3]), s23));
+        uo[iv][0] = u01.x; uo[iv][1] = u01.y; uo[iv][2] = u23.x; uo[iv][3] = u23.y;
+      }
     }
   }
   cp_async_wait<0>();

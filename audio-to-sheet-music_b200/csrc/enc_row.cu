@@ -269,7 +269,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
         ldsm_a(hb, D::K2P, mt * 16, 0, lane, a);
         const int r0 = mt * 16 + g;
         const bool v0 = r0 < Tn, v1 = r0 + 8 < Tn;
-        float sl = 0.f, ql = 0.f, sh = 0.f, qh = 0.f;
+        float2 sl = f2splat(0.f), ql = f2splat(0.f), sh = f2splat(0.f), qh = f2splat(0.f);      // packed (even, odd column) partials
 #pragma unroll 4
         for (int nt = 0; nt < 2 * D::AT; ++nt) {
           float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -277,12 +277,12 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
           frag_b(w2, D::K2P, nt * 8, 0, lane, bb);
           mma16816(d, a, bb);
           const float2 bv = *(const float2*)(b2 + nt * 8 + 2 * q);
-          const float e0 = d[0] + bv.x, e1 = d[1] + bv.y, e2 = d[2] + bv.x, e3 = d[3] + bv.y;
-          sl += e0 + e1; ql = fmaf(e0, e0, fmaf(e1, e1, ql));
-          sh += e2 + e3; qh = fmaf(e2, e2, fmaf(e3, e3, qh));
+          const float2 e01 = f2add(make_float2(d[0], d[1]), bv), e23 = f2add(make_float2(d[2], d[3]), bv);
+          sl = f2add(sl, e01); ql = f2fma(e01, e01, ql);
+          sh = f2add(sh, e23); qh = f2fma(e23, e23, qh);
         }
-        if (v0) { s2 += sl; q2 += ql; }
-        if (v1) { s2 += sh; q2 += qh; }
+        if (v0) { s2 += sl.x + sl.y; q2 += ql.x + ql.y; }
+        if (v1) { s2 += sh.x + sh.y; q2 += qh.x + qh.y; }
       }
       er_block_sum2(s2, q2, red, grp, tid);
       {
@@ -310,17 +310,20 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
           const float2 av = *(const float2*)(al + c), bv = *(const float2*)(be + c);
           const float2 ag = *(const float2*)(al + C + c), bg = *(const float2*)(be + C + c);
           const float2 sc = *(const float2*)(scl + c);
-          const float u0 = fmaf(da[0], av.x, bv.x) * fmaf(0.5f, er_tanh(fmaf(dg[0], ag.x, bg.x)), 0.5f);
-          const float u1 = fmaf(da[1], av.y, bv.y) * fmaf(0.5f, er_tanh(fmaf(dg[1], ag.y, bg.y)), 0.5f);
-          const float u2 = fmaf(da[2], av.x, bv.x) * fmaf(0.5f, er_tanh(fmaf(dg[2], ag.x, bg.x)), 0.5f);
-          const float u3 = fmaf(da[3], av.y, bv.y) * fmaf(0.5f, er_tanh(fmaf(dg[3], ag.y, bg.y)), 0.5f);
+          // packed fp32 pairs: (value * alpha + beta) * (0.5 + 0.5 tanh(gate * alpha' + beta')), then x + scale * u
+          const float2 h2 = f2splat(0.5f);
+          const float2 g01 = f2fma(make_float2(dg[0], dg[1]), ag, bg), g23 = f2fma(make_float2(dg[2], dg[3]), ag, bg);
+          const float2 s01 = f2fma(h2, make_float2(er_tanh(g01.x), er_tanh(g01.y)), h2);
+          const float2 s23 = f2fma(h2, make_float2(er_tanh(g23.x), er_tanh(g23.y)), h2);
+          const float2 u01 = f2mul(f2fma(make_float2(da[0], da[1]), av, bv), s01);
+          const float2 u23 = f2mul(f2fma(make_float2(da[2], da[3]), av, bv), s23);
           if (r0 < Tn) {
-            const float2 x0 = unpack_bf16x2(*(const uint32_t*)(xsi + r0 * D::XP + c));
-            sts_pair(xsi + r0 * D::XP + c, fmaf(sc.x, u0, x0.x), fmaf(sc.y, u1, x0.y));
+            const float2 o = f2fma(sc, u01, unpack_bf16x2(*(const uint32_t*)(xsi + r0 * D::XP + c)));
+            sts_pair(xsi + r0 * D::XP + c, o.x, o.y);
           }
           if (r0 + 8 < Tn) {
-            const float2 x1 = unpack_bf16x2(*(const uint32_t*)(xsi + (r0 + 8) * D::XP + c));
-            sts_pair(xsi + (r0 + 8) * D::XP + c, fmaf(sc.x, u2, x1.x), fmaf(sc.y, u3, x1.y));
+            const float2 o = f2fma(sc, u23, unpack_bf16x2(*(const uint32_t*)(xsi + (r0 + 8) * D::XP + c)));
+            sts_pair(xsi + (r0 + 8) * D::XP + c, o.x, o.y);
           }
         }
       }
@@ -347,10 +350,12 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
         const float2 rv = *(const float2*)(rbs + c), rg = *(const float2*)(rbs + C + c);
         float2 em = make_float2(0.f, 0.f);
         if (P.emb) em = *(const float2*)(embv + c);
-        const float o0 = fmaf(da[0] + rv.x, fmaf(0.5f, er_tanh(fmaf(dg[0], 0.5f, rg.x)), 0.5f), em.x);
-        const float o1 = fmaf(da[1] + rv.y, fmaf(0.5f, er_tanh(fmaf(dg[1], 0.5f, rg.y)), 0.5f), em.y);
-        const float o2 = fmaf(da[2] + rv.x, fmaf(0.5f, er_tanh(fmaf(dg[2], 0.5f, rg.x)), 0.5f), em.x);
-        const float o3 = fmaf(da[3] + rv.y, fmaf(0.5f, er_tanh(fmaf(dg[3], 0.5f, rg.y)), 0.5f), em.y);
+        const float2 h2 = f2splat(0.5f);
+        const float2 g01 = f2fma(make_float2(dg[0], dg[1]), h2, rg), g23 = f2fma(make_float2(dg[2], dg[3]), h2, rg);
+        const float2 s01 = f2fma(h2, make_float2(er_tanh(g01.x), er_tanh(g01.y)), h2);
+        const float2 s23 = f2fma(h2, make_float2(er_tanh(g23.x), er_tanh(g23.y)), h2);
+        const float2 p01 = f2fma(f2add(make_float2(da[0], da[1]), rv), s01, em), p23 = f2fma(f2add(make_float2(da[2], da[3]), rv), s23, em);
+        const float o0 = p01.x, o1 = p01.y, o2 = p23.x, o3 = p23.y;
         if (r0 < Tn) sts_pair(xsi + r0 * D::XP + c, o0, o1);            // rows >= Tn stay zero (conv halo of the next slab)
         if (r0 + 8 < Tn) sts_pair(xsi + (r0 + 8) * D::XP + c, o2, o3);
       }
