@@ -253,20 +253,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(stageA + stageB);
-      int it = 0;
+      // ring position as running counters: no integer divisions on the single-thread critical path (an `it % stages`,
+      // `it / stages`, `kb / kb_per_tap` per K block cost more latency than the MMAs of a narrow tile take to execute)
+      int s = 0; uint32_t ph = 0;
       for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x) {
         const int row0 = (t / p.n_tiles) * TC_BM;
         const int n0 = (t % p.n_tiles) * p.BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % nst;
-          const uint32_t ph = (uint32_t)(it / nst) & 1u;
+        int tap = 0, kin = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
-          const int tap = kb / p.kb_per_tap;
-          const int kin = (kb - tap * p.kb_per_tap) * TC_BK;
           const uint32_t fb = smem_u32(&full[s]);
           mbar_expect_tx(fb, bytes);
           tma_load_2d(smem_u32(sA + s * stageA), &tmA, fb, kin, row0 + p.tapRow[tap]);
           tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
+          kin += TC_BK;
+          if (kin >= p.Ktap) { kin = 0; ++tap; }
+          if (++s == nst) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -274,24 +276,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int it = 0, i = 0;
+      int i = 0, s = 0; uint32_t ph = 0;
+      const uint64_t da0 = make_sw128_desc(smem_u32(sA)), db0 = make_sw128_desc(smem_u32(sB));
+      const uint64_t dstepA = (uint64_t)(stageA >> 4), dstepB = (uint64_t)(stageB >> 4);     // descriptor address field is in 16-B units
       for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x, ++i) {
         const int buf = i & 1;
         mbar_wait(smem_u32(&tempty[buf]), ((uint32_t)(i >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % nst;
-          const uint32_t ph = (uint32_t)(it / nst) & 1u;
+        int kin = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&full[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_sw128_desc(smem_u32(sA + s * stageA));
-          const uint64_t db = make_sw128_desc(smem_u32(sB + s * stageB));
-          const int kin = (kb % p.kb_per_tap) * TC_BK;
+          const uint64_t da = da0 + (uint64_t)s * dstepA, db = db0 + (uint64_t)s * dstepB;
           const int nmma = (min(TC_BK, p.Ktap - kin) + 15) >> 4;     // columns past Ktap are zero-filled by TMA
           for (int k = 0; k < nmma; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
             umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           umma_commit(smem_u32(&empty[s]));
+          kin += TC_BK;
+          if (kin >= p.Ktap) kin = 0;
+          if (++s == nst) { s = 0; ph ^= 1u; }
         }
         umma_commit(smem_u32(&tfull[buf]));
       }
