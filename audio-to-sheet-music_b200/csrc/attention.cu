@@ -116,7 +116,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // the whole warp walks the loop converged (uniform-datapath descriptor arithmetic), one elected lane issues: the
+      // p_ready -> PV MMA issue latency of this role is part of the S -> softmax -> P -> PV chain that bounds the kernel
+      const bool issuer = elect_one();
       // S: M128 N64, A and B K-major.  PV: M128 N64, A K-major (P), B MN-major (V tile is [key][d], d contiguous)
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc_pv = idesc_s | (1u << 16);
@@ -126,10 +129,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_wait(smem_u32(&k_full[sk]), (uint32_t)((j / FA_NK) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dk = make_sw128_desc(smem_u32(sK + sk * FA_KB));
+        if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S + (uint32_t)((j & 1) * 64), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
-        umma_commit(smem_u32(&k_empty[sk]));
-        umma_commit(smem_u32(&s_full[j & 1]));
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_S + (uint32_t)((j & 1) * 64), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+          umma_commit(smem_u32(&k_empty[sk]));
+          umma_commit(smem_u32(&s_full[j & 1]));
+        }
+        __syncwarp();
       };
       mbar_wait(smem_u32(q_full), 0);
       issue_s(0);
@@ -141,11 +147,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tp = tmem_P + (uint32_t)((j & 1) * 32);
         const uint64_t dv = make_sw128_desc(smem_u32(sV + sv * FA_KB));
+        if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // A: 16 keys = 8 TMEM columns of P;  B: 16 key rows of V = 2048 B further
-          umma_bf16_ts(tmem_O, tp + (uint32_t)(8 * k), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j | k) ? 1u : 0u);
-        umma_commit(smem_u32(&v_empty[sv]));
-        umma_commit(smem_u32(&pv_done[j & 1]));
+          for (int k = 0; k < 4; ++k)   // A: 16 keys = 8 TMEM columns of P;  B: 16 key rows of V = 2048 B further
+            umma_bf16_ts(tmem_O, tp + (uint32_t)(8 * k), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j | k) ? 1u : 0u);
+          umma_commit(smem_u32(&v_empty[sv]));
+          umma_commit(smem_u32(&pv_done[j & 1]));
+        }
+        __syncwarp();
         if (j + 2 < nkv) issue_s(j + 2);      // S buffer (j & 1) was drained before p_ready(j)
       }
     }

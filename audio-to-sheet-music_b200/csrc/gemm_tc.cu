@@ -251,7 +251,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool issuer = elect_one();            // converged warp, one lane issues (see the MMA role)
       const uint32_t bytes = (uint32_t)(stageA + stageB);
       // ring position as running counters: no integer divisions on the single-thread critical path (an `it % stages`,
       // `it / stages`, `kb / kb_per_tap` per K block cost more latency than the MMAs of a narrow tile take to execute)
@@ -263,9 +264,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&full[s]);
-          mbar_expect_tx(fb, bytes);
-          tma_load_2d(smem_u32(sA + s * stageA), &tmA, fb, kin, row0 + p.tapRow[tap]);
-          tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
+          if (issuer) {
+            mbar_expect_tx(fb, bytes);
+            tma_load_2d(smem_u32(sA + s * stageA), &tmA, fb, kin, row0 + p.tapRow[tap]);
+            tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
+          }
+          __syncwarp();
           kin += TC_BK;
           if (kin >= p.Ktap) { kin = 0; ++tap; }
           if (++s == nst) { s = 0; ph ^= 1u; }
@@ -273,7 +277,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // the whole warp walks the loop (converged: uniform-datapath address arithmetic), one elected lane issues
+      const bool issuer = elect_one();
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int i = 0, s = 0; uint32_t ph = 0;
@@ -290,14 +296,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = da0 + (uint64_t)s * dstepA, db = db0 + (uint64_t)s * dstepB;
           const int nmma = (min(TC_BK, p.Ktap - kin) + 15) >> 4;     // columns past Ktap are zero-filled by TMA
-          for (int k = 0; k < nmma; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
-            umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(smem_u32(&empty[s]));
+          if (issuer) {
+            for (int k = 0; k < nmma; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
+              umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(smem_u32(&empty[s]));
+          }
+          __syncwarp();
           kin += TC_BK;
           if (kin >= p.Ktap) kin = 0;
           if (++s == nst) { s = 0; ph ^= 1u; }
         }
-        umma_commit(smem_u32(&tfull[buf]));
+        if (issuer) umma_commit(smem_u32(&tfull[buf]));
+        __syncwarp();
       }
     }
   } else {
