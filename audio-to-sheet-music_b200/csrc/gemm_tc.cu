@@ -56,9 +56,21 @@ struct TcParams {
   const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;
   int convt_cout;
   int skip_lo, skip_hi;    // output columns [skip_lo, skip_hi) are computed (statistics) but not stored
+  uint32_t fdRpA[2], fdG2p[2], fdNt[2];   // (multiplier, shift) of the division-free x / RpA, x / G2p, x / n_tiles (x < 2^31)
   int wide;                // 32-byte row accesses allowed (row pitch and base 32-byte aligned, skip range in 16-column units)
 };
 
+// x / d for 0 <= x < 2^31 from a host-computed (multiplier, shift): 3 instructions instead of the ~35-instruction
+// (~100-cycle dependent chain) integer division, four of which sat on the per-tile critical path of the epilogue
+__device__ __forceinline__ int fast_div(int x, const uint32_t (&fd)[2]) {
+  return (int)((__umulhi((uint32_t)x, fd[0]) + (uint32_t)x) >> fd[1]);
+}
+static void fast_div_init(uint32_t d, uint32_t (&fd)[2]) {
+  uint32_t shr = 0;
+  while ((1u << shr) < d) ++shr;
+  fd[0] = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << shr) - d)) / d + 1);
+  fd[1] = shr;
+}
 __device__ __forceinline__ void store8(bf16* dst, const float* v) {
   uint32_t pk[4];
 #pragma unroll
@@ -258,8 +270,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // `it / stages`, `kb / kb_per_tap` per K block cost more latency than the MMAs of a narrow tile take to execute)
       int s = 0; uint32_t ph = 0;
       for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x) {
-        const int row0 = (t / p.n_tiles) * TC_BM;
-        const int n0 = (t % p.n_tiles) * p.BN;
+        const int mt_ = fast_div(t, p.fdNt);
+        const int row0 = mt_ * TC_BM;
+        const int n0 = (t - mt_ * p.n_tiles) * p.BN;
         int tap = 0, kin = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
@@ -345,14 +358,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int i = 0;
     for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
-      const int row0 = (t / p.n_tiles) * TC_BM;
-      const int n0 = (t % p.n_tiles) * p.BN;
+      const int mt_ = fast_div(t, p.fdNt);
+      const int row0 = mt_ * TC_BM;
+      const int n0 = (t - mt_ * p.n_tiles) * p.BN;
       const float* sv = svec + buf * 4 * TC_VEC;
       EpiRow er;
       const int rho = row0 + row;                   // Mflat < 2^31: 32-bit row decode
-      const int q2 = rho / p.RpA;
+      const int q2 = fast_div(rho, p.fdRpA);
       const int fp = rho - q2 * p.RpA;
-      er.b = q2 / p.G2p;
+      er.b = fast_div(q2, p.fdG2p);
       const int tp = q2 - er.b * p.G2p;
       er.valid = rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2;
       er.orow = ((long)er.b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
@@ -365,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // tile i's vectors (stashed during tile i-1) become visible; every warp is done reading the other buffer
       asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
       const int tn = t + (int)gridDim.x;
-      if (tn < n_total_tiles) fetch_vecs((tn % p.n_tiles) * p.BN);
+      if (tn < n_total_tiles) fetch_vecs((tn - fast_div(tn, p.fdNt) * p.n_tiles) * p.BN);
       er.edge_lo = er.m == 0; er.edge_hi = er.m == p.vhi - p.vlo - 1;
       float ssum = 0.f, ssq = 0.f;
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
@@ -716,6 +730,7 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
            (f.skip_hi % 16 == 0);
   p.m_tiles = (int)((f.Mflat + TC_BM - 1) / TC_BM);
   p.n_tiles = (f.N + p.BN - 1) / p.BN;
+  fast_div_init((uint32_t)p.RpA, p.fdRpA); fast_div_init((uint32_t)p.G2p, p.fdG2p); fast_div_init((uint32_t)p.n_tiles, p.fdNt);
   CUtensorMap tmA, tmB;
   // Two taps on ADJACENT rows of a dense activation buffer (row pitch == channels: the transposed-conv layers) are one
   // K = 2 * C view with overlapping rows [x[r], x[r+1]] (row stride C): no half-empty K blocks when C is not a multiple of 64
