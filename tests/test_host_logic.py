@@ -119,3 +119,21 @@ def test_fade_inference_identity_model_reconstructs_interior():
     x = torch.randn(2, T)
     y = ola.fade_inference(lambda c: c, x, 1.0, 0.1)
     assert (y - x).abs().max() < 1e-5
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the reference algorithm on the host cores, tier contract 4): stdout is exactly one JSON
+    line carrying the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--seconds", "12"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "x realtime" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
