@@ -513,50 +513,62 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool issuer = elect_one();            // converged warp, one lane issues; ring position as running counters
       const uint32_t bytes = (uint32_t)(2 * (stageA + stageB));      // both CTAs' shares land on the leader's barrier
-      int it = 0;
+      int s = 0; uint32_t ph = 0;
       for (int u = cid; u < n_pair_tiles; u += ncl) {
-        const int row0 = (2 * (u / p.n_tiles) + (int)rank) * TC_BM;
-        const int nb0 = (u % p.n_tiles) * p.BN + (int)rank * (p.BN / 2);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % nst;
-          const uint32_t ph = (uint32_t)(it / nst) & 1u;
+        const int mp_ = fast_div(u, p.fdNt);
+        const int row0 = (2 * mp_ + (int)rank) * TC_BM;
+        const int nb0 = (u - mp_ * p.n_tiles) * p.BN + (int)rank * (p.BN / 2);
+        int tap = 0, kin = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
-          const int tap = kb / p.kb_per_tap;
-          const int kin = (kb - tap * p.kb_per_tap) * TC_BK;
           const uint32_t fb = smem_u32(&full[s]);
-          if (leader) mbar_expect_tx(fb, bytes);
-          const uint32_t fbl = fb & 0xFEFFFFFFu;                       // the leader CTA's copy of this barrier
-          tma_load_2d_pair(smem_u32(sA + s * stageA), &tmA, fbl, kin, row0 + p.tapRow[tap]);
-          tma_load_2d_pair(smem_u32(sB + s * stageB), &tmB, fbl, tap * p.Ktap + kin, nb0);
+          if (issuer) {
+            if (leader) mbar_expect_tx(fb, bytes);
+            const uint32_t fbl = fb & 0xFEFFFFFFu;                     // the leader CTA's copy of this barrier
+            tma_load_2d_pair(smem_u32(sA + s * stageA), &tmA, fbl, kin, row0 + p.tapRow[tap]);
+            tma_load_2d_pair(smem_u32(sB + s * stageB), &tmB, fbl, tap * p.Ktap + kin, nb0);
+          }
+          __syncwarp();
+          kin += TC_BK;
+          if (kin >= p.Ktap) { kin = 0; ++tap; }
+          if (++s == nst) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
+      const bool issuer = elect_one();
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 across the pair)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      int it = 0, i = 0;
+      int i = 0, s = 0; uint32_t ph = 0;
+      const uint64_t da0 = make_sw128_desc(smem_u32(sA)), db0 = make_sw128_desc(smem_u32(sB));
+      const uint64_t dstepA = (uint64_t)(stageA >> 4), dstepB = (uint64_t)(stageB >> 4);
       for (int u = cid; u < n_pair_tiles; u += ncl, ++i) {
         const int buf = i & 1;
         mbar_wait(smem_u32(&tempty[buf]), ((uint32_t)(i >> 1) & 1u) ^ 1u);     // both CTAs' epilogues drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % nst;
-          const uint32_t ph = (uint32_t)(it / nst) & 1u;
+        int kin = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&full[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_sw128_desc(smem_u32(sA + s * stageA));
-          const uint64_t db = make_sw128_desc(smem_u32(sB + s * stageB));
-          const int kin = (kb % p.kb_per_tap) * TC_BK;
+          const uint64_t da = da0 + (uint64_t)s * dstepA, db = db0 + (uint64_t)s * dstepB;
           const int nmma = (min(TC_BK, p.Ktap - kin) + 15) >> 4;
-          for (int k = 0; k < nmma; ++k)
-            umma_bf16_pair(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-          umma_commit_pair(smem_u32(&empty[s]));
+          if (issuer) {
+            for (int k = 0; k < nmma; ++k)
+              umma_bf16_pair(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_commit_pair(smem_u32(&empty[s]));
+          }
+          __syncwarp();
+          kin += TC_BK;
+          if (kin >= p.Ktap) kin = 0;
+          if (++s == nst) { s = 0; ph ^= 1u; }
         }
-        umma_commit_pair(smem_u32(&tfull[buf]));
+        if (issuer) umma_commit_pair(smem_u32(&tfull[buf]));
+        __syncwarp();
       }
     }
   } else {
@@ -565,27 +577,39 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row = q * 32 + lane;
     const int etid = threadIdx.x - 64;
     const int Nout_ = (EF & EF_GLU) ? p.N / 2 : p.N;
+    // per-tile column vectors staged one tile ahead (as in gemm_tc_kernel)
+    float vr0 = 0.f, vr1 = 0.f, vr2 = 0.f, vr3 = 0.f;
+    auto fetch_vecs = [&](int n0) {
+      if (etid < p.BN) {
+        const int n = min(n0 + etid, p.N - 1);
+        vr0 = p.bias ? __ldg(p.bias + n) : 0.f;
+        if (EF & EF_GN) { vr1 = __ldg(p.gn_w + n); vr2 = __ldg(p.gn_b + n); }
+        if ((EF & EF_POST) && p.colscale) {
+          const int no = (EF & EF_GLU) ? (n0 >> 1) + etid : n0 + etid;
+          vr3 = __ldg(p.colscale + min(no, Nout_ - 1));
+        }
+      }
+    };
+    auto stash_vecs = [&](float* sv) {
+      if (etid < p.BN) {
+        sv[etid] = vr0;
+        if (EF & EF_GN) { sv[TC_VEC + etid] = vr1; sv[2 * TC_VEC + etid] = vr2; }
+        if ((EF & EF_POST) && p.colscale) sv[3 * TC_VEC + etid] = vr3;
+      }
+    };
+    if (cid < n_pair_tiles) { fetch_vecs((cid - fast_div(cid, p.fdNt) * p.n_tiles) * p.BN); stash_vecs(svec); }
     int i = 0;
     for (int u = cid; u < n_pair_tiles; u += ncl, ++i) {
       const int buf = i & 1;
-      const int row0 = (2 * (u / p.n_tiles) + (int)rank) * TC_BM;
-      const int n0 = (u % p.n_tiles) * p.BN;
-      float* sv = svec + buf * 4 * TC_VEC;
-      for (int c = etid; c < p.BN; c += EPI_WARPS * 32) {
-        const int n = min(n0 + c, p.N - 1);
-        sv[c] = p.bias ? __ldg(p.bias + n) : 0.f;
-        if (EF & EF_GN) { sv[TC_VEC + c] = __ldg(p.gn_w + n); sv[2 * TC_VEC + c] = __ldg(p.gn_b + n); }
-        if ((EF & EF_POST) && p.colscale) {
-          const int no = (EF & EF_GLU) ? (n0 >> 1) + c : n0 + c;
-          sv[3 * TC_VEC + c] = __ldg(p.colscale + min(no, Nout_ - 1));
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+      const int mp_ = fast_div(u, p.fdNt);
+      const int row0 = (2 * mp_ + (int)rank) * TC_BM;
+      const int n0 = (u - mp_ * p.n_tiles) * p.BN;
+      const float* sv = svec + buf * 4 * TC_VEC;
       EpiRow er;
-      const long rho = (long)row0 + row;
-      const int q2 = (int)(rho / p.RpA);
-      const int fp = (int)(rho - (long)q2 * p.RpA);
-      er.b = q2 / p.G2p;
+      const int rho = row0 + row;
+      const int q2 = fast_div(rho, p.fdRpA);
+      const int fp = rho - q2 * p.RpA;
+      er.b = fast_div(q2, p.fdG2p);
       const int tp = q2 - er.b * p.G2p;
       er.valid = rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2;
       er.orow = ((long)er.b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
@@ -595,6 +619,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long gi = p.gn_mode == STAT_PER_G1_M ? (long)er.b * p.statR + er.m : (long)er.b;
         er.gmean = p.gn_mr[2 * gi]; er.grstd = p.gn_mr[2 * gi + 1];
       }
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+      const int un = u + ncl;
+      if (un < n_pair_tiles) fetch_vecs((un - fast_div(un, p.fdNt) * p.n_tiles) * p.BN);
       er.edge_lo = er.m == 0; er.edge_hi = er.m == p.vhi - p.vlo - 1;
       float ssum = 0.f, ssq = 0.f;
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
@@ -613,6 +640,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[buf])) : "memory");
         else mbar_arrive_leader(smem_u32(&tempty[buf]));
       }
+      if (un < n_pair_tiles) stash_vecs(svec + (buf ^ 1) * 4 * TC_VEC);
       if (EF & EF_STATS) {      // per-segment sums only (the pair kernel is used for the transformer linears)
         const int key = er.valid ? er.b : -1;
         const int key0 = __reduce_max_sync(0xffffffffu, key);
@@ -676,8 +704,10 @@ bool tensor_map_api_available() { return get_encode() != nullptr; }
 
 static int g_tc_bn_cap = 256;
 static bool g_tc_two_ctas = true;
-static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide tiles: env ATHTD_TC_PAIR=1 (default off: measured
-                                // 5-8 % slower than the single-CTA kernel on the K = 512 / 2048 transformer shapes, profiles/r01_summary.md)
+static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide tiles: env ATHTD_TC_PAIR = 1 every eligible launch,
+                                // 2 only K >= 1536, unset / 0 never (default).  Isolated it reaches 1427 vs 1290 TFLOP/s at K = 2048
+                                // and 959 vs 1026 at K = 512; inside the forward (residual + statistics epilogue, cold operands) the
+                                // K = 2048 launches measure the same 115-117 us either way (profiles/r01_summary.md).
 void tc_set_bn_cap(int cap) { g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); }
 
 int tc_pick_bn(int N) {
@@ -755,7 +785,7 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   dim3 grid((unsigned)std::min<long>(tiles, (long)num_sms() * ctas_per_sm));
   if (g_tc_pair < 0) { const char* e = getenv("ATHTD_TC_PAIR"); g_tc_pair = e ? atoi(e) : 0; }
   // CTA pairs for the 256-wide tiles of long-M problems (transformer linears): 256 x 256 tile per cluster
-  const bool pair = g_tc_pair > 0 && p.BN == 256 && f.N % 256 == 0 && p.m_tiles >= 2 * num_sms() && f.stat_mode != STAT_PER_G1_M &&
+  const bool pair = (g_tc_pair == 1 || (g_tc_pair == 2 && p.ntaps * p.kb_per_tap >= 24)) && p.BN == 256 && f.N % 256 == 0 && p.m_tiles >= 2 * num_sms() && f.stat_mode != STAT_PER_G1_M &&
                     (num_sms() % 2 == 0);
   CUtensorMap tmBh;
   int pair_stages = 0;
