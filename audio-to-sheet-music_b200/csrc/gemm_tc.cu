@@ -13,12 +13,15 @@
 // share an A tile run together and it is fetched from HBM once):
 //   warp 0      : TMA producer  - cp.async.bulk.tensor.2d (SWIZZLE_128B boxes 64 x 128 / 64 x BN) into a deep smem ring
 //                 that runs ahead ACROSS tiles (hides the ~1 us load latency of the short-K layers)
-//   warp 1      : TMEM allocator + MMA issuer - one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//                 (M=128, N=BN, K=16) into one of TWO TMEM accumulators; tcgen05.commit frees the smem stage /
-//                 hands the accumulator to the epilogue
-//   warps 2..9  : epilogue (2 warps per TMEM lane quarter, interleaved 32-column chunks) - tcgen05.ld, fused bias /
-//                 GroupNorm apply / GELU / GLU / LayerScale / residual / frequency-embedding / GroupNorm partial
-//                 sums, 16-byte stores; overlaps the next tile's main loop through the second accumulator
+//   warp 1      : TMEM allocator + MMA issuer - tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) into one of TWO TMEM
+//                 accumulators; tcgen05.commit frees the smem stage / hands the accumulator to the epilogue
+//   warps 2..17 : epilogue (4 warps per TMEM lane quarter, interleaved 32-column chunks; 2 per quarter in the
+//                 two-CTAs-per-SM variant) - tcgen05.ld, fused bias / GroupNorm apply / GELU / GLU / LayerScale / residual /
+//                 frequency-embedding / GroupNorm partial sums in packed fp32 pairs, 32-byte stores; overlaps the next tile's
+//                 main loop through the second accumulator
+// Both single-thread roles keep their warp converged around an elect.sync issuer and track the ring position with running
+// counters: a runtime-divisor `%` / `/` per K block or a divergent `lane == 0` branch (descriptors through R2UR moves) made
+// the issue thread, not the tensor pipe, the bottleneck of the long-K layers.
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
