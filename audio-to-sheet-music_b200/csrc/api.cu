@@ -96,10 +96,18 @@ int athtd_forward(void* plan, const float* wav_dev, const float* emb_dev, float*
 int athtd_encode(void* plan, const float* wav_dev, void* stream) {
   GUARD(((PlanBase*)plan)->encode_only(wav_dev, (cudaStream_t)stream), "athtd_encode");
 }
+int athtd_encode_normalized(void* plan, const float* x_cac_dev, const float* xt_dev, void* stream) {
+  if (!x_cac_dev || !xt_dev) return fail("athtd_encode_normalized: null input");
+  GUARD(((PlanBase*)plan)->encode_only(xt_dev, (cudaStream_t)stream, x_cac_dev), "athtd_encode_normalized");
+}
 int athtd_decode(void* plan, const float* emb_dev, float* out_dev, void* stream) {
   GUARD(((PlanBase*)plan)->decode_only(emb_dev, out_dev, (cudaStream_t)stream), "athtd_decode");
 }
 int athtd_plan_launches(void* plan) { return ((PlanBase*)plan)->launches(); }
+int athtd_plan_set_batch(void* plan, int B) {
+  if (((PlanBase*)plan)->set_batch(B)) return fail("athtd_plan_set_batch: B must be in [1, batch capacity of the plan]");
+  return 0;
+}
 int athtd_plan_set_profile(void* plan, int on) { ((PlanBase*)plan)->set_profile(on != 0); return 0; }
 int athtd_plan_get_profile(void* plan, double* gemm_ms, double* gemm_gflop, int* gemm_launches) {
   ((PlanBase*)plan)->get_profile(gemm_ms, gemm_gflop, gemm_launches);
@@ -169,6 +177,8 @@ int athtd_istft(const float* Z_dev, int B, int L, float* frames_dev, float* out_
 
 int athtd_gather_chunks(const float* track_dev, long T, int C, const long* starts_dev, int n_chunks, int chunk_len,
                         float* segs_dev, void* stream) {
+  if (n_chunks < 0 || chunk_len < 1 || C < 1) return fail("athtd_gather_chunks: need n_chunks >= 0, chunk_len >= 1, C >= 1");
+  if (n_chunks == 0) return 0;      // empty span (more ranks than chunks)
   launch_gather_chunks(track_dev, T, C, starts_dev, n_chunks, chunk_len, segs_dev, (cudaStream_t)stream);
   return check_cuda("athtd_gather_chunks");
 }
@@ -178,6 +188,7 @@ int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int c
                     const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
                     long t_begin, long t_end, void* stream) {
   if (C < 1 || C > 2) return fail("athtd_chunk_ola: C must be 1 or 2");
+  if (t_end <= t_begin) return 0;
   launch_chunk_ola(seg_out_dev, seg_stride, k_base, chunk_len, starts_dev, actual_len_dev, fade_len_dev, flags_dev, n_chunks,
                    stride, ramp_up_dev, ramp_down_dev, ramp_off_dev, out_dev, C, t_begin, t_end, 1, (cudaStream_t)stream);
   return check_cuda("athtd_chunk_ola");
@@ -188,6 +199,7 @@ int athtd_chunk_fade_add(const float* seg_out_dev, long seg_stride, int k_base, 
                          const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
                          long t_begin, long t_end, void* stream) {
   if (C < 1 || C > 2) return fail("athtd_chunk_fade_add: C must be 1 or 2");
+  if (t_end <= t_begin) return 0;
   launch_chunk_ola(seg_out_dev, seg_stride, k_base, chunk_len, starts_dev, actual_len_dev, fade_len_dev, flags_dev, n_chunks,
                    stride, ramp_up_dev, ramp_down_dev, ramp_off_dev, out_dev, C, t_begin, t_end, 0, (cudaStream_t)stream);
   return check_cuda("athtd_chunk_fade_add");

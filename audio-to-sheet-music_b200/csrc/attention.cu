@@ -301,18 +301,21 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
   FaParams p;
   p.Sq = Sq; p.Sk = Sk; p.scale_log2 = 0.125f * 1.4426950408889634f; p.O = o; p.ldo = ldo;
   const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 256;
+  static PerDeviceOnce attr;
+  const bool first = attr.first();
+  if (first) cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((Sq + 127) / 128, 8, B);
+#ifdef ATHTD_ABLATION      // timing-only variants (results are WRONG by construction): measurement builds only
   static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("ATHTD_FA_MODE");
-    mode = e ? atoi(e) : 0;
-    cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (mode < 0) { const char* e = getenv("ATHTD_FA_MODE"); mode = e ? atoi(e) : 0; }
+  if (first) {
     cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(flash_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  dim3 grid((Sq + 127) / 128, 8, B);
-  if (mode == 1) flash_attn_kernel<1><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
-  else if (mode == 2) flash_attn_kernel<2><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
-  else flash_attn_kernel<0><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
+  if (mode == 1) { flash_attn_kernel<1><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); return 0; }
+  if (mode == 2) { flash_attn_kernel<2><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); return 0; }
+#endif
+  flash_attn_kernel<0><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
   return 0;
 }
 

@@ -129,6 +129,31 @@ template <int VEC> struct VecIO<bf16, VEC> {
   }
 };
 
+// One-time-per-device launch setup (cudaFuncSetAttribute is per device / context, and an Engine may live on any GPU of the
+// process) and the SM count of the current device.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+inline int device_sm_count() {
+  static int n[64] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  d &= 63;
+  if (n[d] == 0) {
+    cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+    if (n[d] <= 0) n[d] = 148;
+  }
+  return n[d];
+}
+
 // A padded channels-last row space.  G = B*G2 interior groups (G2 groups per segment: frames on the
 // frequency branch, 1 on the time branch); every segment stores G2p >= G2 groups (gpf zero groups in front) and
 // every group stores Rp >= R rows (pf zero rows in front).  Pads are written once (zero) and never again, which

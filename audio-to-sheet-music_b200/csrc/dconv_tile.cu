@@ -473,20 +473,19 @@ static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
   const size_t smC = (size_t)TMC * (CS + 8) * 2 + (size_t)2 * CS * D::K2P * 2 + (size_t)(7 * CS + 64) * 4 + 16 +
                      (rewrite ? (size_t)(2 * C + TMC) * (CS + 8) * 2 : 0);
   if (smA > 227 * 1024 || smC > 227 * 1024) return 1;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     cudaFuncSetAttribute(dconv_a_kernel<C, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(dconv_b_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if constexpr (CS == C)
       cudaFuncSetAttribute(dconv_c_kernel<C, CS, TMC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr = true;
   }
   const int tiles = (p.g.rows + TM - 1) / TM;
   const int tiles_c = (p.g.rows + TMC - 1) / TMC;
   const int tiles_b = (p.g.rows + 127) / 128;
-  const int gb = std::min(tiles_b, std::max(1, (148 * 16 + B - 1) / B));
+  const int gb = std::min(tiles_b, std::max(1, (device_sm_count() * 16 + B - 1) / B));
   dconv_a_kernel<C, TM><<<dim3(tiles, B), 256, smA, st>>>(p);
   dconv_b_kernel<C><<<dim3(gb, B), 256, smB, st>>>(p);
   if (p.per_row) dconv_c_kernel<C, CS, TMC, true, false><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);

@@ -73,6 +73,14 @@ void launch_finalize_meanstd(const double* stats, double n, float* out, int B, c
   finalize_meanstd_kernel<<<(B + 127) / 128, 128, 0, st>>>(stats, n, out, B);
 }
 
+__global__ void set_meanstd_kernel(float* __restrict__ out, int B, float mean, float stdv) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { out[2 * b] = mean; out[2 * b + 1] = stdv; }
+}
+void launch_set_meanstd(float* out, int B, float mean, float stdv, cudaStream_t st) {
+  set_meanstd_kernel<<<(B + 127) / 128, 128, 0, st>>>(out, B, mean, stdv);
+}
+
 // wav [B,2,L] fp32 -> normalised channels-last padded [B, Rp, 2]
 template <typename T>
 __global__ void pack_wav_kernel(const float* __restrict__ wav, const float* __restrict__ meanstd, T* __restrict__ out,

@@ -385,16 +385,7 @@ bool enc_row_supported(int C, int Tn, bool fuse_conv) {
   return false;
 }
 
-static int er_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int er_num_sms() { return device_sm_count(); }
 
 void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, RowSpace ys, const EncRowParams& P, bool fuse_conv,
                     cudaStream_t st) {

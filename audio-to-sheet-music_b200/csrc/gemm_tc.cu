@@ -733,16 +733,7 @@ bool tc_flat_supported(const TcFlat& f) {
   return get_encode() != nullptr;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms() { return device_sm_count(); }
 
 int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   TcParams p;
@@ -786,7 +777,11 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
   const long tiles = (long)p.m_tiles * p.n_tiles;
   dim3 grid((unsigned)std::min<long>(tiles, (long)num_sms() * ctas_per_sm));
+#ifdef ATHTD_ABLATION      // measurement builds only (python -m ... build.py --ablation): never in the shipped library
   if (g_tc_pair < 0) { const char* e = getenv("ATHTD_TC_PAIR"); g_tc_pair = e ? atoi(e) : 0; }
+#else
+  if (g_tc_pair < 0) g_tc_pair = 0;
+#endif
   // CTA pairs for the 256-wide tiles of long-M problems (transformer linears): 256 x 256 tile per cluster
   const bool pair = (g_tc_pair == 1 || (g_tc_pair == 2 && p.ntaps * p.kb_per_tap >= 24)) && p.BN == 256 && f.N % 256 == 0 && p.m_tiles >= 2 * num_sms() && f.stat_mode != STAT_PER_G1_M &&
                     (num_sms() % 2 == 0);
@@ -807,12 +802,11 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   if (f.stat_mode != STAT_NONE) ef |= EF_STATS;
 #define TC_LAUNCH(E)                                                                                                      \
   case E: {                                                                                                               \
-    static bool attr_set = false;                                                                                         \
-    if (!attr_set) {                                                                                                      \
+    static PerDeviceOnce attr_set;                                                                                        \
+    if (attr_set.first()) {                                                                                               \
       cudaFuncSetAttribute(gemm_tc_kernel<E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                \
       cudaFuncSetAttribute(gemm_tc_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);                \
       cudaFuncSetAttribute(gemm_tc_pair_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);              \
-      attr_set = true;                                                                                                    \
     }                                                                                                                     \
     if (pair) {                                                                                                           \
       TcParams pp = p;                                                                                                    \

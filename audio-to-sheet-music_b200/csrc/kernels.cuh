@@ -10,6 +10,7 @@ namespace athtd {
 void launch_sum_sumsq(const float* x, int B, long n_per_sample, double* stats, cudaStream_t st);
 void launch_finalize_gn(const double* stats, double count, float* mr, long n, int nslot, cudaStream_t st);
 void launch_finalize_meanstd(const double* stats, double n, float* out, int B, cudaStream_t st);
+void launch_set_meanstd(float* out, int B, float mean, float stdv, cudaStream_t st);
 template <typename T> void launch_pack_wav(const float* wav, const float* meanstd, T* out, RowSpace rs, int L, cudaStream_t st);
 template <typename T> void launch_pack_spec(const float* Z, const float* meanstd, T* out, RowSpace rs, int Tf, cudaStream_t st);
 template <typename T> void launch_gn_gelu(T* h, RowSpace rs, int G2, int per_row, const float* mr, const float* w,

@@ -62,6 +62,34 @@ static RowSpace make_space(int B, int G2, int R, int C, bool padded) {
   return r;
 }
 
+// Row spaces for a batch of B segments.  Segment b of every buffer occupies [b, b + 1) * g1_stride(), whatever B is, so a plan
+// laid out for `cap` segments runs any batch B <= cap in place (pads stay where they are).
+template <typename T>
+void PlanT<T>::spaces(int B) {
+  const Shapes& s = sh;
+  const int Tf = s.Tf;
+  xf0_rs = make_space(B, Tf, 2048, 4, true);
+  xt0_rs = make_space(B, 1, s.L, 2, true);
+  for (int i = 0; i < 4; ++i) {
+    yf_rs[i] = make_space(B, Tf, s.Fr[i + 1], kCh[i], true);
+    yt_rs[i] = make_space(B, 1, s.Lt[i + 1], kCh[i], true);
+  }
+  xc_rs = make_space(B, Tf, 8, 384, true);
+  xtc_rs = make_space(B, 1, s.St, 384, true);
+  for (int i = 0; i < 4; ++i) {
+    df_rs[i] = make_space(B, Tf, Tf, kDecCh[i + 1], true);
+    dt_rs[i] = make_space(B, 1, s.Lt[3 - i], kDecCh[i + 1], true);
+  }
+}
+
+template <typename T>
+int PlanT<T>::set_batch(int B) {
+  if (B < 1 || B > cap) return 1;
+  sh.B = B;
+  spaces(B);
+  return 0;
+}
+
 template <typename T>
 void PlanT<T>::layout(char* base) {
   size_t off = 0;
@@ -72,28 +100,21 @@ void PlanT<T>::layout(char* base) {
     return p;
   };
   const Shapes& s = sh;
-  const int B = s.B, Tf = s.Tf;
+  const int B = cap, Tf = s.Tf;      // every size below is for the batch CAPACITY
+  spaces(cap);
   // ---- zero-initialised region (pads must stay zero; interior is always overwritten)
-  xf0_rs = make_space(B, Tf, 2048, 4, true);
   xf0 = (T*)take(xf0_rs.elems() * sizeof(T));
-  xt0_rs = make_space(B, 1, s.L, 2, true);
   xt0 = (T*)take(xt0_rs.elems() * sizeof(T));
   for (int i = 0; i < 4; ++i) {
-    yf_rs[i] = make_space(B, Tf, s.Fr[i + 1], kCh[i], true);
     yf[i] = (T*)take(yf_rs[i].elems() * sizeof(T));
     ef[i] = (T*)take(yf_rs[i].elems() * sizeof(T));
-    yt_rs[i] = make_space(B, 1, s.Lt[i + 1], kCh[i], true);
     yt[i] = (T*)take(yt_rs[i].elems() * sizeof(T));
     et[i] = (T*)take(yt_rs[i].elems() * sizeof(T));
   }
-  xc_rs = make_space(B, Tf, 8, 384, true);
   xc = (T*)take(xc_rs.elems() * sizeof(T));
-  xtc_rs = make_space(B, 1, s.St, 384, true);
   xtc = (T*)take(xtc_rs.elems() * sizeof(T));
   for (int i = 0; i < 4; ++i) {
-    df_rs[i] = make_space(B, Tf, Tf, kDecCh[i + 1], true);
     df[i] = (T*)take(df_rs[i].elems() * sizeof(T));
-    dt_rs[i] = make_space(B, 1, s.Lt[3 - i], kDecCh[i + 1], true);
     dt[i] = (T*)take(dt_rs[i].elems() * sizeof(T));
   }
   zero_bytes = align_up(off, 256);
@@ -109,6 +130,10 @@ void PlanT<T>::layout(char* base) {
         st_dt[i][d][k] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS);
       }
   for (int l = 0; l < 5; ++l) { st_xf[l][0] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS); st_xf[l][1] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS); }
+  // decoder GroupNorm accumulators: LAST in the statistics block -- encode() clears [stats_begin, dec_stats_begin),
+  // decode() clears [dec_stats_begin, stats end) so that one encode can be followed by any number of decodes
+  off = align_up(off, 256);
+  dec_stats_begin = off;
   st_dec = (double*)take(sizeof(double) * 2 * B * 6 * s.P * STAT_SLOTS);
   stats_bytes = align_up(off, 256) - stats_begin;
   off = stats_begin + stats_bytes;
@@ -149,12 +174,13 @@ void PlanT<T>::layout(char* base) {
   ubuf = (T*)take(umax * sizeof(T));
   frames = (float*)take(sizeof(float) * (size_t)B * 2 * Tf * 4096);
   total_bytes = align_up(off, 256);
+  spaces(sh.B);
 }
 
 template <typename T>
 PlanT<T>::PlanT(int B, int L, int P, const ParamTable* pt_, const PackLayout* pl_, const float* params_, const void* packed_,
                 void* workspace, const PlanConsts& c)
-    : sh(B, L, P), pt(pt_), pl(pl_), params(params_), packed((const char*)packed_), consts(c) {
+    : sh(B, L, P), pt(pt_), pl(pl_), params(params_), packed((const char*)packed_), consts(c), cap(B) {
   base_ = (char*)workspace;
   layout((char*)workspace);
 }
@@ -584,16 +610,25 @@ void PlanT<T>::cross_transformer(cudaStream_t st) {
 }
 
 template <typename T>
-void PlanT<T>::encode(const float* wav, cudaStream_t st) {
+void PlanT<T>::encode(const float* wav, cudaStream_t st, const float* xnorm) {
   const Shapes& s = sh;
   const int B = s.B, Tf = s.Tf;
   const RowSpace none{};
-  cudaMemsetAsync((char*)ws_base() + stats_begin, 0, stats_bytes, st);
+  cudaMemsetAsync((char*)ws_base() + stats_begin, 0, dec_stats_begin - stats_begin, st);
   // spectral front end + input normalisation (ATHTDemucs_v2.py:261-275)
-  launch_stft_cac(wav, B, s.L, Tf, Z, st_spec, consts.tw, consts.win, st); ++n_launches;
-  launch_sum_sumsq(wav, B, 2L * s.L, st_wav, st); ++n_launches;
-  launch_finalize_meanstd(st_spec, 4.0 * 2048.0 * Tf, ms_spec, B, st); ++n_launches;
-  launch_finalize_meanstd(st_wav, 2.0 * s.L, ms_wav, B, st); ++n_launches;
+  if (xnorm) {
+    // AudioTextHTDemucs._encode(x, xt) on its own (ATHTDemucs_v2.py:190-236): the caller supplies the ALREADY normalised
+    // complex-as-channels spectrogram [B, Tf, 2048, 4] and waveform [B, 2, L]; they take the place of Z / wav with the
+    // identity normalisation (mean 0, 1e-5 + std == 1 in fp32).  A decode after this would mask the wrong spectrogram.
+    cudaMemcpyAsync(Z, xnorm, sizeof(float) * (size_t)B * Tf * 2048 * 4, cudaMemcpyDeviceToDevice, st);
+    launch_set_meanstd(ms_spec, B, 0.0f, 0.99999f, st); ++n_launches;
+    launch_set_meanstd(ms_wav, B, 0.0f, 0.99999f, st); ++n_launches;
+  } else {
+    launch_stft_cac(wav, B, s.L, Tf, Z, st_spec, consts.tw, consts.win, st); ++n_launches;
+    launch_sum_sumsq(wav, B, 2L * s.L, st_wav, st); ++n_launches;
+    launch_finalize_meanstd(st_spec, 4.0 * 2048.0 * Tf, ms_spec, B, st); ++n_launches;
+    launch_finalize_meanstd(st_wav, 2.0 * s.L, ms_wav, B, st); ++n_launches;
+  }
   // the packed bf16 copy of the normalised spectrogram is only needed when level 0 does not read Z itself (enc_row.cu)
   const bool z_direct = sizeof(T) == 2 && use_tc && use_fused_dconv && enc_row_dispatch(false, 0, nullptr, xf0_rs, nullptr, nullptr, yf_rs[0], st) &&
                         enc_row_supported(kCh[0], Tf, true);
@@ -688,6 +723,7 @@ template <typename T>
 void PlanT<T>::decode(const float* emb, float* out, cudaStream_t st) {
   const Shapes& s = sh;
   const int B = s.B, Tf = s.Tf;
+  cudaMemsetAsync((char*)ws_base() + dec_stats_begin, 0, stats_begin + stats_bytes - dec_stats_begin, st);
   text_vectors(emb, st);
   for (int p = 0; p < s.P; ++p) {
     text_condition(p, xenc, s.Sf, xc, xc_rs, st);
@@ -707,6 +743,7 @@ template <typename T>
 int PlanT<T>::forward(const float* wav, const float* emb, float* out, cudaStream_t st) {
   n_launches = 0; n_tc = 0;
   encode(wav, st);
+  n_enc_launches = n_launches; n_enc_tc = n_tc;
   decode(emb, out, st);
   return (int)cudaGetLastError();
 }

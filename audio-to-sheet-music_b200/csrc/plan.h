@@ -52,12 +52,13 @@ struct ConvOp {
 struct PlanBase {
   virtual ~PlanBase() {}
   virtual int forward(const float* wav, const float* emb, float* out, cudaStream_t st) = 0;
-  virtual int encode_only(const float* wav, cudaStream_t st) = 0;
+  virtual int encode_only(const float* wav, cudaStream_t st, const float* xnorm = nullptr) = 0;
   virtual int decode_only(const float* emb, float* out, cudaStream_t st) = 0;
   virtual bool tap(const std::string& name, TapInfo& ti) const = 0;
   virtual long workspace_bytes() const = 0;
   virtual long zero_region_bytes() const = 0;
   virtual int launches() const = 0;
+  virtual int set_batch(int B) = 0;
   virtual void set_profile(bool on) = 0;
   virtual void set_use_tc(bool on) = 0;
   virtual void set_use_flash(bool on) = 0;
@@ -68,15 +69,16 @@ struct PlanBase {
 
 template <typename T>
 struct PlanT : PlanBase {
-  Shapes sh;
+  Shapes sh;            // sh.B = batch of the next forward (<= cap)
   const ParamTable* pt;
   const PackLayout* pl;
   const float* params;
   const char* packed;
   PlanConsts consts;
+  int cap;              // batch capacity the workspace was laid out for
   char* base_ = nullptr;
-  size_t total_bytes = 0, zero_bytes = 0, stats_begin = 0, stats_bytes = 0;
-  int n_launches = 0, n_tc = 0;
+  size_t total_bytes = 0, zero_bytes = 0, stats_begin = 0, stats_bytes = 0, dec_stats_begin = 0;
+  int n_launches = 0, n_tc = 0, n_enc_launches = 0, n_enc_tc = 0;   // launches(): encode + the last decode
   bool use_tc = true, use_flash = true, use_fused_dconv = true;
   bool profiling = false;
   const float* cur_wav = nullptr;   // waveform of the forward in flight (time-branch level 0 reads it directly)
@@ -94,6 +96,8 @@ struct PlanT : PlanBase {
   PlanT(int B, int L, int P, const ParamTable* pt, const PackLayout* pl, const float* params, const void* packed,
         void* workspace, const PlanConsts& c);
   void layout(char* base);
+  void spaces(int B);
+  int set_batch(int B) override;
   char* ws_base() const { return base_; }
   const float* P32(const std::string& name) const;
   const T* PW(const std::string& key) const;
@@ -111,7 +115,7 @@ struct PlanT : PlanBase {
   void xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, T* n1, const float* n1w,
                        const float* n1b, T* n2, const float* n2w, const float* n2b, cudaStream_t st);
   void cross_transformer(cudaStream_t st);
-  void encode(const float* wav, cudaStream_t st);
+  void encode(const float* wav, cudaStream_t st, const float* xnorm = nullptr);
   void text_vectors(const float* emb, cudaStream_t st);
   void text_condition(int p, const T* x, int S, T* out, RowSpace outs, cudaStream_t st);
   void dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* out, RowSpace os, const T* skip, RowSpace ss,
@@ -119,8 +123,17 @@ struct PlanT : PlanBase {
   void decode(const float* emb, float* out, cudaStream_t st);
 
   int forward(const float* wav, const float* emb, float* out, cudaStream_t st) override;
-  int encode_only(const float* wav, cudaStream_t st) override { n_launches = 0; encode(wav, st); return (int)cudaGetLastError(); }
-  int decode_only(const float* emb, float* out, cudaStream_t st) override { decode(emb, out, st); return (int)cudaGetLastError(); }
+  int encode_only(const float* wav, cudaStream_t st, const float* xnorm = nullptr) override {
+    n_launches = 0; n_tc = 0;
+    encode(wav, st, xnorm);
+    n_enc_launches = n_launches; n_enc_tc = n_tc;
+    return (int)cudaGetLastError();
+  }
+  int decode_only(const float* emb, float* out, cudaStream_t st) override {
+    n_launches = n_enc_launches; n_tc = n_enc_tc;
+    decode(emb, out, st);
+    return (int)cudaGetLastError();
+  }
   bool tap(const std::string& name, TapInfo& ti) const override;
   long workspace_bytes() const override { return (long)total_bytes; }
   long zero_region_bytes() const override { return (long)zero_bytes; }

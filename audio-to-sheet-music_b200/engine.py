@@ -8,7 +8,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Dict, Tuple
+from collections import OrderedDict
+from typing import Optional, Tuple
 
 import torch
 
@@ -48,8 +49,8 @@ def sin_embedding_2d(dim: int, height: int, width: int, max_period: float = 1000
 class Tap:
     """View of an intermediate device buffer of the last forward (tests / debugging)."""
 
-    def __init__(self, ptr: int, numel: int, dtype: int, dims):
-        self.ptr, self.numel, self.dtype, self.dims = ptr, numel, dtype, tuple(dims)
+    def __init__(self, ptr: int, numel: int, dtype: int, dims, device):
+        self.ptr, self.numel, self.dtype, self.dims, self.device = ptr, numel, dtype, tuple(dims), device
 
     def interior(self) -> torch.Tensor:
         """Row-space buffers: strip pad groups / pad rows -> [B*G2, R, C]."""
@@ -59,21 +60,28 @@ class Tap:
 
     def to_torch(self) -> torch.Tensor:
         tdt = torch.float32 if self.dtype == 0 else torch.bfloat16
-        out = torch.empty(self.numel, dtype=tdt, device="cuda")
-        _lib.check(_lib.load().athtd_memcpy_d2d(out.data_ptr(), self.ptr, self.numel * out.element_size(),
-                                                torch.cuda.current_stream().cuda_stream), "athtd_memcpy_d2d")
+        out = torch.empty(self.numel, dtype=tdt, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().athtd_memcpy_d2d(out.data_ptr(), self.ptr, self.numel * out.element_size(),
+                                                    torch.cuda.current_stream(self.device).cuda_stream), "athtd_memcpy_d2d")
         return out
 
 
 class Plan:
-    def __init__(self, engine: "Engine", B: int, L: int, P: int):
+    """One (segment length L, prompts P) launch sequence with a workspace laid out for ``cap`` segments; any batch
+    B <= cap runs in it (``set_batch`` / the leading dimension of ``wav``), so a track's tail batch shares the
+    workspace of the full batches."""
+
+    def __init__(self, engine: "Engine", cap: int, L: int, P: int):
         lib = _lib.load()
-        self.engine, self.B, self.L, self.P = engine, B, L, P
+        self.engine, self.cap, self.B, self.L, self.P = engine, cap, cap, L, P
+        B = cap
         dt = engine.dtype_code
         nbytes = lib.athtd_workspace_bytes(B, L, P, dt)
         if nbytes < 0:
             raise _lib.AthtdError(lib.athtd_last_error().decode())
         dev = engine.device
+        self.nbytes = nbytes
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         Tf = (L + 1023) // 1024
         St = L
@@ -98,20 +106,47 @@ class Plan:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.engine.device).cuda_stream
 
+    def set_batch(self, B: int) -> "Plan":
+        if B != self.B:
+            _lib.check(_lib.load().athtd_plan_set_batch(self.handle, B), "athtd_plan_set_batch")
+            self.B = B
+        return self
+
+    def _check_wav(self, wav: torch.Tensor) -> None:
+        if wav.dim() != 3 or wav.shape[1] != 2 or wav.shape[2] != self.L or not 1 <= wav.shape[0] <= self.cap:
+            raise ValueError(f"wav must be [B<={self.cap}, 2, {self.L}], got {tuple(wav.shape)}")
+        if wav.dtype != torch.float32 or wav.device != self.engine.device or not wav.is_contiguous():
+            raise ValueError("wav must be a contiguous float32 tensor on the engine's device")
+
+    def _check_emb(self, emb: torch.Tensor) -> None:
+        if emb.shape != (self.B, self.P, 512) or emb.dtype != torch.float32 or emb.device != self.engine.device or not emb.is_contiguous():
+            raise ValueError(f"emb must be a contiguous float32 [{self.B}, {self.P}, 512] tensor on the engine's device")
+
     def forward(self, wav: torch.Tensor, emb: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-        assert wav.shape == (self.B, 2, self.L) and wav.dtype == torch.float32 and wav.is_cuda and wav.is_contiguous()
-        assert emb.shape == (self.B, self.P, 512) and emb.dtype == torch.float32 and emb.is_cuda and emb.is_contiguous()
+        self._check_wav(wav)
+        self.set_batch(wav.shape[0])
+        self._check_emb(emb)
         if out is None:
             out = torch.empty(self.B, self.P, 2, self.L, dtype=torch.float32, device=wav.device)
-        _lib.check(_lib.load().athtd_forward(self.handle, wav.data_ptr(), emb.data_ptr(), out.data_ptr(), self._stream()),
-                   "athtd_forward")
+        with torch.cuda.device(self.engine.device):
+            _lib.check(_lib.load().athtd_forward(self.handle, wav.data_ptr(), emb.data_ptr(), out.data_ptr(), self._stream()),
+                       "athtd_forward")
         return out
 
     def encode(self, wav: torch.Tensor) -> None:
-        _lib.check(_lib.load().athtd_encode(self.handle, wav.data_ptr(), self._stream()), "athtd_encode")
+        """Prompt-independent half (ATHTDemucs_v2.py:261-279); the encoder state stays in the workspace."""
+        self._check_wav(wav)
+        self.set_batch(wav.shape[0])
+        with torch.cuda.device(self.engine.device):
+            _lib.check(_lib.load().athtd_encode(self.handle, wav.data_ptr(), self._stream()), "athtd_encode")
 
-    def decode(self, emb: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-        _lib.check(_lib.load().athtd_decode(self.handle, emb.data_ptr(), out.data_ptr(), self._stream()), "athtd_decode")
+    def decode(self, emb: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """Per-prompt half (:282-324) over the state of the last ``encode``; may be called any number of times."""
+        self._check_emb(emb)
+        if out is None:
+            out = torch.empty(self.B, self.P, 2, self.L, dtype=torch.float32, device=emb.device)
+        with torch.cuda.device(self.engine.device):
+            _lib.check(_lib.load().athtd_decode(self.handle, emb.data_ptr(), out.data_ptr(), self._stream()), "athtd_decode")
         return out
 
     @property
@@ -141,19 +176,21 @@ class Plan:
         dims = (C.c_int * 8)()
         _lib.check(_lib.load().athtd_tap(self.handle, name.encode(), C.byref(ptr), C.byref(numel), C.byref(dt),
                                          C.byref(dims)), "athtd_tap")
-        return Tap(ptr.value, numel.value, dt.value, list(dims))
+        return Tap(ptr.value, numel.value, dt.value, list(dims), self.engine.device)
 
 
 class Engine:
     """Owns the flat fp32 parameter buffer, the packed GEMM-layout weights and the plan cache."""
 
-    def __init__(self, device, dtype: str = "bf16"):
+    def __init__(self, device, dtype: str = "bf16", max_workspace_bytes: Optional[int] = None):
         if dtype not in DTYPES:
             raise ValueError(f"dtype must be one of {list(DTYPES)}")
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.AthtdError("AudioTextHTDemucs B200 path needs a CUDA (sm_100a) device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = dtype
         self.dtype_code = DTYPES[dtype]
         self.table = _lib.param_table()
@@ -163,7 +200,12 @@ class Engine:
         ang = -2.0 * math.pi * k / 4096.0
         self.tw = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float().contiguous().to(self.device)
         self.win = torch.hann_window(4096).float().contiguous().to(self.device)
-        self.plans: Dict[Tuple[int, int, int], Plan] = {}
+        # plan cache: one plan per (L, P), least recently used first; workspaces (0.35 GB per segment of capacity at 6 s)
+        # are evicted beyond ``max_workspace_bytes`` (default: half of the device memory)
+        self.plans: "OrderedDict[Tuple[int, int], Plan]" = OrderedDict()
+        if max_workspace_bytes is None:
+            max_workspace_bytes = torch.cuda.get_device_properties(self.device).total_memory // 2
+        self.max_workspace_bytes = int(max_workspace_bytes)
         self.loaded = False
 
     def load_params(self, named: Dict[str, torch.Tensor]) -> None:
@@ -182,12 +224,30 @@ class Engine:
                                                    torch.cuda.current_stream().cuda_stream), "athtd_pack_weights")
         self.loaded = True
 
-    def plan(self, B: int, L: int, P: int = 1) -> Plan:
-        key = (B, L, P)
-        if key not in self.plans:
+    def plan(self, B: int, L: int, P: int = 1, cap: Optional[int] = None) -> Plan:
+        """Plan for segments of L samples and P prompts, set to batch B.  ``cap`` (>= B) is the batch capacity to lay the
+        workspace out for when a new one is needed (a track loop passes its full batch size so that the tail batch
+        reuses the workspace)."""
+        key = (L, P)
+        pl = self.plans.get(key)
+        if pl is not None and pl.cap < B:
+            del self.plans[key]       # outgrown: replaced below
+            pl = None
+        if pl is None:
+            cap = max(B, cap or B)
+            need = _lib.load().athtd_workspace_bytes(cap, L, P, self.dtype_code)
+            if need < 0:
+                raise _lib.AthtdError(_lib.load().athtd_last_error().decode())
+            while self.plans and self.workspace_bytes() + need > self.max_workspace_bytes:
+                self.plans.popitem(last=False)                 # evict the least recently used workspace
             with torch.cuda.device(self.device):
-                self.plans[key] = Plan(self, B, L, P)
-        return self.plans[key]
+                pl = Plan(self, cap, L, P)
+            self.plans[key] = pl
+        self.plans.move_to_end(key)
+        return pl.set_batch(B)
+
+    def workspace_bytes(self) -> int:
+        return sum(p.nbytes for p in self.plans.values())
 
     def gemm_kernel_name(self) -> str:
         return "gemm_tc_kernel + flash_attn_kernel (tcgen05)" if self.dtype == "bf16" else "gemm_simt_kernel (CUDA-core fp32)"

@@ -28,8 +28,10 @@ SYMBOLS = [
     ("athtd_plan_tokens", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     ("athtd_forward", _I, [_P, _P, _P, _P, _P]),
     ("athtd_encode", _I, [_P, _P, _P]),
+    ("athtd_encode_normalized", _I, [_P, _P, _P, _P]),
     ("athtd_decode", _I, [_P, _P, _P, _P]),
     ("athtd_plan_launches", _I, [_P]),
+    ("athtd_plan_set_batch", _I, [_P, _I]),
     ("athtd_plan_set_profile", _I, [_P, _I]),
     ("athtd_plan_get_profile", _I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     ("athtd_tap", _I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I), C.POINTER(_I * 8)]),

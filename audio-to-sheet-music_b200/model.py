@@ -260,6 +260,43 @@ class AudioTextHTDemucsB200(nn.Module):
         plan = eng.plan(B, L, P)
         return plan.forward(wav.float().contiguous(), emb.to(wav.device).float().contiguous())
 
+    @torch.no_grad()
+    def _encode(self, x: torch.Tensor, xt: torch.Tensor):
+        """``AudioTextHTDemucs._encode`` (ATHTDemucs_v2.py:190-236) with the reference's signature and return value:
+        x [B,4,2048,Tf] = the normalised complex-as-channels spectrogram, xt [B,2,L] = the normalised waveform ->
+        (x_enc [B,384,8,Tf], xt_enc [B,384,St], saved, saved_t, lengths, lengths_t).  ``lengths`` holds the FRAME count
+        (the reference stores x.shape[-1] of the 4-D tensor, :198) and ``lengths_t`` the time-branch input lengths (:202).
+        The tensors are copies of the workspace buffers converted to float32 in the reference's layouts; forward() does not
+        go through this method (its encoder state stays on the device in the kernels' own layout)."""
+        if not x.is_cuda:
+            raise AthtdError("x must live on the CUDA device (no CPU fallback)")
+        B, C4, Fq, Tf = x.shape
+        L = xt.shape[-1]
+        if C4 != 4 or Fq != 2048 or xt.shape[:2] != (B, 2) or Tf != (L + 1023) // 1024:
+            raise ValueError(f"_encode expects x [B,4,2048,ceil(L/1024)] and xt [B,2,L], got {tuple(x.shape)} / {tuple(xt.shape)}")
+        from . import lib as _lib
+        eng = self.engine(x.device)
+        plan = eng.plan(B, L, 1)
+        xc = x.float().permute(0, 3, 2, 1).contiguous()                 # [B, Tf, 2048, 4] channels-last
+        xtc = xt.float().contiguous()
+        with torch.cuda.device(eng.device):
+            _lib.check(_lib.load().athtd_encode_normalized(plan.handle, xc.data_ptr(), xtc.data_ptr(),
+                                                           torch.cuda.current_stream(eng.device).cuda_stream), "athtd_encode_normalized")
+        fr = [512, 128, 32, 8]
+        saved, saved_t, lengths, lengths_t = [], [], [], []
+        lt = L
+        for i in range(4):
+            lengths.append(Tf)
+            lengths_t.append(lt)
+            lt = (lt + 3) // 4
+            t = plan.tap(f"enc{i}").interior().float()                   # [B*Tf, F_i, C]
+            saved.append(t.view(B, Tf, fr[i], ENC_CH[i]).permute(0, 3, 2, 1).contiguous())
+            t = plan.tap(f"tenc{i}").interior().float()                  # [B, L_i, C]
+            saved_t.append(t.permute(0, 2, 1).contiguous())
+        x_enc = plan.tap("xenc").to_torch().float().view(B, Tf, 8, 384).permute(0, 3, 2, 1).contiguous()
+        xt_enc = plan.tap("xtenc").to_torch().float().view(B, -1, 384).permute(0, 2, 1).contiguous()
+        return x_enc, xt_enc, saved, saved_t, lengths, lengths_t
+
     def forward(self, wav: torch.Tensor, text: Union[List[str], str, torch.Tensor]) -> torch.Tensor:
         B = wav.shape[0]
         if isinstance(text, torch.Tensor):

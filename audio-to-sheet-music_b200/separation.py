@@ -22,80 +22,21 @@ STEMS = ["drums", "bass", "other", "vocals"]      # benchmark.py:58
 
 
 class SeparationModel(ABC):
-    """Same contract as benchmark.py:81-115."""
+    """Same contract as the reference's plugin base class, benchmark.py:81-115: ``separate`` one stem,
+    ``separate_all`` stems, ``name``."""
 
     @abstractmethod
-    @torch.no_grad()
-    def separate_fade(self, mixture: torch.Tensor, emb: torch.Tensor, segment_seconds: Optional[float] = None,
-                      overlap_seconds: float = 0.1) -> torch.Tensor:
-        """The chunk loop of test_inference.py:96-141 (the reference's older inference script): stride chunk_len - overlap,
-        the last chunk is NOT zero-padded (the model runs on its true length), every chunk is multiplied by a
-        ``torchaudio.transforms.Fade(fade_in, fade_out, "linear")`` mask (fade-in iff start > 0, fade-out iff end < T, both of
-        ``int(overlap * sr)`` samples) and added into the output; there is no weight normalisation.
-        mixture [2, T], emb [P, 512] -> [P, 2, T].  Chunks of equal length share one batched launch sequence."""
-        mixture = mixture.to(self.device, torch.float32).contiguous()
-        emb = emb.to(self.device, torch.float32).contiguous()
-        sr = self.model.sample_rate
-        seg = self.segment_seconds if segment_seconds is None else segment_seconds
-        T = mixture.shape[-1]
-        P = emb.shape[0]
-        L = int(sr * seg)
-        ov = int(overlap_seconds * sr)
-        stride = L - ov
-        if stride <= 0 or 2 * stride <= L:
-            raise ValueError("overlap must be smaller than half a segment")
-        starts = list(range(0, T, stride))
-        ends = [min(s + L, T) for s in starts]
-        actual = [e - s for s, e in zip(starts, ends)]
-        flags = [(1 if s > 0 else 0) | (2 if e < T else 0) for s, e in zip(starts, ends)]
-        for a, f in zip(actual, flags):
-            if f and a < ov:       # torchaudio's Fade would fail on torch.ones(negative)
-                raise ValueError(f"a faded chunk of {a} samples is shorter than the fade ({ov}): the reference loop fails here too")
-            if a < 4096:
-                raise ValueError(f"chunk of {a} samples is shorter than one STFT window")
-        n = len(starts)
-        seg_out = torch.zeros(n, P, 2, L, dtype=torch.float32, device=self.device)
-        eng = self.model.engine(self.device)
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        full = [k for k in range(n) if actual[k] == L]
-        for b0 in range(0, len(full), self.batch):
-            ks = full[b0:b0 + self.batch]                       # consecutive chunk indices
-            segs = torch.empty(len(ks), 2, L, dtype=torch.float32, device=self.device)
-            st_dev = torch.tensor([starts[k] for k in ks], dtype=torch.int64, device=self.device)
-            _lib.check(_lib.load().athtd_gather_chunks(mixture.data_ptr(), T, 2, st_dev.data_ptr(), len(ks), L, segs.data_ptr(), st),
-                       "athtd_gather_chunks")
-            e = emb.unsqueeze(0).expand(len(ks), P, 512).contiguous()
-            eng.plan(len(ks), L, P).forward(segs, e, seg_out[ks[0]:ks[0] + len(ks)])
-        for k in range(n):
-            if actual[k] != L:                                  # ragged tail chunk(s): the model sees the true length
-                chunk = mixture[:, starts[k]:ends[k]].unsqueeze(0).contiguous()
-                o = torch.empty(1, P, 2, actual[k], dtype=torch.float32, device=self.device)
-                eng.plan(1, actual[k], P).forward(chunk, emb.unsqueeze(0).contiguous(), o)
-                seg_out[k, :, :, :actual[k]] = o[0]
-        up = torch.linspace(0, 1, ov).clamp_(0, 1) if ov > 0 else torch.zeros(1)          # Fade._fade_in (linear)
-        down = (-torch.linspace(0, 1, ov) + 1).clamp_(0, 1) if ov > 0 else torch.zeros(1)  # Fade._fade_out (linear)
-        dev = self.device
-        t_starts = torch.tensor(starts, dtype=torch.int64, device=dev)
-        t_actual = torch.tensor(actual, dtype=torch.int32, device=dev)
-        t_fade = torch.full((n,), ov, dtype=torch.int32, device=dev)
-        t_flags = torch.tensor(flags if ov > 0 else [0] * n, dtype=torch.int32, device=dev)
-        t_off = torch.zeros(n, dtype=torch.int32, device=dev)
-        up, down = up.float().to(dev), down.float().to(dev)
-        out = torch.empty(P, 2, T, dtype=torch.float32, device=dev)
-        for p in range(P):
-            _lib.check(_lib.load().athtd_chunk_fade_add(seg_out[:, p].data_ptr(), P * 2 * L, 0, L, t_starts.data_ptr(), t_actual.data_ptr(),
-                                                        t_fade.data_ptr(), t_flags.data_ptr(), n, stride, up.data_ptr(), down.data_ptr(),
-                                                        t_off.data_ptr(), out[p].data_ptr(), 2, 0, T, st), "athtd_chunk_fade_add")
-        return out
-
-    def separate(self, mixture: torch.Tensor, stem_name: str) -> torch.Tensor: ...
+    def separate(self, mixture: torch.Tensor, stem_name: str) -> torch.Tensor:
+        """mixture (C, T) -> the named stem (C, T)."""
 
     @abstractmethod
-    def separate_all(self, mixture: torch.Tensor) -> Dict[str, torch.Tensor]: ...
+    def separate_all(self, mixture: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """mixture (C, T) -> {stem name: (C, T)}."""
 
     @property
     @abstractmethod
-    def name(self) -> str: ...
+    def name(self) -> str:
+        """Model name for display."""
 
 
 class SegmentPlan(NamedTuple):
@@ -186,9 +127,17 @@ class B200SeparationModel(SeparationModel):
                  overlap_seconds: float = 1.5, batch: int = 32):
         self.model = model.to(device).eval()
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.segment_seconds = segment_seconds
         self.overlap = overlap_seconds
         self.batch = batch
+        self.last_launches = 0
+        self._last_seg_out = None
+        self._tables_key = None
+        self._streams = None
+        self._stage = {}
+        self.host_done: Optional[torch.cuda.Event] = None
 
     @property
     def name(self) -> str:
@@ -197,6 +146,23 @@ class B200SeparationModel(SeparationModel):
     def prompt_embeddings(self, prompts: Sequence[str]) -> torch.Tensor:
         return self.model._get_clap_embeddings(list(prompts), self.device)          # [P, 512]
 
+    # ------------------------------------------------------------------ shared pieces
+    def _plan_and_tables(self, T: int):
+        plan = segment_plan(T, self.segment_seconds, self.overlap, self.model.sample_rate)
+        key = (T, self.segment_seconds, self.overlap, str(self.device))
+        if self._tables_key != key:
+            self._tables, self._tables_key = OlaTables(plan, self.device), key
+        return plan, self._tables
+
+    def _forward_batch(self, segs: torch.Tensor, emb: torch.Tensor, out: torch.Tensor) -> int:
+        """segs [b, 2, L] -> out [b, P, 2, L] through the (L, P) plan laid out for ``self.batch`` segments."""
+        b, _, L = segs.shape
+        P = emb.shape[0]
+        fplan = self.model.engine(self.device).plan(b, L, P, cap=self.batch)
+        fplan.forward(segs, emb.unsqueeze(0).expand(b, P, 512).contiguous(), out)
+        return fplan.launches
+
+    # ------------------------------------------------------------------ device-resident span
     @torch.no_grad()
     def separate_span(self, track: torch.Tensor, emb: torch.Tensor, span, halo_exchange=None, track_offset: int = 0,
                       track_len: Optional[int] = None, halo_in: Optional[torch.Tensor] = None):
@@ -206,18 +172,22 @@ class B200SeparationModel(SeparationModel):
                 (it must cover every chunk of the span); ``track_len`` = global track length T.
         emb   : [P, 512].   Returns [P, 2, t_end - t_begin] for global samples [starts[k0], starts[k1]) (to T at the end).
         halo_exchange(last_chunk_out[P,2,L]) -> left neighbour's last chunk output (or None): the one
-        seam exchange a multi-GPU run needs (each sample has at most two contributing chunks)."""
+        seam exchange a multi-GPU run needs (each sample has at most two contributing chunks).  An empty span
+        (k0 == k1: more ranks than chunks) returns [P, 2, 0]; build ``halo_exchange`` with the list of spans so that
+        empty ranks are skipped by their neighbours."""
         T = track.shape[-1] + track_offset if track_len is None else track_len
         P = emb.shape[0]
-        plan = segment_plan(T, self.segment_seconds, self.overlap, self.model.sample_rate)
+        plan, tables = self._plan_and_tables(T)
         n = len(plan.starts)
         k0, k1 = span
-        key = (T, str(self.device))
-        if getattr(self, "_tables_key", None) != key:
-            self._tables, self._tables_key = OlaTables(plan, self.device), key
-        tables = self._tables
         L = plan.chunk_len
         nk = k1 - k0
+        if nk <= 0:
+            if halo_exchange is not None:
+                halo_exchange(torch.zeros(P, 2, L, dtype=torch.float32, device=self.device))
+            self.last_launches = 0
+            self._last_seg_out = None
+            return torch.empty(P, 2, 0, dtype=torch.float32, device=self.device)
         seg_out = torch.empty(nk + 1, P, 2, L, dtype=torch.float32, device=self.device)   # slot 0 = halo chunk k0-1
         local_starts = (tables.starts[k0:k1] - track_offset).contiguous()
         segs = torch.empty(nk, 2, L, dtype=torch.float32, device=self.device)
@@ -225,13 +195,9 @@ class B200SeparationModel(SeparationModel):
         _lib.check(_lib.load().athtd_gather_chunks(track.data_ptr(), track.shape[-1], 2, local_starts.data_ptr(), nk, L,
                                                    segs.data_ptr(), st), "athtd_gather_chunks")
         launches = 1
-        eng = self.model.engine(self.device)
         for b0 in range(0, nk, self.batch):
             b1 = min(b0 + self.batch, nk)
-            e = emb.unsqueeze(0).expand(b1 - b0, P, 512).contiguous()
-            fplan = eng.plan(b1 - b0, L, P)
-            fplan.forward(segs[b0:b1], e, seg_out[1 + b0:1 + b1])
-            launches += fplan.launches
+            launches += self._forward_batch(segs[b0:b1], emb, seg_out[1 + b0:1 + b1])
         if halo_exchange is not None:
             halo_in = halo_exchange(seg_out[nk])
         if k0 > 0:
@@ -247,53 +213,72 @@ class B200SeparationModel(SeparationModel):
         self._last_seg_out = seg_out
         return out
 
+    # ------------------------------------------------------------------ host-staged span (row f-1)
     @torch.no_grad()
     def separate_span_host(self, track_host: torch.Tensor, emb: torch.Tensor, span, out_host: torch.Tensor,
-                           halo_exchange=None, halo_in: Optional[torch.Tensor] = None):
+                           halo_exchange=None, halo_in: Optional[torch.Tensor] = None, wait: bool = True):
         """Host-staged variant of ``separate_span`` (the step either side of the path: app.py:230-231,
         benchmark.py:207/211 move the whole track with ``.to(device)`` / ``.cpu()`` around the loop).
 
         track_host : [2, T] float32 in PINNED host memory (the whole track); out_host : [P, 2, t_end - t_begin] pinned.
-        Inputs are uploaded batch by batch on a copy stream while the previous batch computes; every batch is
-        overlap-added as soon as its chunks (and the chunk before them) are done and its output range is downloaded
-        while the next batch computes.  Results are bit-identical to ``separate_span`` (same kernels, same order of
-        operations per sample).  The device work is ordered on the current stream; the call returns after the last
-        download has completed."""
+        Inputs are uploaded batch by batch on an upload stream while the previous batch computes; every batch is
+        overlap-added as soon as its chunks (and the chunk before them) are done and its output range is downloaded on a
+        separate download stream while the next batch computes.  The device staging buffers are double-buffered per call,
+        so with ``wait=False`` the next call's uploads overlap this call's compute and downloads (a service separating
+        tracks back to back): the caller then waits on ``self.host_done`` (a CUDA event recorded after the last download)
+        before reading ``out_host``.  ``wait=True`` (default) returns after the last download has completed.
+        Results are bit-identical to ``separate_span`` (same kernels, same order of operations per sample)."""
         T = track_host.shape[-1]
         P = emb.shape[0]
-        plan = segment_plan(T, self.segment_seconds, self.overlap, self.model.sample_rate)
+        plan, tables = self._plan_and_tables(T)
         n = len(plan.starts)
         k0, k1 = span
-        key = (T, str(self.device))
-        if getattr(self, "_tables_key", None) != key:
-            self._tables, self._tables_key = OlaTables(plan, self.device), key
-        tables = self._tables
         L = plan.chunk_len
         nk = k1 - k0
+        dev = self.device
+        comp = torch.cuda.current_stream(dev)
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        up, down = self._streams
+        if nk <= 0:
+            if halo_exchange is not None:
+                halo_exchange(torch.zeros(P, 2, L, dtype=torch.float32, device=dev))
+            self.last_launches = 0
+            self._last_seg_out = None
+            self.host_done = torch.cuda.Event()
+            self.host_done.record(down)
+            return out_host
         in_lo, in_hi = plan.starts[k0], min(T, plan.starts[k1 - 1] + L)
         t_begin = plan.starts[k0]
         t_end = plan.T if k1 == n else plan.starts[k1]
-        dev = self.device
-        comp = torch.cuda.current_stream(dev)
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(dev)
-        cps = self._copy_stream
-        track = torch.empty(2, in_hi - in_lo, dtype=torch.float32, device=dev)
+        # double-buffered device staging of the input range: buffer `par` was last read by the gathers of the call before the
+        # previous one, so this call's uploads only wait for THAT (not for the previous call's compute)
+        skey = (in_hi - in_lo, str(dev))
+        stage = self._stage.get(skey)
+        if stage is None:
+            self._stage.clear()
+            stage = {"buf": [torch.empty(2, in_hi - in_lo, dtype=torch.float32, device=dev) for _ in range(2)],
+                     "free": [None, None], "par": 0}
+            self._stage[skey] = stage
+            up.wait_stream(comp)                   # the buffers were allocated on the compute stream
+        par = stage["par"]
+        stage["par"] = 1 - par
+        track = stage["buf"][par]
+        if stage["free"][par] is not None:
+            up.wait_event(stage["free"][par])
         seg_out = torch.empty(nk + 1, P, 2, L, dtype=torch.float32, device=dev)      # slot 0 = halo chunk k0-1
         segs = torch.empty(min(self.batch, nk), 2, L, dtype=torch.float32, device=dev)
         local_starts = (tables.starts[k0:k1] - in_lo).contiguous()
-        eng = self.model.engine(dev)
         batches = [(b0, min(b0 + self.batch, nk)) for b0 in range(0, nk, self.batch)]
-        cps.wait_stream(comp)                       # buffers above are allocated on the compute stream
 
         def upload(i, done_to):
             b0, b1 = batches[i]
             hi = min(T, plan.starts[k0 + b1 - 1] + L)
-            with torch.cuda.stream(cps):
+            with torch.cuda.stream(up):
                 for c in range(2):
                     track[c, done_to - in_lo:hi - in_lo].copy_(track_host[c, done_to:hi], non_blocking=True)
                 ev = torch.cuda.Event()
-                ev.record(cps)
+                ev.record(up)
             return ev, hi
 
         launches = 0
@@ -306,10 +291,10 @@ class B200SeparationModel(SeparationModel):
             st = comp.cuda_stream
             _lib.check(_lib.load().athtd_gather_chunks(track.data_ptr(), track.shape[-1], 2, local_starts[b0:].data_ptr(), b1 - b0, L,
                                                        segs.data_ptr(), st), "athtd_gather_chunks")
-            e = emb.unsqueeze(0).expand(b1 - b0, P, 512).contiguous()
-            fplan = eng.plan(b1 - b0, L, P)
-            fplan.forward(segs[:b1 - b0], e, seg_out[1 + b0:1 + b1])
-            launches += fplan.launches + 1
+            if i == len(batches) - 1:
+                stage["free"][par] = torch.cuda.Event()
+                stage["free"][par].record(comp)
+            launches += self._forward_batch(segs[:b1 - b0], emb, seg_out[1 + b0:1 + b1]) + 1
             if i == len(batches) - 1 and halo_exchange is not None:
                 halo_in = halo_exchange(seg_out[nk])
             # output samples that are complete now: [starts[k0+b0], starts[k0+b1]) (to the span end for the last batch)
@@ -322,32 +307,34 @@ class B200SeparationModel(SeparationModel):
                 if halo_in is None:
                     raise ValueError("span starts inside the track: the left neighbour's last chunk output is required")
                 seg_out[0].copy_(halo_in)
-            self._ola_and_download(seg_out, tables, k0, P, L, ra, rb, t_begin, out_host, comp, cps)
+            self._ola_and_download(seg_out, tables, k0, P, L, ra, rb, t_begin, out_host, comp, down)
             launches += P
         if pending_first is not None:
             if halo_in is None:
                 raise ValueError("span starts inside the track: the left neighbour's last chunk output is required")
             seg_out[0].copy_(halo_in)
-            self._ola_and_download(seg_out, tables, k0, P, L, pending_first[0], pending_first[1], t_begin, out_host, comp, cps)
+            self._ola_and_download(seg_out, tables, k0, P, L, pending_first[0], pending_first[1], t_begin, out_host, comp, down)
             launches += P
-        cps.synchronize()
-        comp.wait_stream(cps)
+        self.host_done = torch.cuda.Event()
+        self.host_done.record(down)
+        if wait:
+            self.host_done.synchronize()
         self.last_launches = launches
         self._last_seg_out = seg_out
         return out_host
 
-    def _ola_and_download(self, seg_out, tables, k0, P, L, ra, rb, t_begin, out_host, comp, cps):
+    def _ola_and_download(self, seg_out, tables, k0, P, L, ra, rb, t_begin, out_host, comp, down):
         piece = torch.empty(P, 2, rb - ra, dtype=torch.float32, device=self.device)
         for p in range(P):
             chunk_ola(seg_out[:, p], P * 2 * L, k0 - 1, tables, ra, rb, piece[p])
         ev = torch.cuda.Event()
         ev.record(comp)
-        with torch.cuda.stream(cps):
-            cps.wait_event(ev)
+        with torch.cuda.stream(down):
+            down.wait_event(ev)
             for p in range(P):
                 for c in range(2):
                     out_host[p, c, ra - t_begin:rb - t_begin].copy_(piece[p, c], non_blocking=True)
-        piece.record_stream(cps)
+        piece.record_stream(down)
 
     def separate_many(self, mixture: torch.Tensor, emb: torch.Tensor, span=None, halo_in: Optional[torch.Tensor] = None):
         """mixture [2,T], emb [P,512] -> ([P,2,T'], raw output [P,2,chunk_len] of the span's last chunk)."""
@@ -357,26 +344,22 @@ class B200SeparationModel(SeparationModel):
             n = len(segment_plan(mixture.shape[-1], self.segment_seconds, self.overlap, self.model.sample_rate).starts)
             span = (0, n)
         out = self.separate_span(mixture, emb, span, halo_in=halo_in)
-        return out, self._last_seg_out[-1]
+        return out, (self._last_seg_out[-1] if self._last_seg_out is not None else None)
 
     @torch.no_grad()
     def profile_gemms(self, track: torch.Tensor, emb: torch.Tensor, span):
-        """Untimed measurement pass: CUDA events around every GEMM launch of one step (bench.py roofline)."""
+        """Untimed measurement pass: CUDA events around every GEMM / attention launch of one step (bench.py roofline)."""
         eng = self.model.engine(self.device)
-        for pl in eng.plans.values():
-            pl.set_profile(True)
-        self.separate_span(track, emb, span, halo_in=torch.zeros(emb.shape[0], 2, int(self.model.sample_rate * self.segment_seconds),
-                                                                device=self.device))
+        L = int(self.model.sample_rate * self.segment_seconds)
+        pl = eng.plan(min(self.batch, max(1, span[1] - span[0])), L, emb.shape[0], cap=self.batch)
+        pl.set_profile(True)
+        self.separate_span(track, emb, span, halo_in=torch.zeros(emb.shape[0], 2, L, device=self.device))
         torch.cuda.synchronize(self.device)
-        ms = gf = 0.0
-        n = 0
-        # every batch of the step reuses one of the cached plans; events are per plan, so run counts add up
-        for pl in eng.plans.values():
-            a, b, c = pl.get_profile()
-            ms, gf, n = ms + a, gf + b, n + c
-            pl.set_profile(False)
+        ms, gf, n = pl.get_profile()
+        pl.set_profile(False)
         return {"kernel": eng.gemm_kernel_name(), "ms": ms, "gflop": gf, "launches": n, "tflops": gf / ms if ms > 0 else 0.0}
 
+    # ------------------------------------------------------------------ test_inference.py loop (row f-4)
     @torch.no_grad()
     def separate_fade(self, mixture: torch.Tensor, emb: torch.Tensor, segment_seconds: Optional[float] = None,
                       overlap_seconds: float = 0.1) -> torch.Tensor:
@@ -407,7 +390,6 @@ class B200SeparationModel(SeparationModel):
                 raise ValueError(f"chunk of {a} samples is shorter than one STFT window")
         n = len(starts)
         seg_out = torch.zeros(n, P, 2, L, dtype=torch.float32, device=self.device)
-        eng = self.model.engine(self.device)
         st = torch.cuda.current_stream(self.device).cuda_stream
         full = [k for k in range(n) if actual[k] == L]
         for b0 in range(0, len(full), self.batch):
@@ -416,8 +398,8 @@ class B200SeparationModel(SeparationModel):
             st_dev = torch.tensor([starts[k] for k in ks], dtype=torch.int64, device=self.device)
             _lib.check(_lib.load().athtd_gather_chunks(mixture.data_ptr(), T, 2, st_dev.data_ptr(), len(ks), L, segs.data_ptr(), st),
                        "athtd_gather_chunks")
-            e = emb.unsqueeze(0).expand(len(ks), P, 512).contiguous()
-            eng.plan(len(ks), L, P).forward(segs, e, seg_out[ks[0]:ks[0] + len(ks)])
+            self._forward_batch(segs, emb, seg_out[ks[0]:ks[0] + len(ks)])
+        eng = self.model.engine(self.device)
         for k in range(n):
             if actual[k] != L:                                  # ragged tail chunk(s): the model sees the true length
                 chunk = mixture[:, starts[k]:ends[k]].unsqueeze(0).contiguous()
@@ -440,10 +422,13 @@ class B200SeparationModel(SeparationModel):
                                                         t_off.data_ptr(), out[p].data_ptr(), 2, 0, T, st), "athtd_chunk_fade_add")
         return out
 
+    # ------------------------------------------------------------------ the reference's plugin interface
     def separate(self, mixture: torch.Tensor, stem_name: str) -> torch.Tensor:
+        """benchmark.py:206-208: one stem of a (C, T) mixture."""
         out, _ = self.separate_many(mixture, self.prompt_embeddings([stem_name]))
         return out[0]
 
     def separate_all(self, mixture: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """benchmark.py:210-215: all four stems; here ONE pass (encode once, decode per prompt) instead of four."""
         out, _ = self.separate_many(mixture, self.prompt_embeddings(STEMS))
         return {s: out[i] for i, s in enumerate(STEMS)}

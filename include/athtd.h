@@ -50,9 +50,17 @@ int athtd_plan_tokens(void* plan, int* Tf, int* Sf, int* St);
 int athtd_forward(void* plan, const float* wav_dev, const float* emb_dev, float* out_dev, void* stream);
 /* prompt-independent half (_spec, normalise, _encode; ATHTDemucs_v2.py:261-279) ... */
 int athtd_encode(void* plan, const float* wav_dev, void* stream);
+/* AudioTextHTDemucs._encode(x, xt) (ATHTDemucs_v2.py:190-236) on its own: x_cac [B, Tf, 2048, 4] fp32 = the NORMALISED
+ * complex-as-channels spectrogram (channels-last: the reference's x [B,4,2048,Tf] permuted), xt [B,2,L] the normalised
+ * waveform.  Outputs are read through athtd_tap ("xenc", "xtenc", "enc{i}", "tenc{i}").  Not followed by athtd_decode. */
+int athtd_encode_normalized(void* plan, const float* x_cac_dev, const float* xt_dev, void* stream);
 /* ... and the per-prompt half (text_attn, decoders, mask, _ispec, time branch; :282-324). */
 int athtd_decode(void* plan, const float* emb_dev, float* out_dev, void* stream);
-int athtd_plan_launches(void* plan);   /* kernels launched by the last forward */
+int athtd_plan_launches(void* plan);   /* kernels launched by the last forward (or the last encode + the last decode) */
+/* A plan created for B segments is a batch CAPACITY: any 1 <= b <= B runs in the same workspace (per-segment buffers are
+ * laid out segment-major, pads stay in place).  Applies to the following forward / encode / decode calls; wav / emb / out
+ * are then [b, ...].  Lets a track's tail batch (54 chunks = 32 + 22) reuse the batch-32 workspace. */
+int athtd_plan_set_batch(void* plan, int B);
 /* measurement aid (bench.py roofline pass): CUDA-event pairs around every GEMM launch of subsequent forwards;
  * get_profile synchronises on the last event and returns summed GEMM ms, algorithmic GFLOP (2*M*N*K) and launches. */
 int athtd_plan_set_profile(void* plan, int on);

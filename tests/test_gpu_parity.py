@@ -1,0 +1,249 @@
+"""GPU (-m gpu): parity of the BENCHMARKED configuration and of every stage with the CPU oracle.
+
+* BASELINE config 3 exactly as bench.py runs it (240 s track, 54 chunks, batch 32 -> 32 + 22, bf16, one prompt) against
+  the restated reference loop driving the oracle forward (benchmark.py:155-204 + ATHTDemucs_v2.py:250-326): SNR >= 40 dB
+  on the track and on EVERY chunk's raw model output.
+* seed sweep: 8 seeds x {unit-norm, un-normalised} embeddings at B = 1, 6 s: the MINIMUM bf16 SNR must clear 40 dB.
+* batch 32 in fp32 against the oracle on 3 of the 32 segments (max-abs <= 1e-3).
+* per-stage taps: fp32 build <= 1e-3 of the tap's scale, bf16 build a stated SNR floor per tap.
+Tolerances are BASELINE.json's: fp32 max-abs 1e-3, bf16 >= 40 dB SNR on the waveform."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import athtd_b200
+from athtd_b200 import synthetic
+from oracle import athtd_oracle, ola
+
+
+@pytest.fixture(scope="module")
+def models(state_dict):
+    out = {}
+    for prec in ("fp32", "bf16"):
+        m = athtd_b200.AudioTextHTDemucsB200(precision=prec)
+        m.load_state_dict(state_dict, strict=False)
+        out[prec] = m.cuda().eval()
+    return out
+
+
+def test_config3_bf16_batch32_track_and_every_chunk_vs_oracle(models, state_dict):
+    torch.set_num_threads(os.cpu_count())
+    track = synthetic.make_track(240.0)
+    emb = synthetic.make_prompt_embeddings(1)
+    chunk_refs = []
+
+    def oracle_fn(chunk):
+        o = athtd_oracle.forward(state_dict, chunk, emb)
+        chunk_refs.append(o[0])
+        return o
+
+    ref = ola.chunked_inference(oracle_fn, track)                       # 54 oracle forwards (the reference loop)
+    sep = athtd_b200.B200SeparationModel(models["bf16"], "cuda", 6.0, 1.5, batch=32)
+    plan = athtd_b200.segment_plan(track.shape[-1])
+    n = len(plan.starts)
+    assert n == 54 and len(chunk_refs) == 54
+    out = sep.separate_span(track.cuda(), emb.cuda(), (0, n))
+    seg = sep._last_seg_out[1:, 0].cpu()                                 # raw model output of every chunk
+    snr_track = athtd_oracle.snr_db(out[0].cpu(), ref)
+    snrs = [athtd_oracle.snr_db(seg[k, :, :plan.actual_len[k]], chunk_refs[k][:, :plan.actual_len[k]]) for k in range(n)]
+    print(f"config 3 bf16 batch 32: track SNR {snr_track:.2f} dB, per-chunk min {min(snrs):.2f} / median {sorted(snrs)[n // 2]:.2f} / "
+          f"max {max(snrs):.2f} dB (chunk {snrs.index(min(snrs))} is the minimum)")
+    assert snr_track >= 40.0
+    assert min(snrs) >= 40.0, snrs
+    # the host-staged path of the bench's e2e number returns the same bits
+    host = track.pin_memory()
+    out_host = torch.empty(1, 2, track.shape[-1]).pin_memory()
+    sep.separate_span_host(host, emb.cuda(), (0, n), out_host)
+    assert torch.equal(out_host, out.cpu())
+
+
+def test_bf16_seed_sweep_min_snr(models, state_dict):
+    torch.set_num_threads(os.cpu_count())
+    m = models["bf16"]
+    rows = []
+    for seed in range(100, 108):
+        for norm in (True, False):
+            wav, emb = synthetic.make_inputs(seed, 1, 264600, emb_norm=norm)
+            ref = athtd_oracle.forward(state_dict, wav, emb)
+            out = m(wav.cuda(), emb.cuda()).cpu()
+            rows.append((athtd_oracle.snr_db(out, ref), seed, norm, float(emb.norm())))
+    for snr, seed, norm, en in rows:
+        print(f"seed {seed} emb {'unit' if norm else 'raw '} |e|={en:5.2f}  SNR {snr:.2f} dB")
+    worst = min(rows)
+    print(f"bf16 seed sweep: min SNR {worst[0]:.2f} dB (seed {worst[1]}, unit-norm={worst[2]})")
+    assert worst[0] >= 40.0, worst
+
+
+def test_fp32_batch32_three_segments_vs_oracle(models, state_dict):
+    torch.set_num_threads(os.cpu_count())
+    wav, emb = synthetic.make_inputs(300, 32, 264600)
+    out = models["fp32"](wav.cuda(), emb.cuda()).cpu()
+    models["fp32"].engine().drop_plans()                                 # 22 GB fp32 workspace: release it for the other tests
+    torch.cuda.empty_cache()
+    for b in (0, 15, 31):
+        ref = athtd_oracle.forward(state_dict, wav[b:b + 1], emb[b:b + 1])
+        err = float((out[b:b + 1] - ref).abs().max())
+        print(f"fp32 batch 32 segment {b}: max-abs {err:.3e}")
+        assert err < 1e-3
+
+
+def test_bf16_batch32_matches_batch1(models):
+    """batch invariance of the benchmarked build: segment 7 of a batch of 32 == the same segment alone (>= 60 dB; not
+    bit-equal by contract: GroupNorm statistics are accumulated with fp64 atomics)."""
+    wav, emb = synthetic.make_inputs(301, 32, 264600)
+    m = models["bf16"]
+    full = m(wav.cuda(), emb.cuda())
+    one = m(wav[7:8].cuda(), emb[7:8].cuda())
+    assert athtd_oracle.snr_db(full[7:8].cpu(), one.cpu()) >= 60.0
+
+
+def _interior(plan, name):
+    return plan.tap(name).interior().float().cpu()
+
+
+# bf16 floors per tap: activations are stored in bf16 (8-bit mantissa) through ~60 chained layers; only the waveform is
+# contractually >= 40 dB.  The floors below are what the build delivers minus a margin and catch a broken stage.
+TAP_FLOOR_DB = {"fp32": None, "bf16": 30.0}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_per_stage_taps_vs_oracle(models, state_dict, prec):
+    torch.set_num_threads(os.cpu_count())
+    B, L = 2, 40000
+    wav, emb = synthetic.make_inputs(11, B, L)
+    taps = {}
+    ref = athtd_oracle.forward(state_dict, wav, emb, taps)
+    m = models[prec]
+    out = m(wav.cuda(), emb.cuda()).cpu()
+    plan = m.engine().plan(B, L, 1)
+    Tf = plan.Tf
+    got = {}
+    zr = torch.view_as_real(taps["z"])
+    want = {"Z": torch.stack([zr[:, 0, :, :, 0], zr[:, 0, :, :, 1], zr[:, 1, :, :, 0], zr[:, 1, :, :, 1]], dim=-1).permute(0, 2, 1, 3)}
+    got["Z"] = plan.tap("Z").to_torch().view(B, Tf, 2048, 4).cpu()
+    fr, ch = [512, 128, 32, 8], [48, 96, 192, 384]
+    for i in range(4):
+        got[f"enc{i}"] = _interior(plan, f"enc{i}").reshape(B, Tf, fr[i], ch[i])
+        want[f"enc{i}"] = taps[f"enc{i}"].permute(0, 3, 2, 1)
+        got[f"tenc{i}"] = _interior(plan, f"tenc{i}")
+        want[f"tenc{i}"] = taps[f"tenc{i}"].permute(0, 2, 1)
+    got["tokf"] = plan.tap("tokf").to_torch().float().view(B, -1, 512).cpu(); want["tokf"] = taps["xf_layer4"]
+    got["tokt"] = plan.tap("tokt").to_torch().float().view(B, -1, 512).cpu(); want["tokt"] = taps["xf_layer4_t"]
+    got["xenc"] = plan.tap("xenc").to_torch().float().view(B, Tf, 8, 384).cpu(); want["xenc"] = taps["x_enc"].permute(0, 3, 2, 1)
+    got["xtenc"] = plan.tap("xtenc").to_torch().float().view(B, -1, 384).cpu(); want["xtenc"] = taps["xt_enc"].permute(0, 2, 1)
+    got["xc"] = _interior(plan, "xc").reshape(B, Tf, 8, 384); want["xc"] = taps["x_cond"].permute(0, 3, 2, 1)
+    got["xtc"] = _interior(plan, "xtc"); want["xtc"] = taps["xt_cond"].permute(0, 2, 1)
+    dch = [192, 96, 48, 4]
+    for i in range(4):
+        got[f"fdec{i}"] = _interior(plan, f"fdec{i}").reshape(B, Tf, Tf, dch[i]); want[f"fdec{i}"] = taps[f"fdec{i}"].permute(0, 3, 2, 1)
+        got[f"tdec{i}"] = _interior(plan, f"tdec{i}"); want[f"tdec{i}"] = taps[f"tdec{i}"].permute(0, 2, 1)
+    got["out"], want["out"] = out, ref
+    bad = []
+    for name in want:
+        g, w = got[name], want[name].float()
+        assert g.shape == w.shape, (name, g.shape, w.shape)
+        err = float((g - w).abs().max())
+        scale = max(1.0, float(w.abs().max()))
+        snr = athtd_oracle.snr_db(g, w)
+        print(f"{prec} tap {name:7s} max-abs {err:9.3e} (scale {scale:7.2f})  SNR {snr:6.2f} dB")
+        if prec == "fp32":
+            if name == "Z" and err > 1e-5:
+                bad.append(name)
+            if err > 1e-3 * scale:
+                bad.append(name)
+        else:
+            floor = 40.0 if name == "out" else (100.0 if name == "Z" else TAP_FLOOR_DB["bf16"])
+            if snr < floor:
+                bad.append(name)
+    assert not bad, bad
+
+
+def test_encode_then_decode_repeatedly(models, state_dict):
+    """C-ABI flow athtd_encode once, athtd_decode per prompt set (include/athtd.h): the decoder GroupNorm accumulators must be
+    cleared by every decode -- decode(A), decode(B), decode(A) gives A's result twice and both match forward()."""
+    for prec, tol in (("fp32", 1e-5), ("bf16", None)):
+        m = models[prec]
+        wav, embA = synthetic.make_inputs(31, 2, 20000)
+        _, embB = synthetic.make_inputs(32, 2, 4096)
+        plan = m.engine().plan(2, 20000, 1)
+        w = wav.cuda()
+        a, b = embA.cuda().unsqueeze(1).contiguous(), embB.cuda().unsqueeze(1).contiguous()
+        fwd_a = plan.forward(w, a).clone()
+        fwd_b = plan.forward(w, b).clone()
+        plan.encode(w)
+        d1 = plan.decode(a).clone()
+        d2 = plan.decode(b).clone()
+        d3 = plan.decode(a).clone()
+        for got, want in ((d1, fwd_a), (d2, fwd_b), (d3, fwd_a)):
+            if tol is not None:
+                assert (got - want).abs().max() < tol
+            else:
+                assert athtd_oracle.snr_db(got.cpu(), want.cpu()) >= 70.0
+        ref = athtd_oracle.forward(state_dict, wav, embB)
+        if prec == "fp32":
+            assert (d2[:, 0].cpu() - ref).abs().max() < 1e-3
+        assert plan.launches > 0
+
+
+def test_encode_mirror_matches_oracle_encode(models, state_dict):
+    """AudioTextHTDemucsB200._encode(x, xt) keeps the reference signature and return value (ATHTDemucs_v2.py:190-236)."""
+    B, L = 2, 30000
+    wav, _ = synthetic.make_inputs(41, B, L)
+    z = athtd_oracle.spec(wav)
+    x = athtd_oracle.magnitude(z)
+    x = (x - x.mean(dim=(1, 2, 3), keepdim=True)) / (1e-5 + x.std(dim=(1, 2, 3), keepdim=True))
+    xt = (wav - wav.mean(dim=(1, 2), keepdim=True)) / (1e-5 + wav.std(dim=(1, 2), keepdim=True))
+    rx, rxt, rsaved, rsaved_t, rl, rlt = athtd_oracle.encode(state_dict, x, xt)
+    gx, gxt, gsaved, gsaved_t, gl, glt = models["fp32"]._encode(x.cuda(), xt.cuda())
+    assert gl == rl and glt == rlt
+    assert gx.shape == rx.shape and gxt.shape == rxt.shape
+    assert (gx.cpu() - rx).abs().max() < 1e-3 and (gxt.cpu() - rxt).abs().max() < 1e-3
+    for g, r in zip(gsaved + gsaved_t, rsaved + rsaved_t):
+        assert g.shape == r.shape
+        assert (g.cpu() - r).abs().max() < 1e-3 * max(1.0, float(r.abs().max()))
+
+
+def test_plugin_interface_separate_and_separate_all(models, state_dict):
+    """SeparationModel contract (benchmark.py:81-115, 206-215): separate(mixture, stem) and separate_all(mixture) through the
+    prompt-embedding cache, against the reference loop (one full pass per stem) driving the oracle."""
+    m = models["fp32"]
+    sep = athtd_b200.B200SeparationModel(m, "cuda", segment_seconds=1.0, overlap_seconds=0.25, batch=3)
+    assert isinstance(sep, athtd_b200.SeparationModel) and sep.name
+    embs = {s: synthetic.make_inputs(500 + i, 1, 4096)[1] for i, s in enumerate(athtd_b200.STEMS)}
+    for s, e in embs.items():
+        m.register_prompt_embedding(s, e[0])
+    T = 44100 * 2 + 3000
+    mix = synthetic.make_inputs(61, 1, T)[0][0]
+    allout = sep.separate_all(mix.cuda())
+    assert list(allout.keys()) == athtd_b200.STEMS
+    for s in athtd_b200.STEMS:
+        r = ola.chunked_inference(lambda c: athtd_oracle.forward(state_dict, c, embs[s]), mix, 1.0, 0.25)
+        assert allout[s].shape == (2, T)
+        assert (allout[s].cpu() - r).abs().max() < 1e-3
+    one = sep.separate(mix.cuda(), "bass")
+    assert (one - allout["bass"]).abs().max() < 1e-5
+
+
+def test_empty_span_and_plan_capacity(models):
+    """More ranks than chunks: an empty span returns [P, 2, 0] without launching; a tail batch runs in the
+    full-batch plan's workspace (one workspace per (L, P), not one per batch size)."""
+    m = models["fp32"]
+    sep = athtd_b200.B200SeparationModel(m, "cuda", segment_seconds=1.0, overlap_seconds=0.25, batch=4)
+    T = 44100 * 5
+    mix = synthetic.make_inputs(62, 1, T)[0][0].cuda()
+    emb = synthetic.make_prompt_embeddings(2).cuda()
+    out = sep.separate_span(mix, emb, (3, 3))
+    assert out.shape == (2, 2, 0)
+    host = mix.cpu().pin_memory()
+    sep.separate_span_host(host, emb, (3, 3), torch.empty(2, 2, 0).pin_memory())
+    eng = m.engine()
+    eng.drop_plans()
+    full, _ = sep.separate_many(mix, emb)          # 7 chunks: batches of 4 + 3
+    assert len(eng.plans) == 1 and next(iter(eng.plans.values())).cap == 4
+    sep1 = athtd_b200.B200SeparationModel(m, "cuda", segment_seconds=1.0, overlap_seconds=0.25, batch=1)
+    eng.drop_plans()
+    one, _ = sep1.separate_many(mix, emb)
+    assert (one - full).abs().max() < 1e-5

@@ -137,3 +137,64 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "x realtime" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_separation_model_abc_keeps_the_reference_contract():
+    """benchmark.py:81-115: abstract separate / separate_all / name; a reference-style plugin that implements exactly those three
+    instantiates, one that forgets ``separate`` does not."""
+    import athtd_b200
+
+    class Plugin(athtd_b200.SeparationModel):
+        def separate(self, mixture, stem_name):
+            return mixture
+
+        def separate_all(self, mixture):
+            return {s: mixture for s in athtd_b200.STEMS}
+
+        @property
+        def name(self):
+            return "plugin"
+
+    assert Plugin().name == "plugin"
+    assert athtd_b200.SeparationModel.__abstractmethods__ == frozenset({"separate", "separate_all", "name"})
+
+    class Broken(athtd_b200.SeparationModel):
+        def separate_all(self, mixture):
+            return {}
+
+        @property
+        def name(self):
+            return "broken"
+
+    with pytest.raises(TypeError):
+        Broken()
+    assert not hasattr(athtd_b200.SeparationModel, "separate_fade")
+    for m in ("separate", "separate_all", "separate_fade", "separate_span", "separate_span_host"):
+        assert callable(getattr(athtd_b200.B200SeparationModel, m))
+
+
+def test_product_package_never_imports_the_oracle():
+    """The product path (package + bench.py's GPU arm) must not route through oracle/: only tests, smoke() and the CPU legs of
+    bench.py may."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "audio-to-sheet-music_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert not pat.search(open(os.path.join(pkg, fn)).read()), fn
+    bench = open(os.path.join(root, "bench.py")).read()
+    for m in pat.finditer(bench):
+        fn_start = bench.rfind("\ndef ", 0, m.start())
+        name = bench[fn_start:bench.find("(", fn_start)].split()[-1]
+        assert name in ("cpu_reference_rate", "cpu_stft_rate"), name
+
+
+def test_bench_track_parts_tile_the_track():
+    from athtd_b200 import synthetic
+    a = synthetic.make_track(1.0)
+    assert a.shape == (2, 44100) and torch.equal(a, synthetic.make_track_part(0, 44100))
+    b = synthetic.make_track_part(1000, 3000)
+    tone = (a - 0.0)[:, 1000:3000] - b           # same tone phase, different noise draw
+    assert float(tone.abs().max()) < 1.0 and b.shape == (2, 2000)
