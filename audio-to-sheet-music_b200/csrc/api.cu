@@ -168,10 +168,9 @@ int athtd_istft(const float* Z_dev, int B, int L, float* frames_dev, float* out_
                 const float* win_dev, void* stream) {
   const int Tf = (L + 1023) / 1024;
   RowSpace none{};
-  launch_mask_istft<float>(Z_dev, Tf, B, 1, nullptr, none, 0, nullptr, nullptr, frames_dev, (const float2*)tw_dev, win_dev,
-                           (cudaStream_t)stream);
-  launch_ola_combine<float>(frames_dev, Tf, L, B, nullptr, none, nullptr, nullptr, nullptr, 1, out_dev, 2L * L,
-                            (cudaStream_t)stream);
+  (void)frames_dev;      // kept in the signature for ABI stability: the fused inverse needs no frame scratch
+  launch_istft_fused<float>(Z_dev, Tf, L, B, 1, nullptr, none, 0, nullptr, nullptr, nullptr, none, nullptr, nullptr, nullptr, 1,
+                            out_dev, 2L * L, (const float2*)tw_dev, win_dev, (cudaStream_t)stream);
   return check_cuda("athtd_istft");
 }
 

@@ -11,10 +11,11 @@
 //             per-segment sum / sum-of-squares partials for the input normalisation.
 //   inverse : freq_out 1x1 conv, 259->2048 linear resize of the mask logits, sigmoid,
 //             the signed-CaC mask*phase product (quirk Q4), Hermitian extension with zero
-//             Nyquist, inverse FFT, window and 1/64 scale -> windowed frames.
-// A second bandwidth kernel overlap-adds 4 frames per sample in fixed order, divides by the
-// constant window-sum envelope 1.5, adds the de-normalised time branch and writes [B,2,L].
+//             Nyquist, inverse FFT, window and 1/64 scale, 4-frame overlap-add in a shared-memory
+//             ring (fixed order), the constant window-sum envelope 1/1.5, the de-normalised
+//             time branch, [B,2,L] store: the windowed frames never reach memory.
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace athtd {
 
@@ -209,25 +210,15 @@ __device__ __forceinline__ void lerp_coords_f(int d, int in, int out, int& i0, i
   lam = src - (float)i0;
 }
 
-// dec : FreqDecoder output rows [g = zb*? ...] see launch; fo_w [2][4], fo_b [2]
-// If dec == nullptr the mask is 1 (plain _ispec of Z[:, :2] semantics is NOT this; used only with use_mask=0 where
-// masked_z := z, i.e. channel 0 = L, channel 1 = R, for the STFT->iSTFT microbenchmark).
+// Front end of the inverse transform for one (output batch bo, frame): reads the spectrogram row Z[bz, frame], applies the
+// freq_out 1x1 conv + 259 -> 2048 resize + sigmoid mask with the signed-CaC phase product (use_mask) or nothing (plain _ispec
+// of channels (L, R): the STFT -> iSTFT microbenchmark), and writes the Hermitian-extended 4096-point spectrum of the packed
+// signal L + iR into sr / si (natural order, un-padded indices).  Ends with __syncthreads().
 template <typename T>
-__global__ void __launch_bounds__(256) mask_istft_kernel(const float4* __restrict__ Z, int Tf, int zb_div,
-                                                          const T* __restrict__ dec, RowSpace ds, int use_mask,
-                                                          const float* __restrict__ fo_w, const float* __restrict__ fo_b,
-                                                          float* __restrict__ frames, const float2* __restrict__ tw,
-                                                          const float* __restrict__ win) {
-  __shared__ float sr[FFT_SMEM], si[FFT_SMEM];
-  const int t = threadIdx.x, frame = blockIdx.x, bo = blockIdx.y;   // bo: output batch index (b*P + p or b)
-  const int bz = bo / zb_div;                                        // spectrogram batch index
-  const float4* zi = Z + ((long)bz * Tf + frame) * 2048;
-  const int g = bo * Tf + frame;                                     // decoder row-space group
-  float w00 = 0, w01 = 0, w02 = 0, w03 = 0, w10 = 0, w11 = 0, w12 = 0, w13 = 0, b0 = 0, b1 = 0;
-  if (use_mask) {
-    w00 = fo_w[0]; w01 = fo_w[1]; w02 = fo_w[2]; w03 = fo_w[3];
-    w10 = fo_w[4]; w11 = fo_w[5]; w12 = fo_w[6]; w13 = fo_w[7]; b0 = fo_b[0]; b1 = fo_b[1];
-  }
+__device__ __forceinline__ void masked_spectrum_to_smem(const float4* __restrict__ zi, const T* __restrict__ dec, const RowSpace& ds,
+                                                        int g, int use_mask, const float (&fw)[8], const float (&fb)[2],
+                                                        float* sr, float* si) {
+  const int t = threadIdx.x;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int k = t + 256 * i;
@@ -246,10 +237,10 @@ __global__ void __launch_bounds__(256) mask_istft_kernel(const float4* __restric
         const float4 ra = *(const float4*)(dec + ds.row_off(g, i0)), rc = *(const float4*)(dec + ds.row_off(g, i1));
         a0 = ra.x; a1 = ra.y; a2 = ra.z; a3 = ra.w; c0 = rc.x; c1 = rc.y; c2 = rc.z; c3 = rc.w;
       }
-      float l0a = w00 * a0 + w01 * a1 + w02 * a2 + w03 * a3 + b0;
-      float l1a = w10 * a0 + w11 * a1 + w12 * a2 + w13 * a3 + b1;
-      float l0b = w00 * c0 + w01 * c1 + w02 * c2 + w03 * c3 + b0;
-      float l1b = w10 * c0 + w11 * c1 + w12 * c2 + w13 * c3 + b1;
+      float l0a = fw[0] * a0 + fw[1] * a1 + fw[2] * a2 + fw[3] * a3 + fb[0];
+      float l1a = fw[4] * a0 + fw[5] * a1 + fw[6] * a2 + fw[7] * a3 + fb[1];
+      float l0b = fw[0] * c0 + fw[1] * c1 + fw[2] * c2 + fw[3] * c3 + fb[0];
+      float l1b = fw[4] * c0 + fw[5] * c1 + fw[6] * c2 + fw[7] * c3 + fb[1];
       const float q0 = (1.f - lam) * l0a + lam * l0b, q1 = (1.f - lam) * l1a + lam * l1b;
       float m0, m1, inv0, inv1;
       if constexpr (sizeof(T) == 2) {      // bf16 build: MUFU exp / reciprocal (relative error ~1e-6, far below the bf16 activations)
@@ -274,6 +265,12 @@ __global__ void __launch_bounds__(256) mask_istft_kernel(const float4* __restric
   }
   if (t == 0) { sr[2048] = 0.f; si[2048] = 0.f; }   // Nyquist bin is zero-padded by _ispec
   __syncthreads();
+}
+
+// Inverse 4096-point transform of the spectrum masked_spectrum_to_smem left in sr / si; on exit sr[n + (n >> 4)] / si[...] hold
+// the left / right time samples n of the frame (before the window and the 1/64 scale).
+__device__ __forceinline__ void ifft4096_smem(float* sr, float* si, const float2* __restrict__ tw) {
+  const int t = threadIdx.x;
   float2 v[16];
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) { v[n1].x = sr[256 * n1 + t]; v[n1].y = si[256 * n1 + t]; }
@@ -286,76 +283,142 @@ __global__ void __launch_bounds__(256) mask_istft_kernel(const float4* __restric
   }
   __syncthreads();
   fft4096_tail<true>(v, sr, si, tw);
-  float* fl = frames + (((long)bo * 2 + 0) * Tf + frame) * FFT_N;
-  float* fr = frames + (((long)bo * 2 + 1) * Tf + frame) * FFT_N;
+}
+
+// ------------------------------------------------------------------ inverse: mask + iFFT + window + overlap-add + time branch
+// htdemucs._ispec (ATHTDemucs_v2.py:310; demucs spec.py ispectro) fused with everything around it:
+//   out[bo, ch, s] = (sum_t w[n] * irfft(64 Z_t)[n], n = s + 1536 - 1024 t) / 1.5  +  (time_out(tdec)[ch] * std_t + mean_t)
+// (the window-sum envelope is the constant 1.5 on the kept samples; time branch: ATHTDemucs_v2.py:313-324).
+// The windowed frames never go to memory: a CTA walks a contiguous run of frames of the flat (output batch, frame) list with
+// a four-hop accumulator ring in shared memory -- the frame t adds its four quarters to the hops t .. t+3 and completes hop
+// t, which is scaled, combined with the time branch and stored.  A run that starts inside a segment first re-transforms the
+// three frames before it (ring warm-up, no stores); runs are equal-sized so that one wave of CTAs fills the chip.
+// Every output sample is the fixed-order sum ((f[t-3] + f[t-2]) + f[t-1]) + f[t] of its (up to) four frames.
+#define IFFT_SMEM_BYTES ((2 * FFT_SMEM + 2 * FFT_N) * 4)
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3) istft_fused_kernel(const float4* __restrict__ Z, int Tf, int L, int Bout, int zb_div,
+                                                           const T* __restrict__ dec, RowSpace ds, int use_mask,
+                                                           const float* __restrict__ fo_w, const float* __restrict__ fo_b,
+                                                           const T* __restrict__ tdec, RowSpace ts, const float* __restrict__ to_w,
+                                                           const float* __restrict__ to_b, const float* __restrict__ meanstd_t,
+                                                           int ms_div, float* __restrict__ out, long out_bstride,
+                                                           const float2* __restrict__ tw, const float* __restrict__ win) {
+  extern __shared__ __align__(16) float fsm[];
+  float* sr = fsm;
+  float* si = fsm + FFT_SMEM;
+  float2* ring = (float2*)(fsm + 2 * FFT_SMEM);      // [4 hops][1024] (left, right) partial overlap-add sums
+  const int t = threadIdx.x;
+  float fw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fb[2] = {0, 0}, tw8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tb[2] = {0, 0};
+  if (use_mask) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    int n = t + 256 * i;
-    float w = win[n] * (1.0f / 64.0f);
-    fl[n] = sr[n + (n >> 4)] * w;
-    fr[n] = si[n + (n >> 4)] * w;
+    for (int i = 0; i < 8; ++i) fw[i] = fo_w[i];
+    fb[0] = fo_b[0]; fb[1] = fo_b[1];
   }
-}
-
-template <typename T>
-void launch_mask_istft(const float* Z, int Tf, int Bout, int zb_div, const T* dec, RowSpace ds, int use_mask,
-                       const float* fo_w, const float* fo_b, float* frames, const float2* tw, const float* win,
-                       cudaStream_t st) {
-  mask_istft_kernel<T><<<dim3(Tf, Bout), 256, 0, st>>>((const float4*)Z, Tf, zb_div, dec, ds, use_mask, fo_w, fo_b, frames, tw, win);
-}
-
-// ------------------------------------------------------------------ frame overlap-add + time branch
-// out[bo, ch, s] = (sum_t frames[bo,ch,t, s+1536-1024t]) / 1.5  +  (time_out(tdec)[ch] * std_t + mean_t)
-//   (_ispec envelope is the constant 1.5 on the kept samples, SURVEY.md Appendix A1;
-//    time branch: ATHTDemucs_v2.py:313-324).   tdec == nullptr -> frequency branch only.
-template <typename T>
-__global__ void ola_combine_kernel(const float* __restrict__ frames, int Tf, int L, const T* __restrict__ tdec, RowSpace ts,
-                                   const float* __restrict__ to_w, const float* __restrict__ to_b,
-                                   const float* __restrict__ meanstd_t, int ms_div, float* __restrict__ out, long out_bstride) {
-  const int bo = blockIdx.y;
-  float w[8], bb[2], mean = 0.f, sd = 1.f;
   if (tdec) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = to_w[i];
-    bb[0] = to_b[0]; bb[1] = to_b[1];
-    mean = meanstd_t[2 * (bo / ms_div)]; sd = meanstd_t[2 * (bo / ms_div) + 1];
+    for (int i = 0; i < 8; ++i) tw8[i] = to_w[i];
+    tb[0] = to_b[0]; tb[1] = to_b[1];
   }
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < L; s += gridDim.x * blockDim.x) {
-    int p = s + 1536;
-    int t_hi = p >> 10; if (t_hi > Tf - 1) t_hi = Tf - 1;
-    int t_lo = (p - 4095 + 1023) >> 10; if (t_lo < 0) t_lo = 0;
-    float a0 = 0.f, a1 = 0.f;
-    for (int t = t_lo; t <= t_hi; ++t) {
-      int n = p - 1024 * t;
-      a0 += frames[(((long)bo * 2 + 0) * Tf + t) * FFT_N + n];
-      a1 += frames[(((long)bo * 2 + 1) * Tf + t) * FFT_N + n];
+  const long total = (long)Bout * Tf;
+  long f_begin = total * blockIdx.x / gridDim.x, f_end = total * (blockIdx.x + 1) / gridDim.x;
+  const bool vec_ok = (L & 3) == 0 && (out_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+
+  while (f_begin < f_end) {
+    const int bo = (int)(f_begin / Tf);
+    const int ta = (int)(f_begin - (long)bo * Tf);
+    const int tb_ = (int)min((long)Tf, (long)ta + (f_end - f_begin));      // piece [ta, tb_) of segment bo
+    const int bz = bo / zb_div;
+    float mean = 0.f, sd = 1.f;
+    if (tdec) { mean = meanstd_t[2 * (bo / ms_div)]; sd = meanstd_t[2 * (bo / ms_div) + 1]; }
+    const int t_start = max(0, ta - 3);
+    float* ob = out + (long)bo * out_bstride;
+
+    auto emit = [&](int h) {            // hop h of the overlap-add buffer is complete: positions p = 1024 h + j, sample s = p - 1536
+      const float2* rg = ring + (h & 3) * 1024;
+      const int s0 = 1024 * h - 1536 + 4 * t;
+      if (s0 + 3 < 0 || s0 >= L) return;
+      const float4 q0 = *(const float4*)(rg + 4 * t), q1 = *(const float4*)(rg + 4 * t + 2);
+      float a0[4] = {q0.x, q0.z, q1.x, q1.z}, a1[4] = {q0.y, q0.w, q1.y, q1.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { a0[e] *= (1.0f / 1.5f); a1[e] *= (1.0f / 1.5f); }
+      if (tdec) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int s = s0 + e;
+          if (s < 0 || s >= L) continue;
+          const T* r = tdec + ts.row_off(bo, s);
+          float x0, x1, x2, x3;
+          if constexpr (sizeof(T) == 2) {
+            const uint2 rr = *(const uint2*)r;
+            const float2 r0 = __bfloat1622float2(*(const __nv_bfloat162*)&rr.x), r1 = __bfloat1622float2(*(const __nv_bfloat162*)&rr.y);
+            x0 = r0.x; x1 = r0.y; x2 = r1.x; x3 = r1.y;
+          } else {
+            const float4 rr = *(const float4*)r;
+            x0 = rr.x; x1 = rr.y; x2 = rr.z; x3 = rr.w;
+          }
+          const float y0 = tw8[0] * x0 + tw8[1] * x1 + tw8[2] * x2 + tw8[3] * x3 + tb[0];
+          const float y1 = tw8[4] * x0 + tw8[5] * x1 + tw8[6] * x2 + tw8[7] * x3 + tb[1];
+          a0[e] += y0 * sd + mean; a1[e] += y1 * sd + mean;
+        }
+      }
+      if (vec_ok && s0 >= 0 && s0 + 3 < L) {
+        *(float4*)(ob + s0) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+        *(float4*)(ob + L + s0) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int s = s0 + e;
+          if (s >= 0 && s < L) { ob[s] = a0[e]; ob[L + s] = a1[e]; }
+        }
+      }
+    };
+
+    for (int fr = t_start; fr < tb_; ++fr) {
+      masked_spectrum_to_smem<T>(Z + ((long)bz * Tf + fr) * 2048, dec, ds, bo * Tf + fr, use_mask, fw, fb, sr, si);
+      ifft4096_smem(sr, si, tw);
+      // quarter qq of the frame belongs to hop fr + qq; the first frame of the run and every quarter 3 open a new hop
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = t + 256 * i, qq = i >> 2;
+        const float w = win[n] * (1.0f / 64.0f);
+        const float2 x = make_float2(sr[n + (n >> 4)] * w, si[n + (n >> 4)] * w);
+        float2* slot = ring + ((fr + qq) & 3) * 1024 + (n & 1023);
+        if (qq == 3 || fr == t_start) *slot = x;
+        else { float2 a = *slot; a.x += x.x; a.y += x.y; *slot = a; }
+      }
+      __syncthreads();
+      if (fr >= ta) emit(fr);
+      // no barrier needed here: the next frame's spectrum overwrites sr / si, which were last read BEFORE the barrier above,
+      // and its quarter 3 overwrites the ring slot emit() is reading only after the barriers inside the next transform
     }
-    a0 *= (1.0f / 1.5f); a1 *= (1.0f / 1.5f);
-    if (tdec) {
-      const T* r = tdec + ts.row_off(bo, s);
-      float x0 = to_f<T>(r[0]), x1 = to_f<T>(r[1]), x2 = to_f<T>(r[2]), x3 = to_f<T>(r[3]);
-      float y0 = w[0] * x0 + w[1] * x1 + w[2] * x2 + w[3] * x3 + bb[0];
-      float y1 = w[4] * x0 + w[5] * x1 + w[6] * x2 + w[7] * x3 + bb[1];
-      a0 += y0 * sd + mean; a1 += y1 * sd + mean;
-    }
-    out[(long)bo * out_bstride + s] = a0;
-    out[(long)bo * out_bstride + L + s] = a1;
+    if (tb_ == Tf)                       // end of the segment: hops Tf .. Tf + 2 only have older frames left
+      for (int h = Tf; h < Tf + 3; ++h) emit(h);
+    f_begin += tb_ - ta;
   }
-}
-template <typename T>
-void launch_ola_combine(const float* frames, int Tf, int L, int Bout, const T* tdec, RowSpace ts, const float* to_w,
-                        const float* to_b, const float* meanstd_t, int ms_div, float* out, long out_bstride, cudaStream_t st) {
-  ola_combine_kernel<T><<<dim3(min((L + 255) / 256, 1024), Bout), 256, 0, st>>>(frames, Tf, L, tdec, ts, to_w, to_b, meanstd_t,
-                                                                              ms_div, out, out_bstride);
 }
 
-template void launch_mask_istft<float>(const float*, int, int, int, const float*, RowSpace, int, const float*, const float*,
-                                       float*, const float2*, const float*, cudaStream_t);
-template void launch_mask_istft<bf16>(const float*, int, int, int, const bf16*, RowSpace, int, const float*, const float*,
-                                      float*, const float2*, const float*, cudaStream_t);
-template void launch_ola_combine<float>(const float*, int, int, int, const float*, RowSpace, const float*, const float*,
-                                        const float*, int, float*, long, cudaStream_t);
-template void launch_ola_combine<bf16>(const float*, int, int, int, const bf16*, RowSpace, const float*, const float*,
-                                       const float*, int, float*, long, cudaStream_t);
+template <typename T>
+void launch_istft_fused(const float* Z, int Tf, int L, int Bout, int zb_div, const T* dec, RowSpace ds, int use_mask,
+                        const float* fo_w, const float* fo_b, const T* tdec, RowSpace ts, const float* to_w, const float* to_b,
+                        const float* meanstd_t, int ms_div, float* out, long out_bstride, const float2* tw, const float* win,
+                        cudaStream_t st) {
+  static PerDeviceOnce attr;
+  if (attr.first()) cudaFuncSetAttribute(istft_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, IFFT_SMEM_BYTES);
+  // equal runs of the flat (batch, frame) list: one wave of 3 CTAs per SM, at least ~12 frames per run (3 warm-up frames)
+  const long total = (long)Bout * Tf;
+  const long slots = 3L * device_sm_count();
+  long grid = std::min(slots, std::max(1L, total / 12));
+  istft_fused_kernel<T><<<(unsigned)grid, 256, IFFT_SMEM_BYTES, st>>>((const float4*)Z, Tf, L, Bout, zb_div, dec, ds, use_mask, fo_w,
+                                                                     fo_b, tdec, ts, to_w, to_b, meanstd_t, ms_div, out, out_bstride,
+                                                                     tw, win);
+}
+
+template void launch_istft_fused<float>(const float*, int, int, int, int, const float*, RowSpace, int, const float*, const float*,
+                                        const float*, RowSpace, const float*, const float*, const float*, int, float*, long,
+                                        const float2*, const float*, cudaStream_t);
+template void launch_istft_fused<bf16>(const float*, int, int, int, int, const bf16*, RowSpace, int, const float*, const float*,
+                                       const bf16*, RowSpace, const float*, const float*, const float*, int, float*, long,
+                                       const float2*, const float*, cudaStream_t);
 
 }  // namespace athtd

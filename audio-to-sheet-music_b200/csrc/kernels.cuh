@@ -71,12 +71,10 @@ void launch_dec_last_time(const bf16* x, RowSpace xs, const bf16* w, const float
 // ---- fft.cu
 void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
                      cudaStream_t st);
-template <typename T> void launch_mask_istft(const float* Z, int Tf, int Bout, int zb_div, const T* dec, RowSpace ds,
-                                             int use_mask, const float* fo_w, const float* fo_b, float* frames,
-                                             const float2* tw, const float* win, cudaStream_t st);
-template <typename T> void launch_ola_combine(const float* frames, int Tf, int L, int Bout, const T* tdec, RowSpace ts,
+template <typename T> void launch_istft_fused(const float* Z, int Tf, int L, int Bout, int zb_div, const T* dec, RowSpace ds,
+                                              int use_mask, const float* fo_w, const float* fo_b, const T* tdec, RowSpace ts,
                                               const float* to_w, const float* to_b, const float* meanstd_t, int ms_div,
-                                              float* out, long out_bstride, cudaStream_t st);
+                                              float* out, long out_bstride, const float2* tw, const float* win, cudaStream_t st);
 
 // ---- attention.cu (bf16 tcgen05 flash attention, 8 heads x 64)
 bool flash_attn_supported(long ldq, long ldkv, long ldo);

@@ -172,7 +172,6 @@ void PlanT<T>::layout(char* base) {
     umax = std::max(umax, (size_t)dt_rs[i - 1].rows_total() * 4 * kDecCh[i + 1]);
   }
   ubuf = (T*)take(umax * sizeof(T));
-  frames = (float*)take(sizeof(float) * (size_t)B * 2 * Tf * 4096);
   total_bytes = align_up(off, 256);
   spaces(sh.B);
 }
@@ -730,12 +729,12 @@ void PlanT<T>::decode(const float* emb, float* out, cudaStream_t st) {
     text_condition(p, xtenc, s.St, xtc, xtc_rs, st);
     const T* x = xc; RowSpace xs = xc_rs;
     for (int i = 0; i < 4; ++i) { dec_layer(true, i, p, x, xs, df[i], df_rs[i], ef[3 - i], yf_rs[3 - i], st); x = df[i]; xs = df_rs[i]; }
-    launch_mask_istft<T>(Z, Tf, B, 1, df[3], df_rs[3], 1, P32("freq_out.weight"), P32("freq_out.bias"), frames, consts.tw,
-                         consts.win, st); ++n_launches;
     x = xtc; xs = xtc_rs;
     for (int i = 0; i < 4; ++i) { dec_layer(false, i, p, x, xs, dt[i], dt_rs[i], et[3 - i], yt_rs[3 - i], st); x = dt[i]; xs = dt_rs[i]; }
-    launch_ola_combine<T>(frames, Tf, s.L, B, dt[3], dt_rs[3], P32("time_out.weight"), P32("time_out.bias"), ms_wav, 1,
-                          out + (size_t)p * 2 * s.L, (long)s.P * 2 * s.L, st); ++n_launches;
+    // mask -> inverse STFT -> overlap-add -> + de-normalised time branch, one kernel (ATHTDemucs_v2.py:294-324)
+    launch_istft_fused<T>(Z, Tf, s.L, B, 1, df[3], df_rs[3], 1, P32("freq_out.weight"), P32("freq_out.bias"), dt[3], dt_rs[3],
+                          P32("time_out.weight"), P32("time_out.bias"), ms_wav, 1, out + (size_t)p * 2 * s.L, (long)s.P * 2 * s.L,
+                          consts.tw, consts.win, st); ++n_launches;
   }
 }
 
@@ -778,7 +777,6 @@ bool PlanT<T>::tap(const std::string& name, TapInfo& ti) const {
   if (name == "xc") return rs(xc, xc_rs);
   if (name == "xtc") return rs(xtc, xtc_rs);
   if (name == "cvec") return set(cvec, 0, (long)s.B * s.P * 384, s.B * s.P, 384, 1, 0);
-  if (name == "frames") return set(frames, 0, (long)s.B * 2 * s.Tf * 4096, s.B, 2, s.Tf, 4096);
   return false;
 }
 

@@ -90,7 +90,7 @@ struct PlanT : PlanBase {
   RowSpace xf0_rs, xt0_rs, yf_rs[4], yt_rs[4], xc_rs, xtc_rs, df_rs[4], dt_rs[4];
   T *xf0, *xt0, *yf[4], *ef[4], *yt[4], *et[4], *xc, *xtc, *df[4], *dt[4];
   double *st_spec, *st_wav, *st_df[4][2][2], *st_dt[4][2][2], *st_xf[5][2], *st_dec;
-  float *mr, *ms_spec, *ms_wav, *Z, *cvec, *frames;
+  float *mr, *ms_spec, *ms_wav, *Z, *cvec;
   T *hbuf, *ebuf, *tokf, *tokt, *hn[5], *qkv, *kvb, *obuf, *ffn, *scores, *xenc, *xtenc, *t1, *t2, *ubuf;
 
   PlanT(int B, int L, int P, const ParamTable* pt, const PackLayout* pl, const float* params, const void* packed,

@@ -415,8 +415,8 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                 "launches_per_step": prof["launches"], "gemm_ms_per_step": prof["ms"], "share_of_step": prof["ms"] / ms_step if ms_step else None,
                 "algorithmic_gflop_per_step": prof["gflop"],
-                "reference_equivalent_tflops": GFLOP_PER_SEG_PROMPT * n * P / world / ms_step / 1e3 if ms_step else None,
-                "executed_model_tflops": (GFLOP_SHARED + GFLOP_PER_PROMPT * P) * n / world / ms_step / 1e3 if ms_step else None}
+                "reference_equivalent_tflops": GFLOP_PER_SEG_PROMPT * n * P / world / ms_step if ms_step else None,
+                "executed_model_tflops": (GFLOP_SHARED + GFLOP_PER_PROMPT * P) * n / world / ms_step if ms_step else None}
         line = {
             "metric": METRIC, "value": value, "unit": "x realtime", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
