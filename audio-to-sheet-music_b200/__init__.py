@@ -7,4 +7,6 @@ from .separation import (B200SeparationModel, SeparationModel, STEMS, segment_pl
 from .engine import Engine, Plan                                     # noqa: F401
 from . import distributed                                     # noqa: F401
 from . import metrics                                         # noqa: F401
+from . import audio                                           # noqa: F401
+from .audio import DeviceResampler, prepare_mixture           # noqa: F401
 from .clap_text import ClapTextModelWithProjectionB200, ClapModelTextB200   # noqa: F401

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libathtd.so")
-SOURCES = ["api.cu", "plan.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "elementwise.cu", "fft.cu", "ola.cu", "dconv_row.cu", "enc_row.cu", "dconv_tile.cu", "small_conv.cu", "metrics.cu", "clap_text.cu"]
+SOURCES = ["api.cu", "plan.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "elementwise.cu", "fft.cu", "ola.cu", "dconv_row.cu", "enc_row.cu", "dconv_tile.cu", "small_conv.cu", "metrics.cu", "clap_text.cu", "resample.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

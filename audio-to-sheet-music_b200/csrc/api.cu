@@ -126,6 +126,8 @@ int athtd_plan_set_tc(void* plan, int on) { ((PlanBase*)plan)->set_use_tc(on != 
 int athtd_plan_set_flash(void* plan, int on) { ((PlanBase*)plan)->set_use_flash(on != 0); return 0; }
 int athtd_plan_set_fused_dconv(void* plan, int on) { ((PlanBase*)plan)->set_use_fused_dconv(on != 0); return 0; }
 int athtd_plan_tc_launches(void* plan) { return ((PlanBase*)plan)->tc_launches(); }
+int athtd_plan_set_graph(void* plan, int on) { ((PlanBase*)plan)->set_use_graph(on != 0); return 0; }
+int athtd_plan_graph_replays(void* plan) { return ((PlanBase*)plan)->graph_replays(); }
 
 int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* stream) {
   cudaError_t e = cudaMemcpyAsync(dst_dev, src_dev, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
@@ -202,6 +204,19 @@ int athtd_chunk_fade_add(const float* seg_out_dev, long seg_stride, int k_base, 
   launch_chunk_ola(seg_out_dev, seg_stride, k_base, chunk_len, starts_dev, actual_len_dev, fade_len_dev, flags_dev, n_chunks,
                    stride, ramp_up_dev, ramp_down_dev, ramp_off_dev, out_dev, C, t_begin, t_end, 0, (cudaStream_t)stream);
   return check_cuda("athtd_chunk_fade_add");
+}
+
+int athtd_load_audio(const float* x_dev, int C_in, long T_in, const float* kernel_t_dev, int orig, int new_, int taps, int width,
+                     float* y_dev, int C_out, long T_out, void* stream) {
+  if (C_in < 1 || C_out < C_in || T_in < 1) return fail("athtd_load_audio: need 1 <= C_in <= C_out and T_in >= 1");
+  if (kernel_t_dev) {
+    if (orig < 1 || new_ < 1 || width < 0 || taps != 2 * width + orig) return fail("athtd_load_audio: taps must be 2 * width + orig (torchaudio kernel shape)");
+    const long want = ((long)new_ * T_in + orig - 1) / orig;
+    if (T_out != want) return fail("athtd_load_audio: T_out must be ceil(new * T_in / orig)");
+  } else if (T_out != T_in) return fail("athtd_load_audio: without a filter bank T_out must equal T_in");
+  if (launch_resample(x_dev, C_in, T_in, kernel_t_dev, orig, new_, taps, width, y_dev, C_out, T_out, (cudaStream_t)stream))
+    return fail("athtd_load_audio: rate ratio needs more than 200 KB of shared memory per block");
+  return check_cuda("athtd_load_audio");
 }
 
 int athtd_attention_test(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev, int B, int Sq, int Sk, void* stream) {

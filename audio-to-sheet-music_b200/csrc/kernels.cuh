@@ -31,6 +31,10 @@ template <typename T> void launch_dec_apply(const T* u, int Uin, RowSpace us, in
                                             RowSpace ss, cudaStream_t st);
 template <typename T> void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int d1, int d2, cudaStream_t st);
 
+// ---- resample.cu (load_audio: polyphase sinc resampler + mono -> stereo)
+int launch_resample(const float* x, int C_in, long T_in, const float* Kt, int o, int nw, int taps, int width, float* y, int C_out,
+                    long T_out, cudaStream_t st);
+
 // ---- dconv_row.cu (fused DConv residual branch of the frequency encoder layers)
 template <typename T> bool dconv_row_supported(int C, int Tn);
 template <typename T> void launch_dconv_row(T* y, RowSpace ys, const float* const* ptrs, cudaStream_t st);

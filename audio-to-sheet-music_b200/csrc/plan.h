@@ -59,6 +59,8 @@ struct PlanBase {
   virtual long zero_region_bytes() const = 0;
   virtual int launches() const = 0;
   virtual int set_batch(int B) = 0;
+  virtual void set_use_graph(bool on) = 0;
+  virtual int graph_replays() const = 0;
   virtual void set_profile(bool on) = 0;
   virtual void set_use_tc(bool on) = 0;
   virtual void set_use_flash(bool on) = 0;
@@ -86,6 +88,17 @@ struct PlanT : PlanBase {
   size_t prof_used = 0;
   double prof_gflop = 0.0;
   std::vector<double> prof_items;
+  // CUDA-graph replay of the launch sequence.  A forward whose (batch, wav, emb, out) was seen
+  // before is captured once on a private stream and replayed from then on: a track loop that reuses its staging buffers
+  // pays ~160 kernel launches per batch once.  Callers with ever-changing pointers simply stay on the eager path.
+  struct GraphEntry { int B; const float* wav; const float* emb; float* out; cudaGraphExec_t exec; int n_launches, n_tc; unsigned long stamp; };
+  std::vector<GraphEntry> graphs;
+  bool use_graph = true, graph_broken = false;
+  cudaStream_t cap_stream = nullptr;
+  unsigned long graph_clock = 0;
+  int n_graph_replays = 0;
+  void drop_graphs();
+  ~PlanT() override;
   // buffers
   RowSpace xf0_rs, xt0_rs, yf_rs[4], yt_rs[4], xc_rs, xtc_rs, df_rs[4], dt_rs[4];
   T *xf0, *xt0, *yf[4], *ef[4], *yt[4], *et[4], *xc, *xtc, *df[4], *dt[4];
@@ -139,9 +152,11 @@ struct PlanT : PlanBase {
   long zero_region_bytes() const override { return (long)zero_bytes; }
   int launches() const override { return n_launches; }
   void set_profile(bool on) override { profiling = on; prof_used = 0; prof_gflop = 0.0; prof_items.clear(); }
-  void set_use_tc(bool on) override { use_tc = on; }
-  void set_use_flash(bool on) override { use_flash = on; }
-  void set_use_fused_dconv(bool on) override { use_fused_dconv = on; }
+  void set_use_tc(bool on) override { use_tc = on; drop_graphs(); }
+  void set_use_flash(bool on) override { use_flash = on; drop_graphs(); }
+  void set_use_fused_dconv(bool on) override { use_fused_dconv = on; drop_graphs(); }
+  void set_use_graph(bool on) override { use_graph = on; if (!on) drop_graphs(); }
+  int graph_replays() const override { return n_graph_replays; }
   int tc_launches() const override { return n_tc; }
   void get_profile(double* ms, double* gflop, int* n) override;
 };

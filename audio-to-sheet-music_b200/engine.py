@@ -160,6 +160,13 @@ class Plan:
     def tc_launches(self) -> int:
         return _lib.load().athtd_plan_tc_launches(self.handle)
 
+    def set_graph(self, on: bool) -> None:
+        _lib.load().athtd_plan_set_graph(self.handle, 1 if on else 0)
+
+    @property
+    def graph_replays(self) -> int:
+        return _lib.load().athtd_plan_graph_replays(self.handle)
+
     def set_fused_dconv(self, on: bool) -> None:
         _lib.load().athtd_plan_set_fused_dconv(self.handle, 1 if on else 0)
 

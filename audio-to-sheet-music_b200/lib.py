@@ -39,6 +39,8 @@ SYMBOLS = [
     ("athtd_plan_set_flash", _I, [_P, _I]),
     ("athtd_plan_set_fused_dconv", _I, [_P, _I]),
     ("athtd_plan_tc_launches", _I, [_P]),
+    ("athtd_plan_set_graph", _I, [_P, _I]),
+    ("athtd_plan_graph_replays", _I, [_P]),
     ("athtd_attention_test", _I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     ("athtd_memcpy_d2d", _I, [_P, _P, _L, _P]),
     ("athtd_sdr_sums", _I, [_P, _P, _I, _L, _P, _P]),
@@ -54,6 +56,7 @@ SYMBOLS = [
     ("athtd_clap_workspace_bytes", _L, [_I, _I]),
     ("athtd_clap_text_forward", _I, [_P, _P, _P, _I, _I, _P, _P, _I, _P]),
     ("athtd_chunk_fade_add", _I, [_P, _L, _I, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _L, _L, _P]),
+    ("athtd_load_audio", _I, [_P, _I, _L, _P, _I, _I, _I, _I, _P, _I, _L, _P]),
     ("athtd_gemm_test", _I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 ]
 

@@ -137,6 +137,7 @@ class B200SeparationModel(SeparationModel):
         self._tables_key = None
         self._streams = None
         self._stage = {}
+        self._bufs = {}
         self.host_done: Optional[torch.cuda.Event] = None
 
     @property
@@ -154,12 +155,38 @@ class B200SeparationModel(SeparationModel):
             self._tables, self._tables_key = OlaTables(plan, self.device), key
         return plan, self._tables
 
-    def _forward_batch(self, segs: torch.Tensor, emb: torch.Tensor, out: torch.Tensor) -> int:
+    def _buffers(self, kind: str, nk: int, P: int, L: int, seg_rows: int):
+        """Staging buffers that persist across calls of the same shape (segments, per-chunk outputs): stable device pointers
+        let the plan replay its launch sequence as a CUDA graph (engine.Plan / athtd_plan_set_graph) instead of re-launching
+        ~160 kernels per batch.  One entry per call kind; a different shape replaces it."""
+        key = (nk, P, L, seg_rows)
+        ent = self._bufs.get(kind)
+        if ent is None or ent["key"] != key:
+            ent = {"key": key,
+                   "segs": torch.empty(seg_rows, 2, L, dtype=torch.float32, device=self.device),
+                   "seg_out": torch.empty(nk + 1, P, 2, L, dtype=torch.float32, device=self.device),     # slot 0 = halo chunk k0-1
+                   "emb": {}}
+            self._bufs[kind] = ent
+        return ent
+
+    def release_buffers(self) -> None:
+        """Free the persistent staging buffers (and with them the graph-friendly pointers)."""
+        self._bufs.clear()
+        self._stage.clear()
+
+    def _forward_batch(self, segs: torch.Tensor, emb: torch.Tensor, out: torch.Tensor, emb_cache: Optional[dict] = None) -> int:
         """segs [b, 2, L] -> out [b, P, 2, L] through the (L, P) plan laid out for ``self.batch`` segments."""
         b, _, L = segs.shape
         P = emb.shape[0]
         fplan = self.model.engine(self.device).plan(b, L, P, cap=self.batch)
-        fplan.forward(segs, emb.unsqueeze(0).expand(b, P, 512).contiguous(), out)
+        if emb_cache is not None:
+            e = emb_cache.get(b)
+            if e is None:
+                e = emb_cache[b] = torch.empty(b, P, 512, dtype=torch.float32, device=self.device)
+            e.copy_(emb.unsqueeze(0).expand(b, P, 512))
+        else:
+            e = emb.unsqueeze(0).expand(b, P, 512).contiguous()
+        fplan.forward(segs, e, out)
         return fplan.launches
 
     # ------------------------------------------------------------------ device-resident span
@@ -188,16 +215,16 @@ class B200SeparationModel(SeparationModel):
             self.last_launches = 0
             self._last_seg_out = None
             return torch.empty(P, 2, 0, dtype=torch.float32, device=self.device)
-        seg_out = torch.empty(nk + 1, P, 2, L, dtype=torch.float32, device=self.device)   # slot 0 = halo chunk k0-1
+        bufs = self._buffers("span", nk, P, L, nk)
+        seg_out, segs = bufs["seg_out"], bufs["segs"]
         local_starts = (tables.starts[k0:k1] - track_offset).contiguous()
-        segs = torch.empty(nk, 2, L, dtype=torch.float32, device=self.device)
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.load().athtd_gather_chunks(track.data_ptr(), track.shape[-1], 2, local_starts.data_ptr(), nk, L,
                                                    segs.data_ptr(), st), "athtd_gather_chunks")
         launches = 1
         for b0 in range(0, nk, self.batch):
             b1 = min(b0 + self.batch, nk)
-            launches += self._forward_batch(segs[b0:b1], emb, seg_out[1 + b0:1 + b1])
+            launches += self._forward_batch(segs[b0:b1], emb, seg_out[1 + b0:1 + b1], bufs["emb"])
         if halo_exchange is not None:
             halo_in = halo_exchange(seg_out[nk])
         if k0 > 0:
@@ -256,6 +283,8 @@ class B200SeparationModel(SeparationModel):
         skey = (in_hi - in_lo, str(dev))
         stage = self._stage.get(skey)
         if stage is None:
+            if self._stage:
+                torch.cuda.synchronize(dev)        # the old staging buffers may still be in use on the copy streams
             self._stage.clear()
             stage = {"buf": [torch.empty(2, in_hi - in_lo, dtype=torch.float32, device=dev) for _ in range(2)],
                      "free": [None, None], "par": 0}
@@ -266,8 +295,8 @@ class B200SeparationModel(SeparationModel):
         track = stage["buf"][par]
         if stage["free"][par] is not None:
             up.wait_event(stage["free"][par])
-        seg_out = torch.empty(nk + 1, P, 2, L, dtype=torch.float32, device=dev)      # slot 0 = halo chunk k0-1
-        segs = torch.empty(min(self.batch, nk), 2, L, dtype=torch.float32, device=dev)
+        bufs = self._buffers("host", nk, P, L, min(self.batch, nk))
+        seg_out, segs = bufs["seg_out"], bufs["segs"]
         local_starts = (tables.starts[k0:k1] - in_lo).contiguous()
         batches = [(b0, min(b0 + self.batch, nk)) for b0 in range(0, nk, self.batch)]
 
@@ -294,7 +323,7 @@ class B200SeparationModel(SeparationModel):
             if i == len(batches) - 1:
                 stage["free"][par] = torch.cuda.Event()
                 stage["free"][par].record(comp)
-            launches += self._forward_batch(segs[:b1 - b0], emb, seg_out[1 + b0:1 + b1]) + 1
+            launches += self._forward_batch(segs[:b1 - b0], emb, seg_out[1 + b0:1 + b1], bufs["emb"]) + 1
             if i == len(batches) - 1 and halo_exchange is not None:
                 halo_in = halo_exchange(seg_out[nk])
             # output samples that are complete now: [starts[k0+b0], starts[k0+b1]) (to the span end for the last batch)
@@ -344,7 +373,8 @@ class B200SeparationModel(SeparationModel):
             n = len(segment_plan(mixture.shape[-1], self.segment_seconds, self.overlap, self.model.sample_rate).starts)
             span = (0, n)
         out = self.separate_span(mixture, emb, span, halo_in=halo_in)
-        return out, (self._last_seg_out[-1] if self._last_seg_out is not None else None)
+        # (a copy: the per-chunk outputs live in a staging buffer that the next call of the same shape overwrites)
+        return out, (self._last_seg_out[-1].clone() if self._last_seg_out is not None else None)
 
     @torch.no_grad()
     def profile_gemms(self, track: torch.Tensor, emb: torch.Tensor, span):

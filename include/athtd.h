@@ -75,6 +75,11 @@ int athtd_plan_set_tc(void* plan, int on);
 int athtd_plan_set_flash(void* plan, int on);   /* fused tcgen05 attention (default on) vs GEMM-softmax-GEMM */
 int athtd_plan_set_fused_dconv(void* plan, int on);   /* per-row fused DConv kernel (default on) vs GEMM passes */
 int athtd_plan_tc_launches(void* plan);
+/* CUDA-graph replay of athtd_forward (default on): the second call with the same (batch, wav, emb, out) pointers captures the
+ * launch sequence on a private stream, later calls replay it with one cudaGraphLaunch on `stream`.  Results are those of the
+ * eager sequence (same kernels, same arguments).  graph_replays counts the forwards served from a graph. */
+int athtd_plan_set_graph(void* plan, int on);
+int athtd_plan_graph_replays(void* plan);
 
 /* async device-to-device copy on `stream` (lets tests read taps without a second CUDA binding) */
 int athtd_memcpy_d2d(void* dst_dev, const void* src_dev, long bytes, void* stream);
@@ -97,6 +102,14 @@ int athtd_chunk_ola(const float* seg_out_dev, long seg_stride, int k_base, int c
                     const int* actual_len_dev, const int* fade_len_dev, const int* flags_dev, int n_chunks, long stride,
                     const float* ramp_up_dev, const float* ramp_down_dev, const int* ramp_off_dev, float* out_dev, int C,
                     long t_begin, long t_end, void* stream);
+
+/* ---- load_audio (app.py:113-126): torchaudio.transforms.Resample(sr, 44100) (sinc_interp_hann, width 6, rolloff 0.99) followed
+ * by mono -> stereo repetition, on the device.  x [C_in, T_in] fp32; kernel_t_dev = the torchaudio filter bank
+ * _get_sinc_resample_kernel(orig, new, gcd) TRANSPOSED to [taps][new] fp32 with orig / new already divided by their gcd and
+ * taps = 2 * width + orig (NULL: same rate, channel copy only); y [C_out, T_out] with T_out = ceil(new * T_in / orig); output
+ * channels beyond C_in repeat the last input channel.  File decoding stays with the caller (torchaudio.load). */
+int athtd_load_audio(const float* x_dev, int C_in, long T_in, const float* kernel_t_dev, int orig, int new_, int taps, int width,
+                     float* y_dev, int C_out, long T_out, void* stream);
 
 /* ---- CLAP text tower (ATHTDemucs_v2.py:238-248: tokenizer output -> ClapTextModelWithProjection(...).text_embeds, or
  * ClapModel.get_text_features with normalize = 1).  Parameters: the "text_model.*" / "text_projection.*" tensors of the HF

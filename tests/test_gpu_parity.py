@@ -247,3 +247,28 @@ def test_empty_span_and_plan_capacity(models):
     eng.drop_plans()
     one, _ = sep1.separate_many(mix, emb)
     assert (one - full).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_graph_replay_matches_eager_launches(models, prec):
+    """athtd_forward replays a captured CUDA graph from the third call with the same (batch, wav, emb, out) on: same kernels, same
+    arguments -> same result as the eager launch sequence, also after the batch size of the shared workspace changed in between."""
+    m = models[prec]
+    wav, emb = synthetic.make_inputs(77, 3, 20000)
+    plan = m.engine().plan(3, 20000, 1)
+    w, e = wav.cuda(), emb.cuda().unsqueeze(1).contiguous()
+    out = torch.empty(3, 1, 2, 20000, device="cuda")
+    plan.set_graph(False)
+    eager = plan.forward(w, e, out).clone()
+    n_eager = plan.launches
+    plan.set_graph(True)
+    r0 = plan.graph_replays
+    a = plan.forward(w, e, out).clone()          # first sighting: eager
+    b = plan.forward(w, e, out).clone()          # second: capture + replay
+    assert plan.graph_replays == r0 + 1 and plan.launches == n_eager
+    plan.forward(w[:2].contiguous(), e[:2].contiguous())      # another batch size in the same workspace
+    c = plan.forward(w, e, out).clone()          # replay
+    assert plan.graph_replays == r0 + 2
+    for t in (a, b, c):
+        assert athtd_oracle.snr_db(t.cpu(), eager.cpu()) >= 100.0
+        assert (t - eager).abs().max() <= 1e-5

@@ -198,3 +198,18 @@ def test_bench_track_parts_tile_the_track():
     b = synthetic.make_track_part(1000, 3000)
     tone = (a - 0.0)[:, 1000:3000] - b           # same tone phase, different noise draw
     assert float(tone.abs().max()) < 1.0 and b.shape == (2, 2000)
+
+
+@pytest.mark.parametrize("orig,new", [(48000, 44100), (22050, 44100), (32000, 44100), (96000, 44100), (8000, 44100), (44100, 16000)])
+def test_resample_filter_bank_is_torchaudios(orig, new):
+    """load_audio (app.py:113-126) resamples with torchaudio.transforms.Resample defaults: the device kernel's filter bank must be
+    the table torchaudio itself builds, bit for bit."""
+    import math
+    from torchaudio.functional import functional as Fn
+    g = math.gcd(orig, new)
+    ref, width = Fn._get_sinc_resample_kernel(orig, new, g)
+    k, w, o, nw = athtd_b200.audio.sinc_resample_kernel(orig, new)
+    assert (w, o, nw) == (width, orig // g, new // g)
+    assert torch.equal(ref[:, 0], k)
+    r = athtd_b200.DeviceResampler(orig, new)
+    assert r.out_length(1000) == math.ceil(new * 1000 / orig) and r.taps == 2 * width + orig // g
