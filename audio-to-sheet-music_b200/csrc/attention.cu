@@ -60,9 +60,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-// MODE 0 = product kernel; 1 / 2 = measurement-only variants (ATHTD_FA_MODE): 1 replaces exp2 by a multiply (no SFU work),
-// 2 also drops the per-element arithmetic (pipeline floor: MMAs, TMEM loads, P stores, barriers).  Results are wrong for != 0.
-template <int MODE>
+__device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __global__ void __launch_bounds__(192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
@@ -165,31 +170,55 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float cs = p.scale_log2;
     const float tau = 8.0f / cs;               // the reference maximum moves only for jumps > 2^8 in the exp2 domain
     float m_used = -INFINITY;
-    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
+    // P = exp2(s * cs - mb) of 32 scores -> 16 bf16 pairs, row-sum partials in (t01, t23); packed fp32 pairs (FFMA2 / FADD2)
+    auto exp_pack = [&](const uint32_t (&r)[32], float mb, uint32_t* pk, float2& t01, float2& t23) {
+      const float2 c2 = make_float2(cs, cs), nm = make_float2(-mb, -mb);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 a = f2fma(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nm);
+        const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        if (i & 1) t23 = f2add(t23, e); else t01 = f2add(t01, e);
+        __nv_bfloat162 t = __floats2bfloat162_rn(e.x, e.y);
+        pk[i] = *(uint32_t*)&t;
+      }
+    };
+    auto max32 = [&](const uint32_t (&r)[32]) {
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(fmaxf(__uint_as_float(r[i]), __uint_as_float(r[8 + i])),
+                                                 fmaxf(__uint_as_float(r[16 + i]), __uint_as_float(r[24 + i])));
+      return fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+    };
     for (int j = 0; j < nkv; ++j) {
       const int nvalid = min(64, p.Sk - j * 64);
+      // s_full(j) also tells that PV(j-2) has completed (the commit tracks every MMA issued before it, and S(j) is issued
+      // after PV(j-2)), i.e. that the P buffer (j & 1) is free again: no separate wait for it
       mbar_wait(smem_u32(&s_full[j & 1]), (uint32_t)((j >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r0[32], r1[32];
       const uint32_t ts = tmem_S + (uint32_t)((j & 1) * 64) + lane_addr;
-      tmem_ld32_nowait(ts, r0);
-      tmem_ld32_nowait(ts + 32u, r1);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const uint32_t tp = tmem_P + (uint32_t)((j & 1) * 32) + lane_addr;
+      tmem_ld32(ts, r0);                       // first half of the row (waits for it) ...
+      tmem_ld32_nowait(ts + 32u, r1);          // ... the second half lands while the first one is exponentiated
+      if (nvalid < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (i >= nvalid) r0[i] = 0xff800000u;     // -inf: exp2 -> 0, ignored by the maximum
+      }
+      uint32_t pk32[32];                       // P row as bf16 pairs: one TMEM column per two keys
+      float2 t01 = make_float2(0.f, 0.f), t23 = make_float2(0.f, 0.f);
+      // speculate that the reference maximum stays where it is (it moves in the first tile and then almost never): the
+      // exponentials start right away and the row maximum (ALU pipe) is computed next to them (SFU pipe)
+      float mb = m_used * cs;
+      if (j > 0) { exp_pack(r0, mb, pk32, t01, t23); tmem_st16_nowait(tp, pk32); }
+      float tmax = max32(r0);
+      tmem_wait_ld();
       if (nvalid < 64) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= nvalid) r0[i] = 0xff800000u;            // -inf: exp2 -> 0, ignored by the maximum
-          if (32 + i >= nvalid) r1[i] = 0xff800000u;
-        }
+        for (int i = 0; i < 32; ++i) if (32 + i >= nvalid) r1[i] = 0xff800000u;
       }
-      float mx[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(fmaxf(__uint_as_float(r0[i]), __uint_as_float(r0[8 + i])),
-                                                 fmaxf(__uint_as_float(r0[16 + i]), __uint_as_float(r0[24 + i])));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], fmaxf(fmaxf(__uint_as_float(r1[i]), __uint_as_float(r1[8 + i])),
-                                                              fmaxf(__uint_as_float(r1[16 + i]), __uint_as_float(r1[24 + i]))));
-      const float tmax = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      if (j > 0) { exp_pack(r1, mb, pk32 + 16, t01, t23); tmem_st16_nowait(tp + 16u, pk32 + 16); }
+      tmax = fmaxf(tmax, max32(r1));
       const bool need = tmax > m_used + tau;              // always true on the first tile (m_used = -inf)
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? tmax : m_used;
@@ -206,57 +235,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st32(tmem_O + lane_addr + (uint32_t)(c * 32), o);
           }
-          l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+          l01 = f2mul(l01, f2splat(alpha)); l23 = f2mul(l23, f2splat(alpha));
         }
         m_used = m_new;
+        // redo the tile against the new reference (the speculative P may have overflowed; it is simply overwritten)
+        mb = m_used * cs;
+        t01 = make_float2(0.f, 0.f); t23 = make_float2(0.f, 0.f);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        exp_pack(r0, mb, pk32, t01, t23);
+        exp_pack(r1, mb, pk32 + 16, t01, t23);
+        tmem_st16_nowait(tp, pk32);
+        tmem_st16_nowait(tp + 16u, pk32 + 16);
       }
-      if (j >= 2) mbar_wait(smem_u32(&pv_done[j & 1]), (uint32_t)(((j - 2) >> 1) & 1));      // P buffer (j & 1) consumed by PV(j-2)
-      const float mb = m_used * cs;
-      uint32_t pk32[32];                              // P row as bf16 pairs: one TMEM column per two keys
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t* pk = pk32 + 4 * g;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float p0, p1;
-          if (MODE == 0) {
-            p0 = ex2_approx(fmaf(__uint_as_float(r0[8 * g + 2 * i]), cs, -mb));
-            p1 = ex2_approx(fmaf(__uint_as_float(r0[8 * g + 2 * i + 1]), cs, -mb));
-          } else if (MODE == 1) {
-            p0 = fmaf(__uint_as_float(r0[8 * g + 2 * i]), cs, -mb) * 1e-3f;
-            p1 = fmaf(__uint_as_float(r0[8 * g + 2 * i + 1]), cs, -mb) * 1e-3f;
-          } else {
-            p0 = __uint_as_float(r0[8 * g + 2 * i]); p1 = __uint_as_float(r0[8 * g + 2 * i + 1]);
-          }
-          if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
-          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-          pk[i] = *(uint32_t*)&t;
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t* pk = pk32 + 16 + 4 * g;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float p0, p1;
-          if (MODE == 0) {
-            p0 = ex2_approx(fmaf(__uint_as_float(r1[8 * g + 2 * i]), cs, -mb));
-            p1 = ex2_approx(fmaf(__uint_as_float(r1[8 * g + 2 * i + 1]), cs, -mb));
-          } else if (MODE == 1) {
-            p0 = fmaf(__uint_as_float(r1[8 * g + 2 * i]), cs, -mb) * 1e-3f;
-            p1 = fmaf(__uint_as_float(r1[8 * g + 2 * i + 1]), cs, -mb) * 1e-3f;
-          } else {
-            p0 = __uint_as_float(r1[8 * g + 2 * i]); p1 = __uint_as_float(r1[8 * g + 2 * i + 1]);
-          }
-          if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
-          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-          pk[i] = *(uint32_t*)&t;
-        }
-      }
-      tmem_st32(tmem_P + (uint32_t)((j & 1) * 32) + lane_addr, pk32);      // includes tcgen05.wait::st
+      l01 = f2add(l01, t01); l23 = f2add(l23, t23);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[j & 1])) : "memory");
     }
+    const float l0 = l01.x, l1 = l01.y, l2 = l23.x, l3 = l23.y;
     mbar_wait(smem_u32(&pv_done[(nkv - 1) & 1]), (uint32_t)(((nkv - 1) >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
@@ -303,19 +299,9 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
   const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 256;
   static PerDeviceOnce attr;
   const bool first = attr.first();
-  if (first) cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (first) cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((Sq + 127) / 128, 8, B);
-#ifdef ATHTD_ABLATION      // timing-only variants (results are WRONG by construction): measurement builds only
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("ATHTD_FA_MODE"); mode = e ? atoi(e) : 0; }
-  if (first) {
-    cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(flash_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-  if (mode == 1) { flash_attn_kernel<1><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); return 0; }
-  if (mode == 2) { flash_attn_kernel<2><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); return 0; }
-#endif
-  flash_attn_kernel<0><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
+  flash_attn_kernel<<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
   return 0;
 }
 

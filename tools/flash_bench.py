@@ -1,5 +1,4 @@
-"""Timing of the fused attention kernel on the path's shapes (B = 32): python tools/flash_bench.py
-ATHTD_FA_MODE=1|2 selects the measurement-only variants (no SFU work / no per-element arithmetic)."""
+"""Timing of the fused attention kernel on the path's shapes (B = 32): python tools/flash_bench.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,4 +16,4 @@ for (Sq, Sk) in [(2072, 2072), (1034, 1034), (2072, 1034), (1034, 2072)]:
     for _ in range(10): lib.athtd_attention_test(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, Sq, Sk, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"mode={os.environ.get('ATHTD_FA_MODE','0')} Sq={Sq} Sk={Sk}: {ms*1e3:.1f} us  {4*B*8*Sq*Sk*64/ms/1e9:.0f} TFLOP/s", flush=True)
+    print(f"Sq={Sq} Sk={Sk}: {ms*1e3:.1f} us  {4*B*8*Sq*Sk*64/ms/1e9:.0f} TFLOP/s", flush=True)
