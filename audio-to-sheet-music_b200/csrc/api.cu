@@ -219,6 +219,8 @@ int athtd_load_audio(const float* x_dev, int C_in, long T_in, const float* kerne
   return check_cuda("athtd_load_audio");
 }
 
+int athtd_attention_set_poly(int npoly) { flash_attn_set_poly(npoly); return 0; }
+
 int athtd_attention_test(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev, int B, int Sq, int Sk, void* stream) {
   if (!flash_attn_supported(512, 512, 512)) return fail("athtd_attention_test: tensor-map API unavailable");
   int rc = launch_flash_attn((const bf16*)q_dev, 512, (const bf16*)k_dev, (const bf16*)v_dev, 512, B, Sq, Sk, (bf16*)o_dev, 512,

@@ -68,6 +68,11 @@ __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t*
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// NPOLY of the 16 score pairs of every half row take their exp2 on the FMA / ALU pipes (Cody-Waite range reduction + a
+// degree-3 minimax polynomial on [-0.5, 0.5], relative error 7.5e-5, far below the bf16 rounding of P) instead of the SFU:
+// MUFU.EX2 issues one warp instruction per 8 cycles and SM sub-partition, which bounds this head-dim-64 kernel (64 exp2 per
+// row and tile = 512 SFU cycles against 256 tensor-pipe cycles); the FMA pipe is ~10 % busy.
+template <int NPOLY>
 __global__ void __launch_bounds__(192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
@@ -176,8 +181,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float2 c2 = make_float2(cs, cs), nm = make_float2(-mb, -mb);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float2 a = f2fma(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nm);
-        const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        float2 a = f2fma(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nm);
+        float2 e;
+        // interleave the polynomial pairs with the SFU pairs so that both pipes stay busy
+        if (NPOLY > 0 && (i * NPOLY) / 16 != ((i + 1) * NPOLY) / 16) {
+          a.x = fmaxf(a.x, -125.0f); a.y = fmaxf(a.y, -125.0f);            // exp2 -> ~0 (masked keys are -inf)
+          const float2 magic = make_float2(12582912.0f, 12582912.0f);      // 1.5 * 2^23: round to nearest integer in the mantissa
+          const float2 t = f2add(a, magic);
+          const float2 f = f2sub(a, f2sub(t, magic));                      // fractional part in [-0.5, 0.5]
+          float2 q = f2fma(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+          q = f2fma(q, f, make_float2(0.6932609677f, 0.6932609677f));
+          q = f2fma(q, f, make_float2(0.9999280572f, 0.9999280572f));
+          e.x = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23));      // * 2^n: the integer sits in t's low bits
+          e.y = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23));
+        } else {
+          e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        }
         if (i & 1) t23 = f2add(t23, e); else t01 = f2add(t01, e);
         __nv_bfloat162 t = __floats2bfloat162_rn(e.x, e.y);
         pk[i] = *(uint32_t*)&t;
@@ -283,6 +302,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+// how many of 16 exp2 pairs go to the polynomial path (every variant computes the same softmax; tuning hook of the tests / tools)
+static int g_fa_npoly = 4;      // measured on B200 (tools/flash_bench.py): 0 -> 438 us, 4 -> 408 us, 6 -> 413 us, 8 -> 431 us (frequency self-attention, B = 32)
+void flash_attn_set_poly(int npoly) { g_fa_npoly = npoly <= 0 ? 0 : npoly <= 4 ? 4 : npoly <= 6 ? 6 : 8; }
+
 bool flash_attn_supported(long ldq, long ldkv, long ldo) {
   return tensor_map_api_available() && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0;
 }
@@ -298,10 +321,19 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
   p.Sq = Sq; p.Sk = Sk; p.scale_log2 = 0.125f * 1.4426950408889634f; p.O = o; p.ldo = ldo;
   const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 256;
   static PerDeviceOnce attr;
-  const bool first = attr.first();
-  if (first) cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr.first()) {
+    cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   dim3 grid((Sq + 127) / 128, 8, B);
-  flash_attn_kernel<<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
+  switch (g_fa_npoly) {
+    case 0: flash_attn_kernel<0><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); break;
+    case 4: flash_attn_kernel<4><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); break;
+    case 6: flash_attn_kernel<6><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); break;
+    default: flash_attn_kernel<8><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); break;
+  }
   return 0;
 }
 

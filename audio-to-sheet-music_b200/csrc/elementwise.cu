@@ -196,7 +196,7 @@ void launch_gn_glu_res(T* x, RowSpace xs, const T* e, RowSpace es, int G2, int p
 //   if gstats: x' = (x-mu_b)*rstd_b*gw + gb  is written to xout (MyGroupNorm over all tokens of a sample)
 //   if lw:     y  = LN(x')*lw + lb (+ pe[row % S])   is written to y
 template <typename T, int RPW>
-__global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, T* __restrict__ y, long rows, int C, int S,
+__global__ void __launch_bounds__(256, 3) norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, T* __restrict__ y, long rows, int C, int S,
                                  const float* __restrict__ gmr, const float* __restrict__ gw,
                                  const float* __restrict__ gb, const float* __restrict__ lw, const float* __restrict__ lb,
                                  const float* __restrict__ pe, RowSpace yrs, T* __restrict__ y2,
@@ -314,15 +314,20 @@ __global__ void norm_rows_kernel(const T* __restrict__ x, T* __restrict__ xout, 
   }
 }
 // LayerNorm-only form for C == 512 (every transformer norm): the affine vectors of a lane's two fixed 8-channel chunks live in
-// registers and the warp walks rows grid-stride with the next row's 2 x 16 B already in flight.  The generic kernel re-read
-// 4 KB of fp32 affine parameters from L1 per 1 KB row (4x the payload) and ran at ~2.5 TB/s.  Same operation order as the
-// generic kernel (bit-identical results).
+// registers and the warp walks rows grid-stride with the NEXT TWO rows (2 x 2 x 16 B, still packed) already in flight.  The
+// generic kernel re-read 4 KB of fp32 affine parameters from L1 per 1 KB row (4x the payload) and ran at ~2.5 TB/s; the
+// one-row-ahead version of this kernel was launched with twice the CTAs its ~90 registers let an SM hold (two waves of a
+// grid-stride loop) and had 1 KB per warp in flight (ncu: 23 % of the warp slots active, long-scoreboard bound, 2.1 TB/s).
+// Now: one resident wave (2 CTAs of 8 warps per SM) and 2 KB per warp in flight.  Same operation order per row as the generic
+// kernel (bit-identical results).
 template <typename T, bool HAS2>
-__global__ void __launch_bounds__(256) ln512_rows_kernel(const T* __restrict__ x, T* __restrict__ y, long rows, int S,
-                                                         const float* __restrict__ lw, const float* __restrict__ lb,
-                                                         const float* __restrict__ pe, RowSpace yrs, T* __restrict__ y2,
-                                                         const float* __restrict__ lw2, const float* __restrict__ lb2) {
+__global__ void __launch_bounds__(256, 2) ln512_rows_kernel(const T* __restrict__ x, T* __restrict__ y, long rows, int S,
+                                                            const float* __restrict__ lw, const float* __restrict__ lb,
+                                                            const float* __restrict__ pe, RowSpace yrs, T* __restrict__ y2,
+                                                            const float* __restrict__ lw2, const float* __restrict__ lb2) {
   constexpr int C = 512;
+  if constexpr (sizeof(T) != 2) return;          // (instantiated for the fp32 build's template, never launched for it)
+  else {
   const int lane = threadIdx.x & 31;
   const long nw = (long)gridDim.x * (blockDim.x >> 5);
   long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -334,12 +339,23 @@ __global__ void __launch_bounds__(256) ln512_rows_kernel(const T* __restrict__ x
     VecIO<float, 8>::load(lw + c, w + 8 * i); VecIO<float, 8>::load(lb + c, b + 8 * i);
     if (HAS2) { VecIO<float, 8>::load(lw2 + c, w2 + 8 * i); VecIO<float, 8>::load(lb2 + c, b2 + 8 * i); }
   }
-  float v[16];
-  VecIO<T, 8>::load(x + row * C + lane * 8, v); VecIO<T, 8>::load(x + row * C + (lane + 32) * 8, v + 8);
+  auto ldrow = [&](long r, uint4& a, uint4& c) {
+    const uint4* p = (const uint4*)(x + r * C);
+    a = p[lane]; c = p[lane + 32];
+  };
+  auto unpack = [&](const uint4& a, float* v) {
+    const float2 f0 = __bfloat1622float2(*(const __nv_bfloat162*)&a.x), f1 = __bfloat1622float2(*(const __nv_bfloat162*)&a.y);
+    const float2 f2 = __bfloat1622float2(*(const __nv_bfloat162*)&a.z), f3 = __bfloat1622float2(*(const __nv_bfloat162*)&a.w);
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+  };
+  uint4 c0a, c0b, n1a = make_uint4(0, 0, 0, 0), n1b = n1a;
+  ldrow(row, c0a, c0b);
+  if (row + nw < rows) ldrow(row + nw, n1a, n1b);
   for (; row < rows; row += nw) {
-    float nx[16];
-    const long rn = row + nw;
-    if (rn < rows) { VecIO<T, 8>::load(x + rn * C + lane * 8, nx); VecIO<T, 8>::load(x + rn * C + (lane + 32) * 8, nx + 8); }
+    uint4 n2a = make_uint4(0, 0, 0, 0), n2b = n2a;
+    if (row + 2 * nw < rows) ldrow(row + 2 * nw, n2a, n2b);
+    float v[16];
+    unpack(c0a, v); unpack(c0b, v + 8);
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) s += v[k];
@@ -371,8 +387,8 @@ __global__ void __launch_bounds__(256) ln512_rows_kernel(const T* __restrict__ x
         VecIO<T, 8>::store(y2 + row * C + c, o);
       }
     }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = nx[k];
+    c0a = n1a; c0b = n1b; n1a = n2a; n1b = n2b;
+  }
   }
 }
 
@@ -381,7 +397,7 @@ void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const 
                       const float* gw, const float* gb, const float* lw, const float* lb, const float* pe,
                       RowSpace yrs, cudaStream_t st, T* y2, const float* lw2, const float* lb2) {
   if (C == 512 && !gmr && lw && sizeof(T) == 2) {
-    const unsigned grid = (unsigned)std::min<long>((rows + 7) / 8, 148L * 4);
+    const unsigned grid = (unsigned)std::min<long>((rows + 7) / 8, 2L * device_sm_count());      // one resident wave
     if (y2) ln512_rows_kernel<T, true><<<grid, 256, 0, st>>>(x, y, rows, S, lw, lb, pe, yrs, y2, lw2, lb2);
     else ln512_rows_kernel<T, false><<<grid, 256, 0, st>>>(x, y, rows, S, lw, lb, pe, yrs, y2, lw2, lb2);
     return;

@@ -81,6 +81,7 @@ template <typename T> void launch_istft_fused(const float* Z, int Tf, int L, int
                                               float* out, long out_bstride, const float2* tw, const float* win, cudaStream_t st);
 
 // ---- attention.cu (bf16 tcgen05 flash attention, 8 heads x 64)
+void flash_attn_set_poly(int npoly);
 bool flash_attn_supported(long ldq, long ldkv, long ldo);
 int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, long ldkv, int B, int Sq, int Sk, bf16* o,
                       long ldo, cudaStream_t st);

@@ -136,6 +136,10 @@ int athtd_chunk_fade_add(const float* seg_out_dev, long seg_stride, int k_base, 
  * (zeroed by the call).  The dB values are closed forms of these sums (audio-to-sheet-music_b200/metrics.py). */
 int athtd_sdr_sums(const float* est_dev, const float* tgt_dev, int items, long n, double* sums_dev, void* stream);
 
+/* tuning hook: how many of every 16 exp2 pairs of the attention softmax are evaluated by the FMA-pipe polynomial instead of the
+ * SFU (0, 4, 6 or 8; every setting computes the same softmax to bf16 accuracy).  Process-wide. */
+int athtd_attention_set_poly(int npoly);
+
 /* kernel-level parity test of the fused attention: q [B*Sq,512], k/v [B*Sk,512] bf16 (8 heads x 64) -> o [B*Sq,512] */
 int athtd_attention_test(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev, int B, int Sq, int Sk,
                          void* stream);

@@ -169,3 +169,30 @@ def test_fused_attention_matches_torch(B, Sq, Sk):
     got = o.float().cpu()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("npoly", [4, 6, 8])
+def test_fused_attention_polynomial_exp2_variants(npoly):
+    """The attention softmax may take part of its exp2 on the FMA pipe (degree-3 polynomial): same result to bf16 accuracy, also
+    with masked key columns (Sk not a multiple of 64) and many key tiles."""
+    lib = alib.load()
+    B, Sq, Sk = 2, 300, 1034
+    g = torch.Generator().manual_seed(npoly)
+    q = (2.0 * torch.randn(B, Sq, 512, generator=g)).bfloat16()
+    k = (2.0 * torch.randn(B, Sk, 512, generator=g)).bfloat16()
+    v = torch.randn(B, Sk, 512, generator=g).bfloat16()
+    o = torch.full((B, Sq, 512), float("nan"), dtype=torch.bfloat16, device="cuda")
+    qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+    try:
+        lib.athtd_attention_set_poly(npoly)
+        alib.check(lib.athtd_attention_test(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, Sq, Sk, _stream()))
+        torch.cuda.synchronize()
+    finally:
+        lib.athtd_attention_set_poly(4)          # the default
+    qh = q.float().view(B, Sq, 8, 64).transpose(1, 2)
+    kh = k.float().view(B, Sk, 8, 64).transpose(1, 2)
+    vh = v.float().view(B, Sk, 8, 64).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B, Sq, 512)
+    got = o.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max() < 2e-2

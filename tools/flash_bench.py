@@ -6,6 +6,8 @@ from athtd_b200 import lib as alib
 lib = alib.load()
 st = torch.cuda.current_stream().cuda_stream
 B = 32
+import sys as _s
+lib.athtd_attention_set_poly(int(_s.argv[1]) if len(_s.argv) > 1 else 0)
 for (Sq, Sk) in [(2072, 2072), (1034, 1034), (2072, 1034), (1034, 2072)]:
     q = torch.randn(B, Sq, 512, device="cuda").bfloat16(); k = torch.randn(B, Sk, 512, device="cuda").bfloat16()
     v = torch.randn(B, Sk, 512, device="cuda").bfloat16(); o = torch.empty(B, Sq, 512, device="cuda", dtype=torch.bfloat16)
@@ -16,4 +18,4 @@ for (Sq, Sk) in [(2072, 2072), (1034, 1034), (2072, 1034), (1034, 2072)]:
     for _ in range(10): lib.athtd_attention_test(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, Sq, Sk, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"Sq={Sq} Sk={Sk}: {ms*1e3:.1f} us  {4*B*8*Sq*Sk*64/ms/1e9:.0f} TFLOP/s", flush=True)
+    print(f"npoly={_s.argv[1] if len(_s.argv) > 1 else 0} Sq={Sq} Sk={Sk}: {ms*1e3:.1f} us  {4*B*8*Sq*Sk*64/ms/1e9:.0f} TFLOP/s", flush=True)
