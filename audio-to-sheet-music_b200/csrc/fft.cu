@@ -89,18 +89,19 @@ __device__ __forceinline__ void twiddle_powers(const float2* __restrict__ tw, in
 }
 
 // Passes 2 and 3 plus the natural-order write-back; on entry v holds pass-1 outputs V[k1]
-// (already multiplied by W4096^(t*k1)) of thread t.  On exit sr/si hold X[k] at index k + (k>>4).
+// (already multiplied by W4096^(t*k1)) of thread t.  On exit sc holds X[k] at index k + (k>>4).
+// The transposes go through ONE array of (re, im) pairs: 64-bit shared-memory accesses, half the LDS / STS instructions of
+// separate real / imaginary planes (ncu of the split version: mio_throttle was the top stall, LSU the busiest pipe at 43 %);
+// every access pattern below is conflict-free per half warp (consecutive pairs, or stride 17 pairs = 34 words).
 template <bool INV>
-__device__ __forceinline__ void fft4096_tail(float2 (&v)[16], float* sr, float* si, const float2* __restrict__ tw) {
+__device__ __forceinline__ void fft4096_tail(float2 (&v)[16], float2* sc, const float2* __restrict__ tw) {
   const int t = threadIdx.x;
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) { sr[k1 * FFT_PITCH + t] = v[k1].x; si[k1 * FFT_PITCH + t] = v[k1].y; }
+  for (int k1 = 0; k1 < 16; ++k1) sc[k1 * FFT_PITCH + t] = v[k1];
   __syncthreads();
   const int hi = t >> 4, lo = t & 15;     // pass 2: (k1 = hi, m2 = lo)
 #pragma unroll
-  for (int m1 = 0; m1 < 16; ++m1) {
-    v[m1].x = sr[hi * FFT_PITCH + 16 * m1 + lo]; v[m1].y = si[hi * FFT_PITCH + 16 * m1 + lo];
-  }
+  for (int m1 = 0; m1 < 16; ++m1) v[m1] = sc[hi * FFT_PITCH + 16 * m1 + lo];
   dft16<INV>(v);
   {
     float2 w[16];
@@ -110,20 +111,17 @@ __device__ __forceinline__ void fft4096_tail(float2 (&v)[16], float* sr, float* 
   }
   __syncthreads();
 #pragma unroll
-  for (int j1 = 0; j1 < 16; ++j1) { sr[hi * FFT_PITCH + lo * 17 + j1] = v[j1].x; si[hi * FFT_PITCH + lo * 17 + j1] = v[j1].y; }
+  for (int j1 = 0; j1 < 16; ++j1) sc[hi * FFT_PITCH + lo * 17 + j1] = v[j1];
   __syncthreads();
   // pass 3: (k1 = hi, j1 = lo) reads over m2
 #pragma unroll
-  for (int m2 = 0; m2 < 16; ++m2) {
-    v[m2].x = sr[hi * FFT_PITCH + m2 * 17 + lo]; v[m2].y = si[hi * FFT_PITCH + m2 * 17 + lo];
-  }
+  for (int m2 = 0; m2 < 16; ++m2) v[m2] = sc[hi * FFT_PITCH + m2 * 17 + lo];
   dft16<INV>(v);
   __syncthreads();
 #pragma unroll
   for (int j2 = 0; j2 < 16; ++j2) {
     int k = hi + 16 * lo + 256 * j2;
-    int a = k + (k >> 4);
-    sr[a] = v[j2].x; si[a] = v[j2].y;
+    sc[k + (k >> 4)] = v[j2];
   }
   __syncthreads();
 }
@@ -132,7 +130,7 @@ __device__ __forceinline__ void fft4096_tail(float2 (&v)[16], float* sr, float* 
 __global__ void __launch_bounds__(256) stft_cac_kernel(const float* __restrict__ wav, int L, int Tf, float4* __restrict__ Z,
                                                         double* __restrict__ stats, const float2* __restrict__ tw,
                                                         const float* __restrict__ win) {
-  __shared__ float sr[FFT_SMEM], si[FFT_SMEM];
+  __shared__ float2 sc[FFT_SMEM];
   __shared__ float red[2][8];
   const int t = threadIdx.x, frame = blockIdx.x, b = blockIdx.y;
   const float* wl = wav + (long)b * 2 * L;
@@ -165,15 +163,15 @@ __global__ void __launch_bounds__(256) stft_cac_kernel(const float* __restrict__
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], w[k1]);
   }
-  fft4096_tail<false>(v, sr, si, tw);
+  fft4096_tail<false>(v, sc, tw);
   float s = 0.f, ss = 0.f;
   float4* zo = Z + ((long)b * Tf + frame) * 2048;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int k = t + 256 * i;
     int kn = (FFT_N - k) & (FFT_N - 1);
-    float ar = sr[k + (k >> 4)], ai = si[k + (k >> 4)];
-    float br = sr[kn + (kn >> 4)], bi = si[kn + (kn >> 4)];
+    const float2 A = sc[k + (k >> 4)], Bc = sc[kn + (kn >> 4)];
+    const float ar = A.x, ai = A.y, br = Bc.x, bi = Bc.y;
     float4 o;
     o.x = (ar + br) * (0.5f / 64.f);       // L.re
     o.y = (ai - bi) * (0.5f / 64.f);       // L.im   (exactly +0 at k = 0)
@@ -217,7 +215,7 @@ __device__ __forceinline__ void lerp_coords_f(int d, int in, int out, int& i0, i
 template <typename T>
 __device__ __forceinline__ void masked_spectrum_to_smem(const float4* __restrict__ zi, const T* __restrict__ dec, const RowSpace& ds,
                                                         int g, int use_mask, const float (&fw)[8], const float (&fb)[2],
-                                                        float* sr, float* si) {
+                                                        float2* sc) {
   const int t = threadIdx.x;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -260,20 +258,20 @@ __device__ __forceinline__ void masked_spectrum_to_smem(const float4* __restrict
     }
     if (k == 0) { xl.y = 0.f; xr.y = 0.f; }        // C2R ignores the imaginary part of DC
     // Y[k] = XL[k] + i XR[k] ; Y[N-k] = conj(XL[k]) + i conj(XR[k])
-    sr[k] = xl.x - xr.y; si[k] = xl.y + xr.x;
-    if (k > 0) { sr[FFT_N - k] = xl.x + xr.y; si[FFT_N - k] = xr.x - xl.y; }
+    sc[k] = make_float2(xl.x - xr.y, xl.y + xr.x);
+    if (k > 0) sc[FFT_N - k] = make_float2(xl.x + xr.y, xr.x - xl.y);
   }
-  if (t == 0) { sr[2048] = 0.f; si[2048] = 0.f; }   // Nyquist bin is zero-padded by _ispec
+  if (t == 0) sc[2048] = make_float2(0.f, 0.f);   // Nyquist bin is zero-padded by _ispec
   __syncthreads();
 }
 
-// Inverse 4096-point transform of the spectrum masked_spectrum_to_smem left in sr / si; on exit sr[n + (n >> 4)] / si[...] hold
-// the left / right time samples n of the frame (before the window and the 1/64 scale).
-__device__ __forceinline__ void ifft4096_smem(float* sr, float* si, const float2* __restrict__ tw) {
+// Inverse 4096-point transform of the spectrum masked_spectrum_to_smem left in sc; on exit sc[n + (n >> 4)] holds the
+// (left, right) time samples n of the frame (before the window and the 1/64 scale).
+__device__ __forceinline__ void ifft4096_smem(float2* sc, const float2* __restrict__ tw) {
   const int t = threadIdx.x;
   float2 v[16];
 #pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) { v[n1].x = sr[256 * n1 + t]; v[n1].y = si[256 * n1 + t]; }
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = sc[256 * n1 + t];
   dft16<true>(v);
   {
     float2 w[16];
@@ -282,7 +280,7 @@ __device__ __forceinline__ void ifft4096_smem(float* sr, float* si, const float2
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], w[k1]);
   }
   __syncthreads();
-  fft4096_tail<true>(v, sr, si, tw);
+  fft4096_tail<true>(v, sc, tw);
 }
 
 // ------------------------------------------------------------------ inverse: mask + iFFT + window + overlap-add + time branch
@@ -294,7 +292,7 @@ __device__ __forceinline__ void ifft4096_smem(float* sr, float* si, const float2
 // t, which is scaled, combined with the time branch and stored.  A run that starts inside a segment first re-transforms the
 // three frames before it (ring warm-up, no stores); runs are equal-sized so that one wave of CTAs fills the chip.
 // Every output sample is the fixed-order sum ((f[t-3] + f[t-2]) + f[t-1]) + f[t] of its (up to) four frames.
-#define IFFT_SMEM_BYTES ((2 * FFT_SMEM + 2 * FFT_N) * 4)
+#define IFFT_SMEM_BYTES ((FFT_SMEM + FFT_N) * 8)
 
 template <typename T>
 __global__ void __launch_bounds__(256, 3) istft_fused_kernel(const float4* __restrict__ Z, int Tf, int L, int Bout, int zb_div,
@@ -304,10 +302,9 @@ __global__ void __launch_bounds__(256, 3) istft_fused_kernel(const float4* __res
                                                            const float* __restrict__ to_b, const float* __restrict__ meanstd_t,
                                                            int ms_div, float* __restrict__ out, long out_bstride,
                                                            const float2* __restrict__ tw, const float* __restrict__ win) {
-  extern __shared__ __align__(16) float fsm[];
-  float* sr = fsm;
-  float* si = fsm + FFT_SMEM;
-  float2* ring = (float2*)(fsm + 2 * FFT_SMEM);      // [4 hops][1024] (left, right) partial overlap-add sums
+  extern __shared__ __align__(16) float2 fsm[];
+  float2* sc = fsm;
+  float2* ring = fsm + FFT_SMEM;                     // [4 hops][1024] (left, right) partial overlap-add sums
   const int t = threadIdx.x;
   float fw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fb[2] = {0, 0}, tw8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tb[2] = {0, 0};
   if (use_mask) {
@@ -375,14 +372,15 @@ __global__ void __launch_bounds__(256, 3) istft_fused_kernel(const float4* __res
     };
 
     for (int fr = t_start; fr < tb_; ++fr) {
-      masked_spectrum_to_smem<T>(Z + ((long)bz * Tf + fr) * 2048, dec, ds, bo * Tf + fr, use_mask, fw, fb, sr, si);
-      ifft4096_smem(sr, si, tw);
+      masked_spectrum_to_smem<T>(Z + ((long)bz * Tf + fr) * 2048, dec, ds, bo * Tf + fr, use_mask, fw, fb, sc);
+      ifft4096_smem(sc, tw);
       // quarter qq of the frame belongs to hop fr + qq; the first frame of the run and every quarter 3 open a new hop
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int n = t + 256 * i, qq = i >> 2;
         const float w = win[n] * (1.0f / 64.0f);
-        const float2 x = make_float2(sr[n + (n >> 4)] * w, si[n + (n >> 4)] * w);
+        const float2 y2 = sc[n + (n >> 4)];
+        const float2 x = make_float2(y2.x * w, y2.y * w);
         float2* slot = ring + ((fr + qq) & 3) * 1024 + (n & 1023);
         if (qq == 3 || fr == t_start) *slot = x;
         else { float2 a = *slot; a.x += x.x; a.y += x.y; *slot = a; }
