@@ -124,8 +124,9 @@ class B200SeparationModel(SeparationModel):
     whose weights were loaded the usual way (load_state_dict(ckpt["model_state_dict"], strict=False))."""
 
     def __init__(self, model: AudioTextHTDemucsB200, device: str = "cuda", segment_seconds: float = 6.0,
-                 overlap_seconds: float = 1.5, batch: int = 32):
+                 overlap_seconds: float = 1.5, batch: int = 32, use_graph: bool = True):
         self.model = model.to(device).eval()
+        self.use_graph = use_graph
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -179,6 +180,8 @@ class B200SeparationModel(SeparationModel):
         b, _, L = segs.shape
         P = emb.shape[0]
         fplan = self.model.engine(self.device).plan(b, L, P, cap=self.batch)
+        if not self.use_graph:
+            fplan.set_graph(False)
         if emb_cache is not None:
             e = emb_cache.get(b)
             if e is None:
@@ -377,13 +380,15 @@ class B200SeparationModel(SeparationModel):
         return out, (self._last_seg_out[-1].clone() if self._last_seg_out is not None else None)
 
     @torch.no_grad()
-    def profile_gemms(self, track: torch.Tensor, emb: torch.Tensor, span):
-        """Untimed measurement pass: CUDA events around every GEMM / attention launch of one step (bench.py roofline)."""
+    def profile_gemms(self, track: torch.Tensor, emb: torch.Tensor, span, track_offset: int = 0, track_len: Optional[int] = None):
+        """Untimed measurement pass: CUDA events around every GEMM / attention launch of one step (bench.py roofline).
+        ``track`` / ``track_offset`` / ``track_len`` as for ``separate_span``."""
         eng = self.model.engine(self.device)
         L = int(self.model.sample_rate * self.segment_seconds)
         pl = eng.plan(min(self.batch, max(1, span[1] - span[0])), L, emb.shape[0], cap=self.batch)
         pl.set_profile(True)
-        self.separate_span(track, emb, span, halo_in=torch.zeros(emb.shape[0], 2, L, device=self.device))
+        self.separate_span(track, emb, span, track_offset=track_offset, track_len=track_len,
+                           halo_in=torch.zeros(emb.shape[0], 2, L, device=self.device))
         torch.cuda.synchronize(self.device)
         ms, gf, n = pl.get_profile()
         pl.set_profile(False)
