@@ -711,10 +711,12 @@ static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide t
                                 // 2 only K >= 1536, unset / 0 never (default).  Isolated it reaches 1427 vs 1290 TFLOP/s at K = 2048
                                 // and 959 vs 1026 at K = 512; inside the forward (residual + statistics epilogue, cold operands) the
                                 // K = 2048 launches measure the same 115-117 us either way (profiles/r01_summary.md).
-void tc_set_bn_cap(int cap) { g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); }
+static bool g_tc_halve_mid = false;      // tuning: N in (128, 256] as two N/2-wide tiles (two CTAs per SM) instead of one N-wide tile
+void tc_set_bn_cap(int cap) { g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0; }
 
 int tc_pick_bn(int N) {
   if (N % 16) return 0;
+  if (g_tc_halve_mid && N > 128 && N <= 256 && (N / 2) % 16 == 0) return N / 2;
   if (N <= g_tc_bn_cap) return N;
   if (g_tc_bn_cap >= 256 && N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;      // (measured: two 128-wide CTAs per SM beat one 192-wide tile for N = 384)

@@ -139,6 +139,9 @@ int athtd_sdr_sums(const float* est_dev, const float* tgt_dev, int items, long n
 /* tuning hook: how many of every 16 exp2 pairs of the attention softmax are evaluated by the FMA-pipe polynomial instead of the
  * SFU (0, 4, 6 or 8; every setting computes the same softmax to bf16 accuracy).  Process-wide. */
 int athtd_attention_set_poly(int npoly);
+/* tuning hook of the tcgen05 GEMM tile selection (tools/): low 16 bits = widest N tile (256), 0x10000 = one CTA per SM only,
+ * 0x20000 = N in (128, 256] as two N/2-wide tiles.  Every setting computes the same GEMM.  Process-wide. */
+int athtd_set_tc_tuning(int flags);
 
 /* kernel-level parity test of the fused attention: q [B*Sq,512], k/v [B*Sk,512] bf16 (8 heads x 64) -> o [B*Sq,512] */
 int athtd_attention_test(const void* q_dev, const void* k_dev, const void* v_dev, void* o_dev, int B, int Sq, int Sk,

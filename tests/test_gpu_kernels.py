@@ -196,3 +196,33 @@ def test_fused_attention_polynomial_exp2_variants(npoly):
     got = o.float().cpu()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("npoly", [0, 4])
+@pytest.mark.parametrize("Sq,Sk", [(200, 64), (128, 65), (300, 1034), (257, 2072)])
+def test_fused_attention_moving_row_maximum(npoly, Sq, Sk):
+    """Online-softmax stress: score magnitudes grow along the key axis, so the running reference maximum of most rows moves in many
+    key tiles (the speculative exponentials are redone there); one key tile, one-key tail tile, odd and even tile counts.
+    Against fp32 softmax(QK^T / 8) V on the bf16-rounded inputs."""
+    lib = alib.load()
+    B = 2
+    g = torch.Generator().manual_seed(Sq * 7 + Sk)
+    ramp = torch.linspace(0.3, 3.0, Sk).view(1, Sk, 1)
+    q = (3.0 * torch.randn(B, Sq, 512, generator=g)).bfloat16()
+    k = (3.0 * torch.randn(B, Sk, 512, generator=g) * ramp).bfloat16()
+    v = torch.randn(B, Sk, 512, generator=g).bfloat16()
+    o = torch.full((B, Sq, 512), float("nan"), dtype=torch.bfloat16, device="cuda")
+    qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+    try:
+        lib.athtd_attention_set_poly(npoly)
+        alib.check(lib.athtd_attention_test(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, Sq, Sk, _stream()))
+        torch.cuda.synchronize()
+    finally:
+        lib.athtd_attention_set_poly(4)          # the default
+    qh = q.float().view(B, Sq, 8, 64).transpose(1, 2)
+    kh = k.float().view(B, Sk, 8, 64).transpose(1, 2)
+    vh = v.float().view(B, Sk, 8, 64).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B, Sq, 512)
+    got = o.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max() < 4e-2
