@@ -173,7 +173,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float cs = p.scale_log2;
-    const float tau = 8.0f / cs;               // the reference maximum moves only for jumps > 2^8 in the exp2 domain
+    const float tau = 16.0f / cs;              // the reference maximum moves only for jumps > 2^16 in the exp2 domain (P <= 2^16: no precision issue in bf16 / fp32)
     float m_used = -INFINITY;
     float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
     // P = exp2(s * cs - mb) of 32 scores -> 16 bf16 pairs, row-sum partials in (t01, t23); packed fp32 pairs (FFMA2 / FADD2)
@@ -185,7 +185,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float2 e;
         // interleave the polynomial pairs with the SFU pairs so that both pipes stay busy
         if (NPOLY > 0 && (i * NPOLY) / 16 != ((i + 1) * NPOLY) / 16) {
-          a.x = fmaxf(a.x, -125.0f); a.y = fmaxf(a.y, -125.0f);            // exp2 -> ~0 (masked keys are -inf)
+          // clamp to [-125, 127]: masked keys are -inf (-> ~0); a runaway score must still blow the row sum (detection below)
+          a.x = fminf(fmaxf(a.x, -125.0f), 127.0f); a.y = fminf(fmaxf(a.y, -125.0f), 127.0f);
           const float2 magic = make_float2(12582912.0f, 12582912.0f);      // 1.5 * 2^23: round to nearest integer in the mantissa
           const float2 t = f2add(a, magic);
           const float2 f = f2sub(a, f2sub(t, magic));                      // fractional part in [-0.5, 0.5]
@@ -230,15 +231,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // exponentials start right away and the row maximum (ALU pipe) is computed next to them (SFU pipe)
       float mb = m_used * cs;
       if (j > 0) { exp_pack(r0, mb, pk32, t01, t23); tmem_st16_nowait(tp, pk32); }
-      float tmax = max32(r0);
       tmem_wait_ld();
       if (nvalid < 64) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) if (32 + i >= nvalid) r1[i] = 0xff800000u;
       }
       if (j > 0) { exp_pack(r1, mb, pk32 + 16, t01, t23); tmem_st16_nowait(tp + 16u, pk32 + 16); }
-      tmax = fmaxf(tmax, max32(r1));
-      const bool need = tmax > m_used + tau;              // always true on the first tile (m_used = -inf)
+      // A move of the reference is DETECTED without a max tree: a score above m_used + tau makes its P exceed 2^16, hence the
+      // tile's row sum -- needed anyway -- exceed 2^16 (or be inf / NaN); only such tiles (and tile 0) form the exact maximum
+      const float tsum = (t01.x + t01.y) + (t23.x + t23.y);
+      const bool sus = (j == 0) || !(tsum <= 65536.0f);
+      bool need = false;
+      float tmax = m_used;
+      if (__any_sync(0xffffffffu, sus)) {
+        tmax = fmaxf(max32(r0), max32(r1));
+        need = tmax > m_used + tau;            // always true on the first tile (m_used = -inf)
+      }
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? tmax : m_used;
         const float alpha = (j == 0 || !need) ? 1.0f : ex2_approx((m_used - m_new) * cs);

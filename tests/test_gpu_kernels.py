@@ -195,7 +195,8 @@ def test_fused_attention_polynomial_exp2_variants(npoly):
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B, Sq, 512)
     got = o.float().cpu()
     assert torch.isfinite(got).all()
-    assert (got - ref).abs().max() < 2e-2
+    # peaky softmax: |o| reaches 4, where one bf16 ulp of the stored output is already 0.03 -> tolerance relative to the value
+    assert ((got - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all()
 
 
 @pytest.mark.parametrize("npoly", [0, 4])
@@ -225,4 +226,4 @@ def test_fused_attention_moving_row_maximum(npoly, Sq, Sk):
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B, Sq, 512)
     got = o.float().cpu()
     assert torch.isfinite(got).all()
-    assert (got - ref).abs().max() < 4e-2
+    assert ((got - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all()
