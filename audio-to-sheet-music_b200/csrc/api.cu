@@ -219,6 +219,7 @@ int athtd_load_audio(const float* x_dev, int C_in, long T_in, const float* kerne
   return check_cuda("athtd_load_audio");
 }
 
+int athtd_set_pdl(int on) { pdl_set_enabled(on != 0); return 0; }
 int athtd_set_tc_tuning(int flags) { tc_set_bn_cap(flags); return 0; }
 int athtd_attention_set_poly(int npoly) { flash_attn_set_poly(npoly); return 0; }
 

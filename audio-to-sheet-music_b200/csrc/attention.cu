@@ -76,6 +76,7 @@ template <int NPOLY>
 __global__ void __launch_bounds__(192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -108,6 +109,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                    // Q / K / V are written by the predecessor: nothing is loaded before this point
   // columns: S buffers [0,64) [64,128), O [128,192), P buffers (bf16 pairs: 64 keys = 32 columns) [192,224) [224,256)
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
 
@@ -341,10 +343,10 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
   }
   dim3 grid((Sq + 127) / 128, 8, B);
   switch (g_fa_npoly) {
-    case 0: flash_attn_kernel<0><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); break;
-    case 4: flash_attn_kernel<4><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); break;
-    case 6: flash_attn_kernel<6><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); break;
-    default: flash_attn_kernel<8><<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p); break;
+    case 0: launch_pdl(flash_attn_kernel<0>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
+    case 4: launch_pdl(flash_attn_kernel<4>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
+    case 6: launch_pdl(flash_attn_kernel<6>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
+    default: launch_pdl(flash_attn_kernel<8>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
   }
   return 0;
 }

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 namespace athtd {
 
@@ -152,6 +153,29 @@ inline int device_sm_count() {
     if (n[d] <= 0) n[d] = 148;
   }
   return n[d];
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the stream is still
+// draining -- its CTAs become resident as soon as every CTA of the predecessor has executed pdl_trigger() (or exited), run
+// their prologue (barrier init, TMEM allocation, staging of CONSTANT data such as weights) and block in pdl_wait() until the
+// predecessor has completed and its memory is visible.  Every kernel that is launched with launch_pdl() calls pdl_wait() before it
+// touches anything a predecessor may have written.  Both instructions are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_begin() { pdl_trigger(); pdl_wait(); }
+bool pdl_enabled();
+void pdl_set_enabled(bool on);
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 
 // A padded channels-last row space.  G = B*G2 interior groups (G2 groups per segment: frames on the

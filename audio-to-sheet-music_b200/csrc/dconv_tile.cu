@@ -128,6 +128,7 @@ __device__ __forceinline__ void dc_row_stats(double* st, int b, int Rr, int r_lo
 // ------------------------------------------------------------------ pass A
 template <int C, int TM>
 __global__ void __launch_bounds__(256) dconv_a_kernel(const DcTileParams p) {
+  pdl_begin();
   typedef DcDims<C> D;
   constexpr int MW = TM / 16, NG = 8 / MW, NPW = (D::HN + NG - 1) / NG;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -218,6 +219,7 @@ __device__ __forceinline__ uint32_t dc_gn_gelu_pair(bf16* hp, int c, float mean,
 // ------------------------------------------------------------------ pass B
 template <int C>
 __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
+  pdl_begin();
   typedef DcDims<C> D;
   constexpr int NT2 = 2 * C / 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -304,6 +306,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // residual update happens after it has landed.
 template <int C, int CS, int TM, bool PER_ROW, bool REWRITE>
 __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
+  pdl_begin();
   typedef DcDims<C> D;
   constexpr int MW = TM / 16, NG = 8 / MW, CV = CS / 8, XPS = CS + 8;
   constexpr int NVT = (CV + NG - 1) / NG;           // value n-tiles per warp
@@ -486,12 +489,12 @@ static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
   const int tiles_c = (p.g.rows + TMC - 1) / TMC;
   const int tiles_b = (p.g.rows + 127) / 128;
   const int gb = std::min(tiles_b, std::max(1, (device_sm_count() * 16 + B - 1) / B));
-  dconv_a_kernel<C, TM><<<dim3(tiles, B), 256, smA, st>>>(p);
-  dconv_b_kernel<C><<<dim3(gb, B), 256, smB, st>>>(p);
-  if (p.per_row) dconv_c_kernel<C, CS, TMC, true, false><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);
+  launch_pdl(dconv_a_kernel<C, TM>, dim3(dim3(tiles, B)), dim3(256), smA, st, p);
+  launch_pdl(dconv_b_kernel<C>, dim3(dim3(gb, B)), dim3(256), smB, st, p);
+  if (p.per_row) launch_pdl(dconv_c_kernel<C, CS, TMC, true, false>, dim3(dim3(tiles_c, B, C / CS)), dim3(256), smC, st, p);
   else if (rewrite) {
-    if constexpr (CS == C) dconv_c_kernel<C, CS, TMC, false, true><<<dim3(tiles_c, B, 1), 256, smC, st>>>(p);
-  } else dconv_c_kernel<C, CS, TMC, false, false><<<dim3(tiles_c, B, C / CS), 256, smC, st>>>(p);
+    if constexpr (CS == C) launch_pdl(dconv_c_kernel<C, CS, TMC, false, true>, dim3(dim3(tiles_c, B, 1)), dim3(256), smC, st, p);
+  } else launch_pdl(dconv_c_kernel<C, CS, TMC, false, false>, dim3(dim3(tiles_c, B, C / CS)), dim3(256), smC, st, p);
   return 0;
 }
 

@@ -6,8 +6,16 @@
 
 namespace athtd {
 
+// measured on B200 inside the bench step (same gpurun call, two repetitions each): 27.44 / 27.50 ms with programmatic dependent
+// launch, 26.31 / 26.78 ms without -- the early-resident CTAs of the next kernel cost more than the overlapped prologues save.
+// Off by default; athtd_set_pdl(1) turns it on.
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+void pdl_set_enabled(bool on) { g_pdl = on; }
+
 // ------------------------------------------------------------------ per-sample sum / sumsq
 __global__ void sum_sumsq_kernel(const float* __restrict__ x, long n_per_sample, double* __restrict__ stats) {
+  pdl_begin();
   const int b = blockIdx.y;
   const float* p = x + (long)b * n_per_sample;
   float s = 0.f, ss = 0.f;
@@ -29,11 +37,12 @@ __global__ void sum_sumsq_kernel(const float* __restrict__ x, long n_per_sample,
 void launch_sum_sumsq(const float* x, int B, long n_per_sample, double* stats, cudaStream_t st) {
   int blocks = (int)min((n_per_sample + 256 * 8 - 1) / (256 * 8), (long)296);
   if (blocks < 1) blocks = 1;
-  sum_sumsq_kernel<<<dim3(blocks, B), 256, 0, st>>>(x, n_per_sample, stats);
+  launch_pdl(sum_sumsq_kernel, dim3(dim3(blocks, B)), dim3(256), 0, st, x, n_per_sample, stats);
 }
 
 // (sum, sumsq) double accumulators -> (mean, rstd) floats, biased variance (GroupNorm semantics)
 __global__ void finalize_gn_kernel(const double* __restrict__ stats, double count, float* __restrict__ mr, long n, int nslot) {
+  pdl_begin();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     double st[2] = {stats[2 * i], stats[2 * i + 1]};
@@ -43,6 +52,7 @@ __global__ void finalize_gn_kernel(const double* __restrict__ stats, double coun
 // slotted accumulators (nslot > 1): one warp per group, lanes over slots, fixed-order tree (a single thread walking the
 // 64 slots was a 10 us dependent-load chain, 16 times per forward)
 __global__ void finalize_gn_slots_kernel(const double* __restrict__ stats, double count, float* __restrict__ mr, long n, int nslot) {
+  pdl_begin();
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
@@ -53,8 +63,8 @@ __global__ void finalize_gn_slots_kernel(const double* __restrict__ stats, doubl
   if (lane == 0) { float m, r; stats_to_mean_rstd(st, count, 1e-5f, m, r); mr[2 * i] = m; mr[2 * i + 1] = r; }
 }
 void launch_finalize_gn(const double* stats, double count, float* mr, long n, int nslot, cudaStream_t st) {
-  if (nslot == 1) finalize_gn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stats, count, mr, n, nslot);
-  else finalize_gn_slots_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(stats, count, mr, n, nslot);
+  if (nslot == 1) launch_pdl(finalize_gn_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, stats, count, mr, n, nslot);
+  else launch_pdl(finalize_gn_slots_kernel, dim3((unsigned)((n * 32 + 127) / 128)), dim3(128), 0, st, stats, count, mr, n, nslot);
 }
 
 // torch.std default (unbiased) and the reference guard (x - mean) / (1e-5 + std)   ATHTDemucs_v2.py:268-275
@@ -66,11 +76,12 @@ __device__ __forceinline__ void unbiased_mean_std(const double* st, double n, fl
 }
 
 __global__ void finalize_meanstd_kernel(const double* __restrict__ stats, double n, float* __restrict__ out, int B) {
+  pdl_begin();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) { float m, s; unbiased_mean_std(stats + 2 * b, n, m, s); out[2 * b] = m; out[2 * b + 1] = s; }
 }
 void launch_finalize_meanstd(const double* stats, double n, float* out, int B, cudaStream_t st) {
-  finalize_meanstd_kernel<<<(B + 127) / 128, 128, 0, st>>>(stats, n, out, B);
+  launch_pdl(finalize_meanstd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, stats, n, out, B);
 }
 
 __global__ void set_meanstd_kernel(float* __restrict__ out, int B, float mean, float stdv) {
@@ -201,6 +212,7 @@ __global__ void __launch_bounds__(256, 3) norm_rows_kernel(const T* __restrict__
                                  const float* __restrict__ gb, const float* __restrict__ lw, const float* __restrict__ lb,
                                  const float* __restrict__ pe, RowSpace yrs, T* __restrict__ y2,
                                  const float* __restrict__ lw2, const float* __restrict__ lb2) {
+  pdl_begin();
   // one warp per RPW consecutive rows; each lane owns up to two 8-channel chunks (C <= 512, C % 8 == 0): 16-byte loads /
   // stores, all RPW rows' loads in flight together, and every affine vector is fetched once per RPW rows (fetched per row,
   // the fp32 parameters were 4-6x the bf16 payload in L1 traffic)
@@ -325,6 +337,7 @@ __global__ void __launch_bounds__(256, 2) ln512_rows_kernel(const T* __restrict_
                                                             const float* __restrict__ lw, const float* __restrict__ lb,
                                                             const float* __restrict__ pe, RowSpace yrs, T* __restrict__ y2,
                                                             const float* __restrict__ lw2, const float* __restrict__ lb2) {
+  pdl_begin();
   constexpr int C = 512;
   if constexpr (sizeof(T) != 2) return;          // (instantiated for the fp32 build's template, never launched for it)
   else {
@@ -398,16 +411,16 @@ void launch_norm_rows(const T* x, T* xout, T* y, long rows, int C, int S, const 
                       RowSpace yrs, cudaStream_t st, T* y2, const float* lw2, const float* lb2) {
   if (C == 512 && !gmr && lw && sizeof(T) == 2) {
     const unsigned grid = (unsigned)std::min<long>((rows + 7) / 8, 2L * device_sm_count());      // one resident wave
-    if (y2) ln512_rows_kernel<T, true><<<grid, 256, 0, st>>>(x, y, rows, S, lw, lb, pe, yrs, y2, lw2, lb2);
-    else ln512_rows_kernel<T, false><<<grid, 256, 0, st>>>(x, y, rows, S, lw, lb, pe, yrs, y2, lw2, lb2);
+    if (y2) launch_pdl(ln512_rows_kernel<T, true>, dim3(grid), dim3(256), 0, st, x, y, rows, S, lw, lb, pe, yrs, y2, lw2, lb2);
+    else launch_pdl(ln512_rows_kernel<T, false>, dim3(grid), dim3(256), 0, st, x, y, rows, S, lw, lb, pe, yrs, y2, lw2, lb2);
     return;
   }
   constexpr int wpb = 8;
   if (C == 512)      // (measured: two rows per warp help the 512-channel GroupNorm + LayerNorm passes, not the narrower ones)
-    norm_rows_kernel<T, 2><<<(unsigned)((rows + wpb * 2 - 1) / (wpb * 2)), wpb * 32, 0, st>>>(x, xout, y, rows, C, S, gmr, gw, gb, lw,
+    launch_pdl(norm_rows_kernel<T, 2>, dim3((unsigned)((rows + wpb * 2 - 1) / (wpb * 2))), dim3(wpb * 32), 0, st, x, xout, y, rows, C, S, gmr, gw, gb, lw,
                                                                                               lb, pe, yrs, y2, lw2, lb2);
   else
-    norm_rows_kernel<T, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, xout, y, rows, C, S, gmr, gw, gb, lw, lb, pe,
+    launch_pdl(norm_rows_kernel<T, 1>, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, x, xout, y, rows, C, S, gmr, gw, gb, lw, lb, pe,
                                                                                     yrs, y2, lw2, lb2);
 }
 
@@ -443,6 +456,7 @@ void launch_softmax_rows(T* s, long rows, int n, cudaStream_t st) {
 template <typename T>
 __global__ void add_rowvec_kernel(const T* __restrict__ x, T* __restrict__ y, long rows_per_b, int C, int B,
                                   const float* __restrict__ vec, long vstride) {
+  pdl_begin();
   long total = (long)B * rows_per_b * C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int c = (int)(i % C); long b = i / ((long)rows_per_b * C);
@@ -453,6 +467,7 @@ __global__ void add_rowvec_kernel(const T* __restrict__ x, T* __restrict__ y, lo
 template <typename T>
 __global__ void add_rowvec_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long rows_per_b, int C, int B,
                                       const float* __restrict__ vec, long vstride) {
+  pdl_begin();
   constexpr int VEC = 16 / (int)sizeof(T);
   const int cv = C / VEC;
   const long total = (long)B * rows_per_b * cv;
@@ -473,11 +488,11 @@ void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const fl
   constexpr int VEC = 16 / (int)sizeof(T);
   if (C % VEC == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {
     long total = (long)B * rows_per_b * (C / VEC);
-    add_rowvec_vec_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(x, y, rows_per_b, C, B, vec, vstride);
+    launch_pdl(add_rowvec_vec_kernel<T>, dim3((int)min((total + 255) / 256, (long)148 * 16)), dim3(256), 0, st, x, y, rows_per_b, C, B, vec, vstride);
     return;
   }
   long total = (long)B * rows_per_b * C;
-  add_rowvec_kernel<T><<<(int)min((total + 255) / 256, (long)148 * 16), 256, 0, st>>>(x, y, rows_per_b, C, B, vec, vstride);
+  launch_pdl(add_rowvec_kernel<T>, dim3((int)min((total + 255) / 256, (long)148 * 16)), dim3(256), 0, st, x, y, rows_per_b, C, B, vec, vstride);
 }
 
 // ------------------------------------------------------------------ text conditioning vector
@@ -511,6 +526,7 @@ __global__ void __launch_bounds__(1024) text_vectors_kernel(const float* __restr
                                                            const float* __restrict__ b1, const float* __restrict__ W2,
                                                            const float* __restrict__ b2, const float* __restrict__ W3,
                                                            const float* __restrict__ b3, float* __restrict__ out) {
+  pdl_begin();
   __shared__ __align__(16) float s0[512], s1[384], s2[384];
   const long row = blockIdx.x;
   for (int i = threadIdx.x; i < 512; i += blockDim.x) s0[i] = emb[row * 512 + i];
@@ -523,7 +539,7 @@ __global__ void __launch_bounds__(1024) text_vectors_kernel(const float* __restr
 }
 void launch_text_vectors(const float* emb, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                          const float* b3, float* out, int rows, cudaStream_t st) {
-  text_vectors_kernel<<<rows, 1024, 0, st>>>(emb, W1, b1, W2, b2, W3, b3, out);
+  launch_pdl(text_vectors_kernel, dim3(rows), dim3(1024), 0, st, emb, W1, b1, W2, b2, W3, b3, out);
 }
 
 // ------------------------------------------------------------------ decoder layer tail
@@ -590,6 +606,7 @@ __global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u,
                                                         RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
                                                         const float* __restrict__ gw, const float* __restrict__ gb,
                                                         const T* __restrict__ skip, RowSpace ss, int TD) {
+  pdl_begin();
   extern __shared__ __align__(16) uint8_t dec_smem[];
   LerpRow* tab = (LerpRow*)dec_smem;                                 // [TD]
   float* act_s = (float*)(dec_smem + (((size_t)TD * sizeof(LerpRow) + 15) & ~(size_t)15));   // STAGE: [n_in][Cu]
@@ -711,7 +728,7 @@ void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace
   size_t smem = (((size_t)TD * sizeof(LerpRow) + 15) & ~(size_t)15);
   if (stage) smem += (size_t)((int)(TD * ratio) + 4) * Cu * sizeof(float);
   dim3 grid(tiles, os.G);
-#define DEC_LAUNCH(V, S) dec_apply_kernel<T, V, S><<<grid, 256, smem, st>>>(u, Uin, us, Cu, out, os, G2, has_gn, mr, gw, gb, skip, ss, TD)
+#define DEC_LAUNCH(V, S) launch_pdl(dec_apply_kernel<T, V, S>, dim3(grid), dim3(256), smem, st, u, Uin, us, Cu, out, os, G2, has_gn, mr, gw, gb, skip, ss, TD)
   if (vec == 8) { if (stage) DEC_LAUNCH(8, true); else DEC_LAUNCH(8, false); }
   else { if (stage) DEC_LAUNCH(4, true); else DEC_LAUNCH(4, false); }
 #undef DEC_LAUNCH

@@ -59,6 +59,7 @@ template <int C, bool FUSE_CONV, int G>
 __global__ void __launch_bounds__(ER_THREADS * G, (C == 48 && G == 1 ? 2 : 1))
 enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restrict__ yin, bf16* __restrict__ out, RowSpace ys,
                const EncRowParams P) {
+  pdl_trigger();
   typedef ErDims<C> D;
   const int Tn = ys.G2;
   const int MT = (Tn + 15) / 16;
@@ -125,6 +126,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
   }
   for (int n = btid; n < 2 * C; n += blockDim.x) rbs[(n & 1) * C + (n >> 1)] = (n & 1) ? 0.5f * P.rb[n] : P.rb[n];
   __syncthreads();
+  pdl_wait();        // the weight staging above (constant data) overlaps the predecessor; activations are read from here on
 
   const int n_slabs = ys.batch() * ys.R;
   for (int slab = blockIdx.x * G + grp; slab < n_slabs; slab += gridDim.x * G) {
@@ -397,17 +399,17 @@ void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, R
     if (g3) {
       const size_t smem = enc_row_smem<48>(Tn, true, 3);
       cudaFuncSetAttribute(enc_row_kernel<48, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      enc_row_kernel<48, true, 3><<<std::min((slabs + 2) / 3, er_num_sms()), 3 * ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+      launch_pdl(enc_row_kernel<48, true, 3>, dim3(std::min((slabs + 2) / 3, er_num_sms())), dim3(3 * ER_THREADS), smem, st, xin, xis, yin, out, ys, P);
       return;
     }
     const size_t smem = enc_row_smem<48>(Tn, fuse_conv, 1);
     const int grid = std::min(slabs, 2 * er_num_sms());
     if (fuse_conv) {
       cudaFuncSetAttribute(enc_row_kernel<48, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      enc_row_kernel<48, true, 1><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+      launch_pdl(enc_row_kernel<48, true, 1>, dim3(grid), dim3(ER_THREADS), smem, st, xin, xis, yin, out, ys, P);
     } else {
       cudaFuncSetAttribute(enc_row_kernel<48, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      enc_row_kernel<48, false, 1><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+      launch_pdl(enc_row_kernel<48, false, 1>, dim3(grid), dim3(ER_THREADS), smem, st, xin, xis, yin, out, ys, P);
     }
   } else {
     // C = 96: the weights alone are 77 KB, so one CTA per SM; two 9-warp slab groups share them (18 warps per SM)
@@ -416,10 +418,10 @@ void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, R
     const int grid = std::min((slabs + G - 1) / G, er_num_sms());
     if (G == 2) {
       cudaFuncSetAttribute(enc_row_kernel<96, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      enc_row_kernel<96, false, 2><<<grid, 2 * ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+      launch_pdl(enc_row_kernel<96, false, 2>, dim3(grid), dim3(2 * ER_THREADS), smem, st, xin, xis, yin, out, ys, P);
     } else {
       cudaFuncSetAttribute(enc_row_kernel<96, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      enc_row_kernel<96, false, 1><<<grid, ER_THREADS, smem, st>>>(xin, xis, yin, out, ys, P);
+      launch_pdl(enc_row_kernel<96, false, 1>, dim3(grid), dim3(ER_THREADS), smem, st, xin, xis, yin, out, ys, P);
     }
   }
 }

@@ -130,6 +130,7 @@ __device__ __forceinline__ void fft4096_tail(float2 (&v)[16], float2* sc, const 
 __global__ void __launch_bounds__(256) stft_cac_kernel(const float* __restrict__ wav, int L, int Tf, float4* __restrict__ Z,
                                                         double* __restrict__ stats, const float2* __restrict__ tw,
                                                         const float* __restrict__ win) {
+  pdl_begin();
   __shared__ float2 sc[FFT_SMEM];
   __shared__ float red[2][8];
   const int t = threadIdx.x, frame = blockIdx.x, b = blockIdx.y;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256) stft_cac_kernel(const float* __restrict__
 
 void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* stats, const float2* tw, const float* win,
                      cudaStream_t st) {
-  stft_cac_kernel<<<dim3(Tf, B), 256, 0, st>>>(wav, L, Tf, (float4*)Z, stats, tw, win);
+  launch_pdl(stft_cac_kernel, dim3(dim3(Tf, B)), dim3(256), 0, st, wav, L, Tf, (float4*)Z, stats, tw, win);
 }
 
 // ------------------------------------------------------------------ inverse: mask + iFFT -> windowed frames
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(256, 3) istft_fused_kernel(const float4* __res
                                                            const float* __restrict__ to_b, const float* __restrict__ meanstd_t,
                                                            int ms_div, float* __restrict__ out, long out_bstride,
                                                            const float2* __restrict__ tw, const float* __restrict__ win) {
+  pdl_begin();
   extern __shared__ __align__(16) float2 fsm[];
   float2* sc = fsm;
   float2* ring = fsm + FFT_SMEM;                     // [4 hops][1024] (left, right) partial overlap-add sums
@@ -407,7 +409,7 @@ void launch_istft_fused(const float* Z, int Tf, int L, int Bout, int zb_div, con
   const long total = (long)Bout * Tf;
   const long slots = 3L * device_sm_count();
   long grid = std::min(slots, std::max(1L, total / 12));
-  istft_fused_kernel<T><<<(unsigned)grid, 256, IFFT_SMEM_BYTES, st>>>((const float4*)Z, Tf, L, Bout, zb_div, dec, ds, use_mask, fo_w,
+  launch_pdl(istft_fused_kernel<T>, dim3((unsigned)grid), dim3(256), IFFT_SMEM_BYTES, st, (const float4*)Z, Tf, L, Bout, zb_div, dec, ds, use_mask, fo_w,
                                                                      fo_b, tdec, ts, to_w, to_b, meanstd_t, ms_div, out, out_bstride,
                                                                      tw, win);
 }

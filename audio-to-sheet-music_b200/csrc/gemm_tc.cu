@@ -229,6 +229,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
 template <int EF, int MINB>
 __global__ void __launch_bounds__(TcCfg<MINB>::THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  pdl_trigger();                 // the next kernel's CTAs may set up while this grid drains (programmatic dependent launch)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stageA = TC_BM * TC_BK * 2;
@@ -264,6 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                    // barrier init / TMEM allocation above overlap the predecessor; its data is visible from here
 
   if (warp == 0) {
     {
@@ -823,8 +825,8 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
       cfg.attrs = at; cfg.numAttrs = 1;                                                                                   \
       return cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<E>, tmA, tmBh, pp) == cudaSuccess ? 0 : 6;                      \
     }                                                                                                                     \
-    if (ctas_per_sm == 2) gemm_tc_kernel<E, 2><<<grid, TcCfg<2>::THREADS, smem, st>>>(tmA, tmB, p);                       \
-    else gemm_tc_kernel<E, 1><<<grid, TcCfg<1>::THREADS, smem, st>>>(tmA, tmB, p);                                        \
+    if (ctas_per_sm == 2) launch_pdl(gemm_tc_kernel<E, 2>, grid, dim3(TcCfg<2>::THREADS), smem, st, tmA, tmB, p);         \
+    else launch_pdl(gemm_tc_kernel<E, 1>, grid, dim3(TcCfg<1>::THREADS), smem, st, tmA, tmB, p);                          \
     return 0;                                                                                                             \
   }
   switch (ef) {

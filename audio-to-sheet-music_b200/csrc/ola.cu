@@ -11,6 +11,7 @@ namespace athtd {
 // segs[k, c, i] = track[c, starts[k] + i]  (zero beyond T: the reference zero-pads the tail chunk)
 __global__ void gather_chunks_kernel(const float* __restrict__ track, long T, int C, const long* __restrict__ starts,
                                      int chunk_len, float* __restrict__ segs) {
+  pdl_begin();
   int k = blockIdx.y / C, c = blockIdx.y % C;
   long s0 = starts[k];
   const float* src = track + (long)c * T;
@@ -22,7 +23,7 @@ __global__ void gather_chunks_kernel(const float* __restrict__ track, long T, in
 }
 void launch_gather_chunks(const float* track, long T, int C, const long* starts, int n_chunks, int chunk_len, float* segs,
                           cudaStream_t st) {
-  gather_chunks_kernel<<<dim3(min((chunk_len + 255) / 256, 1024), n_chunks * C), 256, 0, st>>>(track, T, C, starts, chunk_len, segs);
+  launch_pdl(gather_chunks_kernel, dim3(dim3(min((chunk_len + 255) / 256, 1024), n_chunks * C)), dim3(256), 0, st, track, T, C, starts, chunk_len, segs);
 }
 
 __device__ __forceinline__ float chunk_w(int i, int actual, int fade, int flags, const float* __restrict__ up,
@@ -43,6 +44,7 @@ __global__ void chunk_ola_kernel(const float* __restrict__ seg_out, long seg_str
                                  const float* __restrict__ ramp_up, const float* __restrict__ ramp_down,
                                  const int* __restrict__ ramp_off, float* __restrict__ out, long out_pitch, int C,
                                  long t_begin, long t_end, int normalize) {
+  pdl_begin();
   for (long s = t_begin + (long)blockIdx.x * blockDim.x + threadIdx.x; s < t_end; s += (long)gridDim.x * blockDim.x) {
     int k_hi = (int)(s / stride); if (k_hi > n_chunks - 1) k_hi = n_chunks - 1;
     int k_lo = k_hi;
@@ -68,7 +70,7 @@ void launch_chunk_ola(const float* seg_out, long seg_stride, int k_base, int chu
                       long t_end, int normalize, cudaStream_t st) {
   long n = t_end - t_begin;
   if (n <= 0) return;
-  chunk_ola_kernel<<<(int)min((n + 255) / 256, (long)148 * 16), 256, 0, st>>>(seg_out, seg_stride, k_base, chunk_len, starts,
+  launch_pdl(chunk_ola_kernel, dim3((int)min((n + 255) / 256, (long)148 * 16)), dim3(256), 0, st, seg_out, seg_stride, k_base, chunk_len, starts,
                                                                               actual_len, fade_len, flags, n_chunks, stride,
                                                                               ramp_up, ramp_down, ramp_off, out, n, C,
                                                                               t_begin, t_end, normalize);

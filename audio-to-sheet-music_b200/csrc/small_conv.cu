@@ -14,6 +14,7 @@ namespace athtd {
 __global__ void __launch_bounds__(256) tenc0_conv_kernel(const float* __restrict__ wav, const float* __restrict__ meanstd, int L,
                                                          const bf16* __restrict__ w /*[48][16] k = tap*2 + ci*/,
                                                          const float* __restrict__ bias, bf16* __restrict__ y, RowSpace ys) {
+  pdl_begin();
   __shared__ __align__(16) bf16 stage[8][16][56];
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) tenc0_conv_kernel(const float* __restrict
 void launch_tenc0_conv(const float* wav, const float* meanstd, int L, const bf16* w, const float* bias, bf16* y, RowSpace ys,
                        cudaStream_t st) {
   const int tiles = (ys.R + 127) / 128;
-  tenc0_conv_kernel<<<dim3(tiles, ys.batch()), 256, 0, st>>>(wav, meanstd, L, w, bias, y, ys);
+  launch_pdl(tenc0_conv_kernel, dim3(dim3(tiles, ys.batch())), dim3(256), 0, st, wav, meanstd, L, w, bias, y, ys);
 }
 
 }  // namespace athtd
@@ -82,6 +83,7 @@ __device__ __forceinline__ void lerp_coords_s(int d, int in, int out, int& i0, i
 __global__ void __launch_bounds__(288) dec_last_freq_kernel(const bf16* __restrict__ x, RowSpace xs, const float* __restrict__ w /*[48][4][8]*/,
                                                             const float* __restrict__ bias, const bf16* __restrict__ skip, RowSpace ss,
                                                             bf16* __restrict__ out, RowSpace os) {
+  pdl_begin();
   __shared__ __align__(16) bf16 ws[8][152];
   const int g_ = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(288) dec_last_freq_kernel(const bf16* __restri
 __global__ void __launch_bounds__(256) dec_last_time_kernel(const bf16* __restrict__ x, RowSpace xs, const bf16* __restrict__ w /*[16][96]*/,
                                                             const float* __restrict__ bias4 /*[16]*/, const bf16* __restrict__ skip,
                                                             RowSpace ss, bf16* __restrict__ out, RowSpace os) {
+  pdl_begin();
   __shared__ __align__(16) bf16 ws[16][104];
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -184,12 +187,12 @@ __global__ void __launch_bounds__(256) dec_last_time_kernel(const bf16* __restri
 
 void launch_dec_last_freq(const bf16* x, RowSpace xs, const float* w, const float* bias, const bf16* skip, RowSpace ss, bf16* out,
                           RowSpace os, cudaStream_t st) {
-  dec_last_freq_kernel<<<os.G, 288, 0, st>>>(x, xs, w, bias, skip, ss, out, os);
+  launch_pdl(dec_last_freq_kernel, dim3(os.G), dim3(288), 0, st, x, xs, w, bias, skip, ss, out, os);
 }
 void launch_dec_last_time(const bf16* x, RowSpace xs, const bf16* w, const float* bias4, const bf16* skip, RowSpace ss, bf16* out,
                           RowSpace os, cudaStream_t st) {
   const int tiles = (xs.R + 1 + 127) / 128;
-  dec_last_time_kernel<<<dim3(tiles, os.batch()), 256, 0, st>>>(x, xs, w, bias4, skip, ss, out, os);
+  launch_pdl(dec_last_time_kernel, dim3(dim3(tiles, os.batch())), dim3(256), 0, st, x, xs, w, bias4, skip, ss, out, os);
 }
 
 }  // namespace athtd

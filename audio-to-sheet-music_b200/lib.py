@@ -43,6 +43,7 @@ SYMBOLS = [
     ("athtd_plan_graph_replays", _I, [_P]),
     ("athtd_attention_set_poly", _I, [_I]),
     ("athtd_set_tc_tuning", _I, [_I]),
+    ("athtd_set_pdl", _I, [_I]),
     ("athtd_attention_test", _I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     ("athtd_memcpy_d2d", _I, [_P, _P, _L, _P]),
     ("athtd_sdr_sums", _I, [_P, _P, _I, _L, _P, _P]),

@@ -296,6 +296,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay of the forward)")
+    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch between the kernels (default off: measured slower)")
     ap.add_argument("--no-pin", action="store_true", help="do not give every local rank its own slice of the host cores")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: wait for the downloads of every step before the next one")
     args = ap.parse_args()
@@ -326,6 +327,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
 
+    if args.pdl:
+        athtd_b200.load_library().athtd_set_pdl(1)
     model = athtd_b200.AudioTextHTDemucsB200(precision=args.precision)
     model.load_state_dict(synthetic.make_state_dict(0), strict=False)
     sep = athtd_b200.B200SeparationModel(model, dev, 6.0, 1.5, batch=args.batch, use_graph=not args.no_graph)

@@ -139,6 +139,9 @@ int athtd_sdr_sums(const float* est_dev, const float* tgt_dev, int items, long n
 /* tuning hook: how many of every 16 exp2 pairs of the attention softmax are evaluated by the FMA-pipe polynomial instead of the
  * SFU (0, 4, 6 or 8; every setting computes the same softmax to bf16 accuracy).  Process-wide. */
 int athtd_attention_set_poly(int npoly);
+/* programmatic dependent launch of the path's kernels (default OFF: measured 3 % slower on this path, profiles/r02_summary.md): a kernel's CTAs may set up (barrier init, TMEM allocation,
+ * weight staging) while its predecessor drains; every kernel waits for the predecessor before touching its data.  Process-wide. */
+int athtd_set_pdl(int on);
 /* tuning hook of the tcgen05 GEMM tile selection (tools/): low 16 bits = widest N tile (256), 0x10000 = one CTA per SM only,
  * 0x20000 = N in (128, 256] as two N/2-wide tiles.  Every setting computes the same GEMM.  Process-wide. */
 int athtd_set_tc_tuning(int flags);
