@@ -602,7 +602,7 @@ __device__ __forceinline__ void dec_blend(float (&v)[VEC], const float (&a0)[VEC
 }
 
 template <typename T, int VEC, bool STAGE>
-__global__ void __launch_bounds__(256) dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, int Cu, T* __restrict__ out,
+__global__ void __launch_bounds__(256, 4) dec_apply_kernel(const T* __restrict__ u, int Uin, RowSpace us, int Cu, T* __restrict__ out,
                                                         RowSpace os, int G2, int has_gn, const float* __restrict__ mr,
                                                         const float* __restrict__ gw, const float* __restrict__ gb,
                                                         const T* __restrict__ skip, RowSpace ss, int TD) {

@@ -198,9 +198,9 @@ void launch_stft_cac(const float* wav, int B, int L, int Tf, float* Z, double* s
 }
 
 // ------------------------------------------------------------------ inverse: mask + iFFT -> windowed frames
-__device__ __forceinline__ void lerp_coords_f(int d, int in, int out, int& i0, int& i1, float& lam) {
+// `scale` = (float)in / (float)out, hoisted by the caller (one division per kernel instead of one per element and frame)
+__device__ __forceinline__ void lerp_coords_f(int d, int in, int out, float scale, int& i0, int& i1, float& lam) {
   if (in == out) { i0 = d; i1 = d; lam = 0.f; return; }
-  float scale = (float)in / (float)out;
   float src = scale * ((float)d + 0.5f) - 0.5f;
   if (src < 0.f) src = 0.f;
   i0 = (int)src;
@@ -216,8 +216,9 @@ __device__ __forceinline__ void lerp_coords_f(int d, int in, int out, int& i0, i
 template <typename T>
 __device__ __forceinline__ void masked_spectrum_to_smem(const float4* __restrict__ zi, const T* __restrict__ dec, const RowSpace& ds,
                                                         int g, int use_mask, const float (&fw)[8], const float (&fb)[2],
-                                                        float2* sc) {
+                                                        float lerp_scale, float2* sc) {
   const int t = threadIdx.x;
+  const T* dg = use_mask ? dec + ds.row_off(g, 0) : nullptr;      // rows of one group are contiguous: row r at dg + r * C
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int k = t + 256 * i;
@@ -225,15 +226,15 @@ __device__ __forceinline__ void masked_spectrum_to_smem(const float4* __restrict
     float2 xl, xr;
     if (use_mask) {
       int i0, i1; float lam;
-      lerp_coords_f(k, ds.R, 2048, i0, i1, lam);
+      lerp_coords_f(k, ds.R, 2048, lerp_scale, i0, i1, lam);
       float a0, a1, a2, a3, c0, c1, c2, c3;
       if constexpr (sizeof(T) == 2) {      // the 4 decoder channels of a row are one 8-byte load
-        const uint2 ra = *(const uint2*)(dec + ds.row_off(g, i0)), rc = *(const uint2*)(dec + ds.row_off(g, i1));
+        const uint2 ra = *(const uint2*)(dg + i0 * ds.C), rc = *(const uint2*)(dg + i1 * ds.C);
         const float2 ra0 = __bfloat1622float2(*(const __nv_bfloat162*)&ra.x), ra1 = __bfloat1622float2(*(const __nv_bfloat162*)&ra.y);
         const float2 rc0 = __bfloat1622float2(*(const __nv_bfloat162*)&rc.x), rc1 = __bfloat1622float2(*(const __nv_bfloat162*)&rc.y);
         a0 = ra0.x; a1 = ra0.y; a2 = ra1.x; a3 = ra1.y; c0 = rc0.x; c1 = rc0.y; c2 = rc1.x; c3 = rc1.y;
       } else {
-        const float4 ra = *(const float4*)(dec + ds.row_off(g, i0)), rc = *(const float4*)(dec + ds.row_off(g, i1));
+        const float4 ra = *(const float4*)(dg + i0 * ds.C), rc = *(const float4*)(dg + i1 * ds.C);
         a0 = ra.x; a1 = ra.y; a2 = ra.z; a3 = ra.w; c0 = rc.x; c1 = rc.y; c2 = rc.z; c3 = rc.w;
       }
       float l0a = fw[0] * a0 + fw[1] * a1 + fw[2] * a2 + fw[3] * a3 + fb[0];
@@ -243,7 +244,8 @@ __device__ __forceinline__ void masked_spectrum_to_smem(const float4* __restrict
       const float q0 = (1.f - lam) * l0a + lam * l0b, q1 = (1.f - lam) * l1a + lam * l1b;
       float m0, m1, inv0, inv1;
       if constexpr (sizeof(T) == 2) {      // bf16 build: MUFU exp / reciprocal (relative error ~1e-6, far below the bf16 activations)
-        m0 = __frcp_rn(1.0f + __expf(-q0)); m1 = __frcp_rn(1.0f + __expf(-q1));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(m0) : "f"(1.0f + __expf(-q0)));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(m1) : "f"(1.0f + __expf(-q1)));
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(z.x + 1e-8f));
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(z.y + 1e-8f));
       } else {
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(256, 3) istft_fused_kernel(const float4* __res
     for (int i = 0; i < 8; ++i) tw8[i] = to_w[i];
     tb[0] = to_b[0]; tb[1] = to_b[1];
   }
+  const float lerp_scale = use_mask ? (float)ds.R / 2048.0f : 1.0f;
   const long total = (long)Bout * Tf;
   long f_begin = total * blockIdx.x / gridDim.x, f_end = total * (blockIdx.x + 1) / gridDim.x;
   const bool vec_ok = (L & 3) == 0 && (out_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(256, 3) istft_fused_kernel(const float4* __res
     };
 
     for (int fr = t_start; fr < tb_; ++fr) {
-      masked_spectrum_to_smem<T>(Z + ((long)bz * Tf + fr) * 2048, dec, ds, bo * Tf + fr, use_mask, fw, fb, sc);
+      masked_spectrum_to_smem<T>(Z + ((long)bz * Tf + fr) * 2048, dec, ds, bo * Tf + fr, use_mask, fw, fb, lerp_scale, sc);
       ifft4096_smem(sc, tw);
       // quarter qq of the frame belongs to hop fr + qq; the first frame of the run and every quarter 3 open a new hop
 #pragma unroll

@@ -709,12 +709,15 @@ bool tensor_map_api_available() { return get_encode() != nullptr; }
 
 static int g_tc_bn_cap = 256;
 static bool g_tc_two_ctas = true;
-static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide tiles: env ATHTD_TC_PAIR = 1 every eligible launch,
-                                // 2 only K >= 1536, unset / 0 never (default).  Isolated it reaches 1427 vs 1290 TFLOP/s at K = 2048
+static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide tiles: tuning flag 0x40000 = every eligible launch,
+                                // 0x80000 = only K >= 1536, neither = never (default).  Isolated it reaches 1427 vs 1290 TFLOP/s at K = 2048
                                 // and 959 vs 1026 at K = 512; inside the forward (residual + statistics epilogue, cold operands) the
                                 // K = 2048 launches measure the same 115-117 us either way (profiles/r01_summary.md).
 static bool g_tc_halve_mid = false;      // tuning: N in (128, 256] as two N/2-wide tiles (two CTAs per SM) instead of one N-wide tile
-void tc_set_bn_cap(int cap) { g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0; }
+void tc_set_bn_cap(int cap) {
+  g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0;
+  g_tc_pair = (cap & 0x40000) ? 1 : (cap & 0x80000) ? 2 : 0;
+}
 
 int tc_pick_bn(int N) {
   if (N % 16) return 0;
@@ -781,11 +784,7 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
   const long tiles = (long)p.m_tiles * p.n_tiles;
   dim3 grid((unsigned)std::min<long>(tiles, (long)num_sms() * ctas_per_sm));
-#ifdef ATHTD_ABLATION      // measurement builds only (python -m ... build.py --ablation): never in the shipped library
-  if (g_tc_pair < 0) { const char* e = getenv("ATHTD_TC_PAIR"); g_tc_pair = e ? atoi(e) : 0; }
-#else
   if (g_tc_pair < 0) g_tc_pair = 0;
-#endif
   // CTA pairs for the 256-wide tiles of long-M problems (transformer linears): 256 x 256 tile per cluster
   const bool pair = (g_tc_pair == 1 || (g_tc_pair == 2 && p.ntaps * p.kb_per_tap >= 24)) && p.BN == 256 && f.N % 256 == 0 && p.m_tiles >= 2 * num_sms() && f.stat_mode != STAT_PER_G1_M &&
                     (num_sms() % 2 == 0);

@@ -143,7 +143,8 @@ int athtd_attention_set_poly(int npoly);
  * weight staging) while its predecessor drains; every kernel waits for the predecessor before touching its data.  Process-wide. */
 int athtd_set_pdl(int on);
 /* tuning hook of the tcgen05 GEMM tile selection (tools/): low 16 bits = widest N tile (256), 0x10000 = one CTA per SM only,
- * 0x20000 = N in (128, 256] as two N/2-wide tiles.  Every setting computes the same GEMM.  Process-wide. */
+ * 0x20000 = N in (128, 256] as two N/2-wide tiles, 0x40000 / 0x80000 = route eligible 256-wide tiles (all / only K >= 1536) through
+ * the cta_group::2 CTA-pair kernel.  Every setting computes the same GEMM.  Process-wide. */
 int athtd_set_tc_tuning(int flags);
 
 /* kernel-level parity test of the fused attention: q [B*Sq,512], k/v [B*Sk,512] bf16 (8 heads x 64) -> o [B*Sq,512] */

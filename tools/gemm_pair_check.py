@@ -1,10 +1,12 @@
 """Correctness + timing of the CTA-pair (cta_group::2) GEMM path against torch.matmul on shapes that select it
-(N % 256 == 0, M >= 2 * SMs * 128).  Run under `timeout`: a protocol bug shows up as a hang."""
+(N % 256 == 0, M >= 2 * SMs * 128), selected with the tuning hook athtd_set_tc_tuning(256 | 0x40000).
+Run under `timeout`: a protocol bug shows up as a hang."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from athtd_b200 import lib as alib
 lib = alib.load()
+lib.athtd_set_tc_tuning(256 | 0x40000)
 st = torch.cuda.current_stream().cuda_stream
 ok = True
 for (M, N, K) in [(40000, 256, 64), (40000, 512, 512), (66304, 2048, 512), (66304, 512, 2048), (37889, 1536, 512)]:
