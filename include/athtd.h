@@ -68,6 +68,7 @@ int athtd_plan_get_profile(void* plan, double* gemm_ms, double* gemm_gflop, int*
 
 /* debug / test access to intermediate buffers of the last forward.  Row-space buffers report
  * dims = {stored groups, stored rows per group, channels, front pad rows, G2, G2p, gpf, R} (common.cuh RowSpace). */
+/* (bf16 build: buffers that the fused kernels bypass -- "xf0", "xt0", "yf0", "yf1" -- are not written and hold stale data) */
 int athtd_tap(void* plan, const char* name, const void** ptr, long* numel, int* dtype, int dims[8]);
 /* bf16 build only: route the supported GEMMs through the tcgen05 kernel (default on) or keep everything on the
  * CUDA-core kernel (A/B measurements, kernel-level parity tests). */

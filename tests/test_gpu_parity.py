@@ -272,3 +272,22 @@ def test_graph_replay_matches_eager_launches(models, prec):
     for t in (a, b, c):
         assert athtd_oracle.snr_db(t.cpu(), eager.cpu()) >= 100.0
         assert (t - eager).abs().max() <= 1e-5
+
+
+def test_plan_cache_is_bounded_lru(state_dict):
+    """the plan cache must not grow with every distinct tail length / batch size.  One workspace per (L, P), evicted
+    least-recently-used beyond the byte cap; an outgrown capacity replaces its workspace instead of adding one."""
+    need = athtd_b200.load_library().athtd_workspace_bytes(1, 20000, 1, 1)
+    eng = athtd_b200.Engine("cuda", "bf16", max_workspace_bytes=int(2.5 * need))
+    eng.load_params(state_dict)
+    a = eng.plan(1, 20000, 1)
+    eng.plan(1, 20500, 1)
+    assert len(eng.plans) == 2
+    eng.plan(1, 20000, 1)                       # touch: (20500, 1) is now the least recently used
+    eng.plan(1, 21000, 1)
+    assert list(eng.plans.keys()) == [(20000, 1), (21000, 1)] and eng.workspace_bytes() <= int(2.5 * need)
+    b = eng.plan(2, 20000, 1)                   # outgrown capacity: replaced, not added
+    assert b is not a and b.cap == 2 and len(eng.plans) <= 2
+    wav, emb = synthetic.make_inputs(5, 2, 20000)
+    out = b.forward(wav.cuda(), emb.cuda().unsqueeze(1).contiguous())
+    assert torch.isfinite(out).all()
