@@ -78,7 +78,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // (offset, not a uintptr_t round trip: keeps LDS / STS)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + FA_QB;                       // FA_NK tiles
   uint8_t* sV = sK + FA_NK * FA_KB;               // FA_NV tiles

@@ -72,6 +72,10 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
   float* vec = (float*)(cwt + (FUSE_CONV ? C * D::PP : 0)); // [2][VD] | rb [2C] (gate half pre-scaled by 0.5) | cb [C]
   float* rbs = vec + 2 * D::VD;
   float* cbs = rbs + 2 * C;
+  // GroupNorm-2 statistics without a pass over e = W2 h + b2: sum(e) and sum(e^2) over the slab are LINEAR in the second-moment
+  // matrix D = h~^T h~ of the hidden tile with a constant-one column appended (h~ = [h, 1]), see the statistics step below
+  float* gq = cbs + C;                                      // [2][16][16]  sum(e^2) = sum_ij gq[i][j] D[i][j]
+  float* gs = gq + 2 * 256;                                 // [2][16]      sum(e)   = sum_j gs[j] D[H][j]
   // per slab group (9 warps): activation tiles and per-slab vectors
   constexpr int GF = 4 * C + C + 64;                        // al [2C] be [2C] embv [C] red [64]
   // FUSE_CONV: the hidden operand tile hb aliases the (larger) level-0 patch tile, which is dead after the strided conv
@@ -79,12 +83,12 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
   const int btid = threadIdx.x;
   const int grp = btid / ER_THREADS;
   const int tid = btid - grp * ER_THREADS, lane = tid & 31, warp = tid >> 5, nwarp = ER_THREADS >> 5;
-  float* gvec = cbs + C + grp * GF;
+  float* gvec = gs + 32 + grp * GF;
   float* al = gvec;                                         // [2C] per-slab GroupNorm-2 alpha (gate half x 0.5)
   float* be = al + 2 * C;                                   // [2C] beta
   float* embv = be + 2 * C;                                 // [C]
   float* red = embv + C;                                    // 64 floats
-  bf16* xs = (bf16*)(cbs + C + G * GF) + (size_t)grp * slab_elems;   // [(MT*16 + 4)][XP], rows shifted by +2 (zero halo)
+  bf16* xs = (bf16*)(gs + 32 + G * GF) + (size_t)grp * slab_elems;   // [(MT*16 + 4)][XP], rows shifted by +2 (zero halo)
   bf16* hb = xs + (MT * 16 + 4) * D::XP;                    // [MT*16][K2P]
   bf16* pst = hb;                                           // FUSE_CONV: patch [MT*16][PP] (aliases hb)
   const int g = lane >> 2, q = lane & 3;
@@ -122,9 +126,41 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
   }
   for (int i = btid; i < 2 * C * (C / 8); i += blockDim.x) {
     const int n = i / (C / 8), kc = i - n * (C / 8), nd = (n & 1) * C + (n >> 1);
-    *(uint4*)(wrt + nd * D::KRP + kc * 8) = *(const uint4*)(P.rw + (long)n * C + kc * 8);
+    uint4 w = *(const uint4*)(P.rw + (long)n * C + kc * 8);
+    if (n & 1) {      // gate rows x 0.5 (tanh form of the sigmoid; a power of two: exact in bf16)
+      __nv_bfloat162* h = (__nv_bfloat162*)&w;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(0.5f * __low2float(h[e]), 0.5f * __high2float(h[e]));
+    }
+    *(uint4*)(wrt + nd * D::KRP + kc * 8) = w;
   }
   for (int n = btid; n < 2 * C; n += blockDim.x) rbs[(n & 1) * C + (n >> 1)] = (n & 1) ? 0.5f * P.rb[n] : P.rb[n];
+  __syncthreads();
+  // With W = the staged (bf16) expand weights [2C][H], b = b2, c = H the constant column:
+  //   sum_{t,n} e     = sum_j (sum_n W[n][j]) D[c][j] + (sum_n b[n]) D[c][c]
+  //   sum_{t,n} e^2   = sum_{i,j<H} (W^T W)[i][j] D[i][j] + sum_j 2 (sum_n b[n] W[n][j]) D[c][j] + (sum_n b[n]^2) D[c][c]
+  for (int idx = btid; idx < 2 * 272; idx += blockDim.x) {
+    const int dd = idx / 272, e = idx - dd * 272;
+    const bf16* w2 = w2t + dd * 2 * C * D::K2P;
+    const float* b2v = vec + dd * D::VD + 48;
+    float acc = 0.f;
+    if (e < 256) {
+      const int i = e >> 4, j = e & 15;
+      if (i < D::H && j < D::H) {
+        for (int n = 0; n < 2 * C; ++n) acc += __bfloat162float(w2[n * D::K2P + i]) * __bfloat162float(w2[n * D::K2P + j]);
+      } else if (i == D::H && j < D::H) {
+        for (int n = 0; n < 2 * C; ++n) acc += 2.0f * b2v[n] * __bfloat162float(w2[n * D::K2P + j]);
+      } else if (i == D::H && j == D::H) {
+        for (int n = 0; n < 2 * C; ++n) acc += b2v[n] * b2v[n];
+      }
+      gq[dd * 256 + e] = acc;
+    } else {
+      const int j = e - 256;
+      if (j < D::H) { for (int n = 0; n < 2 * C; ++n) acc += __bfloat162float(w2[n * D::K2P + j]); }
+      else if (j == D::H) { for (int n = 0; n < 2 * C; ++n) acc += b2v[n]; }
+      gs[dd * 16 + j] = acc;
+    }
+  }
   __syncthreads();
   pdl_wait();        // the weight staging above (constant data) overlaps the predecessor; activations are read from here on
 
@@ -250,11 +286,12 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
 #pragma unroll
             for (int nt = 0; nt < D::HN; ++nt) {
               const int c = nt * 8 + 2 * q, r0 = mt * 16 + g;
-              float y[4];
+              float y[4];      // column H carries the constant one of h~; rows past the slab are all-zero (they must not count)
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int cc = c + (e & 1);
-                y[e] = cc < D::H ? gelu_fast((hacc[mi][nt][e] - mean) * rstd * g1w[cc] + g1b[cc]) : 0.f;
+                const bool rv = r0 + (e >> 1) * 8 < Tn;
+                y[e] = !rv ? 0.f : cc < D::H ? gelu_fast((hacc[mi][nt][e] - mean) * rstd * g1w[cc] + g1b[cc]) : cc == D::H ? 1.0f : 0.f;
               }
               sts_pair(hb + r0 * D::K2P + c, y[0], y[1]);
               sts_pair(hb + (r0 + 8) * D::K2P + c, y[2], y[3]);
@@ -264,102 +301,131 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
       }
       er_gsync(grp);
 
-      // ---- e = W2 h + b2 : statistics pass (nothing stored), then GroupNorm + GLU + LayerScale + residual pass
+      // ---- e = W2 h + b2 : GroupNorm(1, 2C) statistics from D = h~^T h~ (one or two MMAs per 16-row tile instead of the 2C-wide
+      //      product), then the GroupNorm + GLU + LayerScale + residual pass
       float s2 = 0.f, q2 = 0.f;
-      for (int mt = warp; mt < MT; mt += nwarp) {
-        uint32_t a[4];
-        ldsm_a(hb, D::K2P, mt * 16, 0, lane, a);
-        const int r0 = mt * 16 + g;
-        const bool v0 = r0 < Tn, v1 = r0 + 8 < Tn;
-        float2 sl = f2splat(0.f), ql = f2splat(0.f), sh = f2splat(0.f), qh = f2splat(0.f);      // packed (even, odd column) partials
-#pragma unroll 4
-        for (int nt = 0; nt < 2 * D::AT; ++nt) {
-          float d[4] = {0.f, 0.f, 0.f, 0.f};
-          uint32_t bb[2];
-          frag_b(w2, D::K2P, nt * 8, 0, lane, bb);
-          mma16816(d, a, bb);
-          const float2 bv = *(const float2*)(b2 + nt * 8 + 2 * q);
-          const float2 e01 = f2add(make_float2(d[0], d[1]), bv), e23 = f2add(make_float2(d[2], d[3]), bv);
-          sl = f2add(sl, e01); ql = f2fma(e01, e01, ql);
-          sh = f2add(sh, e23); qh = f2fma(e23, e23, qh);
+      {
+        float dacc[D::HN][4];
+#pragma unroll
+        for (int nt = 0; nt < D::HN; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dacc[nt][e] = 0.f;
+        for (int mt = warp; mt < MT; mt += nwarp) {
+          uint32_t t[4];
+          ldsm_x4_trans(hb, D::K2P, mt * 16, 0, lane, t);
+          { const uint32_t b0[2] = {t[0], t[2]}; mma16816(dacc[0], t, b0); }
+          if (D::HN == 2) { const uint32_t b1[2] = {t[1], t[3]}; mma16816(dacc[D::HN - 1], t, b1); }
         }
-        if (v0) { s2 += sl.x + sl.y; q2 += ql.x + ql.y; }
-        if (v1) { s2 += sh.x + sh.y; q2 += qh.x + qh.y; }
+        const float* gqd = gq + dd * 256;
+        const float* gsd = gs + dd * 16;
+#pragma unroll
+        for (int nt = 0; nt < D::HN; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = g + (e >> 1) * 8, j = nt * 8 + 2 * q + (e & 1);
+            if (i <= D::H) {       // (rows past the constant one are zero)
+              q2 += gqd[i * 16 + j] * dacc[nt][e];
+              if (i == D::H) s2 += gsd[j] * dacc[nt][e];
+            }
+          }
       }
       er_block_sum2(s2, q2, red, grp, tid);
       {
         const float n2 = (float)(Tn * 2 * C);
         const float mean2 = s2 / n2;
         const float rstd2 = rsqrtf(fmaxf(q2 / n2 - mean2 * mean2, 0.f) + 1e-5f);
-        for (int n = tid; n < 2 * C; n += ER_THREADS) {       // e_norm = d * alpha + beta (gate half carries the x/2 of tanh)
-          const float half = n >= C ? 0.5f : 1.0f;
+        // e_norm = d * alpha + beta; the gate half carries the x/2 of tanh, the value half the LayerScale factor of its column
+        for (int n = tid; n < 2 * C; n += ER_THREADS) {
+          const float half = n >= C ? 0.5f : scl[n];
           const float a_ = rstd2 * g2w[n];
           al[n] = half * a_; be[n] = half * ((b2[n] - mean2) * a_ + g2b[n]);
         }
       }
       er_gsync(grp);
-      for (int mt = warp; mt < MT; mt += nwarp) {
-        uint32_t a[4];
-        ldsm_a(hb, D::K2P, mt * 16, 0, lane, a);
-        const int r0 = mt * 16 + g;
+      {
+        // the warp's two row tiles share the B fragments (one ldmatrix.x4: value + gate n-tile) and the per-column vectors
+        const int mt0 = warp, mt1 = warp + nwarp;
+        uint32_t a0[4], a1[4];
+        if (mt0 < MT) ldsm_a(hb, D::K2P, mt0 * 16, 0, lane, a0);
+        if (mt1 < MT) ldsm_a(hb, D::K2P, mt1 * 16, 0, lane, a1);
 #pragma unroll 2
         for (int nt = 0; nt < D::AT; ++nt) {
-          float da[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
-          uint32_t bb[2];
-          frag_b(w2, D::K2P, nt * 8, 0, lane, bb); mma16816(da, a, bb);
-          frag_b(w2, D::K2P, (nt + D::AT) * 8, 0, lane, bb); mma16816(dg, a, bb);
+          uint32_t bv_[2], bg_[2];
+          ldsm_b_pair(w2, D::K2P, nt * 8, (nt + D::AT) * 8, 0, lane, bv_, bg_);
           const int c = nt * 8 + 2 * q;
           const float2 av = *(const float2*)(al + c), bv = *(const float2*)(be + c);
           const float2 ag = *(const float2*)(al + C + c), bg = *(const float2*)(be + C + c);
-          const float2 sc = *(const float2*)(scl + c);
-          // packed fp32 pairs: (value * alpha + beta) * (0.5 + 0.5 tanh(gate * alpha' + beta')), then x + scale * u
-          const float2 h2 = f2splat(0.5f);
-          const float2 g01 = f2fma(make_float2(dg[0], dg[1]), ag, bg), g23 = f2fma(make_float2(dg[2], dg[3]), ag, bg);
-          const float2 s01 = f2fma(h2, make_float2(er_tanh(g01.x), er_tanh(g01.y)), h2);
-          const float2 s23 = f2fma(h2, make_float2(er_tanh(g23.x), er_tanh(g23.y)), h2);
-          const float2 u01 = f2mul(f2fma(make_float2(da[0], da[1]), av, bv), s01);
-          const float2 u23 = f2mul(f2fma(make_float2(da[2], da[3]), av, bv), s23);
-          if (r0 < Tn) {
-            const float2 o = f2fma(sc, u01, unpack_bf16x2(*(const uint32_t*)(xsi + r0 * D::XP + c)));
-            sts_pair(xsi + r0 * D::XP + c, o.x, o.y);
-          }
-          if (r0 + 8 < Tn) {
-            const float2 o = f2fma(sc, u23, unpack_bf16x2(*(const uint32_t*)(xsi + (r0 + 8) * D::XP + c)));
-            sts_pair(xsi + (r0 + 8) * D::XP + c, o.x, o.y);
-          }
+          auto tile = [&](const uint32_t (&a)[4], int mt) {
+            float da[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(da, a, bv_);
+            mma16816(dg, a, bg_);
+            const int r0 = mt * 16 + g;
+            // packed fp32 pairs: x + (value * alpha + beta) * (0.5 + 0.5 tanh(gate * alpha' + beta')); alpha, beta carry the LayerScale
+            const float2 h2 = f2splat(0.5f);
+            const float2 g01 = f2fma(make_float2(dg[0], dg[1]), ag, bg), g23 = f2fma(make_float2(dg[2], dg[3]), ag, bg);
+            const float2 s01 = f2fma(h2, make_float2(er_tanh(g01.x), er_tanh(g01.y)), h2);
+            const float2 s23 = f2fma(h2, make_float2(er_tanh(g23.x), er_tanh(g23.y)), h2);
+            const float2 u01 = f2fma(make_float2(da[0], da[1]), av, bv), u23 = f2fma(make_float2(da[2], da[3]), av, bv);
+            if (r0 < Tn) {
+              const float2 o = f2fma(u01, s01, unpack_bf16x2(*(const uint32_t*)(xsi + r0 * D::XP + c)));
+              sts_pair(xsi + r0 * D::XP + c, o.x, o.y);
+            }
+            if (r0 + 8 < Tn) {
+              const float2 o = f2fma(u23, s23, unpack_bf16x2(*(const uint32_t*)(xsi + (r0 + 8) * D::XP + c)));
+              sts_pair(xsi + (r0 + 8) * D::XP + c, o.x, o.y);
+            }
+          };
+          if (mt0 < MT) tile(a0, mt0);
+          if (mt1 < MT) tile(a1, mt1);
         }
       }
     }
     er_gsync(grp);
 
     // ---- rewrite 1x1 (C -> 2C) + GLU (+ frequency embedding): result overwrites the slab rows of the owning warp
-    for (int mt = warp; mt < MT; mt += nwarp) {
-      uint32_t a[C / 16][4];
+    {
+      // TPW row tiles per pass of a warp (C = 48: both of them) share the weight fragments of an n-tile; the gate rows were staged
+      // pre-scaled by 0.5 (exact in bf16) and the accumulators start from the bias: GLU = value * (0.5 + 0.5 tanh(gate))
+      constexpr int TPW = 1;
+      for (int mtb = warp; mtb < MT; mtb += TPW * nwarp) {
+        uint32_t a[TPW][C / 16][4];
 #pragma unroll
-      for (int kc = 0; kc < C / 16; ++kc) ldsm_a(xsi, D::XP, mt * 16, kc * 16, lane, a[kc]);
-      __syncwarp();
-      const int r0 = mt * 16 + g;
+        for (int ti = 0; ti < TPW; ++ti)
+          if (mtb + ti * nwarp < MT) {
+#pragma unroll
+            for (int kc = 0; kc < C / 16; ++kc) ldsm_a(xsi, D::XP, (mtb + ti * nwarp) * 16, kc * 16, lane, a[ti][kc]);
+          }
+        __syncwarp();
 #pragma unroll 2
-      for (int nt = 0; nt < D::AT; ++nt) {
-        float da[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int nt = 0; nt < D::AT; ++nt) {
+          uint32_t bvv[C / 16][2], bgg[C / 16][2];
 #pragma unroll
-        for (int kc = 0; kc < C / 16; ++kc) {
-          uint32_t bb[2];
-          frag_b(wrt, D::KRP, nt * 8, kc * 16, lane, bb); mma16816(da, a[kc], bb);
-          frag_b(wrt, D::KRP, (nt + D::AT) * 8, kc * 16, lane, bb); mma16816(dg, a[kc], bb);
+          for (int kc = 0; kc + 1 < C / 16; kc += 2) {
+            ldsm_b2(wrt, D::KRP, nt * 8, kc * 16, lane, bvv[kc], bvv[kc + 1]);
+            ldsm_b2(wrt, D::KRP, (nt + D::AT) * 8, kc * 16, lane, bgg[kc], bgg[kc + 1]);
+          }
+          if ((C / 16) & 1) ldsm_b_pair(wrt, D::KRP, nt * 8, (nt + D::AT) * 8, (C / 16 - 1) * 16, lane, bvv[C / 16 - 1], bgg[C / 16 - 1]);
+          const int c = nt * 8 + 2 * q;
+          const float2 rv = *(const float2*)(rbs + c), rg = *(const float2*)(rbs + C + c);
+          float2 em = make_float2(0.f, 0.f);
+          if (P.emb) em = *(const float2*)(embv + c);
+#pragma unroll
+          for (int ti = 0; ti < TPW; ++ti) {
+            const int mt = mtb + ti * nwarp;
+            if (mt < MT) {
+              float da[4] = {rv.x, rv.y, rv.x, rv.y}, dg[4] = {rg.x, rg.y, rg.x, rg.y};
+#pragma unroll
+              for (int kc = 0; kc < C / 16; ++kc) { mma16816(da, a[ti][kc], bvv[kc]); mma16816(dg, a[ti][kc], bgg[kc]); }
+              const int r0 = mt * 16 + g;
+              const float2 h2 = f2splat(0.5f);
+              const float2 s01 = f2fma(h2, make_float2(er_tanh(dg[0]), er_tanh(dg[1])), h2);
+              const float2 s23 = f2fma(h2, make_float2(er_tanh(dg[2]), er_tanh(dg[3])), h2);
+              const float2 p01 = f2fma(make_float2(da[0], da[1]), s01, em), p23 = f2fma(make_float2(da[2], da[3]), s23, em);
+              if (r0 < Tn) sts_pair(xsi + r0 * D::XP + c, p01.x, p01.y);            // rows >= Tn stay zero (conv halo of the next slab)
+              if (r0 + 8 < Tn) sts_pair(xsi + (r0 + 8) * D::XP + c, p23.x, p23.y);
+            }
+          }
         }
-        const int c = nt * 8 + 2 * q;
-        const float2 rv = *(const float2*)(rbs + c), rg = *(const float2*)(rbs + C + c);
-        float2 em = make_float2(0.f, 0.f);
-        if (P.emb) em = *(const float2*)(embv + c);
-        const float2 h2 = f2splat(0.5f);
-        const float2 g01 = f2fma(make_float2(dg[0], dg[1]), h2, rg), g23 = f2fma(make_float2(dg[2], dg[3]), h2, rg);
-        const float2 s01 = f2fma(h2, make_float2(er_tanh(g01.x), er_tanh(g01.y)), h2);
-        const float2 s23 = f2fma(h2, make_float2(er_tanh(g23.x), er_tanh(g23.y)), h2);
-        const float2 p01 = f2fma(f2add(make_float2(da[0], da[1]), rv), s01, em), p23 = f2fma(f2add(make_float2(da[2], da[3]), rv), s23, em);
-        const float o0 = p01.x, o1 = p01.y, o2 = p23.x, o3 = p23.y;
-        if (r0 < Tn) sts_pair(xsi + r0 * D::XP + c, o0, o1);            // rows >= Tn stay zero (conv halo of the next slab)
-        if (r0 + 8 < Tn) sts_pair(xsi + (r0 + 8) * D::XP + c, o2, o3);
       }
     }
     er_gsync(grp);
@@ -377,13 +443,13 @@ static size_t enc_row_smem(int Tn, bool fuse, int G) {
   const int MT = (Tn + 15) / 16;
   const size_t wbf = (size_t)2 * 8 * D::HN * D::K1P + (size_t)2 * 2 * C * D::K2P + (size_t)2 * C * D::KRP + (fuse ? (size_t)C * D::PP : 0);
   const size_t slab = (size_t)(MT * 16 + 4) * D::XP + (fuse ? (size_t)MT * 16 * D::PP : (size_t)MT * 16 * D::K2P);
-  return wbf * 2 + sizeof(float) * (2 * D::VD + 2 * C + C + (size_t)G * (4 * C + C + 64)) + (size_t)G * slab * 2 + 32;
+  return wbf * 2 + sizeof(float) * (2 * D::VD + 2 * C + C + 2 * 256 + 32 + (size_t)G * (4 * C + C + 64)) + (size_t)G * slab * 2 + 32;
 }
 
 bool enc_row_supported(int C, int Tn, bool fuse_conv) {
   if (Tn > 16 * 2 * (ER_THREADS / 32)) return false;          // two row tiles per warp
   if (C == 48) return enc_row_smem<48>(Tn, fuse_conv, 1) <= 113 * 1024;
-  if (C == 96) return !fuse_conv && enc_row_smem<96>(Tn, false, 1) <= 226 * 1024;
+  if (C == 96) return !fuse_conv && enc_row_smem<96>(Tn, false, 1) <= 227 * 1024;
   return false;
 }
 
@@ -413,7 +479,7 @@ void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, R
     }
   } else {
     // C = 96: the weights alone are 77 KB, so one CTA per SM; two 9-warp slab groups share them (18 warps per SM)
-    const int G = enc_row_smem<96>(Tn, false, 2) <= 226 * 1024 ? 2 : 1;
+    const int G = enc_row_smem<96>(Tn, false, 2) <= 227 * 1024 ? 2 : 1;
     const size_t smem = enc_row_smem<96>(Tn, false, G);
     const int grid = std::min((slabs + G - 1) / G, er_num_sms());
     if (G == 2) {

@@ -107,7 +107,14 @@ __device__ __forceinline__ void load8_add(const bf16* src, float* v) {
 // issued ~4400 instructions per 32-column chunk and dominated the kernel)
 enum { EF_GELU = 1, EF_GLU = 2, EF_GN = 4, EF_POST = 8, EF_STATS = 16 };
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+// 1 / (1 + 2^(-x log2 e)) with the two approximate SFU ops (relative error ~2^-22; +-inf saturate to 0 / 1): the IEEE-rounded
+// __frcp_rn / range-checked __expf pair cost 17 instructions and a branch per gate
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 // per-row state of one epilogue thread for one tile
 struct EpiRow {
@@ -225,13 +232,43 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& 
   }
 }
 
+// All chunks of one accumulator tile that belong to this epilogue warp (interleaved 32-column chunks, `step` columns apart).
+template <int EF>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiRow& er, uint32_t tacc, int n0, int c_first, int step,
+                                              const float* __restrict__ sv, float& ssum, float& ssq) {
+  for (int c0 = c_first; c0 < p.BN; c0 += step) {
+    uint32_t r[32];
+    tmem_ld32(tacc + (uint32_t)c0, r);
+    const int ncol = n0 + c0;
+    const int nc = min(32, min(p.BN - c0, p.N - ncol));      // valid accumulator columns in this chunk (multiple of 8)
+    if (er.valid && nc > 0) epilogue_chunk<EF>(p, er, r, ncol, nc, sv, c0, ssum, ssq);
+  }
+}
+
+// Residual rows of the NEXT tile of this CTA are pulled into the L2 while the current tile is processed (the residual stream, e.g.
+// the token buffer of out_proj, has left the L2 by the time it is read back: the row-per-thread loads then sat on the full DRAM
+// latency, 37 % of the stall samples of those launches).  One 128-byte line per thread: `sub` walks the lines of the row segment.
+__device__ __forceinline__ void prefetch_res_l2(const TcParams& p, bool glu, int rho, int n0, int sub, int nsub) {
+  const int q2 = fast_div(rho, p.fdRpA);
+  const int fp = rho - q2 * p.RpA;
+  const int b = fast_div(q2, p.fdG2p);
+  const int tp = q2 - b * p.G2p;
+  if (!(rho < p.Mflat && fp >= p.vlo && fp < p.vhi && tp >= p.gpf && tp < p.gpf + p.G2)) return;
+  const long orow = ((long)b * p.oG2p + tp + p.ogsh) * p.oRp + fp + p.orsh;
+  const int Nout = glu ? p.N >> 1 : p.N, no = glu ? n0 >> 1 : n0, nco = min(glu ? p.BN >> 1 : p.BN, Nout - no);
+  const char* rp = (const char*)((const bf16*)p.res + orow * p.ldc + no);
+  for (int off = 128 * sub; off < 2 * nco; off += 128 * nsub) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+}
+
 // ------------------------------------------------------------------ kernel
 template <int EF, int MINB>
 __global__ void __launch_bounds__(TcCfg<MINB>::THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   pdl_trigger();                 // the next kernel's CTAs may set up while this grid drains (programmatic dependent launch)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an OFFSET on the shared-memory array: a round trip through uintptr_t makes every later access a
+  // generic LD / ST (long-scoreboard, queued behind the global loads) instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stageA = TC_BM * TC_BK * 2;
   const int stageB = p.BN * TC_BK * 2;             // BN multiple of 8 -> multiple of 1024 B
   const int nst = p.stages;
@@ -359,7 +396,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if ((EF & EF_POST) && p.colscale) sv[3 * TC_VEC + etid] = vr3;
       }
     };
-    if ((int)blockIdx.x < n_total_tiles) { fetch_vecs(((int)blockIdx.x % p.n_tiles) * p.BN); stash_vecs(svec); }
+    if ((int)blockIdx.x < n_total_tiles) {
+      fetch_vecs(((int)blockIdx.x % p.n_tiles) * p.BN); stash_vecs(svec);
+      if ((EF & EF_POST) && p.res) {      // the first tile's residual rows arrive in the L2 behind its main loop
+        const int mt0 = fast_div((int)blockIdx.x, p.fdNt);
+        prefetch_res_l2(p, (EF & EF_GLU) != 0, mt0 * TC_BM + row, ((int)blockIdx.x - mt0 * p.n_tiles) * p.BN, sub, EPI_WARPS / 4);
+      }
+    }
     int i = 0;
     for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
@@ -387,16 +430,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (tn < n_total_tiles) fetch_vecs((tn - fast_div(tn, p.fdNt) * p.n_tiles) * p.BN);
       er.edge_lo = er.m == 0; er.edge_hi = er.m == p.vhi - p.vlo - 1;
       float ssum = 0.f, ssq = 0.f;
+      if ((EF & EF_POST) && p.res && tn < n_total_tiles) {
+        const int mtn = fast_div(tn, p.fdNt);
+        prefetch_res_l2(p, (EF & EF_GLU) != 0, mtn * TC_BM + row, (tn - mtn * p.n_tiles) * p.BN, sub, EPI_WARPS / 4);
+      }
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 32 * sub; c0 < p.BN; c0 += 8 * EPI_WARPS) {
-        uint32_t r[32];
-        tmem_ld32(tacc + (uint32_t)c0, r);
-        const int ncol = n0 + c0;
-        const int nc = min(32, min(p.BN - c0, p.N - ncol));      // valid accumulator columns in this chunk (multiple of 8)
-        if (er.valid && nc > 0) epilogue_chunk<EF>(p, er, r, ncol, nc, sv, c0, ssum, ssq);
-      }
+      epilogue_tile<EF>(p, er, tacc, n0, 32 * sub, 8 * EPI_WARPS, sv, ssum, ssq);
       // this warp is done reading the accumulator: release it to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -416,7 +457,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int slot = (t + sub) % STAT_SLOTS;
             if (uniform) {
               // rows are combined in fp64 so that the result does not depend on which rows share a warp / tile,
-              // i.e. on the position of a segment inside the batch (multi-GPU spans must reproduce one-GPU bits)
+              // i.e. on the position of a segment inside the batch (multi-GPU spans must reproduce one-GPU bits).
+              // (Carrying per-thread fp64 sums across the tiles of a segment and reducing only when the segment changes was
+              // measured: -13 us on the largest transposed-conv launch, +4 us on each of the ten linear2 launches -- not kept.)
               double a = er.valid ? (double)ssum : 0.0, c = er.valid ? (double)ssq : 0.0;
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
@@ -477,7 +520,9 @@ template <int EF>
 __global__ void __launch_bounds__(TcCfg<1>::THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an OFFSET on the shared-memory array: a round trip through uintptr_t makes every later access a
+  // generic LD / ST (long-scoreboard, queued behind the global loads) instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stageA = TC_BM * TC_BK * 2;
   const int stageB = (p.BN / 2) * TC_BK * 2;        // this CTA's half of the B tile
   const int nst = p.stages;
@@ -629,16 +674,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (un < n_pair_tiles) fetch_vecs((un - fast_div(un, p.fdNt) * p.n_tiles) * p.BN);
       er.edge_lo = er.m == 0; er.edge_hi = er.m == p.vhi - p.vlo - 1;
       float ssum = 0.f, ssq = 0.f;
+      if ((EF & EF_POST) && p.res && un < n_pair_tiles) {
+        const int mpn = fast_div(un, p.fdNt);
+        prefetch_res_l2(p, (EF & EF_GLU) != 0, (2 * mpn + (int)rank) * TC_BM + row, (un - mpn * p.n_tiles) * p.BN, sub, EPI_WARPS / 4);
+      }
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)(i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 32 * sub; c0 < p.BN; c0 += 8 * EPI_WARPS) {
-        uint32_t r[32];
-        tmem_ld32(tacc + (uint32_t)c0, r);
-        const int ncol = n0 + c0;
-        const int nc = min(32, min(p.BN - c0, p.N - ncol));
-        if (er.valid && nc > 0) epilogue_chunk<EF>(p, er, r, ncol, nc, sv, c0, ssum, ssq);
-      }
+      epilogue_tile<EF>(p, er, tacc, n0, 32 * sub, 8 * EPI_WARPS, sv, ssum, ssq);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {

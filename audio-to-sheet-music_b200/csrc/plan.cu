@@ -200,11 +200,14 @@ const float* PlanT<T>::PA(const std::string& key) const {
 }
 
 template <typename T>
-void PlanT<T>::prof_begin(double gflop, cudaStream_t st) {
+void PlanT<T>::prof_begin(double gflop, cudaStream_t st, const char* what, long m, int n, int k) {
   if (!profiling) return;      // per-launch CUDA-event timing of the GEMM kernels (bench.py roofline pass only)
   while (prof_ev.size() < prof_used + 2) { cudaEvent_t e; cudaEventCreate(&e); prof_ev.push_back(e); }
   prof_gflop += gflop;
   prof_items.push_back(gflop);
+  char lab[96];
+  snprintf(lab, sizeof(lab), "%-6s M %8ld N %5d K %5d", what, m, n, k);
+  prof_labels.push_back(lab);
   cudaEventRecord(prof_ev[prof_used++], st);
 }
 template <typename T>
@@ -214,7 +217,7 @@ void PlanT<T>::prof_end(cudaStream_t st) {
 
 template <typename T>
 void PlanT<T>::gemm(const GemmDesc& d, cudaStream_t st) {
-  prof_begin(2.0 * (double)d.G1 * d.G2 * d.Mg * d.N * d.K * 1e-9, st);
+  prof_begin(2.0 * (double)d.G1 * d.G2 * d.Mg * d.N * d.K * 1e-9, st, "simt", (long)d.G1 * d.G2 * d.Mg, d.N, d.K);
   launch_gemm_simt<T>(d, st);
   prof_end(st);
   ++n_launches;
@@ -229,7 +232,8 @@ void PlanT<T>::get_profile(double* ms, double* gflop, int* n) {
   if (getenv("ATHTD_PROFILE_DUMP")) {      // per-launch list for tuning: index, GFLOP, us, TFLOP/s
     for (size_t i = 0; i + 1 < prof_used; i += 2) {
       float t = 0.f; cudaEventElapsedTime(&t, prof_ev[i], prof_ev[i + 1]);
-      fprintf(stderr, "gemm %3zu  %9.3f GFLOP  %8.1f us  %7.1f TFLOP/s\n", i / 2, prof_items[i / 2], t * 1e3, prof_items[i / 2] / t);
+      fprintf(stderr, "gemm %3zu  %s  %9.3f GFLOP  %8.1f us  %7.1f TFLOP/s\n", i / 2, prof_labels[i / 2].c_str(), prof_items[i / 2], t * 1e3,
+              prof_items[i / 2] / t);
     }
   }
 }
@@ -271,7 +275,7 @@ void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
     f.n_store = o.n_store; f.no_store = o.no_store; f.skip_lo = o.skip_lo; f.skip_hi = o.skip_hi; f.gn_mr = o.gn_mr; f.gn_w = o.gn_w; f.gn_b = o.gn_b; f.gn_mode = o.gn_mode;
     const bool geom_ok = (o.mode != CONV_K8S4) || (as.Rp % 4 == 0 && as.pf == 2);
     if (geom_ok && tc_flat_supported(f)) {
-      prof_begin(gflop, st);
+      prof_begin(gflop, st, o.mode == CONV_ROWS ? "rows" : o.mode == CONV_K8S4 ? "k8s4" : o.mode == CONV_T ? "convT" : "k3", (long)B * as.G2 * Mg, o.N, K);
       int rc = launch_gemm_tc_flat(f, st);
       prof_end(st);
       if (rc != 0) throw std::runtime_error("athtd: cuTensorMapEncodeTiled failed for a tcgen05 GEMM");
@@ -486,7 +490,7 @@ template <typename T>
 void PlanT<T>::attention(const T* q, long ldq, const T* k, const T* v, long ldkv, int Sq, int Sk, T* o, cudaStream_t st) {
   const int B = sh.B;
   if (use_tc && use_flash) {
-    prof_begin(4.0 * (double)B * 8 * Sq * Sk * 64 * 1e-9, st);
+    prof_begin(4.0 * (double)B * 8 * Sq * Sk * 64 * 1e-9, st, "attn", (long)B * 8 * Sq, Sk, 64);
     int rc = flash_dispatch(q, ldq, k, v, ldkv, B, Sq, Sk, o, st);
     prof_end(st);
     if (rc == 0) { ++n_launches; ++n_tc; return; }

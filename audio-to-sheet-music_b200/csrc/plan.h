@@ -88,6 +88,7 @@ struct PlanT : PlanBase {
   size_t prof_used = 0;
   double prof_gflop = 0.0;
   std::vector<double> prof_items;
+  std::vector<std::string> prof_labels;
   // CUDA-graph replay of the launch sequence.  A forward whose (batch, wav, emb, out) was seen
   // before is captured once on a private stream and replayed from then on: a track loop that reuses its staging buffers
   // pays ~160 kernel launches per batch once.  Callers with ever-changing pointers simply stay on the eager path.
@@ -117,7 +118,7 @@ struct PlanT : PlanBase {
   const float* PA(const std::string& key) const;
   void gemm(const GemmDesc& d, cudaStream_t st);
   void conv(const ConvOp<T>& o, cudaStream_t st);
-  void prof_begin(double gflop, cudaStream_t st);
+  void prof_begin(double gflop, cudaStream_t st, const char* what, long m, int n, int k);
   void prof_end(cudaStream_t st);
   bool enc_row_dispatch(bool run, int i, const T* x, RowSpace xin, const T* y, T* out, RowSpace ys, cudaStream_t st);
   void enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSpace ys, T* out, cudaStream_t st);
@@ -151,7 +152,7 @@ struct PlanT : PlanBase {
   long workspace_bytes() const override { return (long)total_bytes; }
   long zero_region_bytes() const override { return (long)zero_bytes; }
   int launches() const override { return n_launches; }
-  void set_profile(bool on) override { profiling = on; prof_used = 0; prof_gflop = 0.0; prof_items.clear(); }
+  void set_profile(bool on) override { profiling = on; prof_used = 0; prof_gflop = 0.0; prof_items.clear(); prof_labels.clear(); }
   void set_use_tc(bool on) override { use_tc = on; drop_graphs(); }
   void set_use_flash(bool on) override { use_flash = on; drop_graphs(); }
   void set_use_fused_dconv(bool on) override { use_fused_dconv = on; drop_graphs(); }
