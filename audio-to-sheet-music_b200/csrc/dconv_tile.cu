@@ -31,6 +31,7 @@ struct DcTileParams {
   bf16* y; bf16* h;
   const bf16* w1; const float* b1; const float* g1w; const float* g1b;
   const bf16* w2; const float* b2; const float* g2w; const float* g2b; const float* scale;
+  const bf16* ghi; const bf16* glo; const float* gv;      // pass B: G = W2^T W2 (hi + lo halves, [HP][HP]) and [2 W2^T b2 | W2^T 1 | sum b2 | sum b2^2]
   double* st1; double* st2;
   // optional HEncLayer tail fused into pass C of the second residual layer (C <= 96): out = GLU(rewrite_1x1(y) + rb)
   const bf16* rw; const float* rb; bf16* out;      // rw [2C][C], rb [2C]: GLU-interleaved rows like the expand
@@ -217,30 +218,38 @@ __device__ __forceinline__ uint32_t dc_gn_gelu_pair(bf16* hp, int c, float mean,
 }
 
 // ------------------------------------------------------------------ pass B
+// g = GELU(GN1(h)) in place + the GroupNorm-2 partial sums of e = W2 g + b2 WITHOUT forming e: per row
+//   sum_n e_n^2 = g^T G g + 2 (W2^T b2)^T g + sum b2^2 ,   sum_n e_n = (W2^T 1)^T g + sum b2 ,   G = W2^T W2  (packed once per model).
+// Y = g G is HN x KS x 2 MMAs per 16-row tile (G as hi + lo activation-dtype halves: 2^-17 relative) whose accumulators start at the
+// linear term and pair element by element with the A fragments of g; the 2C-wide product took 2C/8 x KS MMAs plus a packed
+// square-accumulate per output pair (12 x more instructions at C = 48, 16 x at C = 384) and 86 KB of staged weights at C = 384.
 template <int C>
 __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
   pdl_begin();
   typedef DcDims<C> D;
-  constexpr int NT2 = 2 * C / 8;
+  constexpr int GP = D::HP + 8;                     // pitch of the staged G halves (conflict-free fragment loads)
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* w2s = (bf16*)smem_raw;                      // [2C][K2P]
-  float* b2s = (float*)(w2s + 2 * C * D::K2P);      // [2C]
-  float* g1ws = b2s + 2 * C;                        // [HP]
+  bf16* ghs = (bf16*)smem_raw;                      // [HP][GP]  G hi (row n = output column j, k = i; G is symmetric)
+  bf16* gls = ghs + D::HP * GP;                     // [HP][GP]  G lo
+  float* gvs = (float*)(gls + D::HP * GP);          // [2 HP + 2]
+  float* g1ws = gvs + 2 * D::HP + 2;                // [HP]
   float* g1bs = g1ws + D::HP;                       // [HP]
   float* mr = g1bs + D::HP;                         // [64]
   float* red = mr + 64;                             // [32]
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  for (int idx = tid; idx < 2 * C * (D::HP / 8); idx += blockDim.x) {
-    const int n = idx / (D::HP / 8), kc = idx - n * (D::HP / 8);
-    cp_async16(w2s + n * D::K2P + kc * 8, p.w2 + (long)n * D::HP + kc * 8, true);
+  for (int idx = tid; idx < 2 * D::HP * (D::HP / 8); idx += blockDim.x) {
+    const int half = idx / (D::HP * (D::HP / 8)), r = idx - half * (D::HP * (D::HP / 8));
+    const int n = r / (D::HP / 8), kc = r - n * (D::HP / 8);
+    cp_async16((half ? gls : ghs) + n * GP + kc * 8, (half ? p.glo : p.ghi) + (long)n * D::HP + kc * 8, true);
   }
   cp_async_commit();
-  for (int i = tid; i < 2 * C; i += blockDim.x) b2s[i] = p.b2[i];
+  for (int i = tid; i < 2 * D::HP + 2; i += blockDim.x) gvs[i] = p.gv[i];
   for (int i = tid; i < D::HP; i += blockDim.x) { g1ws[i] = p.g1w[i]; g1bs[i] = p.g1b[i]; }
   dc_stage_mean_rstd(p.st1, b, p.per_row, p.g.Rr, (double)D::H * (p.per_row ? p.g.nT : p.g.rows), mr);
   cp_async_wait<0>();
   __syncthreads();
+  const float sb = gvs[2 * D::HP], sbb = gvs[2 * D::HP + 1];
   bf16* hb = p.h + (long)b * p.g.rows * D::HP;
   float ts = 0.f, tq = 0.f;
   for (int tile = blockIdx.x; tile * 128 < p.g.rows; tile += gridDim.x) {
@@ -258,22 +267,24 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
       a[ks][2] = v_lo ? dc_gn_gelu_pair<C>(hb + (long)r_lo * D::HP + c1, c1, m_lo, rs_lo, g1ws, g1bs) : 0u;
       a[ks][3] = v_hi ? dc_gn_gelu_pair<C>(hb + (long)r_hi * D::HP + c1, c1, m_hi, rs_hi, g1ws, g1bs) : 0u;
     }
-    float2 sl2 = f2splat(0.f), ql2 = f2splat(0.f), sh2 = f2splat(0.f), qh2 = f2splat(0.f);     // packed (even, odd column) partials
-#pragma unroll 4
-    for (int nt = 0; nt < NT2; ++nt) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
+    // rows g (lo) and g + 8 (hi): this lane's share (columns 2q, 2q+1 of every hidden n-tile); lane q == 0 carries the constants
+    float s_lo = q == 0 ? sb : 0.f, q_lo = q == 0 ? sbb : 0.f, s_hi = s_lo, q_hi = q_lo;
+#pragma unroll
+    for (int nt = 0; nt < D::HN; ++nt) {
+      const int c = nt * 8 + 2 * q;
+      const float2 v2 = *(const float2*)(gvs + c), u2 = *(const float2*)(gvs + D::HP + c);
+      float d[4] = {v2.x, v2.y, v2.x, v2.y};
 #pragma unroll
       for (int ks = 0; ks < D::KS; ++ks) {
+        if (ks * 16 >= D::H) continue;
         uint32_t bb[2];
-        frag_b(w2s, D::K2P, nt * 8, ks * 16, lane, bb);
-        mma16816(d, a[ks], bb);
+        frag_b(ghs, GP, nt * 8, ks * 16, lane, bb); mma16816(d, a[ks], bb);
+        frag_b(gls, GP, nt * 8, ks * 16, lane, bb); mma16816(d, a[ks], bb);
       }
-      const float2 bv = *(const float2*)(b2s + nt * 8 + 2 * q);
-      const float2 e01 = f2add(make_float2(d[0], d[1]), bv), e23 = f2add(make_float2(d[2], d[3]), bv);
-      sl2 = f2add(sl2, e01); ql2 = f2fma(e01, e01, ql2);
-      sh2 = f2add(sh2, e23); qh2 = f2fma(e23, e23, qh2);
+      const float2 gl = unpack_bf16x2(a[nt >> 1][(nt & 1) * 2]), gh = unpack_bf16x2(a[nt >> 1][(nt & 1) * 2 + 1]);
+      q_lo = fmaf(d[0], gl.x, fmaf(d[1], gl.y, q_lo)); s_lo = fmaf(u2.x, gl.x, fmaf(u2.y, gl.y, s_lo));
+      q_hi = fmaf(d[2], gh.x, fmaf(d[3], gh.y, q_hi)); s_hi = fmaf(u2.x, gh.x, fmaf(u2.y, gh.y, s_hi));
     }
-    const float s_lo = sl2.x + sl2.y, q_lo = ql2.x + ql2.y, s_hi = sh2.x + sh2.y, q_hi = qh2.x + qh2.y;
     if (p.per_row) {
       dc_row_stats(p.st2, b, p.g.Rr, r_lo, r_hi, v_lo, v_hi, s_lo, q_lo, s_hi, q_hi);
     } else {
@@ -471,7 +482,7 @@ static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
   typedef DcDims<C> D;
   const int halo = p.dil * p.g.Rr;
   const size_t smA = (size_t)(TM + 2 * halo) * D::XP * 2 + (size_t)8 * D::HN * D::K1P * 2 + 32 * 4 + 16;
-  const size_t smB = (size_t)2 * C * D::K2P * 2 + (size_t)(2 * C + 2 * D::HP + 64 + 32) * 4 + 16;
+  const size_t smB = (size_t)2 * D::HP * (D::HP + 8) * 2 + (size_t)(2 * D::HP + 2 + 2 * D::HP + 64 + 32) * 4 + 16;
   const bool rewrite = p.rw != nullptr && CS == C;
   const size_t smC = (size_t)TMC * (CS + 8) * 2 + (size_t)2 * CS * D::K2P * 2 + (size_t)(7 * CS + 64) * 4 + 16 +
                      (rewrite ? (size_t)(2 * C + TMC) * (CS + 8) * 2 : 0);
@@ -504,7 +515,8 @@ static int dconv_tile_launch(const DcTileParams& p, int B, cudaStream_t st) {
 // (C = 96 also works but measured 16 us slower than the separate tcgen05 rewrite GEMM)
 bool dconv_tile_can_rewrite(int C, bool freq) { return !freq && C == 48; }
 int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
-                      const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
+                      const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const bf16* ghi, const bf16* glo, const float* gv,
+                      const float* scale, double* st1,
                       double* st2, const bf16* rw, const float* rb, bf16* out, cudaStream_t st) {
   DcTileParams p;
   p.rw = rw; p.rb = rb; p.out = out;
@@ -513,7 +525,7 @@ int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, c
   p.g.seg = ys.g1_stride(); p.g.base = ys.origin(); p.g.fs = freq ? (long)ys.Rp * ys.C : ys.C;
   p.dil = dil; p.per_row = freq ? 1 : 0;
   p.y = y; p.h = h; p.w1 = w1p; p.b1 = b1p; p.g1w = g1wp; p.g1b = g1bp; p.w2 = w2p; p.b2 = b2i; p.g2w = g2wi; p.g2b = g2bi;
-  p.scale = scale; p.st1 = st1; p.st2 = st2;
+  p.scale = scale; p.st1 = st1; p.st2 = st2; p.ghi = ghi; p.glo = glo; p.gv = gv;
   const int B = ys.batch();
   if (freq && ys.R > 32) return 1;
   switch (ys.C) {

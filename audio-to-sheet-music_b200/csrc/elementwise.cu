@@ -776,7 +776,39 @@ void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int 
   pack_weight_kernel<T><<<(int)min((n + 255) / 256, (long)2048), 256, 0, st>>>(src, dst, n, kind, d0, d1, d2);
 }
 
+// kinds 8 / 9 / 10: derived from the DConv expand W [C2][H] (fp32 parameters, rounded to the activation dtype like the packed copy
+// the MMAs read) and its bias b [C2]:  sum_n e_n^2 = g^T G g + 2 (W^T b)^T g + sum b^2,  sum_n e_n = (W^T 1)^T g + sum b   for e = W g + b.
+//   8: hi half of G = W^T W as [HP][HP] (zero beyond H), 9: lo half (G - hi), 10: fp32 [2 W^T b (HP) | W^T 1 (HP) | sum b | sum b^2]
+template <typename T>
+__global__ void pack_gram_kernel(const float* __restrict__ w, const float* __restrict__ b, T* __restrict__ dst, float* __restrict__ dstf,
+                                 int kind, int C2, int H, int HP) {
+  const int n_out = kind == 10 ? 2 * HP + 2 : HP * HP;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_out; idx += gridDim.x * blockDim.x) {
+    auto r = [&](int n, int j) { return to_f<T>(from_f<T>(w[(long)n * H + j])); };
+    double acc = 0.0;
+    if (kind == 10) {
+      if (idx < HP) { if (idx < H) for (int n = 0; n < C2; ++n) acc += 2.0 * (double)b[n] * (double)r(n, idx); }
+      else if (idx < 2 * HP) { const int j = idx - HP; if (j < H) for (int n = 0; n < C2; ++n) acc += (double)r(n, j); }
+      else if (idx == 2 * HP) { for (int n = 0; n < C2; ++n) acc += (double)b[n]; }
+      else { for (int n = 0; n < C2; ++n) acc += (double)b[n] * (double)b[n]; }
+      dstf[idx] = (float)acc;
+    } else {
+      const int i = idx / HP, j = idx - i * HP;
+      if (i < H && j < H) for (int n = 0; n < C2; ++n) acc += (double)r(n, i) * (double)r(n, j);
+      const float g = (float)acc;
+      const float hi = to_f<T>(from_f<T>(g));
+      dst[idx] = kind == 8 ? from_f<T>(g) : from_f<T>(g - hi);
+    }
+  }
+}
+template <typename T>
+void launch_pack_gram(const float* w, const float* b, void* dst, int kind, int C2, int H, int HP, cudaStream_t st) {
+  const int n_out = kind == 10 ? 2 * HP + 2 : HP * HP;
+  pack_gram_kernel<T><<<(n_out + 127) / 128, 128, 0, st>>>(w, b, (T*)dst, (float*)dst, kind, C2, H, HP);
+}
+
 #define INST(T)                                                                                                         \
+  template void launch_pack_gram<T>(const float*, const float*, void*, int, int, int, int, cudaStream_t);               \
   template void launch_pack_wav<T>(const float*, const float*, T*, RowSpace, int, cudaStream_t);                        \
   template void launch_pack_spec<T>(const float*, const float*, T*, RowSpace, int, cudaStream_t);                       \
   template void launch_gn_gelu<T>(T*, RowSpace, int, int, const float*, const float*, const float*, cudaStream_t); \

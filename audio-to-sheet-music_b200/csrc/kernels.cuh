@@ -30,6 +30,7 @@ template <typename T> void launch_dec_apply(const T* u, int Uin, RowSpace us, in
                                             int has_gn, const float* mr, const float* gw, const float* gb, const T* skip,
                                             RowSpace ss, cudaStream_t st);
 template <typename T> void launch_pack_weight(const float* src, T* dst, long n, int kind, int d0, int d1, int d2, cudaStream_t st);
+template <typename T> void launch_pack_gram(const float* w, const float* b, void* dst, int kind, int C2, int H, int HP, cudaStream_t st);
 
 // ---- resample.cu (load_audio: polyphase sinc resampler + mono -> stereo)
 int launch_resample(const float* x, int C_in, long T_in, const float* Kt, int o, int nw, int taps, int width, float* y, int C_out,
@@ -58,7 +59,8 @@ void launch_enc_row(const bf16* xin, RowSpace xis, const bf16* yin, bf16* out, R
 // ---- dconv_tile.cu (bf16: DConv residual branch as three tiled mma.sync passes; time branch + frequency levels 3-4)
 bool dconv_tile_supported(int C);
 int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
-                      const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
+                      const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const bf16* ghi, const bf16* glo, const float* gv,
+                      const float* scale, double* st1,
                       double* st2, const bf16* rw, const float* rb, bf16* out, cudaStream_t st);
 bool dconv_tile_can_rewrite(int C, bool freq);
 

@@ -102,7 +102,8 @@ struct PackItem {
   std::string key;      // lookup key used by the forward
   std::string src;      // source parameter name
   long src_off;         // extra element offset inside the source tensor
-  int kind;             // pack_weight_kernel kind (0 copy, 1 conv k-major, 2 convT phases, 3 GLU interleave, 4 replicate x4)
+  int kind;             // pack_weight_kernel kind (0 copy, 1 conv k-major, 2 convT phases, 3 GLU interleave, 4 replicate x4, ...);
+                        // 8 / 9 / 10: derived from the weight AND its bias (pack_gram_kernel)
   int d0, d1, d2;
   long numel;
   bool is_f32;          // stored as fp32 (aux vectors) instead of the activation dtype
@@ -137,6 +138,11 @@ inline std::vector<PackItem> build_pack_list() {
         add(q + ".1.bp", q + ".1.bias", 0, 6, h, 0, 0, hp, true);
         add(q + ".3.wp", q + ".3.weight", 0, 7, 2 * c, h, hp, (long)2 * c * hp, false);
         add(q + ".3.bi", q + ".3.bias", 0, 3, 2 * c, 1, 0, 2 * c, true);
+        // GroupNorm-2 statistics of e = W2 g + b2 as a quadratic form of the narrow g (dconv_tile.cu pass B): G = W2^T W2 split into
+        // two activation-dtype halves (hi + lo), and the fp32 vector [2 W2^T b2 (hp) | column sums of W2 (hp) | sum b2 | sum b2^2]
+        add(q + ".3.ghi", q + ".3.weight", 0, 8, 2 * c, h, hp, (long)hp * hp, false);
+        add(q + ".3.glo", q + ".3.weight", 0, 9, 2 * c, h, hp, (long)hp * hp, false);
+        add(q + ".3.gv", q + ".3.weight", 0, 10, 2 * c, h, hp, (long)2 * hp + 2, true);
         add(q + ".4.wi", q + ".4.weight", 0, 3, 2 * c, 1, 0, 2 * c, true);
         add(q + ".4.bi", q + ".4.bias", 0, 3, 2 * c, 1, 0, 2 * c, true);
       }

@@ -31,6 +31,12 @@ int pack_weights(const ParamTable& pt, const PackLayout& pl, const float* params
   for (auto& it : pl.items) {
     const float* src = params + pt.off(it.src) + it.src_off;
     char* dst = (char*)packed + it.offset_bytes;
+    if (it.kind >= 8) {      // derived from the weight and its bias
+      std::string bn = it.src;
+      bn.replace(bn.rfind("weight"), 6, "bias");
+      launch_pack_gram<T>(src, params + pt.off(bn), dst, it.kind, it.d0, it.d1, it.d2, st);
+      continue;
+    }
     if (it.is_f32) launch_pack_weight<float>(src, (float*)dst, it.numel, it.kind, it.d0, it.d1, it.d2, st);
     else launch_pack_weight<T>(src, (T*)dst, it.numel, it.kind, it.d0, it.d1, it.d2, st);
   }
@@ -316,13 +322,14 @@ static ConvOp<T> conv_op(int mode, const T* a, RowSpace as, const T* w, int N, T
 
 // bf16 only: one DConv residual layer as three tiled mma.sync passes (dconv_tile.cu)
 static int dconv_tile_run(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, const float* b1p, const float* g1wp, const float* g1bp,
-                          const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const float* scale, double* st1,
+                          const bf16* w2p, const float* b2i, const float* g2wi, const float* g2bi, const bf16* ghi, const bf16* glo, const float* gv,
+                      const float* scale, double* st1,
                           double* st2, const bf16* rw, const float* rb, bf16* out, cudaStream_t st) {
-  return launch_dconv_tile(y, ys, h, dil, w1p, b1p, g1wp, g1bp, w2p, b2i, g2wi, g2bi, scale, st1, st2, rw, rb, out, st);
+  return launch_dconv_tile(y, ys, h, dil, w1p, b1p, g1wp, g1bp, w2p, b2i, g2wi, g2bi, ghi, glo, gv, scale, st1, st2, rw, rb, out, st);
 }
 static int dconv_tile_run(float*, RowSpace, float*, int, const float*, const float*, const float*, const float*, const float*,
-                          const float*, const float*, const float*, const float*, double*, double*, const float*, const float*, float*,
-                          cudaStream_t) {
+                          const float*, const float*, const float*, const float*, const float*, const float*, const float*, double*, double*,
+                          const float*, const float*, float*, cudaStream_t) {
   return 1;
 }
 
@@ -421,7 +428,8 @@ void PlanT<T>::enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSp
       // second residual layer of a narrow time-branch level: the 1x1 rewrite + GLU runs on the updated tile inside pass C
       const bool fuse_rw = dd == 1 && dconv_tile_can_rewrite(C, freq);
       const int rc = dconv_tile_run(y, ys, hbuf, 1 << dd, PW(q + ".0.wp"), PA(q + ".0.bp"), PA(q + ".1.wp"), PA(q + ".1.bp"),
-                                    PW(q + ".3.wp"), PA(q + ".3.bi"), PA(q + ".4.wi"), PA(q + ".4.bi"), P32(q + ".6.scale"), st_h, st_e,
+                                    PW(q + ".3.wp"), PA(q + ".3.bi"), PA(q + ".4.wi"), PA(q + ".4.bi"), PW(q + ".3.ghi"), PW(q + ".3.glo"),
+                                    PA(q + ".3.gv"), P32(q + ".6.scale"), st_h, st_e,
                                     fuse_rw ? PW(p + ".rewrite.w") : nullptr, fuse_rw ? PA(p + ".rewrite.b") : nullptr,
                                     fuse_rw ? out : nullptr, st);
       if (rc != 0) throw std::runtime_error("athtd: dconv_tile launch failed");
