@@ -195,6 +195,8 @@ struct RowSpace {
     int b = g / G2, t = g - b * G2;
     return (((long)b * G2p + gpf + t) * Rp + pf + r) * (long)C;
   }
+  // the same with the segment and the group inside it already split (no division: per-element loops of the row kernels)
+  __host__ __device__ long row_off_bt(int b, int t, int r) const { return (((long)b * G2p + gpf + t) * Rp + pf + r) * (long)C; }
   __host__ __device__ long elems() const { return (long)(G / G2) * G2p * Rp * C; }
   __host__ __device__ long rows_total() const { return (long)(G / G2) * G2p * Rp; }
   __host__ __device__ long g1_stride() const { return (long)G2p * Rp * C; }
@@ -202,5 +204,17 @@ struct RowSpace {
   __host__ __device__ long origin() const { return ((long)gpf * Rp + pf) * C; }
   __host__ __device__ int batch() const { return G / G2; }
 };
+
+// x / d for 0 <= x < 2^31 from a host-computed (multiplier, shift): 3 instructions instead of the ~35-instruction
+// (~100-cycle dependent chain) integer division, four of which sat on the per-tile critical path of the epilogue
+__device__ __forceinline__ int fast_div(int x, const uint32_t (&fd)[2]) {
+  return (int)((__umulhi((uint32_t)x, fd[0]) + (uint32_t)x) >> fd[1]);
+}
+inline void fast_div_init(uint32_t d, uint32_t (&fd)[2]) {
+  uint32_t shr = 0;
+  while ((1u << shr) < d) ++shr;
+  fd[0] = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << shr) - d)) / d + 1);
+  fd[1] = shr;
+}
 
 }  // namespace athtd

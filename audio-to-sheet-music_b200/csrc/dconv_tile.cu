@@ -22,6 +22,7 @@ namespace athtd {
 
 struct DcGeom {
   int nT, Rr, rows;      // rows = nT * Rr logical rows per segment
+  uint32_t fdRr[2];      // division-free i / Rr (common.cuh: fast_div)
   long seg, base, fs;
 };
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ void dc_load_rows(bf16* dst, const bf16* __restrict__
     const int row = idx / CV, cv = idx - row * CV;
     const int i = i_start + row;
     const bool valid = i >= 0 && i < g.rows;
-    const int t = valid ? i / g.Rr : 0, f = valid ? i - t * g.Rr : 0;
+    const int t = valid ? fast_div(i, g.fdRr) : 0, f = valid ? i - t * g.Rr : 0;
     const bf16* src = yb + (long)t * g.fs + (long)f * C + c0 + cv * 8;
     if (!ASYNC) {       // few copies per thread (C = 48 conv pass): register-staged loads beat LDGSTS + wait (measured)
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
   for (int tile = blockIdx.x; tile * 128 < p.g.rows; tile += gridDim.x) {
     const int r_lo = tile * 128 + warp * 16 + g, r_hi = r_lo + 8;
     const bool v_lo = r_lo < p.g.rows, v_hi = r_hi < p.g.rows;
-    const int f_lo = p.per_row ? r_lo % p.g.Rr : 0, f_hi = p.per_row ? r_hi % p.g.Rr : 0;
+    const int f_lo = p.per_row ? r_lo - fast_div(r_lo, p.g.fdRr) * p.g.Rr : 0, f_hi = p.per_row ? r_hi - fast_div(r_hi, p.g.fdRr) * p.g.Rr : 0;
     const float m_lo = mr[2 * f_lo], rs_lo = mr[2 * f_lo + 1], m_hi = mr[2 * f_hi], rs_hi = mr[2 * f_hi + 1];
     uint32_t a[D::KS][4];
 #pragma unroll
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
   const int mt = warp % MW, ng = warp / MW;
   const int r_lo = i0 + mt * 16 + g, r_hi = r_lo + 8;
   const bool v_lo = r_lo < p.g.rows, v_hi = r_hi < p.g.rows;
-  const int f_lo = PER_ROW ? r_lo % p.g.Rr : 0, f_hi = PER_ROW ? r_hi % p.g.Rr : 0;
+  const int f_lo = PER_ROW ? r_lo - fast_div(r_lo, p.g.fdRr) * p.g.Rr : 0, f_hi = PER_ROW ? r_hi - fast_div(r_hi, p.g.fdRr) * p.g.Rr : 0;
   const float m_lo = mr[2 * f_lo], rs_lo = mr[2 * f_lo + 1], m_hi = mr[2 * f_hi], rs_hi = mr[2 * f_hi + 1];
   const bf16* hb = p.h + (long)b * p.g.rows * D::HP;
   uint32_t a[D::KS][4];
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
     const int row = idx / CV, cv = idx - row * CV;
     const int i = i0 + row;
     if (i < p.g.rows) {
-      const int t = i / p.g.Rr, f = i - t * p.g.Rr;
+      const int t = fast_div(i, p.g.fdRr), f = i - t * p.g.Rr;
       *(uint4*)(dstb + (long)t * p.g.fs + (long)f * C + ch0 + cv * 8) = *(const uint4*)(src_tile + row * XPS + cv * 8);
     }
   }
@@ -522,6 +523,7 @@ int launch_dconv_tile(bf16* y, RowSpace ys, bf16* h, int dil, const bf16* w1p, c
   p.rw = rw; p.rb = rb; p.out = out;
   const bool freq = ys.G2 > 1;
   p.g.nT = freq ? ys.G2 : ys.R; p.g.Rr = freq ? ys.R : 1; p.g.rows = p.g.nT * p.g.Rr;
+  fast_div_init((uint32_t)p.g.Rr, p.g.fdRr);
   p.g.seg = ys.g1_stride(); p.g.base = ys.origin(); p.g.fs = freq ? (long)ys.Rp * ys.C : ys.C;
   p.dil = dil; p.per_row = freq ? 1 : 0;
   p.y = y; p.h = h; p.w1 = w1p; p.b1 = b1p; p.g1w = g1wp; p.g1b = g1bp; p.w2 = w2p; p.b2 = b2i; p.g2w = g2wi; p.g2b = g2bi;

@@ -195,7 +195,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
       for (int i = tid; i < MT * 16 * 4; i += ER_THREADS) {   // 4 x 16-byte chunks per frame; frames >= Tn are zero
         const int t = i >> 2, ch = i & 3;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (t < Tn) v = *(const uint4*)(xin + xis.row_off(b * Tn + t, 4 * f - 2) + ch * 8);
+        if (t < Tn) v = *(const uint4*)(xin + xis.row_off_bt(b, t, 4 * f - 2) + ch * 8);
         *(uint4*)(pst + t * D::PP + ch * 8) = v;
       }
       er_gsync(grp);
@@ -219,7 +219,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
     } else {
       for (int i = tid; i < Tn * (C / 8); i += ER_THREADS) {
         const int t = i / (C / 8), c = (i - t * (C / 8)) * 8;
-        *(uint4*)(xsi + t * D::XP + c) = *(const uint4*)(yin + ys.row_off(b * Tn + t, f) + c);
+        *(uint4*)(xsi + t * D::XP + c) = *(const uint4*)(yin + ys.row_off_bt(b, t, f) + c);
       }
     }
 
@@ -431,7 +431,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
     er_gsync(grp);
     for (int i = tid; i < Tn * (C / 8); i += ER_THREADS) {
       const int t = i / (C / 8), c = (i - t * (C / 8)) * 8;
-      *(uint4*)(out + ys.row_off(b * Tn + t, f) + c) = *(const uint4*)(xsi + t * D::XP + c);
+      *(uint4*)(out + ys.row_off_bt(b, t, f) + c) = *(const uint4*)(xsi + t * D::XP + c);
     }
     er_gsync(grp);
   }

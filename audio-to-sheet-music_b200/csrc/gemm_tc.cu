@@ -63,17 +63,6 @@ struct TcParams {
   int wide;                // 32-byte row accesses allowed (row pitch and base 32-byte aligned, skip range in 16-column units)
 };
 
-// x / d for 0 <= x < 2^31 from a host-computed (multiplier, shift): 3 instructions instead of the ~35-instruction
-// (~100-cycle dependent chain) integer division, four of which sat on the per-tile critical path of the epilogue
-__device__ __forceinline__ int fast_div(int x, const uint32_t (&fd)[2]) {
-  return (int)((__umulhi((uint32_t)x, fd[0]) + (uint32_t)x) >> fd[1]);
-}
-static void fast_div_init(uint32_t d, uint32_t (&fd)[2]) {
-  uint32_t shr = 0;
-  while ((1u << shr) < d) ++shr;
-  fd[0] = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << shr) - d)) / d + 1);
-  fd[1] = shr;
-}
 __device__ __forceinline__ void store8(bf16* dst, const float* v) {
   uint32_t pk[4];
 #pragma unroll
