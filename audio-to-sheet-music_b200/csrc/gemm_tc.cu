@@ -36,7 +36,10 @@ static constexpr int TC_MAX_STAGES = 8;
 // utilisation and cost more than the MMAs of a K = 512 tile), so the one-CTA-per-SM variant runs 16 of them (4 per TMEM
 // lane quarter); the two-CTAs-per-SM variant keeps 8 per CTA (16 per SM)
 template <int MINB> struct TcCfg {
-  static constexpr int EPI_WARPS = MINB == 1 ? 16 : 8;
+  // MINB == 3: one CTA per SM with 12 epilogue warps, for 192-wide tiles (6 chunks: two per warp; with 16 warps half of them took two
+  // chunks and the other half waited at the per-tile barrier, and the per-tile row decode of the extra warps is a third of the work)
+  static constexpr int EPI_WARPS = MINB == 1 ? 16 : MINB == 3 ? 12 : 8;
+  static constexpr int CTAS = MINB == 2 ? 2 : 1;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 static constexpr int TC_VEC = 256;       // staged per-tile column vectors (bias, GroupNorm weight / bias, column scale)
@@ -251,7 +254,7 @@ __device__ __forceinline__ void prefetch_res_l2(const TcParams& p, bool glu, int
 
 // ------------------------------------------------------------------ kernel
 template <int EF, int MINB>
-__global__ void __launch_bounds__(TcCfg<MINB>::THREADS, MINB)
+__global__ void __launch_bounds__(TcCfg<MINB>::THREADS, TcCfg<MINB>::CTAS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   pdl_trigger();                 // the next kernel's CTAs may set up while this grid drains (programmatic dependent launch)
   extern __shared__ uint8_t smem_raw[];
@@ -745,9 +748,10 @@ static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide t
                                 // 0x80000 = only K >= 1536, neither = never (default).  Isolated it reaches 1427 vs 1290 TFLOP/s at K = 2048
                                 // and 959 vs 1026 at K = 512; inside the forward (residual + statistics epilogue, cold operands) the
                                 // K = 2048 launches measure the same 115-117 us either way (profiles/r01_summary.md).
+static bool g_tc_w12 = true;             // 192-wide tiles on the 12-epilogue-warp variant (tuning flag 0x100000 turns it off)
 static bool g_tc_halve_mid = false;      // tuning: N in (128, 256] as two N/2-wide tiles (two CTAs per SM) instead of one N-wide tile
 void tc_set_bn_cap(int cap) {
-  g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0;
+  g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0; g_tc_w12 = !(cap & 0x100000);
   g_tc_pair = (cap & 0x40000) ? 1 : (cap & 0x80000) ? 2 : 0;
 }
 
@@ -841,6 +845,7 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
     if (attr_set.first()) {                                                                                               \
       cudaFuncSetAttribute(gemm_tc_kernel<E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                \
       cudaFuncSetAttribute(gemm_tc_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);                \
+      cudaFuncSetAttribute(gemm_tc_kernel<E, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                \
       cudaFuncSetAttribute(gemm_tc_pair_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);              \
     }                                                                                                                     \
     if (pair) {                                                                                                           \
@@ -857,6 +862,7 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
       return cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<E>, tmA, tmBh, pp) == cudaSuccess ? 0 : 6;                      \
     }                                                                                                                     \
     if (ctas_per_sm == 2) launch_pdl(gemm_tc_kernel<E, 2>, grid, dim3(TcCfg<2>::THREADS), smem, st, tmA, tmB, p);         \
+    else if (p.BN == 192 && g_tc_w12) launch_pdl(gemm_tc_kernel<E, 3>, grid, dim3(TcCfg<3>::THREADS), smem, st, tmA, tmB, p);  \
     else launch_pdl(gemm_tc_kernel<E, 1>, grid, dim3(TcCfg<1>::THREADS), smem, st, tmA, tmB, p);                          \
     return 0;                                                                                                             \
   }
