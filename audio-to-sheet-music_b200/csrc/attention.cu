@@ -3,19 +3,22 @@
 // /root/reference/src/models/stem_separation/ATHTDemucs_v2.py:228).  Replaces the unfused
 // QK^T GEMM -> softmax -> PV GEMM sequence: scores never touch HBM.
 //
-// One CTA = one (segment, head, 128-query tile); 192 threads; keys in tiles of 64:
+// One CTA = one (segment, head, 128-query tile); 320 threads (192 in the one-thread-per-row variant); keys in tiles of 64:
 //   warp 0     : TMA producer  (Q once; K and V rings of three 64-key tiles each, SWIZZLE_128B)
 //   warp 1     : TMEM allocator + MMA issuer.  S(j) = Q K_j^T (M128 N64 K64) alternates between TWO TMEM buffers and is
 //                issued two tiles ahead of the softmax; O += P_j V_j (M128 N64 K64, V consumed MN-major from its [key][d]
 //                tile) accumulates IN TMEM across all key tiles.
-//   warps 2..5 : softmax, one query row per thread: the 64 scores of a tile are read from TMEM once, the row maximum is
-//                a register tree, P = exp2((s - m) * scale) goes as bf16 pairs into one of two 32-column TMEM buffers
-//                (one tcgen05.st per row) and is consumed by the PV MMA as its TMEM A operand: no shared-memory round
-//                trip and no generic -> async proxy fence on the critical path.
-//                The reference maximum m only moves when the tile maximum exceeds it by more than 2^8 (softmax is
-//                invariant to m; P <= 256 is exact in fp32 / bf16 range): then -- rarely, mostly in the first tiles --
-//                the warp rescales its O rows in TMEM (tcgen05.ld / st) before publishing P.  No per-tile O traffic.
-// TMEM use is 256 columns and shared memory 66 KB, so two CTAs share an SM and one CTA's softmax overlaps
+//   warps 2..9 : softmax, TWO threads per query row, each taking 32 of the 64 keys of every tile (warps w and w + 4 share a TMEM
+//                lane quarter; the one-thread-per-row variant runs warps 2..5 only): the scores of a tile are read from TMEM
+//                once, P = exp2(s * scale - m) goes as bf16 pairs into one of two 32-column TMEM buffers and is consumed by
+//                the PV MMA as its TMEM A operand: no shared-memory round trip, no generic -> async proxy fence.
+//                The exponentials run speculatively against the current reference m (a quarter of them as a degree-3
+//                polynomial on the FMA pipe: the SFU bounds this head-dim-64 kernel).  m only moves when a score exceeds it by
+//                more than 2^16 in the exp2 domain (softmax is invariant to m; P <= 2^16 is harmless in bf16 / fp32), which is
+//                DETECTED from the tile's row sum (needed anyway) instead of a per-tile maximum tree.  Then -- rarely, mostly
+//                in the first tiles -- the exact row maximum is formed (the two threads of a row exchange theirs through
+//                shared memory behind a 64-thread named barrier), the row's O is rescaled in TMEM and the tile is redone.
+// TMEM use is 256 columns and shared memory 69 KB, so two CTAs share an SM and one CTA's softmax overlaps
 // the other's MMAs; inside a CTA the double-buffered S / P let the tensor core run one tile ahead of the softmax.
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
@@ -72,8 +75,11 @@ __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t*
 // degree-3 minimax polynomial on [-0.5, 0.5], relative error 7.5e-5, far below the bf16 rounding of P) instead of the SFU:
 // MUFU.EX2 issues one warp instruction per 8 cycles and SM sub-partition, which bounds this head-dim-64 kernel (64 exp2 per
 // row and tile = 512 SFU cycles against 256 tensor-pipe cycles); the FMA pipe is ~10 % busy.
-template <int NPOLY>
-__global__ void __launch_bounds__(192, 2)
+// SPLIT: EIGHT softmax warps, two threads per query row that take 32 of the 64 keys of every tile each (warps w and w + 4 share a
+// TMEM lane quarter).  Four instead of two softmax warps per SM sub-partition keep the SFU fed while other warps sit in their
+// FMA / pack / TMEM phases; the pair agrees on the (rare) moves of the reference maximum through a per-tile named barrier.
+template <int NPOLY, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 320 : 192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
   pdl_trigger();
@@ -86,6 +92,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = k_full + FA_NK, *v_full = k_empty + FA_NK, *v_empty = v_full + FA_NV,
            *s_full = v_empty + FA_NV, *p_ready = s_full + 2, *pv_done = p_ready + 2;
   uint32_t* tmem_slot = (uint32_t*)(pv_done + 2);
+  // SPLIT: pair exchange area behind the barriers: flags [2 tiles][4 quarters][2 halves], tmax [2 halves][128], lsum [2 halves][128]
+  int* xflag = (int*)(tmem_slot + 4);
+  float* xtmax = (float*)(xflag + 16);
+  float* xlsum = xtmax + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -98,7 +108,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_init(smem_u32(q_full), 1);
     for (int i = 0; i < FA_NK; ++i) { mbar_init(smem_u32(&k_full[i]), 1); mbar_init(smem_u32(&k_empty[i]), 1); }
     for (int i = 0; i < FA_NV; ++i) { mbar_init(smem_u32(&v_full[i]), 1); mbar_init(smem_u32(&v_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&p_ready[i]), 128); mbar_init(smem_u32(&pv_done[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&p_ready[i]), SPLIT ? 256 : 128); mbar_init(smem_u32(&pv_done[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -170,6 +180,124 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (j + 2 < nkv) issue_s(j + 2);      // S buffer (j & 1) was drained before p_ready(j)
       }
     }
+  } else if (SPLIT) {
+    const int qd = warp & 3, half = (warp - 2) >> 2;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float cs = p.scale_log2;
+    const float tau = 16.0f / cs;
+    float m_used = -INFINITY;
+    float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
+    auto exp_pack = [&](const uint32_t (&r)[32], float mb, uint32_t* pk, float2& t01, float2& t23) {
+      const float2 c2 = make_float2(cs, cs), nm = make_float2(-mb, -mb);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float2 a = f2fma(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nm);
+        float2 e;
+        if (NPOLY > 0 && (i * NPOLY) / 16 != ((i + 1) * NPOLY) / 16) {
+          a.x = fminf(fmaxf(a.x, -125.0f), 127.0f); a.y = fminf(fmaxf(a.y, -125.0f), 127.0f);
+          const float2 magic = make_float2(12582912.0f, 12582912.0f);
+          const float2 t = f2add(a, magic);
+          const float2 f = f2sub(a, f2sub(t, magic));
+          float2 q = f2fma(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+          q = f2fma(q, f, make_float2(0.6932609677f, 0.6932609677f));
+          q = f2fma(q, f, make_float2(0.9999280572f, 0.9999280572f));
+          e.x = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23));
+          e.y = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23));
+        } else {
+          e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        }
+        if (i & 1) t23 = f2add(t23, e); else t01 = f2add(t01, e);
+        __nv_bfloat162 t = __floats2bfloat162_rn(e.x, e.y);
+        pk[i] = *(uint32_t*)&t;
+      }
+    };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory"); };
+    for (int j = 0; j < nkv; ++j) {
+      const int nvalid = min(64, p.Sk - j * 64) - half * 32;      // valid keys of MY half (may be <= 0)
+      mbar_wait(smem_u32(&s_full[j & 1]), (uint32_t)((j >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[32];
+      const uint32_t ts = tmem_S + (uint32_t)((j & 1) * 64 + half * 32) + lane_addr;
+      const uint32_t tp = tmem_P + (uint32_t)((j & 1) * 32 + half * 16) + lane_addr;
+      tmem_ld32(ts, r);
+      if (nvalid < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (i >= nvalid) r[i] = 0xff800000u;     // -inf: exp2 -> 0, ignored by the maximum
+      }
+      uint32_t pk[16];
+      float2 t01 = make_float2(0.f, 0.f), t23 = make_float2(0.f, 0.f);
+      float mb = m_used * cs;
+      if (j > 0) { exp_pack(r, mb, pk, t01, t23); tmem_st16_nowait(tp, pk); }
+      // a move of the reference shows in the row sum of either half (> 2^16 or inf / NaN); the two warps of a row tell each other
+      const float tsum = (t01.x + t01.y) + (t23.x + t23.y);
+      const bool sus = (j == 0) || !(tsum <= 65536.0f);
+      const int wsus = __any_sync(0xffffffffu, sus) ? 1 : 0;
+      int* fl = xflag + (j & 1) * 8 + qd * 2;
+      if (lane == 0) fl[half] = wsus;
+      pair_sync();
+      if (wsus | fl[half ^ 1]) {
+        // rare: exact row maximum over both halves, the same decision in both warps
+        float mx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = fmaxf(fmaxf(__uint_as_float(r[i]), __uint_as_float(r[8 + i])),
+                                                   fmaxf(__uint_as_float(r[16 + i]), __uint_as_float(r[24 + i])));
+        const float tm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+        xtmax[half * 128 + row] = tm;
+        pair_sync();
+        const float tmax = fmaxf(tm, xtmax[(half ^ 1) * 128 + row]);
+        const bool need = tmax > m_used + tau;            // always true on the first tile (m_used = -inf)
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? tmax : m_used;
+          const float alpha = (j == 0 || !need) ? 1.0f : ex2_approx((m_used - m_new) * cs);
+          if (j > 0) {
+            // this thread rescales ITS 32 columns of the row's O in TMEM: PV(j-1) must have landed, PV(j) waits for p_ready(j)
+            mbar_wait(smem_u32(&pv_done[(j - 1) & 1]), (uint32_t)(((j - 1) >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_addr + (uint32_t)(half * 32), o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_addr + (uint32_t)(half * 32), o);
+            l01 = f2mul(l01, f2splat(alpha)); l23 = f2mul(l23, f2splat(alpha));
+          }
+          m_used = m_new;
+          mb = m_used * cs;
+          t01 = make_float2(0.f, 0.f); t23 = make_float2(0.f, 0.f);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          exp_pack(r, mb, pk, t01, t23);
+          tmem_st16_nowait(tp, pk);
+        }
+      }
+      l01 = f2add(l01, t01); l23 = f2add(l23, t23);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[j & 1])) : "memory");
+    }
+    const float lmine = (l01.x + l01.y) + (l23.x + l23.y);
+    xlsum[half * 128 + row] = lmine;
+    pair_sync();
+    const float inv = 1.0f / (lmine + xlsum[(half ^ 1) * 128 + row]);
+    mbar_wait(smem_u32(&pv_done[(nkv - 1) & 1]), (uint32_t)(((nkv - 1) >> 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    bf16* dst = p.O + ((long)b * p.Sq + q0 + row) * p.ldo + h * 64 + half * 32;
+    {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_addr + (uint32_t)(half * 32), o);
+      if (q0 + row < p.Sq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(o[8 * g + 2 * i]) * inv, __uint_as_float(o[8 * g + 2 * i + 1]) * inv);
+            pk[i] = *(uint32_t*)&t;
+          }
+          *(uint4*)(dst + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
@@ -318,7 +446,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // row and tile = 512 SFU cycles against 256 tensor-pipe cycles); the FMA pipe is ~10 % busy.
 // how many of 16 exp2 pairs go to the polynomial path (every variant computes the same softmax; tuning hook of the tests / tools)
 static int g_fa_npoly = 4;      // measured on B200 (tools/flash_bench.py): 0 -> 438 us, 4 -> 408 us, 6 -> 413 us, 8 -> 431 us (frequency self-attention, B = 32)
-void flash_attn_set_poly(int npoly) { g_fa_npoly = npoly <= 0 ? 0 : npoly <= 4 ? 4 : npoly <= 6 ? 6 : 8; }
+static bool g_fa_split = true;      // two threads per query row (SPLIT variant); flash_attn_set_poly(npoly | 0x100) selects the one-thread-per-row kernel
+void flash_attn_set_poly(int npoly) {
+  g_fa_split = !(npoly & 0x100);
+  npoly &= 0xff;
+  g_fa_npoly = npoly <= 0 ? 0 : npoly <= 4 ? 4 : npoly <= 6 ? 6 : 8;
+}
 
 bool flash_attn_supported(long ldq, long ldkv, long ldo) {
   return tensor_map_api_available() && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0;
@@ -333,20 +466,33 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
   if (!make_tensor_map_2d(&tmV, v, 512, (uint64_t)B * Sk, (uint64_t)ldkv * 2, 64, 64)) return 4;
   FaParams p;
   p.Sq = Sq; p.Sk = Sk; p.scale_log2 = 0.125f * 1.4426950408889634f; p.O = o; p.ldo = ldo;
-  const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 256;
+  const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 256 + 64 + 512 * 4;
   static PerDeviceOnce attr;
   if (attr.first()) {
-    cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(flash_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(flash_attn_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(flash_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   dim3 grid((Sq + 127) / 128, 8, B);
+  if (g_fa_split) {
+    switch (g_fa_npoly) {
+      case 0: launch_pdl(flash_attn_kernel<0, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
+      case 4: launch_pdl(flash_attn_kernel<4, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
+      case 6: launch_pdl(flash_attn_kernel<6, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
+      default: launch_pdl(flash_attn_kernel<8, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
+    }
+    return 0;
+  }
   switch (g_fa_npoly) {
-    case 0: launch_pdl(flash_attn_kernel<0>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
-    case 4: launch_pdl(flash_attn_kernel<4>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
-    case 6: launch_pdl(flash_attn_kernel<6>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
-    default: launch_pdl(flash_attn_kernel<8>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
+    case 0: launch_pdl(flash_attn_kernel<0, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
+    case 4: launch_pdl(flash_attn_kernel<4, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
+    case 6: launch_pdl(flash_attn_kernel<6, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
+    default: launch_pdl(flash_attn_kernel<8, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
   }
   return 0;
 }

@@ -252,7 +252,9 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
   __syncthreads();
   const float sb = gvs[2 * D::HP], sbb = gvs[2 * D::HP + 1];
   bf16* hb = p.h + (long)b * p.g.rows * D::HP;
-  float ts = 0.f, tq = 0.f;
+  // per-thread sums over the tiles of this CTA in fp64: which tiles a CTA walks depends on the grid, i.e. on the batch size, and the
+  // result must not (per-row partials are deterministic; fp64 adds of fp32 values are order-independent in practice)
+  double ts = 0.0, tq = 0.0;
   for (int tile = blockIdx.x; tile * 128 < p.g.rows; tile += gridDim.x) {
     const int r_lo = tile * 128 + warp * 16 + g, r_hi = r_lo + 8;
     const bool v_lo = r_lo < p.g.rows, v_hi = r_hi < p.g.rows;
@@ -289,15 +291,16 @@ __global__ void __launch_bounds__(256) dconv_b_kernel(const DcTileParams p) {
     if (p.per_row) {
       dc_row_stats(p.st2, b, p.g.Rr, r_lo, r_hi, v_lo, v_hi, s_lo, q_lo, s_hi, q_hi);
     } else {
-      if (v_lo) { ts += s_lo; tq += q_lo; }
-      if (v_hi) { ts += s_hi; tq += q_hi; }
+      if (v_lo) { ts += (double)s_lo; tq += (double)q_lo; }
+      if (v_hi) { ts += (double)s_hi; tq += (double)q_hi; }
     }
   }
   if (!p.per_row) {
-    dc_block_sum2(ts, tq, red);
-    if (tid == 0) {
-      double* sp = p.st2 + 2 * ((long)b * STAT_SLOTS + blockIdx.x % STAT_SLOTS);
-      atomicAdd(sp, (double)ts); atomicAdd(sp + 1, (double)tq);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ts += __shfl_xor_sync(0xffffffffu, ts, o); tq += __shfl_xor_sync(0xffffffffu, tq, o); }
+    if (lane == 0) {
+      double* sp = p.st2 + 2 * ((long)b * STAT_SLOTS + (blockIdx.x + warp) % STAT_SLOTS);
+      atomicAdd(sp, ts); atomicAdd(sp + 1, tq);
     }
   }
 }

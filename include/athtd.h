@@ -138,14 +138,16 @@ int athtd_chunk_fade_add(const float* seg_out_dev, long seg_stride, int k_base, 
 int athtd_sdr_sums(const float* est_dev, const float* tgt_dev, int items, long n, double* sums_dev, void* stream);
 
 /* tuning hook: how many of every 16 exp2 pairs of the attention softmax are evaluated by the FMA-pipe polynomial instead of the
- * SFU (0, 4, 6 or 8; every setting computes the same softmax to bf16 accuracy).  Process-wide. */
+ * SFU (0, 4, 6 or 8; every setting computes the same softmax to bf16 accuracy); | 0x100 selects the one-thread-per-row softmax instead
+ * of the default two threads per query row.  Process-wide. */
 int athtd_attention_set_poly(int npoly);
 /* programmatic dependent launch of the path's kernels (default OFF: measured 3 % slower on this path, profiles/r02_summary.md): a kernel's CTAs may set up (barrier init, TMEM allocation,
  * weight staging) while its predecessor drains; every kernel waits for the predecessor before touching its data.  Process-wide. */
 int athtd_set_pdl(int on);
 /* tuning hook of the tcgen05 GEMM tile selection (tools/): low 16 bits = widest N tile (256), 0x10000 = one CTA per SM only,
  * 0x20000 = N in (128, 256] as two N/2-wide tiles, 0x40000 / 0x80000 = route eligible 256-wide tiles (all / only K >= 1536) through
- * the cta_group::2 CTA-pair kernel.  Every setting computes the same GEMM.  Process-wide. */
+ * the cta_group::2 CTA-pair kernel, 0x100000 = 192-wide tiles on the 16- instead of the 12-epilogue-warp variant.  Every setting computes
+ * the same GEMM.  Process-wide. */
 int athtd_set_tc_tuning(int flags);
 
 /* kernel-level parity test of the fused attention: q [B*Sq,512], k/v [B*Sk,512] bf16 (8 heads x 64) -> o [B*Sq,512] */

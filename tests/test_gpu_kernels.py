@@ -171,10 +171,11 @@ def test_fused_attention_matches_torch(B, Sq, Sk):
     assert (got - ref).abs().max() < 2e-2
 
 
-@pytest.mark.parametrize("npoly", [4, 6, 8])
+@pytest.mark.parametrize("npoly", [4, 6, 8, 0x100 | 4, 0x100 | 8])
 def test_fused_attention_polynomial_exp2_variants(npoly):
     """The attention softmax may take part of its exp2 on the FMA pipe (degree-3 polynomial): same result to bf16 accuracy, also
-    with masked key columns (Sk not a multiple of 64) and many key tiles."""
+    with masked key columns (Sk not a multiple of 64) and many key tiles.  Flag 0x100 selects the one-thread-per-row softmax (the
+    default splits every row between two threads)."""
     lib = alib.load()
     B, Sq, Sk = 2, 300, 1034
     g = torch.Generator().manual_seed(npoly)
@@ -199,8 +200,8 @@ def test_fused_attention_polynomial_exp2_variants(npoly):
     assert ((got - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all()
 
 
-@pytest.mark.parametrize("npoly", [0, 4])
-@pytest.mark.parametrize("Sq,Sk", [(200, 64), (128, 65), (300, 1034), (257, 2072)])
+@pytest.mark.parametrize("npoly", [0, 4, 0x100 | 4])
+@pytest.mark.parametrize("Sq,Sk", [(200, 64), (128, 65), (128, 33), (300, 1034), (257, 2072)])
 def test_fused_attention_moving_row_maximum(npoly, Sq, Sk):
     """Online-softmax stress: score magnitudes grow along the key axis, so the running reference maximum of most rows moves in many
     key tiles (the speculative exponentials are redone there); one key tile, one-key tail tile, odd and even tile counts.
