@@ -393,11 +393,10 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
       float dv[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < D::KS; ++ks) {
-        uint32_t bb[2];
-        frag_b(w2s, D::K2P, vt * 8, ks * 16, lane, bb);
-        mma16816(dv, a[ks], bb);
-        frag_b(w2s, D::K2P, CS + vt * 8, ks * 16, lane, bb);
-        mma16816(dg, a[ks], bb);
+        uint32_t bvf[2], bgf[2];      // value + gate n-tile fragments of this k step through one ldmatrix.x4
+        ldsm_b_pair(w2s, D::K2P, vt * 8, CS + vt * 8, ks * 16, lane, bvf, bgf);
+        mma16816(dv, a[ks], bvf);
+        mma16816(dg, a[ks], bgf);
       }
       const int j = vt * 8 + 2 * q;
       const float2 av = *(const float2*)(al + j), bv = *(const float2*)(be + j);
@@ -450,9 +449,10 @@ __global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
         float dv[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kc = 0; kc < C / 16; ++kc) {
-          uint32_t bb[2];
-          frag_b(wrs, XPS, vt * 8, kc * 16, lane, bb); mma16816(dv, ar[kc], bb);
-          frag_b(wrs, XPS, C + vt * 8, kc * 16, lane, bb); mma16816(dg, ar[kc], bb);
+          uint32_t bvf[2], bgf[2];
+          ldsm_b_pair(wrs, XPS, vt * 8, C + vt * 8, kc * 16, lane, bvf, bgf);
+          mma16816(dv, ar[kc], bvf);
+          mma16816(dg, ar[kc], bgf);
         }
         const int j = vt * 8 + 2 * q;
         const float rv0 = p.rb[2 * j], rg0 = 0.5f * p.rb[2 * j + 1], rv1 = p.rb[2 * j + 2], rg1 = 0.5f * p.rb[2 * j + 3];

@@ -209,7 +209,7 @@ class Engine:
         self.win = torch.hann_window(4096).float().contiguous().to(self.device)
         # plan cache: one plan per (L, P), least recently used first; workspaces (0.35 GB per segment of capacity at 6 s)
         # are evicted beyond ``max_workspace_bytes`` (default: half of the device memory)
-        self.plans: "OrderedDict[Tuple[int, int], Plan]" = OrderedDict()
+        self.plans: "OrderedDict[Tuple[int, ...], Plan]" = OrderedDict()
         if max_workspace_bytes is None:
             max_workspace_bytes = torch.cuda.get_device_properties(self.device).total_memory // 2
         self.max_workspace_bytes = int(max_workspace_bytes)
@@ -231,11 +231,12 @@ class Engine:
                                                    torch.cuda.current_stream().cuda_stream), "athtd_pack_weights")
         self.loaded = True
 
-    def plan(self, B: int, L: int, P: int = 1, cap: Optional[int] = None) -> Plan:
+    def plan(self, B: int, L: int, P: int = 1, cap: Optional[int] = None, slot: int = 0) -> Plan:
         """Plan for segments of L samples and P prompts, set to batch B.  ``cap`` (>= B) is the batch capacity to lay the
         workspace out for when a new one is needed (a track loop passes its full batch size so that the tail batch
-        reuses the workspace)."""
-        key = (L, P)
+        reuses the workspace).  ``slot`` > 0 asks for a further workspace of the same shape (a track loop that keeps two
+        batches in flight on two streams)."""
+        key = (L, P) if slot == 0 else (L, P, slot)
         pl = self.plans.get(key)
         if pl is not None and pl.cap < B:
             del self.plans[key]       # outgrown: replaced below

@@ -297,6 +297,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay of the forward)")
     ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch between the kernels (default off: measured slower)")
+    ap.add_argument("--no-overlap-batches", action="store_true", help="one batch at a time (default: two batches in flight on two streams / workspaces)")
     ap.add_argument("--no-pin", action="store_true", help="do not give every local rank its own slice of the host cores")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: wait for the downloads of every step before the next one")
     args = ap.parse_args()
@@ -331,7 +332,8 @@ def main():
         athtd_b200.load_library().athtd_set_pdl(1)
     model = athtd_b200.AudioTextHTDemucsB200(precision=args.precision)
     model.load_state_dict(synthetic.make_state_dict(0), strict=False)
-    sep = athtd_b200.B200SeparationModel(model, dev, 6.0, 1.5, batch=args.batch, use_graph=not args.no_graph)
+    sep = athtd_b200.B200SeparationModel(model, dev, 6.0, 1.5, batch=args.batch, use_graph=not args.no_graph,
+                                         overlap_batches=not args.no_overlap_batches)
     T, P, scaling, what = workload(args.config, world, args.seconds, args.prompts)
     plan = athtd_b200.segment_plan(T)
     n = len(plan.starts)
@@ -432,7 +434,7 @@ def main():
                                    f"{P} prompt(s), random-init AudioTextHTDemucs",
                        "batch": args.batch, "prompts": P, "chunks": n, "l2": "inputs+activations per step (>10 GB) exceed the 126 MB L2",
                        "parallelism": f"segment-span x{world}", "host_cores_per_rank": cores,
-                       "e2e_pipelined_steps": not args.no_pipeline},
+                       "e2e_pipelined_steps": not args.no_pipeline, "batches_in_flight": 1 if args.no_overlap_batches else 2},
             "stem_seconds_per_s": value * P,
             "roofline": roof,
             "e2e": {"value": e2e_v, "unit": "x realtime", "h2d_bytes_per_step": int(h2d[0].item()),

@@ -127,7 +127,7 @@ def test_full_track_properties_bf16(models):
     properties instead of an oracle -- (1) the result does not depend on the batch size (7 vs 16 segments per launch:
     every statistic is per segment), (2) the track output equals the reference overlap-add
     (oracle/ola.py, the restated benchmark.py loop) applied to the per-chunk model outputs, bit for bit,
-    (3) linearity of the track loop: separating with two prompts at once == one prompt at a time."""
+    (3) linearity of the track loop: separating with two prompts at once == one prompt at a time, (4) overlapped batches."""
     m = models["bf16"]
     T = 44100 * 90 + 1234
     wav, emb = weights.make_inputs(91, 1, T)
@@ -143,6 +143,14 @@ def test_full_track_properties_bf16(models):
     assert torch.equal(b[0].cpu(), ref)
     c, _ = sep16.separate_many(mix, embs[1:])
     assert torch.equal(c[0], b[1])
+    # (4) the default keeps two batches in flight on two streams / workspaces: one batch at a time gives the same bits, and so do
+    #     the replayed (CUDA graph) later calls of the overlapped loop
+    d, _ = athtd_b200.B200SeparationModel(m, "cuda", batch=7, overlap_batches=False).separate_many(mix, embs)
+    assert torch.equal(d, a)
+    sep_ov = athtd_b200.B200SeparationModel(m, "cuda", batch=7, overlap_batches=True)
+    for _ in range(3):
+        d, _ = sep_ov.separate_many(mix, embs)
+        assert torch.equal(d, a)
 
 
 def test_fade_loop_matches_test_inference_semantics(models, state_dict):

@@ -229,7 +229,7 @@ def test_plugin_interface_separate_and_separate_all(models, state_dict):
 
 def test_empty_span_and_plan_capacity(models):
     """More ranks than chunks: an empty span returns [P, 2, 0] without launching; a tail batch runs in the
-    full-batch plan's workspace (one workspace per (L, P), not one per batch size)."""
+    full-batch plan's workspace (one workspace per (L, P) and batch in flight, not one per batch size)."""
     m = models["fp32"]
     sep = athtd_b200.B200SeparationModel(m, "cuda", segment_seconds=1.0, overlap_seconds=0.25, batch=4)
     T = 44100 * 5
@@ -241,8 +241,13 @@ def test_empty_span_and_plan_capacity(models):
     sep.separate_span_host(host, emb, (3, 3), torch.empty(2, 2, 0).pin_memory())
     eng = m.engine()
     eng.drop_plans()
-    full, _ = sep.separate_many(mix, emb)          # 7 chunks: batches of 4 + 3
+    full, _ = sep.separate_many(mix, emb)          # 7 chunks: batches of 4 + 3, two batches in flight -> two workspaces of capacity 4
+    assert len(eng.plans) == 2 and all(pl.cap == 4 for pl in eng.plans.values())
+    eng.drop_plans()
+    seq = athtd_b200.B200SeparationModel(m, "cuda", segment_seconds=1.0, overlap_seconds=0.25, batch=4, overlap_batches=False)
+    full_seq, _ = seq.separate_many(mix, emb)      # one batch at a time: one workspace, the tail batch runs in it
     assert len(eng.plans) == 1 and next(iter(eng.plans.values())).cap == 4
+    assert torch.equal(full_seq, full)
     sep1 = athtd_b200.B200SeparationModel(m, "cuda", segment_seconds=1.0, overlap_seconds=0.25, batch=1)
     eng.drop_plans()
     one, _ = sep1.separate_many(mix, emb)
