@@ -428,9 +428,13 @@ class B200SeparationModel(SeparationModel):
         L = int(self.model.sample_rate * self.segment_seconds)
         pl = eng.plan(min(self.batch, max(1, span[1] - span[0])), L, emb.shape[0], cap=self.batch)
         pl.set_profile(True)
-        self.separate_span(track, emb, span, track_offset=track_offset, track_len=track_len,
-                           halo_in=torch.zeros(emb.shape[0], 2, L, device=self.device))
-        torch.cuda.synchronize(self.device)
+        overlap, self.overlap_batches = self.overlap_batches, False      # one batch at a time through the profiled workspace: the
+        try:                                                             # per-launch events must not see another stream's kernels
+            self.separate_span(track, emb, span, track_offset=track_offset, track_len=track_len,
+                               halo_in=torch.zeros(emb.shape[0], 2, L, device=self.device))
+            torch.cuda.synchronize(self.device)
+        finally:
+            self.overlap_batches = overlap
         ms, gf, n = pl.get_profile()
         pl.set_profile(False)
         return {"kernel": eng.gemm_kernel_name(), "ms": ms, "gflop": gf, "launches": n, "tflops": gf / ms if ms > 0 else 0.0}
