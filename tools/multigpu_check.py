@@ -13,9 +13,10 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4      # 2: several batches per rank (two in flight) next to the halo exchange
 model = athtd_b200.AudioTextHTDemucsB200(precision=prec)
 model.load_state_dict(weights.make_state_dict(0), strict=False)
-sep = athtd_b200.B200SeparationModel(model, dev, 6.0, 1.5, batch=4)
+sep = athtd_b200.B200SeparationModel(model, dev, 6.0, 1.5, batch=batch)
 T = 198450 * 3 * world + 12345                       # a few chunks per rank, ragged tail
 wav, _ = weights.make_inputs(77, 1, T)
 mix = wav[0].to(dev)
@@ -33,7 +34,7 @@ ok = True
 if rank == 0:
     ref, _ = sep.separate_many(mix, emb)
     ok = bool(torch.equal(ref, full))
-    print(f"multigpu_check world={world} precision={prec} chunks={len(plan.starts)} bit_exact={ok} max|diff|={(ref - full).abs().max().item():.3e}")
+    print(f"multigpu_check world={world} precision={prec} batch={batch} chunks={len(plan.starts)} bit_exact={ok} max|diff|={(ref - full).abs().max().item():.3e}")
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()
