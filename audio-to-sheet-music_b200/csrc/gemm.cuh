@@ -67,10 +67,14 @@ struct TcFlat {
   const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;   // GroupNorm apply right after the bias
   void* dbg;            // unused (kept for the micro-benchmark ABI)
   int skip_lo, skip_hi; // output columns [skip_lo, skip_hi) feed the statistics but are not stored
+  // fused finalisation of per-segment statistics (stat_mode == STAT_PER_G1): the CTA that finishes last (ticket on *fin_counter, zeroed
+  // with the statistics) turns the fin_n x STAT_SLOTS slot sums into (mean, rstd) pairs in fin_mr -- no finalize launch
+  float* fin_mr; double fin_count; int fin_n; unsigned* fin_counter;
 };
 void tc_set_bn_cap(int cap);   // 128 or 256: largest N tile (A/B tuning knob)
 bool tensor_map_api_available();              // cuTensorMapEncodeTiled reachable through the runtime's driver entry point
 bool tc_flat_supported(const TcFlat& f);
 int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st);   // bf16 in, fp32 accumulate; 0 = launched
+bool tc_flat_fuses_finalize(const TcFlat& f);                // whether that launch also writes f.fin_mr
 
 }  // namespace athtd

@@ -63,6 +63,7 @@ struct TcParams {
   int convt_cout;
   int skip_lo, skip_hi;    // output columns [skip_lo, skip_hi) are computed (statistics) but not stored
   uint32_t fdRpA[2], fdG2p[2], fdNt[2];   // (multiplier, shift) of the division-free x / RpA, x / G2p, x / n_tiles (x < 2^31)
+  float* fin_mr; double fin_count; int fin_n; unsigned* fin_counter;      // fused statistics finalisation (TcFlat)
   int wide;                // 32-byte row accesses allowed (row pitch and base 32-byte aligned, skip range in 16-column units)
 };
 
@@ -463,11 +464,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if ((EF & EF_STATS) && p.fin_mr) __threadfence();      // this thread's statistics atomics are visible before the CTA's ticket
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+  if ((EF & EF_STATS) && p.fin_mr) {
+    // The CTA that draws the last ticket finalises the per-segment statistics (same slot order and butterfly as
+    // finalize_gn_slots_kernel: identical bits): one launch and its ~6 us less per GroupNorm of the transformer / decoder.
+    int* s_last = (int*)(tmem_slot + 1);
+    if (threadIdx.x == 0) *s_last = atomicAdd(p.fin_counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (*s_last) {
+      __threadfence();
+      for (int i = warp; i < p.fin_n; i += (int)(blockDim.x >> 5)) {
+        double st[2] = {0.0, 0.0};
+        for (int sl = lane; sl < STAT_SLOTS; sl += 32) {
+          st[0] += __ldcg(p.stats + 2 * ((long)i * STAT_SLOTS + sl)); st[1] += __ldcg(p.stats + 2 * ((long)i * STAT_SLOTS + sl) + 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { st[0] += __shfl_xor_sync(0xffffffffu, st[0], o); st[1] += __shfl_xor_sync(0xffffffffu, st[1], o); }
+        if (lane == 0) { float m, r; stats_to_mean_rstd(st, p.fin_count, 1e-5f, m, r); p.fin_mr[2 * i] = m; p.fin_mr[2 * i + 1] = r; }
+      }
+    }
   }
 }
 
@@ -749,9 +770,10 @@ static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide t
                                 // and 959 vs 1026 at K = 512; inside the forward (residual + statistics epilogue, cold operands) the
                                 // K = 2048 launches measure the same 115-117 us either way (profiles/r01_summary.md).
 static bool g_tc_w12 = true;             // 192-wide tiles on the 12-epilogue-warp variant (tuning flag 0x100000 turns it off)
+static bool g_tc_fuse_fin = true;        // statistics finalised by the GEMM's last CTA (tuning flag 0x200000: separate finalize launch)
 static bool g_tc_halve_mid = false;      // tuning: N in (128, 256] as two N/2-wide tiles (two CTAs per SM) instead of one N-wide tile
 void tc_set_bn_cap(int cap) {
-  g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0; g_tc_w12 = !(cap & 0x100000);
+  g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0; g_tc_w12 = !(cap & 0x100000); g_tc_fuse_fin = !(cap & 0x200000);
   g_tc_pair = (cap & 0x40000) ? 1 : (cap & 0x80000) ? 2 : 0;
 }
 
@@ -778,6 +800,11 @@ bool tc_flat_supported(const TcFlat& f) {
 
 static int num_sms() { return device_sm_count(); }
 
+// (the CTA-pair kernel does not finalise; it is only reachable through the tuning flags)
+bool tc_flat_fuses_finalize(const TcFlat& f) {
+  return g_tc_fuse_fin && f.fin_mr != nullptr && f.fin_counter != nullptr && f.stats != nullptr && f.stat_mode == STAT_PER_G1 && g_tc_pair <= 0;
+}
+
 int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -793,6 +820,7 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   p.stats = f.stats; p.stat_mode = f.stat_mode; p.statR = f.statR; p.convt_cout = f.convt_cout;
   p.gn_mr = f.gn_mr; p.gn_w = f.gn_w; p.gn_b = f.gn_b; p.gn_mode = f.gn_mode;
   p.skip_lo = f.skip_lo; p.skip_hi = f.skip_hi;
+  p.fin_mr = nullptr; p.fin_count = f.fin_count; p.fin_n = f.fin_n; p.fin_counter = f.fin_counter;
   p.wide = (f.ldc % 16 == 0) && ((uintptr_t)f.C % 32 == 0) && (!f.res || (uintptr_t)f.res % 32 == 0) && (f.skip_lo % 16 == 0) &&
            (f.skip_hi % 16 == 0);
   p.m_tiles = (int)((f.Mflat + TC_BM - 1) / TC_BM);
@@ -824,6 +852,7 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   // CTA pairs for the 256-wide tiles of long-M problems (transformer linears): 256 x 256 tile per cluster
   const bool pair = (g_tc_pair == 1 || (g_tc_pair == 2 && p.ntaps * p.kb_per_tap >= 24)) && p.BN == 256 && f.N % 256 == 0 && p.m_tiles >= 2 * num_sms() && f.stat_mode != STAT_PER_G1_M &&
                     (num_sms() % 2 == 0);
+  if (!pair && tc_flat_fuses_finalize(f)) p.fin_mr = f.fin_mr;
   CUtensorMap tmBh;
   int pair_stages = 0;
   size_t pair_smem = 0;

@@ -136,11 +136,13 @@ void PlanT<T>::layout(char* base) {
         st_dt[i][d][k] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS);
       }
   for (int l = 0; l < 5; ++l) { st_xf[l][0] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS); st_xf[l][1] = (double*)take(sizeof(double) * 2 * B * STAT_SLOTS); }
+  fin_xf = (unsigned*)take(sizeof(unsigned) * 16);
   // decoder GroupNorm accumulators: LAST in the statistics block -- encode() clears [stats_begin, dec_stats_begin),
   // decode() clears [dec_stats_begin, stats end) so that one encode can be followed by any number of decodes
   off = align_up(off, 256);
   dec_stats_begin = off;
   st_dec = (double*)take(sizeof(double) * 2 * B * 6 * s.P * STAT_SLOTS);
+  fin_dec = (unsigned*)take(sizeof(unsigned) * 6 * s.P);
   stats_bytes = align_up(off, 256) - stats_begin;
   off = stats_begin + stats_bytes;
   // ---- plain scratch
@@ -247,7 +249,7 @@ void PlanT<T>::get_profile(double* ms, double* gflop, int* n) {
 // ---- lower one convolution-shaped op either to the tcgen05 flat-row kernel (bf16 build, supported shapes) or to
 //      the SIMT kernel.  Both read the same buffers and produce the same layout.
 template <typename T>
-void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
+bool PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
   const RowSpace& as = o.as;
   const RowSpace& cs = o.cs;
   const int C = as.C;
@@ -279,6 +281,7 @@ void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
     f.rowtab = o.rowtab; f.rowtab_scale = o.rowtab_scale; f.stats = o.stats; f.stat_mode = o.stat_mode; f.statR = as.R;
     f.convt_cout = o.mode == CONV_T ? o.N / 4 : 0;
     f.n_store = o.n_store; f.no_store = o.no_store; f.skip_lo = o.skip_lo; f.skip_hi = o.skip_hi; f.gn_mr = o.gn_mr; f.gn_w = o.gn_w; f.gn_b = o.gn_b; f.gn_mode = o.gn_mode;
+    f.fin_mr = o.fin_mr; f.fin_count = o.fin_count; f.fin_n = B; f.fin_counter = o.fin_counter;
     const bool geom_ok = (o.mode != CONV_K8S4) || (as.Rp % 4 == 0 && as.pf == 2);
     if (geom_ok && tc_flat_supported(f)) {
       prof_begin(gflop, st, o.mode == CONV_ROWS ? "rows" : o.mode == CONV_K8S4 ? "k8s4" : o.mode == CONV_T ? "convT" : "k3", (long)B * as.G2 * Mg, o.N, K);
@@ -286,7 +289,7 @@ void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
       prof_end(st);
       if (rc != 0) throw std::runtime_error("athtd: cuTensorMapEncodeTiled failed for a tcgen05 GEMM");
       ++n_launches; ++n_tc;
-      return;
+      return tc_flat_fuses_finalize(f);
     }
   }
   if (o.no_store || o.gn_mr || o.n_store) throw std::runtime_error("athtd: fused DConv epilogue needs the tcgen05 kernel");
@@ -310,6 +313,7 @@ void PlanT<T>::conv(const ConvOp<T>& o, cudaStream_t st) {
   d.stats = o.stats; d.stat_mode = o.stat_mode;
   d.convt_cout = o.mode == CONV_T ? o.N / 4 : 0;
   gemm(d, st);
+  return false;
 }
 
 template <typename T>
@@ -534,27 +538,30 @@ void PlanT<T>::linear(const T* a, int S, int K, const T* w, int N, const float* 
 
 // x <- x + gamma * (a W^T + b), optional per-sample (sum, sumsq) of the result
 template <typename T>
-void PlanT<T>::linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x,
-                          double* stats, cudaStream_t st) {
+bool PlanT<T>::linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x,
+                          double* stats, cudaStream_t st, unsigned* fin_counter) {
   ConvOp<T> o = conv_op<T>(CONV_ROWS, a, make_space(sh.B, 1, S, K, false), w, N, x, make_space(sh.B, 1, S, N, false));
   o.bias = bias; o.colscale = gamma; o.res = x;
   if (stats) { o.stats = stats; o.stat_mode = STAT_PER_G1; }
-  conv(o, st);
+  if (stats && fin_counter) { o.fin_mr = mr; o.fin_count = (double)S * N; o.fin_counter = fin_counter; }
+  return conv(o, st);
 }
 
 // FFN half of a transformer layer + norm_out (MyGroupNorm over all tokens of the segment).  The norm_out apply pass also
 // emits the LayerNorm(s) the NEXT layer starts with (same row statistics, the next layer's affine): n1 = next layer's norm1
 // of this branch, n2 = the other branch's next-layer norm2 applied to this branch (cross-attention keys / values).
 template <typename T>
-void PlanT<T>::xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, T* n1, const float* n1w,
-                               const float* n1b, T* n2, const float* n2w, const float* n2b, cudaStream_t st) {
+void PlanT<T>::xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, unsigned* fin_counter, T* n1,
+                               const float* n1w, const float* n1b, T* n2, const float* n2w, const float* n2b, cudaStream_t st) {
   const long rows = (long)sh.B * S;
   const RowSpace none{};
   launch_norm_rows<T>(x, nullptr, hn[4], rows, 512, S, nullptr, nullptr, nullptr, P32(p + "." + ffn_norm + ".weight"),
                       P32(p + "." + ffn_norm + ".bias"), nullptr, none, st); ++n_launches;
   linear(hn[4], S, 512, PW(p + ".linear1.w"), 2048, P32(p + ".linear1.bias"), ACT_GELU, ffn, st);
-  linear_res(ffn, S, 2048, PW(p + ".linear2.w"), 512, P32(p + ".linear2.bias"), P32(p + ".gamma_2.scale"), x, stats, st);
-  launch_finalize_gn(stats, (double)S * 512, mr, sh.B, STAT_SLOTS, st); ++n_launches;
+  // (the tcgen05 GEMM finalises the per-segment sums itself: its last CTA turns the slots into (mean, rstd))
+  if (!linear_res(ffn, S, 2048, PW(p + ".linear2.w"), 512, P32(p + ".linear2.bias"), P32(p + ".gamma_2.scale"), x, stats, st, fin_counter)) {
+    launch_finalize_gn(stats, (double)S * 512, mr, sh.B, STAT_SLOTS, st); ++n_launches;
+  }
   launch_norm_rows<T>(x, x, n1, rows, 512, S, mr, P32(p + ".norm_out.weight"), P32(p + ".norm_out.bias"), n1w, n1b,
                       nullptr, none, st, n2, n2w, n2b); ++n_launches;
 }
@@ -597,7 +604,7 @@ void PlanT<T>::cross_transformer(cudaStream_t st) {
                    P32(p + ".gamma_1.scale"), X[br], nullptr, st);
         T *n1, *n2; const float *n1w, *n1b, *n2w, *n2b;
         next_norms(l, br, n1, n1w, n1b, n2, n2w, n2b);
-        xf_ffn_and_norm(p, "norm2", X[br], S[br], st_xf[l][br], n1, n1w, n1b, n2, n2w, n2b, st);
+        xf_ffn_and_norm(p, "norm2", X[br], S[br], st_xf[l][br], fin_xf + 2 * l + br, n1, n1w, n1b, n2, n2w, n2b, st);
       }
     } else {
       // both branches read the PRE-update other branch (old_x, demucs transformer.py): hn[0..3] were all written by the
@@ -614,7 +621,7 @@ void PlanT<T>::cross_transformer(cudaStream_t st) {
                    P32(p + ".gamma_1.scale"), X[br], nullptr, st);
         T *n1, *n2; const float *n1w, *n1b, *n2w, *n2b;
         next_norms(l, br, n1, n1w, n1b, n2, n2w, n2b);
-        xf_ffn_and_norm(p, "norm3", X[br], S[br], st_xf[l][br], n1, n1w, n1b, n2, n2w, n2b, st);
+        xf_ffn_and_norm(p, "norm3", X[br], S[br], st_xf[l][br], fin_xf + 2 * l + br, n1, n1w, n1b, n2, n2w, n2b, st);
       }
     }
   }
@@ -724,8 +731,9 @@ void PlanT<T>::dec_layer(bool freq, int i, int p, const T* x, RowSpace xs, T* ou
   // exact 4:1 resize (4*Rin -> Rin rows) reads only rows 4d+1, 4d+2 = phases 3 and 0: phases 1, 2 feed the GroupNorm
   // statistics but are never stored; tensor-core path only
   if (sizeof(T) == 2 && use_tc && os.R == Rin) { o.skip_lo = Cout; o.skip_hi = 3 * Cout; }
-  conv(o, st);
-  if (i < 3) { launch_finalize_gn(stt, (double)Cout * 4.0 * Rin * G2, mr, s.B, STAT_SLOTS, st); ++n_launches; }
+  if (i < 3) { o.fin_mr = mr; o.fin_count = (double)Cout * 4.0 * Rin * G2; o.fin_counter = fin_dec + (size_t)p * 6 + (freq ? 0 : 3) + i; }
+  const bool finalized = conv(o, st);
+  if (i < 3 && !finalized) { launch_finalize_gn(stt, (double)Cout * 4.0 * Rin * G2, mr, s.B, STAT_SLOTS, st); ++n_launches; }
   launch_dec_apply<T>(ubuf, 4 * Rin, us, Cout, out, os, G2, i < 3 ? 1 : 0, mr, i < 3 ? P32(q + ".1.weight") : nullptr,
                       i < 3 ? P32(q + ".1.bias") : nullptr, skip, ss, st); ++n_launches;
 }

@@ -47,6 +47,7 @@ struct ConvOp {
   const float* bias; int act; int glu; const float* colscale; const T* res;
   const float* rowtab; float rowtab_scale; double* stats; int stat_mode;
   int n_store, no_store, skip_lo, skip_hi; const float* gn_mr; const float* gn_w; const float* gn_b; int gn_mode;   // tensor-core path only
+  float* fin_mr; double fin_count; unsigned* fin_counter;   // per-segment statistics finalised by the GEMM itself (gemm.cuh: TcFlat)
 };
 
 struct PlanBase {
@@ -104,6 +105,7 @@ struct PlanT : PlanBase {
   RowSpace xf0_rs, xt0_rs, yf_rs[4], yt_rs[4], xc_rs, xtc_rs, df_rs[4], dt_rs[4];
   T *xf0, *xt0, *yf[4], *ef[4], *yt[4], *et[4], *xc, *xtc, *df[4], *dt[4];
   double *st_spec, *st_wav, *st_df[4][2][2], *st_dt[4][2][2], *st_xf[5][2], *st_dec;
+  unsigned *fin_xf, *fin_dec;      // tickets of the fused statistics finalisation: [5][2] / [P][6], zeroed with the statistics
   float *mr, *ms_spec, *ms_wav, *Z, *cvec;
   T *hbuf, *ebuf, *tokf, *tokt, *hn[5], *qkv, *kvb, *obuf, *ffn, *scores, *xenc, *xtenc, *t1, *t2, *ubuf;
 
@@ -117,17 +119,17 @@ struct PlanT : PlanBase {
   const T* PW(const std::string& key) const;
   const float* PA(const std::string& key) const;
   void gemm(const GemmDesc& d, cudaStream_t st);
-  void conv(const ConvOp<T>& o, cudaStream_t st);
+  bool conv(const ConvOp<T>& o, cudaStream_t st);      // true: the launch also finalised o.stats into o.fin_mr
   void prof_begin(double gflop, cudaStream_t st, const char* what, long m, int n, int k);
   void prof_end(cudaStream_t st);
   bool enc_row_dispatch(bool run, int i, const T* x, RowSpace xin, const T* y, T* out, RowSpace ys, cudaStream_t st);
   void enc_layer(bool freq, int i, const T* x, RowSpace xin, T* y, RowSpace ys, T* out, cudaStream_t st);
   void attention(const T* q, long ldq, const T* k, const T* v, long ldkv, int Sq, int Sk, T* o, cudaStream_t st);
   void linear(const T* a, int S, int K, const T* w, int N, const float* bias, int act, T* c, cudaStream_t st);
-  void linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x, double* stats,
-                  cudaStream_t st);
-  void xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, T* n1, const float* n1w,
-                       const float* n1b, T* n2, const float* n2w, const float* n2b, cudaStream_t st);
+  bool linear_res(const T* a, int S, int K, const T* w, int N, const float* bias, const float* gamma, T* x, double* stats,
+                  cudaStream_t st, unsigned* fin_counter = nullptr);      // true: stats already finalised into mr
+  void xf_ffn_and_norm(const std::string& p, const char* ffn_norm, T* x, int S, double* stats, unsigned* fin_counter, T* n1,
+                       const float* n1w, const float* n1b, T* n2, const float* n2w, const float* n2b, cudaStream_t st);
   void cross_transformer(cudaStream_t st);
   void encode(const float* wav, cudaStream_t st, const float* xnorm = nullptr);
   void text_vectors(const float* emb, cudaStream_t st);
