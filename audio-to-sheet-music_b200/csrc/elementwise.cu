@@ -229,6 +229,13 @@ __global__ void __launch_bounds__(256, 3) norm_rows_kernel(const T* __restrict__
       if (lane + 32 * i < nchunk) VecIO<T, 8>::load(x + row * C + (lane + 32 * i) * 8, v[r] + 8 * i);
   }
   if (gmr) {
+    // (mean, rstd) of the row's segment: one 32-bit division per row (rows < 2^31), not a 64-bit one per row and chunk
+    float gm_[RPW], gr_[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int seg = (int)min(row0 + r, rows - 1) / S;
+      gm_[r] = gmr[2 * seg]; gr_[r] = gmr[2 * seg + 1];
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int c = (lane + 32 * i) * 8;
@@ -238,8 +245,7 @@ __global__ void __launch_bounds__(256, 3) norm_rows_kernel(const T* __restrict__
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
           const long row = row0 + r;
-          const long rc = min(row, rows - 1);
-          const float gm = gmr[2 * (rc / S)], gr = gmr[2 * (rc / S) + 1];
+          const float gm = gm_[r], gr = gr_[r];
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[r][8 * i + k] = (v[r][8 * i + k] - gm) * gr * w8[k] + b8[k];
           if (row < rows) VecIO<T, 8>::store(xout + row * C + c, v[r] + 8 * i);
@@ -300,12 +306,12 @@ __global__ void __launch_bounds__(256, 3) norm_rows_kernel(const T* __restrict__
           for (int k = 0; k < 8; ++k) o[k] = (v[r][8 * i + k] - mean[r]) * rstd[r] * w8[k] + b8[k];
           if (pe) {
             float p8[8];
-            VecIO<float, 8>::load(pe + (row % S) * C + c, p8);
+            VecIO<float, 8>::load(pe + (long)((int)row % S) * C + c, p8);
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] += p8[k];
           }
           long yoff = row * C;
-          if (yrs.C > 0) yoff = yrs.row_off((int)(row / yrs.R), (int)(row % yrs.R));   // scatter into a padded row space
+          if (yrs.C > 0) yoff = yrs.row_off((int)row / yrs.R, (int)row % yrs.R);   // scatter into a padded row space (rows < 2^31)
           VecIO<T, 8>::store(y + yoff + c, o);
         }
       }
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(256, 2) ln512_rows_kernel(const T* __restrict_
     q = warp_sum(q);
     const float rstd = rsqrtf(q / C + 1e-5f);
     long yoff = row * C;
-    if (yrs.C > 0) yoff = yrs.row_off((int)(row / yrs.R), (int)(row % yrs.R));
+    if (yrs.C > 0) yoff = yrs.row_off((int)row / yrs.R, (int)row % yrs.R);      // (rows < 2^31: 32-bit divisions)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int c = (lane + 32 * i) * 8;
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(256, 2) ln512_rows_kernel(const T* __restrict_
       for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * w[8 * i + k] + b[8 * i + k];
       if (pe) {
         float p8[8];
-        VecIO<float, 8>::load(pe + (row % S) * C + c, p8);
+        VecIO<float, 8>::load(pe + (long)((int)row % S) * C + c, p8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] += p8[k];
       }
@@ -470,23 +476,23 @@ __global__ void add_rowvec_vec_kernel(const T* __restrict__ x, T* __restrict__ y
   pdl_begin();
   constexpr int VEC = 16 / (int)sizeof(T);
   const int cv = C / VEC;
-  const long total = (long)B * rows_per_b * cv;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long row = i / cv;
-    const int c = (int)(i - row * cv) * VEC;
-    const long b = row / rows_per_b;
-    uint4 raw = *(const uint4*)(x + i * VEC);
+  const int total = B * (int)rows_per_b * cv;      // (< 2^31 vectors, checked by the launcher: 32-bit index arithmetic)
+  const int per_b = (int)rows_per_b * cv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / per_b;
+    const int c = (i % cv) * VEC;
+    uint4 raw = *(const uint4*)(x + (long)i * VEC);
     T* e = (T*)&raw;
-    const float* vp = vec + b * vstride + c;
+    const float* vp = vec + (long)b * vstride + c;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) e[k] = from_f<T>(to_f<T>(e[k]) + __ldg(vp + k));
-    *(uint4*)(y + i * VEC) = raw;
+    *(uint4*)(y + (long)i * VEC) = raw;
   }
 }
 template <typename T>
 void launch_add_rowvec(const T* x, T* y, long rows_per_b, int C, int B, const float* vec, long vstride, cudaStream_t st) {
   constexpr int VEC = 16 / (int)sizeof(T);
-  if (C % VEC == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {
+  if (C % VEC == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && (long)B * rows_per_b * (C / VEC) < (1L << 31)) {
     long total = (long)B * rows_per_b * (C / VEC);
     launch_pdl(add_rowvec_vec_kernel<T>, dim3((int)min((total + 255) / 256, (long)148 * 16)), dim3(256), 0, st, x, y, rows_per_b, C, B, vec, vstride);
     return;
