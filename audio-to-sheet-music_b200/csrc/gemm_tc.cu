@@ -64,6 +64,7 @@ struct TcParams {
   int skip_lo, skip_hi;    // output columns [skip_lo, skip_hi) are computed (statistics) but not stored
   uint32_t fdRpA[2], fdG2p[2], fdNt[2];   // (multiplier, shift) of the division-free x / RpA, x / G2p, x / n_tiles (x < 2^31)
   float* fin_mr; double fin_count; int fin_n; unsigned* fin_counter;      // fused statistics finalisation (TcFlat)
+  int b_res;               // weight-stationary: the whole-K B tile of this CTA's (fixed) n-tile is loaded ONCE; the ring carries only A
   int wide;                // 32-byte row accesses allowed (row pitch and base 32-byte aligned, skip range in 16-column units)
 };
 
@@ -265,11 +266,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stageA = TC_BM * TC_BK * 2;
   const int stageB = p.BN * TC_BK * 2;             // BN multiple of 8 -> multiple of 1024 B
   const int nst = p.stages;
+  const int nkb_all = p.ntaps * p.kb_per_tap;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + nst * stageA;
-  uint64_t* bars = (uint64_t*)(sB + nst * stageB);
+  uint8_t* sB = smem + nst * stageA;               // b_res: nkb_all resident K blocks of B instead of a ring
+  uint64_t* bars = (uint64_t*)(sB + (p.b_res ? nkb_all : nst) * stageB);
   uint64_t* full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES, *tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* bres_full = bars + 2 * TC_MAX_STAGES + 6;      // (bytes 176..183 of the barrier block: free)
   float* svec = (float*)(bars + 2 * TC_MAX_STAGES + 8);        // [2 tiles][4 vectors][TC_VEC]
   constexpr int EPI_WARPS = TcCfg<MINB>::EPI_WARPS;
 
@@ -284,6 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
     for (int s = 0; s < nst; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull[i]), 1); mbar_init(smem_u32(&tempty[i]), EPI_WARPS); }
+    mbar_init(smem_u32(bres_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -300,7 +304,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     {
       const bool issuer = elect_one();            // converged warp, one lane issues (see the MMA role)
-      const uint32_t bytes = (uint32_t)(stageA + stageB);
+      const uint32_t bytes = (uint32_t)(stageA + (p.b_res ? 0 : stageB));
+      if (p.b_res && (int)blockIdx.x < n_total_tiles) {
+        // weight-stationary: gridDim.x is a multiple of n_tiles, so t % n_tiles (this CTA's n-tile) never changes: its B tile is
+        // fetched once for all K blocks and stays; short-K layers streamed more weight bytes than activation bytes per tile
+        const int n0 = ((int)blockIdx.x - fast_div((int)blockIdx.x, p.fdNt) * p.n_tiles) * p.BN;
+        if (issuer) {
+          mbar_expect_tx(smem_u32(bres_full), (uint32_t)(nkb_all * stageB));
+          int tap = 0, kin = 0;
+          for (int kb = 0; kb < nkb_all; ++kb) {
+            tma_load_2d(smem_u32(sB + kb * stageB), &tmB, smem_u32(bres_full), tap * p.Ktap + kin, n0);
+            kin += TC_BK;
+            if (kin >= p.Ktap) { kin = 0; ++tap; }
+          }
+        }
+        __syncwarp();
+      }
       // ring position as running counters: no integer divisions on the single-thread critical path (an `it % stages`,
       // `it / stages`, `kb / kb_per_tap` per K block cost more latency than the MMAs of a narrow tile take to execute)
       int s = 0; uint32_t ph = 0;
@@ -315,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (issuer) {
             mbar_expect_tx(fb, bytes);
             tma_load_2d(smem_u32(sA + s * stageA), &tmA, fb, kin, row0 + p.tapRow[tap]);
-            tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
+            if (!p.b_res) tma_load_2d(smem_u32(sB + s * stageB), &tmB, fb, tap * p.Ktap + kin, n0);
           }
           __syncwarp();
           kin += TC_BK;
@@ -333,6 +352,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int i = 0, s = 0; uint32_t ph = 0;
       const uint64_t da0 = make_sw128_desc(smem_u32(sA)), db0 = make_sw128_desc(smem_u32(sB));
       const uint64_t dstepA = (uint64_t)(stageA >> 4), dstepB = (uint64_t)(stageB >> 4);     // descriptor address field is in 16-B units
+      if (p.b_res && (int)blockIdx.x < n_total_tiles) {
+        mbar_wait(smem_u32(bres_full), 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       for (int t = blockIdx.x; t < n_total_tiles; t += gridDim.x, ++i) {
         const int buf = i & 1;
         mbar_wait(smem_u32(&tempty[buf]), ((uint32_t)(i >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
@@ -342,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&full[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = da0 + (uint64_t)s * dstepA, db = db0 + (uint64_t)s * dstepB;
+          const uint64_t da = da0 + (uint64_t)s * dstepA, db = db0 + (uint64_t)(p.b_res ? kb : s) * dstepB;
           const int nmma = (min(TC_BK, p.Ktap - kin) + 15) >> 4;     // columns past Ktap are zero-filled by TMA
           if (issuer) {
             for (int k = 0; k < nmma; ++k)      // advance 16 bf16 = 32 B inside the 128-B swizzle atom
@@ -771,9 +794,10 @@ static int g_tc_pair = -1;      // CTA-pair (cta_group::2) kernel for 256-wide t
                                 // K = 2048 launches measure the same 115-117 us either way (profiles/r01_summary.md).
 static bool g_tc_w12 = true;             // 192-wide tiles on the 12-epilogue-warp variant (tuning flag 0x100000 turns it off)
 static bool g_tc_fuse_fin = true;        // statistics finalised by the GEMM's last CTA (tuning flag 0x200000: separate finalize launch)
+static bool g_tc_bres = true;            // weight-stationary B tiles for short-K layers (tuning flag 0x400000 turns it off)
 static bool g_tc_halve_mid = false;      // tuning: N in (128, 256] as two N/2-wide tiles (two CTAs per SM) instead of one N-wide tile
 void tc_set_bn_cap(int cap) {
-  g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0; g_tc_w12 = !(cap & 0x100000); g_tc_fuse_fin = !(cap & 0x200000);
+  g_tc_bn_cap = cap & 0xffff; g_tc_two_ctas = !(cap & 0x10000); g_tc_halve_mid = (cap & 0x20000) != 0; g_tc_w12 = !(cap & 0x100000); g_tc_fuse_fin = !(cap & 0x200000); g_tc_bres = !(cap & 0x400000);
   g_tc_pair = (cap & 0x40000) ? 1 : (cap & 0x80000) ? 2 : 0;
 }
 
@@ -838,6 +862,18 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   }
   if (!merged &&
       !make_tensor_map_2d(&tmA, f.A, (uint64_t)f.Ktap, (uint64_t)f.a_rows, (uint64_t)f.a_pitch * 2, TC_BK, TC_BM)) return 2;
+  // N = 384 (three 128-wide tiles on two CTAs per SM) cannot keep a whole-K weight tile next to the A ring in 112 KB; as two 192-wide
+  // tiles on one CTA per SM (12 epilogue warps) it can when K <= 384: weight-stationary beats the narrower tiles there
+  // (N = 384, K = 384 transposed conv of the frequency decoder: 734 -> 690 us)
+  if (g_tc_bres && p.BN == 128 && f.N % 192 == 0 && f.N % 256 != 0) {
+    const int nkb_all = p.ntaps * p.kb_per_tap;
+    const int room = 227 * 1024 - 1024 - (512 + 2 * 4 * TC_VEC * 4) - nkb_all * 192 * TC_BK * 2;
+    const long nt192 = f.N / 192, gx = ((long)num_sms() / nt192) * nt192;
+    if (nkb_all >= 4 && room >= 3 * TC_BM * TC_BK * 2 && (long)p.m_tiles * nt192 >= 4 * gx) {      // (K = 192: measured 4 us slower)
+      p.BN = 192; p.n_tiles = (int)nt192;
+      fast_div_init((uint32_t)p.n_tiles, p.fdNt);
+    }
+  }
   if (!make_tensor_map_2d(&tmB, f.B, (uint64_t)f.ntaps * f.Ktap, (uint64_t)f.N, (uint64_t)f.ntaps * f.Ktap * 2, TC_BK, p.BN)) return 3;
   const int stage_bytes = TC_BM * TC_BK * 2 + p.BN * TC_BK * 2;
   // narrow tiles are epilogue-bound: two CTAs per SM (2 x 8 epilogue warps, 2 x 2 accumulators <= 512 TMEM columns)
@@ -845,9 +881,24 @@ int launch_gemm_tc_flat(const TcFlat& f, cudaStream_t st) {
   const int tail_bytes = 512 + 2 * 4 * TC_VEC * 4;          // barriers + staged column vectors
   const int smem_budget = (ctas_per_sm == 2 ? 112 : 227) * 1024 - 1024 - tail_bytes;
   p.stages = std::min(TC_MAX_STAGES, std::max(2, smem_budget / stage_bytes));
-  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
+  size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
   const long tiles = (long)p.m_tiles * p.n_tiles;
-  dim3 grid((unsigned)std::min<long>(tiles, (long)num_sms() * ctas_per_sm));
+  long grid_x = std::min<long>(tiles, (long)num_sms() * ctas_per_sm);
+  // weight-stationary variant: the whole-K B tile of one n-tile stays in shared memory when it leaves room for >= 3 A stages and
+  // every CTA has several m-tiles to amortise it over (short-K layers: transposed convs, strided encoder convs, rewrites)
+  {
+    const int nkb_all = p.ntaps * p.kb_per_tap;
+    const int stA = TC_BM * TC_BK * 2, stB = p.BN * TC_BK * 2;
+    const long gx = ((long)num_sms() * ctas_per_sm / p.n_tiles) * p.n_tiles;
+    const int a_stages = (smem_budget - nkb_all * stB) / stA;
+    if (g_tc_bres && gx >= p.n_tiles && a_stages >= 3 && tiles >= 4 * gx) {
+      p.b_res = 1;
+      p.stages = std::min(TC_MAX_STAGES, a_stages);
+      smem = 1024 + (size_t)p.stages * stA + (size_t)nkb_all * stB + tail_bytes;
+      grid_x = gx;
+    }
+  }
+  dim3 grid((unsigned)grid_x);
   if (g_tc_pair < 0) g_tc_pair = 0;
   // CTA pairs for the 256-wide tiles of long-M problems (transformer linears): 256 x 256 tile per cluster
   const bool pair = (g_tc_pair == 1 || (g_tc_pair == 2 && p.ntaps * p.kb_per_tap >= 24)) && p.BN == 256 && f.N % 256 == 0 && p.m_tiles >= 2 * num_sms() && f.stat_mode != STAT_PER_G1_M &&

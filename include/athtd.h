@@ -147,7 +147,8 @@ int athtd_set_pdl(int on);
 /* tuning hook of the tcgen05 GEMM tile selection (tools/): low 16 bits = widest N tile (256), 0x10000 = one CTA per SM only,
  * 0x20000 = N in (128, 256] as two N/2-wide tiles, 0x40000 / 0x80000 = route eligible 256-wide tiles (all / only K >= 1536) through
  * the cta_group::2 CTA-pair kernel, 0x100000 = 192-wide tiles on the 16- instead of the 12-epilogue-warp variant,
- * 0x200000 = per-segment statistics finalised by a separate launch instead of the GEMM's last CTA.  Every setting computes
+ * 0x200000 = per-segment statistics finalised by a separate launch instead of the GEMM's last CTA, 0x400000 = no weight-stationary
+ * B tiles (short-K layers stream the weight tile with every K block again).  Every setting computes
  * the same GEMM.  Process-wide. */
 int athtd_set_tc_tuning(int flags);
 
