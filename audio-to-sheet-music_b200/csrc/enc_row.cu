@@ -348,7 +348,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
         uint32_t a0[4], a1[4];
         if (mt0 < MT) ldsm_a(hb, D::K2P, mt0 * 16, 0, lane, a0);
         if (mt1 < MT) ldsm_a(hb, D::K2P, mt1 * 16, 0, lane, a1);
-#pragma unroll 2
+#pragma unroll
         for (int nt = 0; nt < D::AT; ++nt) {
           uint32_t bv_[2], bg_[2];
           ldsm_b_pair(w2, D::K2P, nt * 8, (nt + D::AT) * 8, 0, lane, bv_, bg_);
@@ -396,7 +396,7 @@ enc_row_kernel(const bf16* __restrict__ xin, RowSpace xis, const bf16* __restric
             for (int kc = 0; kc < C / 16; ++kc) ldsm_a(xsi, D::XP, (mtb + ti * nwarp) * 16, kc * 16, lane, a[ti][kc]);
           }
         __syncwarp();
-#pragma unroll 2
+#pragma unroll
         for (int nt = 0; nt < D::AT; ++nt) {
           uint32_t bvv[C / 16][2], bgg[C / 16][2];
 #pragma unroll
