@@ -30,7 +30,12 @@ struct FaParams {
   int Sq, Sk;
   float scale_log2;      // (1/sqrt(64)) * log2(e)
   bf16* O; long ldo;     // output rows [B*Sq, ldo], head h at columns h*64
+  int mode;              // two-threads-per-row kernel: 0 = optimistic fixed-reference pass, exact pass only where a row sum left the
+                         // safe window; 1 = exact pass only; 2 = optimistic pass + forced exact redo (test hook of the redo path)
 };
+// optimistic pass: reference = row maximum of the FIRST key tile + 2^60 of headroom in the exp2 domain (see the kernel header)
+static constexpr float FA_HEADROOM = 60.0f;
+static constexpr float FA_LSUM_MAX = 1.2676506e30f;      // 2^100
 
 static constexpr int FA_QB = 16384;     // Q tile: 128 rows x 64 bf16
 static constexpr int FA_KB = 8192;      // K / V tile: 64 keys x 64 bf16
@@ -101,15 +106,19 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (p.Sk + 63) / 64;
 
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQ) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmK) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmV) : "memory");
+  auto init_barriers = [&]() {
     mbar_init(smem_u32(q_full), 1);
     for (int i = 0; i < FA_NK; ++i) { mbar_init(smem_u32(&k_full[i]), 1); mbar_init(smem_u32(&k_empty[i]), 1); }
     for (int i = 0; i < FA_NV; ++i) { mbar_init(smem_u32(&v_full[i]), 1); mbar_init(smem_u32(&v_empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&p_ready[i]), SPLIT ? 256 : 128); mbar_init(smem_u32(&pv_done[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  };
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmV) : "memory");
+    init_barriers();
+    tmem_slot[1] = 0u;       // "some row of the optimistic pass left the safe window": the CTA repeats with the exact softmax
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
@@ -123,6 +132,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   // columns: S buffers [0,64) [64,128), O [128,192), P buffers (bf16 pairs: 64 keys = 32 columns) [192,224) [224,256)
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
 
+  // Softmax warps whose 32 query rows all lie beyond Sq (tail tile: 10 of 128 rows at Sq = 1034, 24 at Sq = 2072) only keep the
+  // barrier protocol going: their P rows stay garbage, which touches nothing but their own (never stored) O rows.
+  const bool live = q0 + (warp & 3) * 32 < p.Sq;
+  bool exact = !SPLIT || p.mode == 1;
+  for (;;) {
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(smem_u32(q_full), FA_QB);
@@ -213,6 +227,45 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     };
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory"); };
+    if (!live) {
+      for (int j = 0; j < nkv; ++j) {      // in step with the tile sequence: p_ready(j) may only be signalled in ITS phase
+        mbar_wait(smem_u32(&s_full[j & 1]), (uint32_t)((j >> 1) & 1));
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[j & 1])) : "memory");
+      }
+    } else if (!exact) {
+      // OPTIMISTIC pass: one reference per row for ALL key tiles, m = (row maximum of key tile 0) + 2^60 of headroom in the exp2
+      // domain, agreed by the row's two threads once.  No per-tile decision, no pair barrier in the tile loop.
+      float mb = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        const int nvalid = min(64, p.Sk - j * 64) - half * 32;
+        mbar_wait(smem_u32(&s_full[j & 1]), (uint32_t)((j >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t r[32];
+        const uint32_t ts = tmem_S + (uint32_t)((j & 1) * 64 + half * 32) + lane_addr;
+        const uint32_t tp = tmem_P + (uint32_t)((j & 1) * 32 + half * 16) + lane_addr;
+        tmem_ld32(ts, r);
+        if (nvalid < 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i >= nvalid) r[i] = 0xff800000u;
+        }
+        if (j == 0) {
+          float mx[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mx[i] = fmaxf(fmaxf(__uint_as_float(r[i]), __uint_as_float(r[8 + i])),
+                                                     fmaxf(__uint_as_float(r[16 + i]), __uint_as_float(r[24 + i])));
+          const float tm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+          xtmax[half * 128 + row] = tm;
+          pair_sync();
+          mb = fmaxf(tm, xtmax[(half ^ 1) * 128 + row]) * cs + FA_HEADROOM;
+        }
+        uint32_t pk[16];
+        exp_pack(r, mb, pk, l01, l23);
+        tmem_st16_nowait(tp, pk);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[j & 1])) : "memory");
+      }
+    } else
     for (int j = 0; j < nkv; ++j) {
       const int nvalid = min(64, p.Sk - j * 64) - half * 32;      // valid keys of MY half (may be <= 0)
       mbar_wait(smem_u32(&s_full[j & 1]), (uint32_t)((j >> 1) & 1));
@@ -274,10 +327,19 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[j & 1])) : "memory");
     }
+    if (live) {
     const float lmine = (l01.x + l01.y) + (l23.x + l23.y);
     xlsum[half * 128 + row] = lmine;
     pair_sync();
-    const float inv = 1.0f / (lmine + xlsum[(half ^ 1) * 128 + row]);
+    const float ltot = lmine + xlsum[(half ^ 1) * 128 + row];
+    if (!exact) {
+      // the optimistic result of a row is valid iff its sum stayed below 2^100: then no P overflowed (the row's largest P is
+      // >= 2^-60, so nothing that matters was flushed either).  Otherwise -- a score more than 160 / scale_log2 above the first
+      // tile's maximum, or inf / NaN -- the whole CTA repeats with the exact running-maximum softmax.
+      const bool bad = (!(ltot < FA_LSUM_MAX) && q0 + row < p.Sq) || p.mode == 2;
+      if (bad) ((volatile uint32_t*)tmem_slot)[1] = 1u;
+    }
+    const float inv = 1.0f / ltot;
     mbar_wait(smem_u32(&pv_done[(nkv - 1) & 1]), (uint32_t)(((nkv - 1) >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     bf16* dst = p.O + ((long)b * p.Sq + q0 + row) * p.ldo + h * 64 + half * 32;
@@ -297,6 +359,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
     }
+    }      // live
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
     const int qd = warp & 3;
@@ -435,6 +498,29 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (!SPLIT || exact || ((volatile uint32_t*)tmem_slot)[1] == 0u) break;
+  // Rare: a row of the optimistic pass left the safe window.  Every role runs the tile sequence again with the exact
+  // running-maximum softmax (Q / K / V are loaded again, O restarts from zero, every result row of the CTA is stored again).
+  // Before the barriers are re-initialised the tensor core's last commit arrivals must have landed.
+  if (warp == 1) {
+    for (int s = 0; s < 3; ++s) {
+      if (s >= nkv) continue;
+      const int jl = ((nkv - 1 - s) / 3) * 3 + s;           // last tile that used ring slot s (FA_NK = FA_NV = 3)
+      mbar_wait(smem_u32(&k_empty[s]), (uint32_t)((jl / 3) & 1));
+      mbar_wait(smem_u32(&v_empty[s]), (uint32_t)((jl / 3) & 1));
+    }
+    if (nkv > 1) mbar_wait(smem_u32(&pv_done[(nkv - 2) & 1]), (uint32_t)(((nkv - 2) >> 1) & 1));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 1 + 2 * FA_NK + 2 * FA_NV + 6; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[i])) : "memory");
+    init_barriers();
+    tmem_slot[1] = 0u;
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  exact = true;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
@@ -447,8 +533,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // how many of 16 exp2 pairs go to the polynomial path (every variant computes the same softmax; tuning hook of the tests / tools)
 static int g_fa_npoly = 4;      // measured on B200 (tools/flash_bench.py): 0 -> 438 us, 4 -> 408 us, 6 -> 413 us, 8 -> 431 us (frequency self-attention, B = 32)
 static bool g_fa_split = true;      // two threads per query row (SPLIT variant); flash_attn_set_poly(npoly | 0x100) selects the one-thread-per-row kernel
+static int g_fa_mode = 0;           // FaParams::mode; flash_attn_set_poly(npoly | 0x200): exact softmax only, | 0x400: optimistic pass + forced redo
 void flash_attn_set_poly(int npoly) {
   g_fa_split = !(npoly & 0x100);
+  g_fa_mode = (npoly & 0x200) ? 1 : (npoly & 0x400) ? 2 : 0;
   npoly &= 0xff;
   g_fa_npoly = npoly <= 0 ? 0 : npoly <= 4 ? 4 : npoly <= 6 ? 6 : 8;
 }
@@ -465,7 +553,7 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
   if (!make_tensor_map_2d(&tmK, k, 512, (uint64_t)B * Sk, (uint64_t)ldkv * 2, 64, 64)) return 3;
   if (!make_tensor_map_2d(&tmV, v, 512, (uint64_t)B * Sk, (uint64_t)ldkv * 2, 64, 64)) return 4;
   FaParams p;
-  p.Sq = Sq; p.Sk = Sk; p.scale_log2 = 0.125f * 1.4426950408889634f; p.O = o; p.ldo = ldo;
+  p.Sq = Sq; p.Sk = Sk; p.scale_log2 = 0.125f * 1.4426950408889634f; p.O = o; p.ldo = ldo; p.mode = g_fa_mode;
   const size_t smem = 1024 + FA_QB + (FA_NK + FA_NV) * FA_KB + 256 + 64 + 512 * 4;
   static PerDeviceOnce attr;
   if (attr.first()) {

@@ -171,11 +171,12 @@ def test_fused_attention_matches_torch(B, Sq, Sk):
     assert (got - ref).abs().max() < 2e-2
 
 
-@pytest.mark.parametrize("npoly", [4, 6, 8, 0x100 | 4, 0x100 | 8])
+@pytest.mark.parametrize("npoly", [4, 6, 8, 0x100 | 4, 0x100 | 8, 0x200 | 4, 0x400 | 4])
 def test_fused_attention_polynomial_exp2_variants(npoly):
     """The attention softmax may take part of its exp2 on the FMA pipe (degree-3 polynomial): same result to bf16 accuracy, also
     with masked key columns (Sk not a multiple of 64) and many key tiles.  Flag 0x100 selects the one-thread-per-row softmax (the
-    default splits every row between two threads)."""
+    default splits every row between two threads), 0x200 the exact running-maximum softmax only, 0x400 the optimistic pass followed
+    by a forced exact redo."""
     lib = alib.load()
     B, Sq, Sk = 2, 300, 1034
     g = torch.Generator().manual_seed(npoly)
@@ -200,7 +201,7 @@ def test_fused_attention_polynomial_exp2_variants(npoly):
     assert ((got - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all()
 
 
-@pytest.mark.parametrize("npoly", [0, 4, 0x100 | 4])
+@pytest.mark.parametrize("npoly", [0, 4, 0x100 | 4, 0x200 | 4, 0x400 | 4])
 @pytest.mark.parametrize("Sq,Sk", [(200, 64), (128, 65), (128, 33), (300, 1034), (257, 2072)])
 def test_fused_attention_moving_row_maximum(npoly, Sq, Sk):
     """Online-softmax stress: score magnitudes grow along the key axis, so the running reference maximum of most rows moves in many
@@ -228,3 +229,43 @@ def test_fused_attention_moving_row_maximum(npoly, Sq, Sk):
     got = o.float().cpu()
     assert torch.isfinite(got).all()
     assert ((got - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all()
+
+
+@pytest.mark.parametrize("Sq,Sk", [(300, 1034), (130, 200), (1034, 2072)])
+def test_fused_attention_optimistic_pass_and_exact_redo(Sq, Sk):
+    """The default softmax keeps ONE reference per row (first key tile's maximum + 2^60 headroom) and a CTA repeats with the exact
+    running-maximum softmax when a row sum leaves the safe window.  Steep case: logits of the late keys are hundreds of nats above
+    the first tile's (a jump beyond the 2^160 window), so the redo runs by itself; it must return exactly what the exact-only
+    kernel returns (flag 0x200), as must the forced redo (0x400), and all of them the fp32 softmax on the bf16-rounded inputs."""
+    lib = alib.load()
+    B = 2
+    g = torch.Generator().manual_seed(Sq + 3 * Sk)
+    ramp = torch.cat([torch.full((64,), 0.02), torch.linspace(0.02, 8.0, Sk - 64)]).view(1, Sk, 1)
+    q = (3.0 * torch.randn(B, Sq, 512, generator=g)).bfloat16()
+    k = (3.0 * torch.randn(B, Sk, 512, generator=g) * ramp).bfloat16()
+    v = torch.randn(B, Sk, 512, generator=g).bfloat16()
+    qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+    outs = {}
+    try:
+        for flags in (4, 0x200 | 4, 0x400 | 4):
+            o = torch.full((B, Sq, 512), float("nan"), dtype=torch.bfloat16, device="cuda")
+            lib.athtd_attention_set_poly(flags)
+            alib.check(lib.athtd_attention_test(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, Sq, Sk, _stream()))
+            torch.cuda.synchronize()
+            outs[flags] = o.float().cpu()
+    finally:
+        lib.athtd_attention_set_poly(4)          # the default
+    qh = q.float().view(B, Sq, 8, 64).transpose(1, 2)
+    kh = k.float().view(B, Sk, 8, 64).transpose(1, 2)
+    vh = v.float().view(B, Sk, 8, 64).transpose(1, 2)
+    logits = qh @ kh.transpose(-1, -2) / 8.0
+    jump = (logits.amax(-1) - logits[..., :64].amax(-1)).max().item()
+    assert jump > 160 * 0.6931472, f"test data do not leave the optimistic window (largest jump {jump:.0f} nats)"
+    ref = (torch.softmax(logits, dim=-1) @ vh).transpose(1, 2).reshape(B, Sq, 512)
+    for flags, got in outs.items():
+        assert torch.isfinite(got).all(), hex(flags)
+        assert ((got - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all(), hex(flags)
+    assert torch.equal(outs[0x400 | 4], outs[0x200 | 4])
+    # rows of CTAs that did not leave the window keep their optimistic result; all others are the exact kernel's
+    frac_equal = (outs[4] == outs[0x200 | 4]).all(-1).float().mean().item()
+    assert frac_equal > 0.5, frac_equal
