@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace athtd {
 
@@ -235,20 +236,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     } else if (!exact) {
       // OPTIMISTIC pass: one reference per row for ALL key tiles, m = (row maximum of key tile 0) + 2^60 of headroom in the exp2
       // domain, agreed by the row's two threads once.  No per-tile decision, no pair barrier in the tile loop.
+      // The first and the last key tile (reference / key mask) are peeled off; the loop in between is unrolled by two so that the
+      // S / P buffer of a tile is a compile-time constant.
       float mb = 0.f;
-      for (int j = 0; j < nkv; ++j) {
-        const int nvalid = min(64, p.Sk - j * 64) - half * 32;
-        mbar_wait(smem_u32(&s_full[j & 1]), (uint32_t)((j >> 1) & 1));
+      auto opt_tile = [&](const int j, const uint32_t buf, auto first, auto edge) {
+        mbar_wait(smem_u32(&s_full[buf]), (uint32_t)((j >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t r[32];
-        const uint32_t ts = tmem_S + (uint32_t)((j & 1) * 64 + half * 32) + lane_addr;
-        const uint32_t tp = tmem_P + (uint32_t)((j & 1) * 32 + half * 16) + lane_addr;
-        tmem_ld32(ts, r);
-        if (nvalid < 32) {
+        tmem_ld32(tmem_S + (buf * 64u + (uint32_t)(half * 32)) + lane_addr, r);
+        if constexpr (decltype(edge)::value) {
+          const int nvalid = min(64, p.Sk - j * 64) - half * 32;      // valid keys of MY half (may be <= 0)
+          if (nvalid < 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (i >= nvalid) r[i] = 0xff800000u;
+            for (int i = 0; i < 32; ++i) if (i >= nvalid) r[i] = 0xff800000u;     // -inf: exp2 -> 0, ignored by the maximum
+          }
         }
-        if (j == 0) {
+        if constexpr (decltype(first)::value) {
           float mx[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) mx[i] = fmaxf(fmaxf(__uint_as_float(r[i]), __uint_as_float(r[8 + i])),
@@ -260,11 +263,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         uint32_t pk[16];
         exp_pack(r, mb, pk, l01, l23);
-        tmem_st16_nowait(tp, pk);
+        tmem_st16_nowait(tmem_P + (buf * 32u + (uint32_t)(half * 16)) + lane_addr, pk);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[j & 1])) : "memory");
-      }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p_ready[buf])) : "memory");
+      };
+      const std::true_type yes; const std::false_type no;
+      opt_tile(0, 0u, yes, yes);
+      int j = 1;
+      for (; j + 2 < nkv; j += 2) { opt_tile(j, 1u, no, no); opt_tile(j + 1, 0u, no, no); }
+      if (j + 1 < nkv) { opt_tile(j, 1u, no, no); ++j; }
+      if (j < nkv) opt_tile(j, (uint32_t)(j & 1), no, yes);
     } else
     for (int j = 0; j < nkv; ++j) {
       const int nvalid = min(64, p.Sk - j * 64) - half * 32;      // valid keys of MY half (may be <= 0)
@@ -538,7 +547,7 @@ void flash_attn_set_poly(int npoly) {
   g_fa_split = !(npoly & 0x100);
   g_fa_mode = (npoly & 0x200) ? 1 : (npoly & 0x400) ? 2 : 0;
   npoly &= 0xff;
-  g_fa_npoly = npoly <= 0 ? 0 : npoly <= 4 ? 4 : npoly <= 6 ? 6 : 8;
+  g_fa_npoly = npoly <= 0 ? 0 : npoly <= 4 ? 4 : npoly <= 5 ? 5 : npoly <= 6 ? 6 : 8;
 }
 
 bool flash_attn_supported(long ldq, long ldkv, long ldo) {
@@ -563,6 +572,7 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
     cudaFuncSetAttribute(flash_attn_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(flash_attn_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(flash_attn_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(flash_attn_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(flash_attn_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
@@ -571,6 +581,7 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
     switch (g_fa_npoly) {
       case 0: launch_pdl(flash_attn_kernel<0, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
       case 4: launch_pdl(flash_attn_kernel<4, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
+      case 5: launch_pdl(flash_attn_kernel<5, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
       case 6: launch_pdl(flash_attn_kernel<6, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
       default: launch_pdl(flash_attn_kernel<8, true>, grid, dim3(320), smem, st, tmQ, tmK, tmV, p); break;
     }
@@ -578,7 +589,7 @@ int launch_flash_attn(const bf16* q, long ldq, const bf16* k, const bf16* v, lon
   }
   switch (g_fa_npoly) {
     case 0: launch_pdl(flash_attn_kernel<0, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
-    case 4: launch_pdl(flash_attn_kernel<4, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
+    case 4: case 5: launch_pdl(flash_attn_kernel<4, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
     case 6: launch_pdl(flash_attn_kernel<6, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
     default: launch_pdl(flash_attn_kernel<8, false>, grid, dim3(192), smem, st, tmQ, tmK, tmV, p); break;
   }
