@@ -171,7 +171,7 @@ def test_fused_attention_matches_torch(B, Sq, Sk):
     assert (got - ref).abs().max() < 2e-2
 
 
-@pytest.mark.parametrize("npoly", [4, 6, 8, 0x100 | 4, 0x100 | 8, 0x200 | 4, 0x400 | 4])
+@pytest.mark.parametrize("npoly", [4, 5, 6, 8, 0x100 | 4, 0x100 | 8, 0x200 | 4, 0x400 | 4])
 def test_fused_attention_polynomial_exp2_variants(npoly):
     """The attention softmax may take part of its exp2 on the FMA pipe (degree-3 polynomial): same result to bf16 accuracy, also
     with masked key columns (Sk not a multiple of 64) and many key tiles.  Flag 0x100 selects the one-thread-per-row softmax (the
