@@ -12,12 +12,19 @@
 //                lane quarter; the one-thread-per-row variant runs warps 2..5 only): the scores of a tile are read from TMEM
 //                once, P = exp2(s * scale - m) goes as bf16 pairs into one of two 32-column TMEM buffers and is consumed by
 //                the PV MMA as its TMEM A operand: no shared-memory round trip, no generic -> async proxy fence.
-//                The exponentials run speculatively against the current reference m (a quarter of them as a degree-3
-//                polynomial on the FMA pipe: the SFU bounds this head-dim-64 kernel).  m only moves when a score exceeds it by
-//                more than 2^16 in the exp2 domain (softmax is invariant to m; P <= 2^16 is harmless in bf16 / fp32), which is
-//                DETECTED from the tile's row sum (needed anyway) instead of a per-tile maximum tree.  Then -- rarely, mostly
-//                in the first tiles -- the exact row maximum is formed (the two threads of a row exchange theirs through
-//                shared memory behind a 64-thread named barrier), the row's O is rescaled in TMEM and the tile is redone.
+//                OPTIMISTIC pass (default): ONE reference per row for all key tiles, m = (row maximum of key tile 0) + 2^60 of
+//                headroom in the exp2 domain, agreed once by the row's two threads.  Softmax is invariant to m, bf16 / fp32 keep
+//                their relative precision down to 2^-126, so the result is exact as long as no P overflows: a row is valid iff
+//                its sum stays below 2^100 (then every P did; the row's largest P is >= 2^-60, so nothing that matters was
+//                flushed).  The tile loop has no per-tile decision and no pair barrier (a quarter of the exponentials run as a
+//                degree-3 polynomial on the FMA pipe: the SFU is the busiest pipe of this head-dim-64 kernel).  If a row sum
+//                leaves the window -- a score more than 160 / scale_log2 = 111 nats above the first tile's maximum, or inf /
+//                NaN -- the WHOLE CTA repeats the tile sequence with the EXACT pass (barriers re-initialised, O restarted):
+//                EXACT pass: running reference that moves when a score exceeds it by more than 2^16 in the exp2 domain; the
+//                exponentials run speculatively against the current reference and a move is DETECTED from the tile's row sum
+//                instead of a per-tile maximum tree.  Then the exact row maximum is formed (the two threads of a row exchange
+//                theirs through shared memory behind a 64-thread named barrier), the row's O is rescaled in TMEM and the tile
+//                is redone.  Softmax warps whose 32 rows lie beyond Sq (tail query tile) only keep the barrier protocol going.
 // TMEM use is 256 columns and shared memory 69 KB, so two CTAs share an SM and one CTA's softmax overlaps
 // the other's MMAs; inside a CTA the double-buffered S / P let the tensor core run one tile ahead of the softmax.
 #include "kernels.cuh"
@@ -83,7 +90,8 @@ __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t*
 // row and tile = 512 SFU cycles against 256 tensor-pipe cycles); the FMA pipe is ~10 % busy.
 // SPLIT: EIGHT softmax warps, two threads per query row that take 32 of the 64 keys of every tile each (warps w and w + 4 share a
 // TMEM lane quarter).  Four instead of two softmax warps per SM sub-partition keep the SFU fed while other warps sit in their
-// FMA / pack / TMEM phases; the pair agrees on the (rare) moves of the reference maximum through a per-tile named barrier.
+// FMA / pack / TMEM phases; in the exact pass the pair agrees on the moves of the reference maximum through a per-tile named
+// barrier, in the optimistic pass only once (first key tile) and for the final row sum.
 template <int NPOLY, bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? 320 : 192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
