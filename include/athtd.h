@@ -138,8 +138,10 @@ int athtd_chunk_fade_add(const float* seg_out_dev, long seg_stride, int k_base, 
 int athtd_sdr_sums(const float* est_dev, const float* tgt_dev, int items, long n, double* sums_dev, void* stream);
 
 /* tuning hook: how many of every 16 exp2 pairs of the attention softmax are evaluated by the FMA-pipe polynomial instead of the
- * SFU (0, 4, 6 or 8; every setting computes the same softmax to bf16 accuracy); | 0x100 selects the one-thread-per-row softmax instead
- * of the default two threads per query row.  Process-wide. */
+ * SFU (0, 4, 5, 6 or 8; every setting computes the same softmax to bf16 accuracy); | 0x100 selects the one-thread-per-row softmax instead
+ * of the default two threads per query row; | 0x200 runs only the exact running-maximum pass (the default runs an optimistic
+ * fixed-reference pass and repeats a CTA with the exact pass when a row sum leaves its safe window); | 0x400 forces that repeat
+ * (test hook).  Every combination returns the same softmax.  Process-wide. */
 int athtd_attention_set_poly(int npoly);
 /* programmatic dependent launch of the path's kernels (default OFF: measured 3 % slower on this path, profiles/r02_summary.md): a kernel's CTAs may set up (barrier init, TMEM allocation,
  * weight staging) while its predecessor drains; every kernel waits for the predecessor before touching its data.  Process-wide. */
