@@ -722,8 +722,10 @@ void launch_dec_apply(const T* u, int Uin, RowSpace us, int Cu, T* out, RowSpace
                       const float* mr, const float* gw, const float* gb, const T* skip, RowSpace ss,
                       cudaStream_t st) {
   const int vec = os.C % 8 == 0 ? 8 : 4;
-  const bool stage = Uin <= os.R + 8 && Cu == os.C;       // all input rows are stored and used
   const double ratio = (double)Uin / (double)os.R;
+  // all input rows are stored and used AND a staged row serves several outputs or the group is short; the long ~1:1 resizes of
+  // the time branch take the direct form
+  const bool stage = Uin <= os.R + 8 && Cu == os.C && !(ratio > 0.9 && os.R >= 2048);
   const int RW = 256 / (os.C / vec);
   // staged: as many output rows per block as 40 KB of staged fp32 input rows allow (amortises the load -> GELU -> sync
   // latency chain); direct: ~128 rows per block
