@@ -320,7 +320,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // (occupancy instead of one 150 KB CTA per SM).  The y tile arrives through cp.async while the expand is evaluated; the
 // residual update happens after it has landed.
 template <int C, int CS, int TM, bool PER_ROW, bool REWRITE>
-__global__ void __launch_bounds__(256) dconv_c_kernel(const DcTileParams p) {
+__global__ void __launch_bounds__(256, (!REWRITE && C <= 96) ? 5 : 0) dconv_c_kernel(const DcTileParams p) {
   pdl_begin();
   typedef DcDims<C> D;
   constexpr int MW = TM / 16, NG = 8 / MW, CV = CS / 8, XPS = CS + 8;
