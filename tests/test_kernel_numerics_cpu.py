@@ -90,3 +90,18 @@ def test_optimistic_reference_is_exact_inside_its_window_and_flags_outside():
     assert not valid.any()
     head, lmax = float(_const("FA_HEADROOM")), float(_const("FA_LSUM_MAX"))
     assert head == 60.0 and lmax == 2.0 ** 100
+
+
+def test_fast_gelu_fit_matches_erf_gelu():
+    """common.cuh gelu_fast: erf(x / sqrt 2) ~ tanh(x (a0 + a1 x^2 + a2 x^4)) with x^2 clamped at 32; the header states |GELU error| <= 2.9e-5
+    with an exact tanh (tanh.approx adds a relative 2^-11 on top, covered by the GPU parity tests)."""
+    from math import erf
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "audio-to-sheet-music_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float gelu_fast(float x)"):]
+    a2, a1 = [float(v) for v in re.search(r"fmaf\((-?[0-9.e+-]+)f, x2, ([0-9.e+-]+)f\)", body).groups()]
+    a0 = float(re.search(r"fmaf\(p, x2, ([0-9.e+-]+)f\)", body).group(1))
+    x = np.linspace(-12.0, 12.0, 480001)
+    x2 = np.minimum(x * x, 32.0)
+    fast = 0.5 * x * (1.0 + np.tanh(x * ((a2 * x2 + a1) * x2 + a0)))
+    ref = 0.5 * x * (1.0 + np.vectorize(erf)(x / np.sqrt(2.0)))
+    assert np.abs(fast - ref).max() <= 2.9e-5 * 1.05
